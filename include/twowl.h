@@ -1,0 +1,249 @@
+/*
+ * twowl.h - C ABI of libtwowl_b200.so: the TwoWL (local 2-WL link prediction) message-passing
+ * hot path of NguyenTrieu903/Link-Prediction-GNN as hand-written CUDA kernels for sm_100a.
+ *
+ * Reference interfaces replaced (file:line relative to the reference repository):
+ *   TwoWL/utils.py:8-90            graph operators (degree, set_mul, check_in_set, get_ei2, blockei2,
+ *                                  idx2mask, sample_block, reverse, double)
+ *   TwoWL/model/model.py:37,73,77  torch_geometric.nn.GCNConv  (gcn_norm + linear + propagate + bias)
+ *   TwoWL/model/model.py:38,54     torch_geometric.nn.GraphNorm (+ the Dropout / ReLU that follow it
+ *                                  in Seq, model.py:36-41)
+ *   TwoWL/model/model.py:53,71     nn.Embedding lookup by degree
+ *   TwoWL/model/model.py:75        pair init  x[pos[:,0]] * x[pos[:,1]]
+ *   TwoWL/model/model.py:78-83     readout    x[idx]; even*odd; Linear(c2, 1)
+ *   TwoWL/utils.py:5,10            torch_scatter.scatter_add
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with h_. The library never allocates,
+ *     frees or retains device memory: outputs and workspaces are caller-owned (the PyTorch caching
+ *     allocator on the Python side). `*_workspace_bytes` gives the scratch size an op needs.
+ *   - Index tensors at the API are int64, exactly as the reference passes them; `stride` arguments are
+ *     element strides so that transposed views (get_ei2 returns cat(...).t(), utils.py:45) need no copy.
+ *     Internally ids are narrowed to int32 (requires row counts < 2^31); wedge offsets stay int64.
+ *   - Features are fp32 row-major [rows, C]; every feature base pointer must be 16-byte aligned and
+ *     C % 4 == 0 for the vectorised kernels (C <= 1024). Other widths are TWOWL_EINVAL.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*). No call synchronises the
+ *     device; data-dependent sizes come back through device scalars the caller reads.
+ *   - Return 0 on success, a positive cudaError_t, or a negative TWOWL_E*; twowl_last_error() gives
+ *     a thread-local message. No exception crosses the ABI. There is no CPU fallback.
+ */
+#ifndef TWOWL_H_
+#define TWOWL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWOWL_OK 0
+#define TWOWL_EINVAL (-22)
+#define TWOWL_ENOSPC (-28)
+
+/* Rows of a CSR longer than this are split into chunks of this many entries (load balance for
+ * power-law degree); see twowl_rowplan_build. */
+#define TWOWL_CHUNK 1024
+
+int twowl_version(void);
+const char* twowl_last_error(void);
+
+/* ------------------------------------------------------------------ integer operators ---------- */
+
+/* degree (utils.py:8-10): out[v] = #{e : keys[e*stride] == v}, v in [0,num_node). out is int64[num_node]
+ * and is zeroed by the call. Keys outside the range are ignored. */
+int twowl_degree(const int64_t* keys, int64_t stride, int64_t n, int64_t num_node, int64_t* out,
+                 void* stream);
+
+/* Stable counting sort of the positions 0..n-1 by key = keys[i*stride] ^ key_xor:
+ *   ptr[k]   (int64[num_keys+1]) start of key k, ptr[num_keys] = number of in-range keys
+ *   ids[...] (int32[n])          positions ordered by (key, position); out-of-range keys sort last.
+ * This is the in-list / out-list build of get_ei2 (utils.py:41-44 `idx[edge[0]==i]` for all i at once)
+ * and the CSR-by-target build the aggregation kernels consume. */
+size_t twowl_csr_build_workspace_bytes(int64_t n, int64_t num_keys);
+int twowl_csr_build(const int64_t* keys, int64_t stride, int64_t n, int64_t key_xor, int64_t num_keys,
+                    int64_t* ptr, int32_t* ids, void* ws, size_t ws_bytes, void* stream);
+
+/* out[k] = (int32)(vals[ids[k]*stride] ^ val_xor) - payload gather after twowl_csr_build. */
+int twowl_gather_cols(const int32_t* ids, int64_t n, const int64_t* vals, int64_t stride, int64_t val_xor,
+                      int32_t* out, void* stream);
+
+/* get_ei2 (utils.py:36-45), step 1: off[i] = sum_{j<i} cin[j]*cout[j] for i in [0,n_node], from the two
+ * CSR pointer arrays (in-list of observed edges by target, out-list of all pairs by source).
+ * off[n_node] = T. */
+size_t twowl_ei2_count_workspace_bytes(int64_t n_node);
+int twowl_ei2_count(const int64_t* in_ptr, const int64_t* out_ptr, int64_t n_node, int64_t* off, void* ws,
+                    size_t ws_bytes, void* stream);
+/* step 2: write wedges t in [t_begin, t_end) as interleaved (a, b) int64 pairs: out_ab[(t-t_begin)*2+0] = a,
+ * +1 = b. The [T,2] layout viewed transposed is byte-identical to the reference's return value. A rank of a
+ * multi-GPU job fills only its own [t_begin, t_end). */
+int twowl_ei2_fill(const int64_t* in_ptr, const int32_t* in_ids, const int64_t* out_ptr, const int32_t* out_ids,
+                   const int64_t* off, int64_t n_node, int64_t t_begin, int64_t t_end, int64_t* out_ab,
+                   void* stream);
+
+/* idx2mask (utils.py:53-57): mask[0..num) = 0 then mask[idx[j]] = 1 (uint8). */
+int twowl_mask_from_idx(const int64_t* idx, int64_t k, uint8_t* mask, int64_t num, void* stream);
+
+/* Order-preserving column selection of a [2,T] int64 matrix (blockei2 utils.py:48-50; the ei filter of
+ * sample_block utils.py:62-63):
+ *   mode 0: keep column t iff !mask[t]            mode 1: keep column t iff !mask[row0[t]]
+ * count writes tile_off (int64[ntiles+1], ntiles = ceil(T/TWOWL_SELECT_TILE)); tile_off[ntiles] = T'.
+ * fill writes out0/out1 (int64[T'] each). */
+#define TWOWL_SELECT_TILE 2048
+size_t twowl_select_workspace_bytes(int64_t T);
+int twowl_select_count(const int64_t* row0, int64_t s0, int64_t T, const uint8_t* mask, int64_t mask_len, int mode,
+                       int64_t* tile_off, void* ws, size_t ws_bytes, void* stream);
+int twowl_select_fill(const int64_t* row0, int64_t s0, const int64_t* row1, int64_t s1, int64_t T,
+                      const uint8_t* mask, int64_t mask_len, int mode, const int64_t* tile_off, int64_t* out0,
+                      int64_t* out1, void* stream);
+
+/* check_in_set (utils.py:22-33): out[t] = #{j : set[j] == target[t]} for values in [0, range). */
+int twowl_check_in_set(const int64_t* target, int64_t st, int64_t n, const int64_t* set, int64_t m, int64_t range,
+                       int32_t* counts_ws /* int32[range] */, int64_t* out, void* stream);
+
+/* reverse (utils.py:71-78): edge = [row0^1; row1], edge_r = [row0; row1^1], both contiguous [2,T]. */
+int twowl_reverse(const int64_t* row0, int64_t s0, const int64_t* row1, int64_t s1, int64_t T, int64_t* edge,
+                  int64_t* edge_r, void* stream);
+
+/* double (utils.py:81-90). edges: out[2,2M] with columns 2k=(r,c), 2k+1=(c,r). index: out[2B] = 2k,2k+1. */
+int twowl_double_edges(const int64_t* r, int64_t sr, const int64_t* c, int64_t sc, int64_t M, int64_t* out,
+                       void* stream);
+int twowl_double_index(const int64_t* x, int64_t sx, int64_t B, int64_t* out, void* stream);
+
+/* set_mul (utils.py:13-19): out[(i*q+j)*2+0] = a[i], +1 = b[j]. */
+int twowl_set_mul(const int64_t* a, int64_t p, const int64_t* b, int64_t q, int64_t* out, void* stream);
+
+/* int64 -> int32 narrowing copy with stride (pair table columns, index vectors). */
+int twowl_narrow_i32(const int64_t* in, int64_t stride, int64_t n, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------ aggregation ---------------- */
+
+/* Load-balance plan for a CSR: rows longer than TWOWL_CHUNK are cut into chunks handled by whole CTAs.
+ *   plan (int32[twowl_rowplan_ints(M, nnz)]) layout: [0]=number of chunks, then chunk_row[cap], then
+ *   chunk_begin as int64[cap] (8-byte aligned).  */
+int64_t twowl_rowplan_ints(int64_t M, int64_t nnz);
+size_t twowl_rowplan_workspace_bytes(int64_t M);
+int twowl_rowplan_build(const int64_t* ptr, int64_t M, int64_t nnz, int32_t* plan, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* gcn_norm degree (PyG 2.3.1 gcn_norm as used by GCNConv, model.py:37): for the CSR-by-target (ptr, col)
+ * dinv[m] = (1 + #{k in row m : col[k] != m})^-1/2  - self-loops removed, one self-loop added. */
+int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, float* dinv, void* stream);
+
+/* The one segmented gather-reduce all aggregations run through. For each row m of the CSR (ptr, col):
+ *   acc      = sum_{k in row m, kept} src_scale[s] * X[s] (* X2[mul_idx[col[k]]] if X2)   with s = col[k] ^ flip
+ *   kept     = !(skip_self && s == m) && !(skip_mask && skip_mask[col[k]])
+ *   out[m]   = (dst_scale ? dst_scale[m] : 1) * acc
+ *            + (self_mode == 1 ? dst_scale[m]^2 * X[m] : 0)          (the GCN self-loop)
+ *            + (bias ? bias : 0)                        (+ previous out[m] if accumulate)
+ * Sums run in CSR order inside fixed-shape trees: deterministic, no atomics. */
+typedef struct twowl_seg_args {
+  const int64_t* ptr;        /* [M+1] */
+  const int32_t* col;        /* [nnz] */
+  const int32_t* plan;       /* from twowl_rowplan_build */
+  int64_t M;                 /* output rows */
+  int64_t nnz;
+  const float* X;            /* [rows_src, C] gathered rows */
+  int32_t C;
+  int32_t flip;              /* 0 or 1: gathered row id = col ^ flip */
+  const float* src_scale;    /* [rows_src] or NULL */
+  const uint8_t* skip_mask;  /* indexed by col[k] (before flip) or NULL */
+  int32_t skip_self;
+  int32_t self_mode;
+  const float* dst_scale;    /* [M] or NULL */
+  const float* bias;         /* [C] or NULL */
+  const float* X2;           /* optional second factor [rows2, C] */
+  const int32_t* mul_idx;    /* row of X2 = mul_idx[col[k]] */
+  float* out;                /* [M, C] */
+  int32_t accumulate;
+} twowl_seg_args;
+size_t twowl_seg_reduce_workspace_bytes(int64_t M, int64_t nnz, int32_t C);
+int twowl_seg_reduce(const twowl_seg_args* h_args, void* ws, size_t ws_bytes, void* stream);
+
+/* nn.Embedding forward / any row gather: out[r] = W[idx[r*stride]]  ([n, C]). */
+int twowl_gather_rows(const float* W, int64_t rows_w, const int64_t* idx, int64_t stride, int64_t n, int32_t C,
+                      float* out, void* stream);
+
+/* pair init (model.py:75): out[p] = X[src[p]] * X[dst[p]]. */
+int twowl_pair_init_fwd(const float* X, const int32_t* src, const int32_t* dst, int64_t R, int32_t C, float* out,
+                        void* stream);
+
+/* readout (model.py:78-83): pred[l] = sum_c H[idx[2l],c] * H[idx[2l+1],c] * w[c] + b.
+ * bwd: dH must be zero-filled by the caller; rows idx[j] receive their gradient (duplicates in idx are
+ * summed in index order via the sorted (key, position) list from twowl_csr_build-style sort: `order` is
+ * int32[2L] positions sorted by idx value, `sorted_idx` the idx values in that order).
+ * dw[C], db[1] are written (not accumulated). */
+int twowl_readout_fwd(const float* H, const int64_t* idx, int64_t sidx, int64_t L, int32_t C, const float* w,
+                      const float* b, float* pred, void* stream);
+size_t twowl_readout_bwd_workspace_bytes(int64_t L, int32_t C);
+int twowl_readout_bwd(const float* H, const int64_t* idx, int64_t sidx, int64_t L, int32_t C, const float* w,
+                      const float* dpred, const int32_t* order, float* dH, float* dw, float* db, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ GraphNorm (+Dropout+ReLU) --- */
+
+/* Column statistics of x[M,C] for GraphNorm (model.py:38,54; PyG 2.3.1, batch=None):
+ *   stats[0:C] = mean_c(x),  stats[C:2C] = 1/sqrt(mean_c((x - mean_scale*mean)^2) + eps)
+ * computed in one pass over x with shifted sums (shift = mean of the first rows) and a double-precision
+ * combine using  E[(x-a*mu)^2] = Var(x) + (1-a)^2 mu^2. */
+size_t twowl_graphnorm_stats_workspace_bytes(int64_t M, int32_t C);
+int twowl_graphnorm_stats(const float* x, int64_t M, int32_t C, const float* mean_scale, float eps, float* stats,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* y = weight*(x - mean_scale*mean)*inv_std + bias ; then dropout(p, seed) if p > 0 ; then ReLU if relu.
+ * out = y  or  out += y (accumulate: the conv2s + conv2s_r branch sum of model.py:77). out may alias x. */
+int twowl_graphnorm_apply(const float* x, int64_t M, int32_t C, const float* stats, const float* weight,
+                          const float* bias, const float* mean_scale, float p_drop, uint64_t seed, int32_t relu,
+                          int32_t accumulate, float* out, void* stream);
+
+/* Backward of the fused GraphNorm+Dropout+ReLU. Given dout (gradient w.r.t. the fused output) and the saved
+ * input x + stats:  dx[M,C] and dparams[3C] = (dweight, dbias, dmean_scale) are written. */
+size_t twowl_graphnorm_bwd_workspace_bytes(int64_t M, int32_t C);
+int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M, int32_t C, const float* stats,
+                        const float* weight, const float* bias, const float* mean_scale, float p_drop,
+                        uint64_t seed, int32_t relu, float* dx, float* dparams, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* out[c] = sum_m x[m,c] (bias gradients). Deterministic two-level sum. */
+size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C);
+int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ dense linear layers --------- */
+
+/* PyG Linear without bias (GCNConv.lin, model.py:37): Z[M,Co] = X[M,Ci] * W[Co,Ci]^T, fp32 in/out.
+ * impl 0: SIMT FFMA tiles.  impl 1: tcgen05.mma kind::tf32 with 3xTF32 split operands (fp32-accurate).
+ * bwd_input: dX[M,Ci] = dZ[M,Co] * W[Co,Ci].   bwd_weight: dW[Co,Ci] = dZ^T X (split over M, fixed order). */
+int twowl_linear_fwd(const float* X, const float* W, int64_t M, int32_t Ci, int32_t Co, float* Z, int32_t impl,
+                     void* stream);
+int twowl_linear_bwd_input(const float* dZ, const float* W, int64_t M, int32_t Ci, int32_t Co, float* dX,
+                           int32_t impl, void* stream);
+size_t twowl_linear_bwd_weight_workspace_bytes(int64_t M, int32_t Ci, int32_t Co);
+int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t M, int32_t Ci, int32_t Co, float* dW,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ structured wedge path ------- */
+
+/* When ei2 is the full wedge join of (pos_edge, pred_edge) minus the wedges whose source edge is blocked
+ * (what get_ei2 + blockei2 produce), the pair-level GCNConv factorises exactly through a per-node sum
+ * (DESIGN.md "Factorised pair aggregation"); [2,T] is never materialised.
+ * prepare: for every pair row b in [0,R) and both directions d (0: edge2=[a^1;b], 1: edge2_r=[a;b^1])
+ *   centre[d][b] (int32)  node whose in-list feeds row b      dinv[d][b] = deg^-1/2
+ *   selfw[d][b] = 0 if the row's own id-self-loop is among its wedges (unblocked edge) else dinv^2
+ * cnt[i] = number of unblocked observed edges with target i (int32[N]). */
+int twowl_wedge_prepare(const int32_t* src /*[R]*/, const int32_t* dst_e /*[E]*/, int64_t E, int64_t R, int64_t N,
+                        const uint8_t* blocked /*[E] or NULL*/, const int64_t* in_ptr, const int32_t* in_ids,
+                        int32_t* cnt, int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/,
+                        void* stream);
+/* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias */
+int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,
+                          const float* selfw, const float* bias, int64_t R, int32_t C, float* out, void* stream);
+/* apply (backward): dZ[e] = selfw[e]*dO[e] + (edge_live[e] ? dinv[e]*dS[node_of[e]] : 0)
+ * where for direction 0 node_of[e] = dst_e[e^1], live = e<E && !blocked[e^1]; direction 1: dst_e[e], !blocked[e]. */
+int twowl_wedge_apply_bwd(const float* dS, const float* dO, const int32_t* dst_e, const uint8_t* blocked, int64_t E,
+                          const float* dinv, const float* selfw, int32_t direction, int64_t R, int32_t C, float* dZ,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWOWL_H_ */

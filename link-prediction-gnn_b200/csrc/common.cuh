@@ -1,0 +1,131 @@
+// common.cuh - shared host/device helpers for libtwowl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/twowl.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libtwowl_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace twowl {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void set_error(const char* fmt, ...);
+
+#define TW_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::twowl::set_error(__VA_ARGS__);          \
+      return TWOWL_EINVAL;                      \
+    }                                           \
+  } while (0)
+
+#define TW_CHECK_WS(have, need)                                                            \
+  do {                                                                                     \
+    if ((size_t)(have) < (size_t)(need)) {                                                 \
+      ::twowl::set_error("workspace too small: have %zu need %zu", (size_t)(have), (size_t)(need)); \
+      return TWOWL_ENOSPC;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define TW_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::twowl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+#define TW_LAUNCH_CHECK()                                                               \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::twowl::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                   \
+    }                                                                                   \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// grid for a grid-stride kernel: enough CTAs to cover `work_items` at `per_cta`, capped at a
+// multiple of the SM count so every SM holds the same number of resident CTAs.
+inline int grid_for(int64_t work_items, int64_t per_cta, int ctas_per_sm = 8) {
+  int64_t g = cdiv(work_items, per_cta);
+  int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Bump allocator over a caller-provided workspace.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return r;
+  }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  // read-once data: bypass L1 allocation (guide G13/G14)
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_cached(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void f4_add(float4& a, const float4& x) {
+  a.x += x.x;
+  a.y += x.y;
+  a.z += x.z;
+  a.w += x.w;
+}
+__device__ __forceinline__ float4 f4_mul(const float4& a, const float4& b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ float4 f4_shfl_xor(const float4& v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+#endif
+
+// ---- primitives implemented in prims.cu (device-side building blocks, all on `stream`) ----------
+
+// out[i] = sum_{j<i} in[j] for i in [0,n]; out has n+1 slots (out[n] = total). in == out allowed when
+// both are int64. ws: scan_workspace_bytes(n).
+size_t scan_workspace_bytes(int64_t n);
+int scan_exclusive_i64(const int64_t* in, int64_t* out, int64_t n, void* ws, cudaStream_t s);
+
+// Stable LSD radix sort of (key, val) uint32 pairs on the low `bits` bits of key. Result ends in
+// (keys_out, vals_out); keys_in/vals_in are clobbered. ws: radix_workspace_bytes(n).
+size_t radix_workspace_bytes(int64_t n);
+int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int64_t n,
+                     int bits, void* ws, cudaStream_t s);
+
+}  // namespace twowl
