@@ -41,10 +41,6 @@ extern "C" {
 #define TWOWL_EINVAL (-22)
 #define TWOWL_ENOSPC (-28)
 
-/* Rows of a CSR longer than this are split into chunks of this many entries (load balance for
- * power-law degree); see twowl_rowplan_build. */
-#define TWOWL_CHUNK 1024
-
 int twowl_version(void);
 const char* twowl_last_error(void);
 
@@ -56,7 +52,7 @@ int twowl_degree(const int64_t* keys, int64_t stride, int64_t n, int64_t num_nod
                  void* stream);
 
 /* Stable counting sort of the positions 0..n-1 by key = keys[i*stride] ^ key_xor:
- *   ptr[k]   (int64[num_keys+1]) start of key k, ptr[num_keys] = number of in-range keys
+ *   ptr[k]   (int64[num_keys+1], or NULL to skip) start of key k, ptr[num_keys] = number of in-range keys
  *   ids[...] (int32[n])          positions ordered by (key, position); out-of-range keys sort last.
  * This is the in-list / out-list build of get_ei2 (utils.py:41-44 `idx[edge[0]==i]` for all i at once)
  * and the CSR-by-target build the aggregation kernels consume. */
@@ -118,47 +114,45 @@ int twowl_narrow_i32(const int64_t* in, int64_t stride, int64_t n, int32_t* out,
 
 /* ------------------------------------------------------------------ aggregation ---------------- */
 
-/* Load-balance plan for a CSR: rows longer than TWOWL_CHUNK are cut into chunks handled by whole CTAs.
- *   plan (int32[twowl_rowplan_ints(M, nnz)]) layout: [0]=number of chunks, then chunk_row[cap], then
- *   chunk_begin as int64[cap] (8-byte aligned).  */
-int64_t twowl_rowplan_ints(int64_t M, int64_t nnz);
-size_t twowl_rowplan_workspace_bytes(int64_t M);
-int twowl_rowplan_build(const int64_t* ptr, int64_t M, int64_t nnz, int32_t* plan, void* ws, size_t ws_bytes,
-                        void* stream);
+/* gcn_norm degree (PyG 2.3.1 gcn_norm as used by GCNConv, model.py:37) from a CSR-by-target (ptr, col):
+ *   dinv[m] = (1 + #{k in CSR row (m ^ row_flip) : (col[k] ^ flip) != m, !skip_mask[col[k]]})^-1/2
+ * i.e. self-loops removed, one self-loop added. A CSR row r with row_skip_mask[r] set counts as empty. */
+int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, int32_t flip, int32_t row_flip,
+                   const uint8_t* skip_mask, const uint8_t* row_skip_mask, float* dinv, void* stream);
 
-/* gcn_norm degree (PyG 2.3.1 gcn_norm as used by GCNConv, model.py:37): for the CSR-by-target (ptr, col)
- * dinv[m] = (1 + #{k in row m : col[k] != m})^-1/2  - self-loops removed, one self-loop added. */
-int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, float* dinv, void* stream);
-
-/* The one segmented gather-reduce all aggregations run through. For each row m of the CSR (ptr, col):
- *   acc      = sum_{k in row m, kept} src_scale[s] * X[s] (* X2[mul_idx[col[k]]] if X2)   with s = col[k] ^ flip
+/* The one segmented gather-reduce all aggregations run through. For each output row m, with its entries
+ * taken from CSR row r = m ^ row_flip (empty if row_skip_mask[r]):
+ *   acc      = sum_{k in row r, kept} src_scale[s] * X[s] (* X2[mul_idx[col[k]]] if X2)   with s = col[k] ^ flip
  *   kept     = !(skip_self && s == m) && !(skip_mask && skip_mask[col[k]])
  *   out[m]   = (dst_scale ? dst_scale[m] : 1) * acc
  *            + (self_mode == 1 ? dst_scale[m]^2 * X[m] : 0)          (the GCN self-loop)
  *            + (bias ? bias : 0)                        (+ previous out[m] if accumulate)
- * Sums run in CSR order inside fixed-shape trees: deterministic, no atomics. */
+ * Sums run in CSR order in registers: deterministic, no atomics. With a CSR built by the stable
+ * twowl_csr_build the order equals the reference's scatter_add_ column order.
+ * The pair-level directions of model.py:77 (reverse(), utils.py:71-78) are (flip=1,row_flip=0) for
+ * edge2=[a^1;b] and (flip=0,row_flip=1) for edge2_r=[a;b^1] over ONE CSR-by-b of ei2: reverse() is folded
+ * into the kernel and its two [2,T] outputs are never materialised. */
 typedef struct twowl_seg_args {
-  const int64_t* ptr;        /* [M+1] */
-  const int32_t* col;        /* [nnz] */
-  const int32_t* plan;       /* from twowl_rowplan_build */
-  int64_t M;                 /* output rows */
-  int64_t nnz;
-  const float* X;            /* [rows_src, C] gathered rows */
+  const int64_t* ptr;            /* [M+1] */
+  const int32_t* col;            /* [nnz] */
+  int64_t M;                     /* output rows */
+  const float* X;                /* [rows_src, C] gathered rows */
   int32_t C;
-  int32_t flip;              /* 0 or 1: gathered row id = col ^ flip */
-  const float* src_scale;    /* [rows_src] or NULL */
-  const uint8_t* skip_mask;  /* indexed by col[k] (before flip) or NULL */
+  int32_t flip;                  /* 0 or 1: gathered row id = col ^ flip */
+  int32_t row_flip;              /* 0 or 1: entries of output row m live in CSR row m ^ row_flip */
+  const float* src_scale;        /* [rows_src] or NULL */
+  const uint8_t* skip_mask;      /* indexed by col[k] (before flip) or NULL */
+  const uint8_t* row_skip_mask;  /* indexed by CSR row or NULL */
   int32_t skip_self;
   int32_t self_mode;
-  const float* dst_scale;    /* [M] or NULL */
-  const float* bias;         /* [C] or NULL */
-  const float* X2;           /* optional second factor [rows2, C] */
-  const int32_t* mul_idx;    /* row of X2 = mul_idx[col[k]] */
-  float* out;                /* [M, C] */
+  const float* dst_scale;        /* [M] or NULL */
+  const float* bias;             /* [C] or NULL */
+  const float* X2;               /* optional second factor [rows2, C] */
+  const int32_t* mul_idx;        /* row of X2 = mul_idx[col[k]] */
+  float* out;                    /* [M, C] */
   int32_t accumulate;
 } twowl_seg_args;
-size_t twowl_seg_reduce_workspace_bytes(int64_t M, int64_t nnz, int32_t C);
-int twowl_seg_reduce(const twowl_seg_args* h_args, void* ws, size_t ws_bytes, void* stream);
+int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
 
 /* nn.Embedding forward / any row gather: out[r] = W[idx[r*stride]]  ([n, C]). */
 int twowl_gather_rows(const float* W, int64_t rows_w, const int64_t* idx, int64_t stride, int64_t n, int32_t C,
@@ -191,10 +185,11 @@ int twowl_graphnorm_stats(const float* x, int64_t M, int32_t C, const float* mea
                           void* ws, size_t ws_bytes, void* stream);
 
 /* y = weight*(x - mean_scale*mean)*inv_std + bias ; then dropout(p, seed) if p > 0 ; then ReLU if relu.
- * out = y  or  out += y (accumulate: the conv2s + conv2s_r branch sum of model.py:77). out may alias x. */
+ * out = y + (addend ? addend : 0)  - addend carries the other branch of the conv2s + conv2s_r sum of
+ * model.py:77; it may alias out. */
 int twowl_graphnorm_apply(const float* x, int64_t M, int32_t C, const float* stats, const float* weight,
                           const float* bias, const float* mean_scale, float p_drop, uint64_t seed, int32_t relu,
-                          int32_t accumulate, float* out, void* stream);
+                          const float* addend, float* out, void* stream);
 
 /* Backward of the fused GraphNorm+Dropout+ReLU. Given dout (gradient w.r.t. the fused output) and the saved
  * input x + stats:  dx[M,C] and dparams[3C] = (dweight, dbias, dmean_scale) are written. */
@@ -211,7 +206,7 @@ int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, siz
 /* ------------------------------------------------------------------ dense linear layers --------- */
 
 /* PyG Linear without bias (GCNConv.lin, model.py:37): Z[M,Co] = X[M,Ci] * W[Co,Ci]^T, fp32 in/out.
- * impl 0: SIMT FFMA tiles.  impl 1: tcgen05.mma kind::tf32 with 3xTF32 split operands (fp32-accurate).
+ * impl 0: SIMT FFMA tiles (exact fp32 accumulation).
  * bwd_input: dX[M,Ci] = dZ[M,Co] * W[Co,Ci].   bwd_weight: dW[Co,Ci] = dZ^T X (split over M, fixed order). */
 int twowl_linear_fwd(const float* X, const float* W, int64_t M, int32_t Ci, int32_t Co, float* Z, int32_t impl,
                      void* stream);
@@ -231,17 +226,16 @@ int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t M, int32_t 
  *   selfw[d][b] = 0 if the row's own id-self-loop is among its wedges (unblocked edge) else dinv^2
  * cnt[i] = number of unblocked observed edges with target i (int32[N]). */
 int twowl_wedge_prepare(const int32_t* src /*[R]*/, const int32_t* dst_e /*[E]*/, int64_t E, int64_t R, int64_t N,
-                        const uint8_t* blocked /*[E] or NULL*/, const int64_t* in_ptr, const int32_t* in_ids,
-                        int32_t* cnt, int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/,
-                        void* stream);
-/* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias */
+                        const uint8_t* blocked /*[E] or NULL*/, const int64_t* in_ptr /*[N+1]*/, int32_t* cnt /*[N]*/,
+                        int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/, void* stream);
+/* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias   (centre < 0: no S term) */
 int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,
                           const float* selfw, const float* bias, int64_t R, int32_t C, float* out, void* stream);
-/* apply (backward): dZ[e] = selfw[e]*dO[e] + (edge_live[e] ? dinv[e]*dS[node_of[e]] : 0)
- * where for direction 0 node_of[e] = dst_e[e^1], live = e<E && !blocked[e^1]; direction 1: dst_e[e], !blocked[e]. */
+/* apply (backward): dZ[r] = selfw[r]*dO[r] + (live(a) ? dinv[r]*dS[dst_e[a]] : 0) with a = r^1 for direction 0,
+ * a = r for direction 1, live(a) = a < E && !blocked[a] && dst_e[a] in [0,N). */
 int twowl_wedge_apply_bwd(const float* dS, const float* dO, const int32_t* dst_e, const uint8_t* blocked, int64_t E,
-                          const float* dinv, const float* selfw, int32_t direction, int64_t R, int32_t C, float* dZ,
-                          void* stream);
+                          int64_t N, const float* dinv, const float* selfw, int32_t direction, int64_t R, int32_t C,
+                          float* dZ, void* stream);
 
 #ifdef __cplusplus
 }

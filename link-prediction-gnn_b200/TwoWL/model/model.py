@@ -1,0 +1,218 @@
+"""Drop-in for the reference's TwoWL/model/model.py: ``LocalWLNet`` and ``Seq`` with the same
+constructor / forward signatures and the same state_dict keys (emb.0.weight, emb.1.*,
+conv{1s,2s,2s_r}.K.modlist.0.{bias,lin.weight}, conv*.K.modlist.1.{weight,bias,mean_scale},
+pred.{weight,bias}), plus ``GCNConv`` / ``GraphNorm`` replacing the torch_geometric 2.3.1 modules the
+reference imports at model.py:3. Every tensor op in forward and backward is a libtwowl_b200.so kernel.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+from torch.nn.modules.dropout import Dropout
+
+from TwoWL.utils import *  # noqa: F401,F403  (the reference does the same, model.py:5)
+from TwoWL.utils import _struct_of
+from twowl_b200 import functional as F2
+from twowl_b200 import graph as G
+
+
+def _seed() -> int:
+    # drawn from torch's default CPU generator: reproducible under torch.manual_seed, no device sync
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class _Lin(nn.Module):
+    """torch_geometric.nn.dense.linear.Linear(bias=False, weight_initializer='glorot')."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        a = math.sqrt(6.0 / (in_channels + out_channels))
+        nn.init.uniform_(self.weight, -a, a)
+
+    def forward(self, x):
+        return F2.linear(x, self.weight)
+
+
+class GCNConv(nn.Module):
+    """torch_geometric.nn.GCNConv(in_channels, out_channels) with its defaults (add_self_loops, normalize,
+    bias, not cached) - reference call site model.py:37. ``edge_index`` is an int64 [2,E] tensor."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index):
+        g = G.node_graph(edge_index, x.shape[0])
+        z = self.lin(x)
+        return F2.gcn_aggregate(z, self.bias, g.dinv, g.ptr, g.col, g.tptr, g.tcol, None, 0, 0)
+
+    def forward_pairs(self, x, wedges, direction: int):
+        """The pair-level call of model.py:77: direction 0 = conv(x, edge2), 1 = conv_r(x, edge2_r)."""
+        z = self.lin(x)
+        if isinstance(wedges, G.WedgeStruct):
+            _, centre, dinv, selfw = wedges.prepared()
+            return F2.wedge_aggregate(z, self.bias, wedges.in_ptr, wedges.in_ids, wedges.out_ptr, wedges.out_ids,
+                                      centre[direction], dinv[direction], selfw[direction], wedges.dst_e,
+                                      wedges.blocked, wedges.E, wedges.n_node, direction)
+        flip, row_flip = (1, 0) if direction == 0 else (0, 1)
+        return F2.gcn_aggregate(z, self.bias, wedges.dinv[direction], wedges.ptr_b, wedges.col_b, wedges.ptr_a,
+                                wedges.col_a, None, flip, row_flip)
+
+
+class GraphNorm(nn.Module):
+    """torch_geometric.nn.GraphNorm(in_channels, eps=1e-5), batch=None - reference model.py:38,54."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.in_channels, self.eps = in_channels, eps
+        self.weight = nn.Parameter(torch.ones(in_channels))
+        self.bias = nn.Parameter(torch.zeros(in_channels))
+        self.mean_scale = nn.Parameter(torch.ones(in_channels))
+
+    def forward(self, x, batch=None):
+        if batch is not None:
+            raise NotImplementedError("the TwoWL path never passes a batch vector")
+        return self.fused(x, 0.0, False, None)
+
+    def fused(self, x, p_drop: float, relu: bool, addend):
+        seed = _seed() if p_drop > 0.0 else 0
+        out, _ = F2.graphnorm_act(x, self.weight, self.bias, self.mean_scale, addend, self.eps, p_drop, seed, relu)
+        return out
+
+
+def _norm_tail(mods, x, training: bool, addend=None):
+    """[GraphNorm, Dropout, ReLU|Identity] of the reference's relu_conv / emb blocks as ONE fused kernel pair."""
+    gn, dp, act = mods
+    p = dp.p if (training and dp.p > 0.0) else 0.0
+    return gn.fused(x, p, isinstance(act, nn.ReLU), addend)
+
+
+class Seq(nn.Module):
+    """model.py:87-96. When modlist is the reference's [GCNConv, GraphNorm, Dropout, ReLU|Identity] block the
+    tail runs fused; any other modlist runs module by module exactly like the reference."""
+
+    def __init__(self, modlist):
+        super().__init__()
+        self.modlist = nn.ModuleList(modlist)
+
+    def _is_conv_block(self):
+        m = self.modlist
+        return (len(m) == 4 and isinstance(m[0], GCNConv) and isinstance(m[1], GraphNorm)
+                and isinstance(m[2], Dropout) and isinstance(m[3], (nn.ReLU, nn.Identity)))
+
+    def forward(self, *args, **kwargs):
+        out = self.modlist[0](*args, **kwargs)
+        if self._is_conv_block():
+            return _norm_tail(list(self.modlist)[1:], out, self.training)
+        for i in range(1, len(self.modlist)):
+            out = self.modlist[i](out)
+        return out
+
+    def forward_pairs(self, x, wedges, direction: int, addend=None):
+        out = self.modlist[0].forward_pairs(x, wedges, direction)
+        return _norm_tail(list(self.modlist)[1:], out, self.training, addend)
+
+
+class LocalWLNet(nn.Module):
+    def __init__(self,
+                 max_x,
+                 use_node_feat,
+                 node_feat,
+                 channels_1wl=256,
+                 channels_2wl=32,
+                 depth1=1,
+                 depth2=1,
+                 dp_lin0=0.7,
+                 dp_lin1=0.7,
+                 dp_emb=0.5,
+                 dp_1wl0=0.5,
+                 dp_2wl=0.5,
+                 dp_1wl1=0.5,
+                 act0=True,
+                 act1=True,
+                 ):
+        super().__init__()
+        use_affine = False
+
+        relu_lin = lambda a, b, dp, lnx, actx: nn.Sequential(  # noqa: E731
+            nn.Linear(a, b),
+            nn.LayerNorm(b, elementwise_affine=use_affine) if lnx else nn.Identity(),
+            nn.Dropout(p=dp, inplace=True),
+            nn.ReLU(inplace=True) if actx else nn.Identity())
+
+        relu_conv = lambda insize, outsize, dp, act: Seq([  # noqa: E731
+            GCNConv(insize, outsize),
+            GraphNorm(outsize),
+            Dropout(p=dp, inplace=True),
+            nn.ReLU(inplace=True) if act else nn.Identity()
+        ])
+
+        self.max_x = max_x
+        self.use_node_feat = use_node_feat
+        self.node_feat = node_feat
+        # "structured" | "explicit" | "auto": how the pair-level GCNConv consumes ei2 (see forward)
+        self.pair_path = "auto"
+
+        if use_node_feat:
+            self.lin1 = nn.Sequential(
+                nn.Dropout(dp_lin0),
+                relu_lin(node_feat.shape[-1], channels_1wl, dp_lin1, True, False)
+            )
+        else:
+            self.emb = nn.Sequential(nn.Embedding(max_x + 1, channels_1wl),
+                                     GraphNorm(channels_1wl),
+                                     Dropout(p=dp_emb, inplace=True))
+
+        self.conv1s = nn.ModuleList(
+            [relu_conv(channels_1wl, channels_1wl, dp_1wl0, act0) for _ in range(depth1 - 1)] +
+            [relu_conv(channels_1wl, channels_2wl, dp_1wl1, act1)])
+
+        self.conv2s = nn.ModuleList(
+            [relu_conv(channels_2wl, channels_2wl, dp_2wl, True) for _ in range(depth2)])
+        self.conv2s_r = nn.ModuleList(
+            [relu_conv(channels_2wl, channels_2wl, dp_2wl, True) for _ in range(depth2)])
+
+        self.pred = nn.Linear(channels_2wl, 1)
+
+    def _wedges(self, ei2, R: int):
+        """Pick the representation of ei2 the pair-level kernels read.
+        structured: ei2 came from this package's get_ei2 / blockei2 / sample_block (or is a WedgeIndex) and
+                    matches the pair table -> the factorised kernels, O(E + R) instead of O(T);
+        explicit:   any int64 [2,T] tensor -> two CSRs over the wedges (built once per tensor, cached)."""
+        struct = ei2.struct if isinstance(ei2, G.WedgeIndex) else _struct_of(ei2)
+        ok = struct is not None and struct.R == R and struct.E % 2 == 0 and R % 2 == 0
+        if self.pair_path == "structured" and not ok:
+            raise RuntimeError("pair_path='structured' needs an ei2 produced by TwoWL.utils.get_ei2/sample_block "
+                               "for this pair table")
+        if ok and self.pair_path in ("auto", "structured"):
+            return struct
+        if isinstance(ei2, G.WedgeIndex):
+            ei2 = ei2.materialize()
+        return G.explicit_wedges(ei2, R)
+
+    def forward(self, x, edge1, pos, idx=None, ei2=None, test=False):
+        """model.py:68-84. x: int64 [N] degrees; edge1: int64 [2,E']; pos: int64 [R,2]; idx: int64 [2L];
+        ei2: int64 [2,T'] (or a WedgeIndex). Returns fp32 [L,1] logits. ``test`` is unused, as in the
+        reference. reverse(ei2) (model.py:69) is folded into the aggregation kernels."""
+        if self.use_node_feat:
+            x = self.lin1(self.node_feat)
+        else:
+            emb, gn, dp = self.emb[0], self.emb[1], self.emb[2]
+            x = F2.embedding(emb.weight, x)
+            x = gn.fused(x, dp.p if (self.training and dp.p > 0.0) else 0.0, False, None)
+        for conv1 in self.conv1s:
+            x = conv1(x, edge1)
+
+        pt = G.pair_table(pos, x.shape[0])
+        x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.ptr_d, pt.ids_d)
+        if len(self.conv2s):
+            wedges = self._wedges(ei2, pt.R)
+            for i in range(len(self.conv2s)):
+                a = self.conv2s[i].forward_pairs(x, wedges, 0)
+                x = self.conv2s_r[i].forward_pairs(x, wedges, 1, addend=a)
+        return F2.readout(x, idx, self.pred.weight, self.pred.bias)

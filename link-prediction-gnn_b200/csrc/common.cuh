@@ -93,6 +93,8 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                "f"(v.w)
                : "memory");
 }
+// deg^-1/2 with IEEE-rounded sqrt and divide (the reference's deg.pow(-0.5) on CPU), deg >= 1
+__device__ __forceinline__ float rsqrtf_exact(float x) { return __fdiv_rn(1.f, __fsqrt_rn(x)); }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float s, const float4& x) {
   a.x = fmaf(s, x.x, a.x);

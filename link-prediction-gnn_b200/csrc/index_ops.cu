@@ -273,7 +273,7 @@ extern "C" int twowl_csr_build(const int64_t* keys, int64_t stride, int64_t n, i
   TW_CHECK_ARG(num_keys >= 0 && num_keys < 0x7fffffffLL, "csr_build: num_keys=%lld out of range", (long long)num_keys);
   TW_CHECK_WS(ws_bytes, twowl_csr_build_workspace_bytes(n, num_keys));
   cudaStream_t s = (cudaStream_t)stream;
-  TW_CUDA(cudaMemsetAsync(ptr, 0, (size_t)(num_keys + 1) * sizeof(int64_t), s));
+  if (ptr) TW_CUDA(cudaMemsetAsync(ptr, 0, (size_t)(num_keys + 1) * sizeof(int64_t), s));
   if (n == 0) return 0;
   Carver c(ws);
   const size_t nn = (size_t)n;
@@ -285,7 +285,7 @@ extern "C" int twowl_csr_build(const int64_t* keys, int64_t stride, int64_t n, i
   void* scan_ws = c.take<char>(scan_workspace_bytes(num_keys + 1));
   k_csr_keys<<<grid_for(n, kThreads), kThreads, 0, s>>>(keys, stride, n, key_xor, num_keys, k0, v0);
   // histogram of the in-range keys into ptr[0..num_keys), then exclusive scan in place -> ptr[num_keys] = total
-  if (num_keys > 0) {
+  if (ptr && num_keys > 0) {
     k_hist_i64<<<grid_for(n, kThreads), kThreads, 0, s>>>(keys, stride, n, key_xor, num_keys, (unsigned long long*)ptr);
     int rc = scan_exclusive_i64(ptr, ptr, num_keys, scan_ws, s);
     if (rc) return rc;

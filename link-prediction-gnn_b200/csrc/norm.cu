@@ -1,0 +1,376 @@
+// norm.cu - GraphNorm (PyG 2.3.1 semantics, batch=None) fused with the Dropout and ReLU that follow it in
+// the reference's Seq block (TwoWL/model/model.py:36-41, :53-55), forward and backward, plus column sums.
+//
+// All kernels stream [M, C] fp32 row-major matrices with 128-bit accesses: thread t of a 256-thread CTA owns
+// float4 column (t % cv) of row-slot (t / cv), cv = C/4, so a warp reads consecutive 16-byte words of
+// consecutive rows (fully coalesced for every C % 4 == 0, including C = 24). Column reductions are
+// two-level with a fixed order (per-thread fp32 partials over shifted values -> per-CTA double ->
+// finalize in CTA order): deterministic, no atomics. HBM-bound: stats = 1 read, apply = 1 read + 1 write,
+// bwd = 2 reads + (2 reads + 1 write).
+#include "common.cuh"
+
+namespace twowl {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxCtas = kNumSMs * 4;
+
+struct RowMap {
+  int cv;        // float4 per row
+  int slots;     // row slots per CTA iteration
+  int slot;      // this thread's row slot (or -1 when idle)
+  int c4;        // this thread's float4 column
+  __device__ RowMap(int C) {
+    cv = C >> 2;
+    slots = kNormThreads / cv;
+    const int t = threadIdx.x;
+    slot = (t < slots * cv) ? t / cv : -1;
+    c4 = t % cv;
+  }
+};
+
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the mask
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// 1/(1-p) if element kept else 0
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
+  return hash_u32(seed, idx) >= thresh ? inv_keep : 0.f;
+}
+static inline uint32_t drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+// Reduce NV float4 values per thread over the CTA's row slots, in slot order, into doubles:
+// part[blockIdx.x][v][C].  smem: slots*cv float4 per value.
+template <int NV>
+__device__ __forceinline__ void cta_col_reduce(const RowMap& rm, const float4 (&val)[NV], double* __restrict__ part, int C) {
+  extern __shared__ float4 s_red[];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (rm.slot >= 0) s_red[(v * rm.slots + rm.slot) * rm.cv + rm.c4] = val[v];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV * rm.cv; i += kNormThreads) {
+    const int v = i / rm.cv, c4 = i % rm.cv;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int s = 0; s < rm.slots; ++s) {
+      const float4 x = s_red[(v * rm.slots + s) * rm.cv + c4];
+      a0 += x.x, a1 += x.y, a2 += x.z, a3 += x.w;
+    }
+    double* o = part + ((size_t)blockIdx.x * NV + v) * C + c4 * 4;
+    o[0] = a0, o[1] = a1, o[2] = a2, o[3] = a3;
+  }
+}
+
+// ---------------------------------------------------------------- forward statistics -------------
+__global__ void __launch_bounds__(kNormThreads) k_gn_stats_partial(const float* __restrict__ x, int64_t M, int C,
+                                                                   double* __restrict__ part) {
+  const RowMap rm(C);
+  float4 v[2] = {f4_zero(), f4_zero()};
+  if (rm.slot >= 0) {
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    const float4 sh = __ldg(x4 + rm.c4);  // shift = first row: keeps the squared sums well conditioned
+    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+      float4 a = ldg_stream(x4 + r * rm.cv + rm.c4);
+      a.x -= sh.x, a.y -= sh.y, a.z -= sh.z, a.w -= sh.w;
+      f4_add(v[0], a);
+      v[1].x = fmaf(a.x, a.x, v[1].x), v[1].y = fmaf(a.y, a.y, v[1].y);
+      v[1].z = fmaf(a.z, a.z, v[1].z), v[1].w = fmaf(a.w, a.w, v[1].w);
+    }
+  }
+  cta_col_reduce<2>(rm, v, part, C);
+}
+
+__global__ void k_gn_stats_final(const double* __restrict__ part, int nparts, const float* __restrict__ x, int64_t M, int C,
+                                 const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int b = 0; b < nparts; ++b) {
+    s += part[((size_t)b * 2 + 0) * C + c];
+    q += part[((size_t)b * 2 + 1) * C + c];
+  }
+  const double sh = (double)x[c];
+  const double ms = s / (double)M;                 // mean of shifted values
+  const double mean = sh + ms;
+  double var = q / (double)M - ms * ms;            // Var(x)
+  if (var < 0) var = 0;
+  const double a = (double)mean_scale[c];
+  const double var_shifted = var + (1.0 - a) * (1.0 - a) * mean * mean;  // E[(x - a*mean)^2]
+  stats[c] = (float)mean;
+  stats[C + c] = (float)(1.0 / sqrt(var_shifted + (double)eps));
+}
+
+// ---------------------------------------------------------------- forward apply ------------------
+__global__ void __launch_bounds__(kNormThreads) k_gn_apply(const float* __restrict__ x, int64_t M, int C,
+                                                           const float* __restrict__ stats, const float* __restrict__ weight,
+                                                           const float* __restrict__ bias, const float* __restrict__ mean_scale,
+                                                           uint32_t thresh, float inv_keep, uint64_t seed, int relu,
+                                                           const float* addend, float* out) {
+  const RowMap rm(C);
+  if (rm.slot < 0) return;
+  const int c0 = rm.c4 * 4;
+  float sc[4], of[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = weight[c0 + i] * stats[C + c0 + i];
+    of[i] = bias[c0 + i] - sc[i] * mean_scale[c0 + i] * stats[c0 + i];
+  }
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  const float4* a4 = reinterpret_cast<const float4*>(addend);
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+    const int64_t e = r * rm.cv + rm.c4;
+    const float4 a = ldg_stream(x4 + e);
+    float y[4] = {fmaf(sc[0], a.x, of[0]), fmaf(sc[1], a.y, of[1]), fmaf(sc[2], a.z, of[2]), fmaf(sc[3], a.w, of[3])};
+    if (thresh) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] *= drop_scale(seed, (uint64_t)e * 4 + i, thresh, inv_keep);
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
+    }
+    float4 o = make_float4(y[0], y[1], y[2], y[3]);
+    if (a4) f4_add(o, a4[e]);
+    o4[e] = o;
+  }
+}
+
+// ---------------------------------------------------------------- backward -----------------------
+// g_y = dout * dropout_scale * [relu: y_dropped > 0];  n = (x - a*mean)*inv
+__device__ __forceinline__ void gn_gy(const float4& a, const float4& d, const float (&sc)[4], const float (&of)[4],
+                                      const float (&nm)[4], const float (&ni)[4], uint32_t thresh, float inv_keep,
+                                      uint64_t seed, uint64_t e, int relu, float (&gy)[4], float (&n)[4]) {
+  const float xa[4] = {a.x, a.y, a.z, a.w};
+  const float da[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    n[i] = (xa[i] - nm[i]) * ni[i];
+    float g = da[i];
+    float keep = 1.f;
+    if (thresh) keep = drop_scale(seed, e * 4 + i, thresh, inv_keep);
+    g *= keep;
+    if (relu) {
+      const float y = fmaf(sc[i], xa[i], of[i]) * keep;
+      if (!(y > 0.f)) g = 0.f;
+    }
+    gy[i] = g;
+  }
+}
+
+struct GnCols {
+  float sc[4], of[4], nm[4], ni[4];
+  __device__ GnCols(int C, int c0, const float* stats, const float* weight, const float* bias, const float* mean_scale) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ni[i] = stats[C + c0 + i];
+      nm[i] = mean_scale[c0 + i] * stats[c0 + i];
+      sc[i] = weight[c0 + i] * ni[i];
+      of[i] = bias[c0 + i] - sc[i] * nm[i];
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dout,
+                                                                 int64_t M, int C, const float* __restrict__ stats,
+                                                                 const float* __restrict__ weight, const float* __restrict__ bias,
+                                                                 const float* __restrict__ mean_scale, uint32_t thresh,
+                                                                 float inv_keep, uint64_t seed, int relu,
+                                                                 double* __restrict__ part) {
+  const RowMap rm(C);
+  float4 v[2] = {f4_zero(), f4_zero()};
+  if (rm.slot >= 0) {
+    const GnCols cc(C, rm.c4 * 4, stats, weight, bias, mean_scale);
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dout);
+    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+      const int64_t e = r * rm.cv + rm.c4;
+      float gy[4], n[4];
+      gn_gy(ldg_cached(x4 + e), ldg_cached(d4 + e), cc.sc, cc.of, cc.nm, cc.ni, thresh, inv_keep, seed, (uint64_t)e, relu, gy, n);
+      v[0].x += gy[0], v[0].y += gy[1], v[0].z += gy[2], v[0].w += gy[3];
+      v[1].x = fmaf(gy[0], n[0], v[1].x), v[1].y = fmaf(gy[1], n[1], v[1].y);
+      v[1].z = fmaf(gy[2], n[2], v[1].z), v[1].w = fmaf(gy[3], n[3], v[1].w);
+    }
+  }
+  cta_col_reduce<2>(rm, v, part, C);
+}
+
+// sums[0:C] = A = sum g_y, sums[C:2C] = B = sum g_y*n, sums[2C:3C] = (alpha/M) * sum g_o   (fp32, for pass 2)
+// dparams[0:C] = dweight = B, [C:2C] = dbias = A, [2C:3C] = dmean_scale = -mean * sum g_o
+__global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int64_t M, int C, const float* __restrict__ stats,
+                               const float* __restrict__ weight, const float* __restrict__ mean_scale, float* __restrict__ sums,
+                               float* __restrict__ dparams) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double A = 0, B = 0;
+  for (int b = 0; b < nparts; ++b) {
+    A += part[((size_t)b * 2 + 0) * C + c];
+    B += part[((size_t)b * 2 + 1) * C + c];
+  }
+  const double mean = stats[c], inv = stats[C + c], w = weight[c], a = mean_scale[c];
+  // sum_rows n = inv * M * mean * (1 - a);  sum g_o = inv*w*(A - (B/M) * sum n)
+  const double sum_go = inv * w * (A - B * inv * mean * (1.0 - a));
+  sums[c] = (float)A;
+  sums[C + c] = (float)(B / (double)M);
+  sums[2 * C + c] = (float)(a * sum_go / (double)M);
+  dparams[c] = (float)B;
+  dparams[C + c] = (float)A;
+  dparams[2 * C + c] = (float)(-mean * sum_go);
+}
+
+__global__ void __launch_bounds__(kNormThreads) k_gn_bwd_dx(const float* __restrict__ x, const float* __restrict__ dout, int64_t M,
+                                                            int C, const float* __restrict__ stats, const float* __restrict__ weight,
+                                                            const float* __restrict__ bias, const float* __restrict__ mean_scale,
+                                                            uint32_t thresh, float inv_keep, uint64_t seed, int relu,
+                                                            const float* __restrict__ sums, float* __restrict__ dx) {
+  const RowMap rm(C);
+  if (rm.slot < 0) return;
+  const int c0 = rm.c4 * 4;
+  const GnCols cc(C, c0, stats, weight, bias, mean_scale);
+  float bm[4], corr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bm[i] = sums[C + c0 + i];
+    corr[i] = sums[2 * C + c0 + i];
+  }
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dout);
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(dx);
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+    const int64_t e = r * rm.cv + rm.c4;
+    float gy[4], n[4], o[4];
+    gn_gy(ldg_stream(x4 + e), ldg_stream(d4 + e), cc.sc, cc.of, cc.nm, cc.ni, thresh, inv_keep, seed, (uint64_t)e, relu, gy, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = cc.sc[i] * (gy[i] - n[i] * bm[i]) - corr[i];
+    o4[e] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------- column sum ---------------------
+__global__ void __launch_bounds__(kNormThreads) k_colsum_partial(const float* __restrict__ x, int64_t M, int C,
+                                                                 double* __restrict__ part) {
+  const RowMap rm(C);
+  float4 v[1] = {f4_zero()};
+  if (rm.slot >= 0) {
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots)
+      f4_add(v[0], ldg_stream(x4 + r * rm.cv + rm.c4));
+  }
+  cta_col_reduce<1>(rm, v, part, C);
+}
+__global__ void k_colsum_final(const double* __restrict__ part, int nparts, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0;
+  for (int b = 0; b < nparts; ++b) s += part[(size_t)b * C + c];
+  out[c] = (float)s;
+}
+
+static int norm_grid(int64_t M, int C) {
+  const int slots = kNormThreads / (C >> 2);
+  // at least 4 row iterations per CTA before adding CTAs; never more than 4 CTAs per SM
+  int64_t g = cdiv(M, (int64_t)slots * 4);
+  if (g > kNormMaxCtas) g = kNormMaxCtas;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static size_t red_smem(int C, int nv) { return (size_t)nv * (kNormThreads / (C >> 2)) * (C >> 2) * sizeof(float4); }
+static int check_mc(const char* op, int64_t M, int C) {
+  TW_CHECK_ARG(M >= 0 && C >= 4 && (C & 3) == 0 && C <= 1024, "%s: C=%d must be a multiple of 4 in [4,1024]", op, C);
+  return 0;
+}
+
+}  // namespace twowl
+
+using namespace twowl;
+
+extern "C" size_t twowl_graphnorm_stats_workspace_bytes(int64_t M, int32_t C) {
+  (void)M;
+  return align_up((size_t)kNormMaxCtas * 2 * (size_t)C * sizeof(double));
+}
+
+extern "C" int twowl_graphnorm_stats(const float* x, int64_t M, int32_t C, const float* mean_scale, float eps, float* stats,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("graphnorm_stats", M, C)) return rc;
+  TW_CHECK_ARG(M > 0, "graphnorm_stats: needs at least one row");
+  TW_CHECK_ARG(aligned16(x), "graphnorm_stats: x must be 16-byte aligned");
+  TW_CHECK_WS(ws_bytes, twowl_graphnorm_stats_workspace_bytes(M, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = norm_grid(M, C);
+  k_gn_stats_partial<<<grid, kNormThreads, red_smem(C, 2), s>>>(x, M, C, (double*)ws);
+  k_gn_stats_final<<<(int)cdiv(C, 128), 128, 0, s>>>((const double*)ws, grid, x, M, C, mean_scale, eps, stats);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_graphnorm_apply(const float* x, int64_t M, int32_t C, const float* stats, const float* weight,
+                                     const float* bias, const float* mean_scale, float p_drop, uint64_t seed, int32_t relu,
+                                     const float* addend, float* out, void* stream) {
+  if (int rc = check_mc("graphnorm_apply", M, C)) return rc;
+  TW_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(addend), "graphnorm_apply: x/out/addend must be 16-byte aligned");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_apply: dropout p=%f outside [0,1)", p_drop);
+  if (M == 0) return 0;
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  k_gn_apply<<<norm_grid(M, C), kNormThreads, 0, (cudaStream_t)stream>>>(x, M, C, stats, weight, bias, mean_scale, thresh,
+                                                                        1.f / (1.f - p_drop), seed, relu, addend, out);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_graphnorm_bwd_workspace_bytes(int64_t M, int32_t C) {
+  (void)M;
+  return align_up((size_t)kNormMaxCtas * 2 * (size_t)C * sizeof(double)) + align_up(3 * (size_t)C * sizeof(float));
+}
+
+extern "C" int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M, int32_t C, const float* stats,
+                                   const float* weight, const float* bias, const float* mean_scale, float p_drop, uint64_t seed,
+                                   int32_t relu, float* dx, float* dparams, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("graphnorm_bwd", M, C)) return rc;
+  TW_CHECK_ARG(M > 0, "graphnorm_bwd: needs at least one row");
+  TW_CHECK_ARG(aligned16(x) && aligned16(dout) && aligned16(dx), "graphnorm_bwd: x/dout/dx must be 16-byte aligned");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_bwd: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_graphnorm_bwd_workspace_bytes(M, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver c(ws);
+  double* part = c.take<double>((size_t)kNormMaxCtas * 2 * C);
+  float* sums = c.take<float>(3 * (size_t)C);
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  const int grid = norm_grid(M, C);
+  k_gn_bwd_partial<<<grid, kNormThreads, red_smem(C, 2), s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep,
+                                                              seed, relu, part);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, M, C, stats, weight, mean_scale, sums, dparams);
+  k_gn_bwd_dx<<<grid, kNormThreads, 0, s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep, seed, relu, sums,
+                                            dx);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C) {
+  (void)M;
+  return align_up((size_t)kNormMaxCtas * (size_t)C * sizeof(double));
+}
+
+extern "C" int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("colsum", M, C)) return rc;
+  TW_CHECK_ARG(aligned16(x), "colsum: x must be 16-byte aligned");
+  TW_CHECK_WS(ws_bytes, twowl_colsum_workspace_bytes(M, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M == 0) {
+    TW_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), s));
+    return 0;
+  }
+  const int grid = norm_grid(M, C);
+  k_colsum_partial<<<grid, kNormThreads, red_smem(C, 1), s>>>(x, M, C, (double*)ws);
+  k_colsum_final<<<(int)cdiv(C, 128), 128, 0, s>>>((const double*)ws, grid, C, out);
+  TW_LAUNCH_CHECK();
+  return 0;
+}

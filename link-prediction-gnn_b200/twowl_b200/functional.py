@@ -1,0 +1,244 @@
+"""The differentiable TwoWL ops, registered as torch custom ops (namespace ``twowl::``) whose
+forward AND backward are calls into libtwowl_b200.so. They replace, on the hot path, the
+torch_geometric / torch_scatter kernels the reference reaches through
+TwoWL/model/model.py:37-38,53-55,73,75,77-83.
+
+Every backward is the hand-derived transpose of its forward over the same index (CSR by source
+instead of CSR by target), not an autograd trace of torch ops.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+# ------------------------------------------------------------------------------ linear (GCNConv.lin)
+
+
+@torch.library.custom_op("twowl::linear", mutates_args=())
+def linear(x: Tensor, weight: Tensor) -> Tensor:
+    """PyG Linear(bias=False): x @ weight.T, fp32-exact accumulation."""
+    return ops.linear_fwd(x.contiguous(), weight.contiguous())
+
+
+@linear.register_fake
+def _(x, weight):
+    return x.new_empty((x.shape[0], weight.shape[0]))
+
+
+def _linear_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _linear_bwd(ctx, g):
+    x, w = ctx.saved_tensors
+    g = g.contiguous()
+    dx = ops.linear_bwd_input(g, w.contiguous()) if ctx.needs_input_grad[0] else None
+    dw = ops.linear_bwd_weight(g, x.contiguous()) if ctx.needs_input_grad[1] else None
+    return dx, dw
+
+
+linear.register_autograd(_linear_bwd, setup_context=_linear_setup)
+
+# ------------------------------------------------------------------------------ explicit GCN propagate
+
+
+@torch.library.custom_op("twowl::gcn_aggregate", mutates_args=())
+def gcn_aggregate(z: Tensor, bias: Tensor, dinv: Tensor, ptr: Tensor, col: Tensor, tptr: Tensor, tcol: Tensor,
+                  mask: Optional[Tensor], flip: int, row_flip: int) -> Tensor:
+    """out[m] = dinv[m] * sum_{k in row m^row_flip, s=col[k]^flip != m, !mask[col[k]]} dinv[s] z[s]
+               + dinv[m]^2 z[m] + bias   (PyG GCNConv.propagate with gcn_norm)."""
+    return ops.seg_reduce(ptr, col, z.shape[0], z.contiguous(), flip=flip, row_flip=row_flip, src_scale=dinv,
+                          dst_scale=dinv, skip_self=True, self_mode=1, bias=bias, skip_mask=mask)
+
+
+@gcn_aggregate.register_fake
+def _(z, bias, dinv, ptr, col, tptr, tcol, mask, flip, row_flip):
+    return torch.empty_like(z)
+
+
+def _gcn_setup(ctx, inputs, output):
+    z, bias, dinv, ptr, col, tptr, tcol, mask, flip, row_flip = inputs
+    ctx.save_for_backward(dinv, tptr, tcol, mask)
+    ctx.flip, ctx.row_flip = flip, row_flip
+
+
+def _gcn_bwd(ctx, g):
+    dinv, tptr, tcol, mask = ctx.saved_tensors
+    g = g.contiguous()
+    dz = dbias = None
+    if ctx.needs_input_grad[0]:
+        # transpose: rows by SOURCE; the roles of flip / row_flip swap; the column mask becomes a row mask
+        dz = ops.seg_reduce(tptr, tcol, g.shape[0], g, flip=ctx.row_flip, row_flip=ctx.flip, src_scale=dinv,
+                            dst_scale=dinv, skip_self=True, self_mode=1, row_skip_mask=mask)
+    if ctx.needs_input_grad[1]:
+        dbias = ops.colsum(g)
+    return dz, dbias, None, None, None, None, None, None, None, None
+
+
+gcn_aggregate.register_autograd(_gcn_bwd, setup_context=_gcn_setup)
+
+# ------------------------------------------------------------------------------ structured pair-level propagate
+
+
+@torch.library.custom_op("twowl::wedge_aggregate", mutates_args=())
+def wedge_aggregate(z: Tensor, bias: Tensor, in_ptr: Tensor, in_ids: Tensor, out_ptr: Tensor, out_ids: Tensor,
+                    centre: Tensor, dinv: Tensor, selfw: Tensor, dst_e: Tensor, blocked: Optional[Tensor], n_edge: int,
+                    n_node: int, direction: int) -> Tensor:
+    """Pair-level GCNConv for a wedge index that is the full join of get_ei2 minus blocked source edges:
+    S[i] = sum over unblocked in-edges of i; out[b] = dinv[b] S[centre[b]] + selfw[b] z[b] + bias
+    (DESIGN.md 'Factorised pair aggregation'). direction 0 = edge2, 1 = edge2_r of utils.py:71-78."""
+    z = z.contiguous()
+    S = ops.seg_reduce(in_ptr, in_ids, n_node, z, flip=1 - direction, src_scale=dinv, skip_mask=blocked)
+    return ops.wedge_apply_fwd(S, z, centre, dinv, selfw, bias)
+
+
+@wedge_aggregate.register_fake
+def _(z, bias, in_ptr, in_ids, out_ptr, out_ids, centre, dinv, selfw, dst_e, blocked, n_edge, n_node, direction):
+    return torch.empty_like(z)
+
+
+def _wedge_setup(ctx, inputs, output):
+    (z, bias, in_ptr, in_ids, out_ptr, out_ids, centre, dinv, selfw, dst_e, blocked, n_edge, n_node, direction) = inputs
+    ctx.save_for_backward(out_ptr, out_ids, dinv, selfw, dst_e, blocked)
+    ctx.meta = (n_edge, n_node, direction)
+
+
+def _wedge_bwd(ctx, g):
+    out_ptr, out_ids, dinv, selfw, dst_e, blocked = ctx.saved_tensors
+    n_edge, n_node, direction = ctx.meta
+    g = g.contiguous()
+    dz = dbias = None
+    if ctx.needs_input_grad[0]:
+        dS = ops.seg_reduce(out_ptr, out_ids, n_node, g, flip=direction, src_scale=dinv)
+        dz = ops.wedge_apply_bwd(dS, g, dst_e, blocked, n_edge, n_node, dinv, selfw, direction)
+    if ctx.needs_input_grad[1]:
+        dbias = ops.colsum(g)
+    return (dz, dbias) + (None,) * 12
+
+
+wedge_aggregate.register_autograd(_wedge_bwd, setup_context=_wedge_setup)
+
+# ------------------------------------------------------------------------------ GraphNorm + Dropout + ReLU
+
+
+@torch.library.custom_op("twowl::graphnorm_act", mutates_args=())
+def graphnorm_act(x: Tensor, weight: Tensor, bias: Tensor, mean_scale: Tensor, addend: Optional[Tensor], eps: float,
+                  p_drop: float, seed: int, relu: bool) -> Tuple[Tensor, Tensor]:
+    """relu?(dropout_p(GraphNorm(x))) + addend?  ->  (out, stats[2C] = (mean, inv_std))."""
+    x = x.contiguous()
+    stats = ops.graphnorm_stats(x, mean_scale, eps)
+    out = ops.graphnorm_apply(x, stats, weight, bias, mean_scale, p_drop, seed, relu,
+                              None if addend is None else addend.contiguous())
+    return out, stats
+
+
+@graphnorm_act.register_fake
+def _(x, weight, bias, mean_scale, addend, eps, p_drop, seed, relu):
+    return torch.empty_like(x), x.new_empty((2 * x.shape[1],))
+
+
+def _gn_setup(ctx, inputs, output):
+    x, weight, bias, mean_scale, addend, eps, p_drop, seed, relu = inputs
+    ctx.save_for_backward(x, weight, bias, mean_scale, output[1])
+    ctx.meta = (p_drop, seed, relu)
+    ctx.has_addend = addend is not None
+    ctx.mark_non_differentiable(output[1])
+
+
+def _gn_bwd(ctx, g, _g_stats):
+    x, weight, bias, mean_scale, stats = ctx.saved_tensors
+    p_drop, seed, relu = ctx.meta
+    g = g.contiguous()
+    dx, dparams = ops.graphnorm_bwd(x.contiguous(), g, stats, weight, bias, mean_scale, p_drop, seed, relu)
+    C = x.shape[1]
+    return (dx, dparams[:C], dparams[C:2 * C], dparams[2 * C:], g if ctx.has_addend else None, None, None, None, None)
+
+
+graphnorm_act.register_autograd(_gn_bwd, setup_context=_gn_setup)
+
+# ------------------------------------------------------------------------------ embedding lookup
+
+
+@torch.library.custom_op("twowl::embedding", mutates_args=())
+def embedding(weight: Tensor, x: Tensor) -> Tensor:
+    return ops.gather_rows(weight.contiguous(), x)
+
+
+@embedding.register_fake
+def _(weight, x):
+    return weight.new_empty((x.numel(), weight.shape[1]))
+
+
+def _emb_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+    ctx.rows = inputs[0].shape[0]
+
+
+def _emb_bwd(ctx, g):
+    (x,) = ctx.saved_tensors
+    ptr, ids = ops.csr_build(x.reshape(-1), ctx.rows)
+    return ops.seg_reduce(ptr, ids, ctx.rows, g.contiguous()), None
+
+
+embedding.register_autograd(_emb_bwd, setup_context=_emb_setup)
+
+# ------------------------------------------------------------------------------ pair init
+
+
+@torch.library.custom_op("twowl::pair_init", mutates_args=())
+def pair_init(x: Tensor, src: Tensor, dst: Tensor, ptr_s: Tensor, ids_s: Tensor, ptr_d: Tensor, ids_d: Tensor) -> Tensor:
+    """H[p] = x[src[p]] * x[dst[p]] (model.py:75); (ptr_s, ids_s) / (ptr_d, ids_d) = pair rows grouped by
+    src / dst node, used by the backward."""
+    return ops.pair_init_fwd(x.contiguous(), src, dst)
+
+
+@pair_init.register_fake
+def _(x, src, dst, ptr_s, ids_s, ptr_d, ids_d):
+    return x.new_empty((src.numel(), x.shape[1]))
+
+
+def _pi_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _pi_bwd(ctx, g):
+    x, src, dst, ptr_s, ids_s, ptr_d, ids_d = ctx.saved_tensors
+    g = g.contiguous()
+    N = x.shape[0]
+    # dx[n] = sum_{p: src[p]=n} g[p]*x[dst[p]] + sum_{p: dst[p]=n} g[p]*x[src[p]]
+    dx = ops.seg_reduce(ptr_s, ids_s, N, g, X2=x, mul_idx=dst)
+    ops.seg_reduce(ptr_d, ids_d, N, g, X2=x, mul_idx=src, out=dx, accumulate=True)
+    return dx, None, None, None, None, None, None
+
+
+pair_init.register_autograd(_pi_bwd, setup_context=_pi_setup)
+
+# ------------------------------------------------------------------------------ readout
+
+
+@torch.library.custom_op("twowl::readout", mutates_args=())
+def readout(h: Tensor, idx: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """pred[l] = (h[idx[2l]] * h[idx[2l+1]]) @ weight.T + bias  (model.py:78-83)."""
+    return ops.readout_fwd(h.contiguous(), idx, weight.contiguous(), bias)
+
+
+@readout.register_fake
+def _(h, idx, weight, bias):
+    return h.new_empty((idx.numel() // 2, 1))
+
+
+def _ro_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _ro_bwd(ctx, g):
+    h, idx, weight, bias = ctx.saved_tensors
+    dH, dw, db = ops.readout_bwd(h.contiguous(), idx, weight.contiguous(), g.reshape(-1))
+    return dH, None, dw, db
+
+
+readout.register_autograd(_ro_bwd, setup_context=_ro_setup)

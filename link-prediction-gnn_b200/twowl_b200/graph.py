@@ -1,0 +1,200 @@
+"""Device-side index structures the kernels consume, built once per index tensor and cached.
+
+The reference rebuilds gcn_norm (self-loop surgery + degree + edge weights) inside every GCNConv
+call - depth1 + 2*depth2 times per forward. Here each index tensor is turned ONCE
+into CSR-by-target (forward) and CSR-by-source (backward) plus its dinv vector, keyed by the
+tensor's storage and version counter.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class _Cache:
+    """Tiny LRU keyed by (data_ptr, shape, strides, version). Entries keep the key tensor alive, so a
+    data_ptr can never be recycled by the allocator while its entry exists."""
+
+    def __init__(self, cap: int = 8):
+        self.cap = cap
+        self.d: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+    @staticmethod
+    def key(t: torch.Tensor, *extra):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, t.device.index) + extra
+
+    def get(self, t: torch.Tensor, extra, build):
+        k = self.key(t, *extra)
+        hit = self.d.get(k)
+        if hit is not None:
+            self.d.move_to_end(k)
+            return hit[1]
+        val = build()
+        self.d[k] = (t, val)
+        while len(self.d) > self.cap:
+            self.d.popitem(last=False)
+        return val
+
+    def clear(self):
+        self.d.clear()
+
+
+_cache = _Cache()
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def _i64(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.int64 else t.to(torch.int64)
+
+
+# ------------------------------------------------------------------------------ node-level graph (edge1)
+
+@dataclass
+class NodeGraph:
+    n: int
+    ptr: torch.Tensor    # CSR by target: rows = ei[1], col = ei[0]
+    col: torch.Tensor
+    tptr: torch.Tensor   # CSR by source: rows = ei[0], col = ei[1]
+    tcol: torch.Tensor
+    dinv: torch.Tensor   # (1 + in-degree without self-loops)^-1/2
+
+
+def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
+    def build():
+        ei = _i64(edge1)
+        ptr, ids = ops.csr_build(ei[1], n)
+        col = ops.gather_cols(ids, ei[0])
+        tptr, tids = ops.csr_build(ei[0], n)
+        tcol = ops.gather_cols(tids, ei[1])
+        return NodeGraph(n, ptr, col, tptr, tcol, ops.gcn_dinv(ptr, col, n))
+    return _cache.get(edge1, ("node", n), build)
+
+
+# ------------------------------------------------------------------------------ pair table (pos)
+
+@dataclass
+class PairTable:
+    n: int               # number of nodes the features have
+    R: int
+    src: torch.Tensor    # int32 [R]
+    dst: torch.Tensor
+    ptr_s: torch.Tensor  # pair rows grouped by src node
+    ids_s: torch.Tensor
+    ptr_d: torch.Tensor  # pair rows grouped by dst node
+    ids_d: torch.Tensor
+
+
+def pair_table(pos: torch.Tensor, n: int) -> PairTable:
+    def build():
+        p = _i64(pos)
+        ptr_s, ids_s = ops.csr_build(p[:, 0], n)
+        ptr_d, ids_d = ops.csr_build(p[:, 1], n)
+        return PairTable(n, p.shape[0], ops.narrow_i32(p[:, 0]), ops.narrow_i32(p[:, 1]), ptr_s, ids_s, ptr_d, ids_d)
+    return _cache.get(pos, ("pos", n), build)
+
+
+# ------------------------------------------------------------------------------ explicit wedge index (any ei2)
+
+@dataclass
+class ExplicitWedges:
+    R: int
+    ptr_b: torch.Tensor   # CSR by target pair b, col = source edge a
+    col_b: torch.Tensor
+    ptr_a: torch.Tensor   # CSR by source edge a, col = target pair b
+    col_a: torch.Tensor
+    dinv: tuple           # (dinv for edge2 = [a^1; b], dinv for edge2_r = [a; b^1])
+
+
+def explicit_wedges(ei2: torch.Tensor, R: int) -> ExplicitWedges:
+    """reverse() (utils.py:71-78) is never materialised: both directions read the same two CSRs with the
+    id^1 flips folded into the kernel (flip / row_flip)."""
+    if R % 2:
+        raise RuntimeError("the pair table must have an even number of rows (ids 2k/2k+1 are mates, utils.py:81-90)")
+
+    def build():
+        e = _i64(ei2)
+        ptr_b, ids_b = ops.csr_build(e[1], R)
+        col_b = ops.gather_cols(ids_b, e[0])
+        ptr_a, ids_a = ops.csr_build(e[0], R)
+        col_a = ops.gather_cols(ids_a, e[1])
+        d0 = ops.gcn_dinv(ptr_b, col_b, R, flip=1, row_flip=0)
+        d1 = ops.gcn_dinv(ptr_b, col_b, R, flip=0, row_flip=1)
+        return ExplicitWedges(R, ptr_b, col_b, ptr_a, col_a, (d0, d1))
+    return _cache.get(ei2, ("ei2", R), build)
+
+
+# ------------------------------------------------------------------------------ structured wedge index
+
+@dataclass
+class WedgeStruct:
+    """What get_ei2(n_node, pos_edge, pred_edge) joins, kept in factored form: the in-list of observed
+    edges per node and the out-list of pair rows per node. ``blocked`` (uint8[E]) marks source edges
+    removed by blockei2. T = sum_i cin(i)*cout(i) wedges are implied, never stored."""
+    n_node: int
+    E: int
+    R: int
+    src: torch.Tensor      # int32 [R]  pos[:,0] of every pair row
+    dst_e: torch.Tensor    # int32 [E]  target node of every observed edge
+    in_ptr: torch.Tensor   # int64 [n+1], in_ids int32: observed edge ids grouped by target node (ascending id)
+    in_ids: torch.Tensor
+    out_ptr: torch.Tensor  # int64 [n+1], out_ids int32: pair rows grouped by source node (ascending id)
+    out_ids: torch.Tensor
+    blocked: Optional[torch.Tensor] = None
+    _prep: Optional[tuple] = field(default=None, repr=False)
+
+    def with_blocked(self, blocked: torch.Tensor) -> "WedgeStruct":
+        if self.blocked is not None:
+            blocked = torch.maximum(blocked, self.blocked)
+        return WedgeStruct(self.n_node, self.E, self.R, self.src, self.dst_e, self.in_ptr, self.in_ids, self.out_ptr,
+                           self.out_ids, blocked)
+
+    def prepared(self):
+        """(cnt[N], centre[2,R], dinv[2,R], selfw[2,R]) - per-row constants of both directions."""
+        if self._prep is None:
+            if self.E % 2 or self.R % 2:
+                raise RuntimeError("structured wedge path needs the doubled layout (even E and R)")
+            self._prep = ops.wedge_prepare(self.src, self.dst_e, self.E, self.R, self.n_node, self.blocked, self.in_ptr)
+        return self._prep
+
+    def num_wedges(self) -> int:
+        """T' = sum over unblocked a of cout(dst(a)) - one host read."""
+        cin = (self.in_ptr[1:] - self.in_ptr[:-1]) if self.blocked is None else self.prepared()[0][: self.n_node].to(torch.int64)
+        cout = self.out_ptr[1:] - self.out_ptr[:-1]
+        return int((cin * cout).sum().item())
+
+
+def build_wedge_struct(n_node: int, pos_edge: torch.Tensor, pred_edge: torch.Tensor) -> WedgeStruct:
+    pos_edge, pred_edge = _i64(pos_edge), _i64(pred_edge)
+    E, P = pos_edge.shape[1], pred_edge.shape[1]
+    src_all = torch.cat((pos_edge[0], pred_edge[0]))
+    in_ptr, in_ids = ops.csr_build(pos_edge[1], n_node)
+    out_ptr, out_ids = ops.csr_build(src_all, n_node)
+    return WedgeStruct(int(n_node), E, E + P, ops.narrow_i32(src_all), ops.narrow_i32(pos_edge[1]), in_ptr, in_ids,
+                       out_ptr, out_ids)
+
+
+class WedgeIndex:
+    """A wedge index that is NOT materialised (T = sum deg^2 reaches 6.5e10 on R-MAT 1M/16M - 1 TB as
+    int64 [2,T]). Accepted wherever the drop-in API takes ``ei2``: sample_block, LocalWLNet.forward."""
+
+    def __init__(self, struct: WedgeStruct):
+        self.struct = struct
+
+    @property
+    def device(self):
+        return self.struct.src.device
+
+    def num_wedges(self) -> int:
+        return self.struct.num_wedges()
+
+    def materialize(self) -> torch.Tensor:
+        from TwoWL.utils import _materialize
+        return _materialize(self.struct)

@@ -1,0 +1,410 @@
+"""Tensor-level wrappers over the C ABI (include/twowl.h): allocate outputs and workspaces with
+the PyTorch caching allocator, pass raw device pointers and the current CUDA stream.
+
+Nothing here computes on the host and nothing falls back to torch ops: a CPU tensor raises.
+Data-dependent sizes (T of get_ei2, T' of blockei2) cost one device->host scalar read each,
+exactly where the reference's own torch ops (cat / boolean indexing) synchronise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import SegArgs, check, lib
+
+SELECT_TILE = 2048
+_launches = 0  # number of C-ABI compute calls issued (bench.py reports kernels through this)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int = 1):
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("twowl_b200: tensors must live on a CUDA device (no CPU fallback exists)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _row(t: torch.Tensor) -> Tuple[int, int]:
+    """(data pointer, element stride) of a 1-D int64 view."""
+    assert t.dim() == 1 and t.dtype == torch.int64, "expected a 1-D int64 tensor"
+    return t.data_ptr(), (t.stride(0) if t.numel() > 1 else 1)
+
+
+# ------------------------------------------------------------------------------ integer operators
+
+def degree(keys: torch.Tensor, num_node: int) -> torch.Tensor:
+    _need_cuda(keys)
+    out = torch.empty(int(num_node), dtype=torch.int64, device=keys.device)
+    p, s = _row(keys)
+    check(lib.twowl_degree(p, s, keys.numel(), int(num_node), out.data_ptr(), _stream()), "degree")
+    _count(2)
+    return out
+
+
+def csr_build(keys: torch.Tensor, num_keys: int, key_xor: int = 0, want_ptr: bool = True):
+    """Stable counting sort of positions by key -> (ptr int64[num_keys+1] | None, ids int32[n])."""
+    _need_cuda(keys)
+    n = keys.numel()
+    dev = keys.device
+    ptr = torch.empty(int(num_keys) + 1, dtype=torch.int64, device=dev) if want_ptr else None
+    ids = torch.empty(n, dtype=torch.int32, device=dev)
+    nb = lib.twowl_csr_build_workspace_bytes(n, int(num_keys))
+    ws = _ws(nb, dev)
+    p, s = _row(keys)
+    check(lib.twowl_csr_build(p, s, n, int(key_xor), int(num_keys), _p(ptr), ids.data_ptr(), ws.data_ptr(), nb,
+                              _stream()), "csr_build")
+    _count(4 + 3 * 4)
+    return ptr, ids
+
+
+def gather_cols(ids: torch.Tensor, vals: torch.Tensor, val_xor: int = 0) -> torch.Tensor:
+    _need_cuda(ids, vals)
+    out = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
+    p, s = _row(vals)
+    check(lib.twowl_gather_cols(ids.data_ptr(), ids.numel(), p, s, int(val_xor), out.data_ptr(), _stream()),
+          "gather_cols")
+    _count()
+    return out
+
+
+def narrow_i32(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    out = torch.empty(x.numel(), dtype=torch.int32, device=x.device)
+    p, s = _row(x)
+    check(lib.twowl_narrow_i32(p, s, x.numel(), out.data_ptr(), _stream()), "narrow_i32")
+    _count()
+    return out
+
+
+def ei2_offsets(in_ptr: torch.Tensor, out_ptr: torch.Tensor, n_node: int) -> torch.Tensor:
+    off = torch.empty(n_node + 1, dtype=torch.int64, device=in_ptr.device)
+    nb = lib.twowl_ei2_count_workspace_bytes(n_node)
+    ws = _ws(nb, in_ptr.device)
+    check(lib.twowl_ei2_count(in_ptr.data_ptr(), out_ptr.data_ptr(), n_node, off.data_ptr(), ws.data_ptr(), nb,
+                              _stream()), "ei2_count")
+    _count(4)
+    return off
+
+
+def ei2_fill(in_ptr, in_ids, out_ptr, out_ids, off, n_node: int, t_begin: int, t_end: int) -> torch.Tensor:
+    """-> int64 [t_end - t_begin, 2] rows (a, b); its .t() is the reference's get_ei2 layout."""
+    out = torch.empty((t_end - t_begin, 2), dtype=torch.int64, device=in_ptr.device)
+    check(lib.twowl_ei2_fill(in_ptr.data_ptr(), in_ids.data_ptr(), out_ptr.data_ptr(), out_ids.data_ptr(),
+                             off.data_ptr(), n_node, int(t_begin), int(t_end), out.data_ptr(), _stream()), "ei2_fill")
+    _count()
+    return out
+
+
+def mask_from_idx(idx: torch.Tensor, num: int) -> torch.Tensor:
+    _need_cuda(idx)
+    idx = idx.reshape(-1)
+    if idx.dtype != torch.int64:
+        idx = idx.to(torch.int64)
+    idx = idx.contiguous()
+    mask = torch.empty(int(num), dtype=torch.uint8, device=idx.device)
+    check(lib.twowl_mask_from_idx(idx.data_ptr(), idx.numel(), mask.data_ptr(), int(num), _stream()), "mask_from_idx")
+    _count(2)
+    return mask
+
+
+def select_columns(mat: torch.Tensor, mask: torch.Tensor, mode: int) -> torch.Tensor:
+    """Order-preserving column selection of an int64 [2,T] matrix (any strides).
+    mode 0: keep column t iff !mask[t]; mode 1: keep iff !mask[mat[0,t]]."""
+    _need_cuda(mat, mask)
+    assert mat.dim() == 2 and mat.shape[0] == 2 and mat.dtype == torch.int64
+    T = mat.shape[1]
+    dev = mat.device
+    if T == 0:
+        return torch.empty((2, 0), dtype=torch.int64, device=dev)
+    ntiles = (T + SELECT_TILE - 1) // SELECT_TILE
+    tile_off = torch.empty(ntiles + 1, dtype=torch.int64, device=dev)
+    nb = lib.twowl_select_workspace_bytes(T)
+    ws = _ws(nb, dev)
+    (p0, s0), (p1, s1) = _row(mat[0]), _row(mat[1])
+    check(lib.twowl_select_count(p0, s0, T, mask.data_ptr(), mask.numel(), mode, tile_off.data_ptr(), ws.data_ptr(), nb,
+                                 _stream()), "select_count")
+    t_new = int(tile_off[-1].item())  # the reference's boolean indexing synchronises here as well
+    out = torch.empty((2, t_new), dtype=torch.int64, device=dev)
+    check(lib.twowl_select_fill(p0, s0, p1, s1, T, mask.data_ptr(), mask.numel(), mode, tile_off.data_ptr(),
+                                out[0].data_ptr() if t_new else None, out[1].data_ptr() if t_new else None, _stream()),
+          "select_fill")
+    _count(5)
+    return out
+
+
+def check_in_set(target: torch.Tensor, set_: torch.Tensor) -> torch.Tensor:
+    _need_cuda(target, set_)
+    target, set_ = target.reshape(-1), set_.reshape(-1).contiguous()
+    n, m = target.numel(), set_.numel()
+    dev = target.device
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out
+    rng = int(torch.max(target.max(), set_.max() if m else target.max()).item()) + 1 if (n or m) else 1
+    rng = max(rng, 1)
+    counts = torch.empty(rng, dtype=torch.int32, device=dev)
+    p, s = _row(target)
+    check(lib.twowl_check_in_set(p, s, n, set_.data_ptr(), m, rng, counts.data_ptr(), out.data_ptr(), _stream()),
+          "check_in_set")
+    _count(3)
+    return out
+
+
+def reverse(ei2: torch.Tensor):
+    _need_cuda(ei2)
+    T = ei2.shape[1]
+    edge = torch.empty((2, T), dtype=torch.int64, device=ei2.device)
+    edge_r = torch.empty((2, T), dtype=torch.int64, device=ei2.device)
+    if T:
+        (p0, s0), (p1, s1) = _row(ei2[0]), _row(ei2[1])
+        check(lib.twowl_reverse(p0, s0, p1, s1, T, edge.data_ptr(), edge_r.data_ptr(), _stream()), "reverse")
+        _count()
+    return edge, edge_r
+
+
+def double_edges(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    M = x.shape[1]
+    out = torch.empty((2, 2 * M), dtype=torch.int64, device=x.device)
+    if M:
+        (p0, s0), (p1, s1) = _row(x[0]), _row(x[1])
+        check(lib.twowl_double_edges(p0, s0, p1, s1, M, out.data_ptr(), _stream()), "double_edges")
+        _count()
+    return out
+
+
+def double_index(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.reshape(-1)
+    out = torch.empty(2 * x.numel(), dtype=torch.int64, device=x.device)
+    if x.numel():
+        p, s = _row(x)
+        check(lib.twowl_double_index(p, s, x.numel(), out.data_ptr(), _stream()), "double_index")
+        _count()
+    return out
+
+
+def set_mul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _need_cuda(a, b)
+    a, b = a.reshape(-1).contiguous(), b.reshape(-1).contiguous()
+    out = torch.empty((a.numel() * b.numel(), 2), dtype=torch.int64, device=a.device)
+    if out.numel():
+        check(lib.twowl_set_mul(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), out.data_ptr(), _stream()), "set_mul")
+        _count()
+    return out
+
+
+# ------------------------------------------------------------------------------ aggregation
+
+def gcn_dinv(ptr, col, M: int, flip: int = 0, row_flip: int = 0, skip_mask=None, row_skip_mask=None) -> torch.Tensor:
+    _need_cuda(ptr, col)
+    dinv = torch.empty(M, dtype=torch.float32, device=ptr.device)
+    check(lib.twowl_gcn_dinv(ptr.data_ptr(), col.data_ptr(), M, flip, row_flip, _p(skip_mask), _p(row_skip_mask),
+                             dinv.data_ptr(), _stream()), "gcn_dinv")
+    _count()
+    return dinv
+
+
+def seg_reduce(ptr, col, M: int, X, *, flip=0, row_flip=0, src_scale=None, skip_mask=None, row_skip_mask=None,
+               skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None, out=None,
+               accumulate=False) -> torch.Tensor:
+    _need_cuda(ptr, col, X)
+    assert X.dtype == torch.float32 and X.is_contiguous()
+    C = X.shape[1]
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=X.device)
+    a = SegArgs(ptr=ptr.data_ptr(), col=col.data_ptr(), M=M, X=X.data_ptr(), C=C, flip=int(flip), row_flip=int(row_flip),
+                src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
+                skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
+                mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate))
+    check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
+    _count()
+    return out
+
+
+def gather_rows(W: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need_cuda(W, idx)
+    idx = idx.reshape(-1)
+    out = torch.empty((idx.numel(), W.shape[1]), dtype=torch.float32, device=W.device)
+    p, s = _row(idx)
+    check(lib.twowl_gather_rows(W.data_ptr(), W.shape[0], p, s, idx.numel(), W.shape[1], out.data_ptr(), _stream()),
+          "gather_rows")
+    _count()
+    return out
+
+
+def pair_init_fwd(X, src32, dst32) -> torch.Tensor:
+    _need_cuda(X, src32, dst32)
+    R = src32.numel()
+    out = torch.empty((R, X.shape[1]), dtype=torch.float32, device=X.device)
+    check(lib.twowl_pair_init_fwd(X.data_ptr(), src32.data_ptr(), dst32.data_ptr(), R, X.shape[1], out.data_ptr(),
+                                  _stream()), "pair_init_fwd")
+    _count()
+    return out
+
+
+def readout_fwd(H, idx, w, b) -> torch.Tensor:
+    _need_cuda(H, idx, w, b)
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    pred = torch.empty((L, 1), dtype=torch.float32, device=H.device)
+    p, s = _row(idx)
+    check(lib.twowl_readout_fwd(H.data_ptr(), p, s, L, H.shape[1], w.data_ptr(), b.data_ptr(), pred.data_ptr(),
+                                _stream()), "readout_fwd")
+    _count()
+    return pred
+
+
+def readout_bwd(H, idx, w, dpred):
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    C = H.shape[1]
+    dev = H.device
+    _, order = csr_build(idx[: 2 * L], H.shape[0], want_ptr=False)
+    dH = torch.zeros_like(H)
+    dw = torch.empty((1, C), dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    nb = lib.twowl_readout_bwd_workspace_bytes(L, C)
+    ws = _ws(nb, dev)
+    p, s = _row(idx)
+    dpred = dpred.contiguous()
+    check(lib.twowl_readout_bwd(H.data_ptr(), p, s, L, C, w.data_ptr(), dpred.data_ptr(), order.data_ptr(),
+                                dH.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, _stream()), "readout_bwd")
+    _count(6)
+    return dH, dw, db
+
+
+# ------------------------------------------------------------------------------ GraphNorm
+
+def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
+    _need_cuda(x)
+    M, C = x.shape
+    stats = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    nb = lib.twowl_graphnorm_stats_workspace_bytes(M, C)
+    ws = _ws(nb, x.device)
+    check(lib.twowl_graphnorm_stats(x.data_ptr(), M, C, mean_scale.data_ptr(), float(eps), stats.data_ptr(),
+                                    ws.data_ptr(), nb, _stream()), "graphnorm_stats")
+    _count(2)
+    return stats
+
+
+def graphnorm_apply(x, stats, weight, bias, mean_scale, p_drop: float, seed: int, relu: bool, addend=None):
+    M, C = x.shape
+    out = torch.empty_like(x)
+    check(lib.twowl_graphnorm_apply(x.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                    mean_scale.data_ptr(), float(p_drop), int(seed), int(relu), _p(addend),
+                                    out.data_ptr(), _stream()), "graphnorm_apply")
+    _count()
+    return out
+
+
+def graphnorm_bwd(x, dout, stats, weight, bias, mean_scale, p_drop: float, seed: int, relu: bool):
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    dparams = torch.empty(3 * C, dtype=torch.float32, device=x.device)
+    nb = lib.twowl_graphnorm_bwd_workspace_bytes(M, C)
+    ws = _ws(nb, x.device)
+    check(lib.twowl_graphnorm_bwd(x.data_ptr(), dout.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(),
+                                  bias.data_ptr(), mean_scale.data_ptr(), float(p_drop), int(seed), int(relu),
+                                  dx.data_ptr(), dparams.data_ptr(), ws.data_ptr(), nb, _stream()), "graphnorm_bwd")
+    _count(3)
+    return dx, dparams
+
+
+def colsum(x) -> torch.Tensor:
+    M, C = x.shape
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    nb = lib.twowl_colsum_workspace_bytes(M, C)
+    ws = _ws(nb, x.device)
+    check(lib.twowl_colsum(x.data_ptr(), M, C, out.data_ptr(), ws.data_ptr(), nb, _stream()), "colsum")
+    _count(2)
+    return out
+
+
+# ------------------------------------------------------------------------------ linear
+
+def linear_fwd(X, W, impl: int = 0) -> torch.Tensor:
+    _need_cuda(X, W)
+    M, Ci = X.shape
+    Co = W.shape[0]
+    Z = torch.empty((M, Co), dtype=torch.float32, device=X.device)
+    check(lib.twowl_linear_fwd(X.data_ptr(), W.data_ptr(), M, Ci, Co, Z.data_ptr(), impl, _stream()), "linear_fwd")
+    _count()
+    return Z
+
+
+def linear_bwd_input(dZ, W, impl: int = 0) -> torch.Tensor:
+    M, Co = dZ.shape
+    Ci = W.shape[1]
+    dX = torch.empty((M, Ci), dtype=torch.float32, device=dZ.device)
+    check(lib.twowl_linear_bwd_input(dZ.data_ptr(), W.data_ptr(), M, Ci, Co, dX.data_ptr(), impl, _stream()),
+          "linear_bwd_input")
+    _count()
+    return dX
+
+
+def linear_bwd_weight(dZ, X) -> torch.Tensor:
+    M, Co = dZ.shape
+    Ci = X.shape[1]
+    dW = torch.empty((Co, Ci), dtype=torch.float32, device=dZ.device)
+    nb = lib.twowl_linear_bwd_weight_workspace_bytes(M, Ci, Co)
+    ws = _ws(nb, dZ.device)
+    check(lib.twowl_linear_bwd_weight(dZ.data_ptr(), X.data_ptr(), M, Ci, Co, dW.data_ptr(), ws.data_ptr(), nb,
+                                      _stream()), "linear_bwd_weight")
+    _count(2)
+    return dW
+
+
+# ------------------------------------------------------------------------------ structured wedge path
+
+def wedge_prepare(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr):
+    dev = src32.device
+    cnt = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    centre = torch.empty((2, R), dtype=torch.int32, device=dev)
+    dinv = torch.empty((2, R), dtype=torch.float32, device=dev)
+    selfw = torch.empty((2, R), dtype=torch.float32, device=dev)
+    check(lib.twowl_wedge_prepare(src32.data_ptr(), dst_e32.data_ptr(), E, R, N, _p(blocked), in_ptr.data_ptr(),
+                                  cnt.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(), _stream()),
+          "wedge_prepare")
+    _count(3)
+    return cnt, centre, dinv, selfw
+
+
+def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
+    R, C = Z.shape
+    out = torch.empty_like(Z)
+    check(lib.twowl_wedge_apply_fwd(S.data_ptr(), Z.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(),
+                                    _p(bias), R, C, out.data_ptr(), _stream()), "wedge_apply_fwd")
+    _count()
+    return out
+
+
+def wedge_apply_bwd(dS, dO, dst_e32, blocked, E: int, N: int, dinv, selfw, direction: int) -> torch.Tensor:
+    R, C = dO.shape
+    dZ = torch.empty_like(dO)
+    check(lib.twowl_wedge_apply_bwd(dS.data_ptr(), dO.data_ptr(), dst_e32.data_ptr(), _p(blocked), E, N,
+                                    dinv.data_ptr(), selfw.data_ptr(), direction, R, C, dZ.data_ptr(), _stream()),
+          "wedge_apply_bwd")
+    _count()
+    return dZ

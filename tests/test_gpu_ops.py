@@ -1,0 +1,298 @@
+"""GPU parity of the individual C-ABI kernels (through the Python operator layer) against the CPU
+oracle and the reference-generated golden fixtures. Integer/index work is compared BIT-EXACT;
+floating point within |a-b| <= 1e-6 + 1e-5*|b| (north_star tolerance) against an fp64 evaluation.
+Run on a B200 box:  python -m pytest tests -m gpu -q
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, fb_split, sha
+from oracle import twowl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import TwoWL.utils as utils
+    return utils
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def same(t, ref):
+    t = t.detach().cpu().numpy()
+    ref = np.asarray(ref)
+    return t.shape == ref.shape and np.array_equal(t, ref)
+
+
+# ------------------------------------------------------------------------------ golden vectors
+
+def test_three_node_golden(U, golden):
+    g = golden("three_node.npz")
+    pos, pred = dev(g["pos"]), dev(g["pred"])
+    assert same(U.double(dev(np.array([[0, 1], [1, 2]]))), g["pos"])
+    assert same(U.double(dev(np.array([0, 2])), for_index=True), g["double_index"])
+    ei2 = U.get_ei2(3, pos, pred)
+    assert ei2.dtype == torch.int64 and not ei2.is_contiguous()  # cat(...).t() view, like utils.py:45
+    assert same(ei2, g["ei2"])
+    edge, edge_r = U.reverse(ei2)
+    assert same(edge, g["edge"]) and same(edge_r, g["edge_r"])
+    assert same(U.degree(pos, 3), g["degree"])
+    ei_new, x_new, ei2_new = U.sample_block(dev(np.array([0, 1])), 3, pos, ei2)
+    assert same(ei_new, g["sb_ei"]) and same(x_new, g["sb_x"]) and same(ei2_new, g["sb_ei2"])
+    assert same(U.set_mul(dev(np.array([5, 7])), dev(np.array([1, 2, 3]))), g["set_mul"])
+    assert same(U.check_in_set(dev(np.array([1, 2, 3, 2])), dev(np.array([2, 2, 9]))), g["check_in_set"])
+    m = U.idx2mask(5, dev(np.array([1, 3])))
+    assert m.dtype == torch.bool and same(m, g["idx2mask"])
+
+
+def test_ragged_golden(U, golden):
+    """Irregular inputs: duplicates, self-loop edges, isolated nodes, empty pred / empty pos lists, n_node
+    smaller than the largest id."""
+    g = golden("ragged.npz")
+    k = 0
+    while f"c{k}_n" in g.files:
+        n = int(g[f"c{k}_n"][0])
+        pos, pred = dev(g[f"c{k}_pos"]), dev(g[f"c{k}_pred"])
+        ei2 = U.get_ei2(n, pos, pred)
+        assert same(ei2, g[f"c{k}_ei2"]), f"case {k} get_ei2"
+        if f"c{k}_blocked" in g.files:
+            blk = dev(g[f"c{k}_blocked"])
+            if f"c{k}_blockei2" in g.files:
+                assert same(U.blockei2(ei2, blk), g[f"c{k}_blockei2"]), f"case {k} blockei2 (structured tag)"
+                assert same(U.blockei2(ei2.contiguous(), blk), g[f"c{k}_blockei2"]), f"case {k} blockei2 (plain)"
+            n_sb = g[f"c{k}_sb_x"].shape[0]
+            ei_new, x_new, _ = U.sample_block(blk, n_sb, pos, None)
+            assert same(ei_new, g[f"c{k}_sb_ei"]) and same(x_new, g[f"c{k}_sb_x"]), f"case {k} sample_block"
+            assert same(U.degree(pos, g[f"c{k}_degree"].shape[0]), g[f"c{k}_degree"]), f"case {k} degree"
+        k += 1
+    assert k >= 6
+
+
+def test_fb_pages_food_index_golden(U, fb):
+    """configs[0]: the three wedge indices, the train batch's sample_block and reverse, by sha256 of the
+    int64 bytes the reference produced."""
+    n = int(fb["num_nodes"][0])
+    for s in range(3):
+        ei, pred, pos1 = fb_split(fb, s)
+        ei2 = U.get_ei2(n, dev(ei), dev(pred))
+        assert tuple(ei2.shape) == tuple(fb[f"ei2_{s}_shape"])
+        assert sha(ei2) == str(fb[f"ei2_{s}_sha"])
+    ei, pred, _ = fb_split(fb, 0)
+    assert same(U.degree(dev(ei), n), fb["x0"].astype(np.int64))
+    ei2 = U.get_ei2(n, dev(ei), dev(pred))
+    idx1 = dev(fb["idx1"].astype(np.int64))
+    ei_new, x_new, ei2_new = U.sample_block(idx1, n, dev(ei), ei2)
+    assert sha(ei_new) == str(fb["sb_ei_sha"]) and same(x_new, fb["sb_x"].astype(np.int64))
+    assert sha(ei2_new) == str(fb["sb_ei2_sha"]) and ei2_new.is_contiguous()
+    e, er = U.reverse(ei2_new)
+    assert sha(e) == str(fb["rev_edge_sha"]) and sha(er) == str(fb["rev_edge_r_sha"])
+    # implicit index: same wedge count, same tensor once materialised
+    wi = U.blockei2(U.get_ei2_implicit(n, dev(ei), dev(pred)), idx1)
+    assert wi.num_wedges() == ei2_new.shape[1]
+    assert sha(wi.materialize()) == str(fb["sb_ei2_sha"])
+
+
+# ------------------------------------------------------------------------------ seeded random vs oracle
+
+@pytest.mark.parametrize("n,e,p,seed", [(50, 400, 300, 0), (1000, 6000, 6000, 1), (17, 0, 5, 2), (40, 64, 0, 3),
+                                        (5000, 60000, 20000, 4)])
+def test_get_ei2_random_vs_oracle(U, n, e, p, seed):
+    rng = np.random.default_rng(seed)
+    # skewed endpoints (hubs) so that long in/out lists and multi-tile segments occur
+    pick = lambda m: np.minimum((rng.pareto(1.2, size=m) * n / 20).astype(np.int64), n - 1)
+    pos = np.stack([pick(e), pick(e)])
+    pred = np.stack([pick(p), pick(p)])
+    ref = O.get_ei2(n, pos, pred)
+    got = U.get_ei2(n, dev(pos), dev(pred))
+    assert same(got, ref)
+    if e:
+        blk = rng.choice(e, size=max(1, e // 7), replace=False)
+        assert same(U.blockei2(got, dev(blk)), O.blockei2(ref, blk))
+        r1, r2 = U.reverse(got)
+        o1, o2 = O.reverse(ref)
+        assert same(r1, o1) and same(r2, o2)
+
+
+def test_check_in_set_duplicates_and_degree(U):
+    rng = np.random.default_rng(7)
+    t = rng.integers(0, 500, size=10000)
+    s = rng.integers(0, 600, size=300)   # duplicates count twice (the reference sums the equality matrix)
+    assert same(U.check_in_set(dev(t), dev(s)), O.check_in_set(t, s))
+    ei = rng.integers(0, 3000, size=(2, 200000))
+    assert same(U.degree(dev(ei), 3000), O.degree(ei, 3000))
+    assert same(U.degree(dev(ei), 100), np.bincount(ei[1][ei[1] < 100], minlength=100))  # out-of-range dropped
+
+
+def test_csr_build_is_a_stable_sort(U):
+    from twowl_b200 import ops
+    rng = np.random.default_rng(11)
+    for n, nk in [(1, 1), (2047, 3), (2049, 70000), (300000, 1 << 20), (1000003, 257)]:
+        keys = rng.integers(0, nk + 3, size=n)        # some keys out of range: they sort last
+        ptr, ids = ops.csr_build(dev(keys), nk)
+        kk = np.where(keys < nk, keys, nk)
+        ref = np.argsort(kk, kind="stable")
+        assert np.array_equal(ids.cpu().numpy(), ref.astype(np.int32)), (n, nk)
+        refptr = np.concatenate([[0], np.cumsum(np.bincount(kk[kk < nk], minlength=nk))])
+        assert np.array_equal(ptr.cpu().numpy(), refptr), (n, nk)
+
+
+def test_full_size_properties(U):
+    """BASELINE-scale property checks that need no oracle: wedge count identity, sortedness by centre,
+    blockei2 == boolean mask, reverse is an involution pair."""
+    rng = np.random.default_rng(5)
+    n, m = 200000, 1500000
+    und = rng.integers(0, n, size=(2, m))
+    pos, pred = O.synthetic_split(n, und[:, : m // 2], seed=1)
+    # cap T: keep only low-degree nodes' edges out of the way by using the uniform graph (T ~ sum deg^2)
+    dpos, dpred = dev(pos), dev(pred)
+    ei2 = U.get_ei2(n, dpos, dpred)
+    cin = torch.bincount(dpos[1], minlength=n)
+    cout = torch.bincount(torch.cat((dpos[0], dpred[0])), minlength=n)
+    assert ei2.shape[1] == int((cin * cout).sum())
+    centre = dpos[1][ei2[0]]
+    assert bool((centre[1:] >= centre[:-1]).all())                       # centre ascending
+    src_all = torch.cat((dpos[0], dpred[0]))
+    assert bool((src_all[ei2[1]] == centre).all())                       # every wedge is a real join
+    blk = dev(rng.choice(pos.shape[1], size=pos.shape[1] // 10, replace=False))
+    mask = torch.zeros(pos.shape[1], dtype=torch.bool, device="cuda")
+    mask[blk] = True
+    assert torch.equal(U.blockei2(ei2, blk), ei2[:, ~mask[ei2[0]]])
+    e, er = U.reverse(ei2)
+    assert torch.equal(e[0] ^ 1, ei2[0]) and torch.equal(er[1] ^ 1, ei2[1])
+    assert torch.equal(e[1], ei2[1]) and torch.equal(er[0], ei2[0])
+
+
+# ------------------------------------------------------------------------------ floating-point kernels
+
+def _csr_from(rows, cols, M):
+    order = np.argsort(rows, kind="stable")
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=M))]).astype(np.int64)
+    return dev(ptr), dev(cols[order].astype(np.int32))
+
+
+@pytest.mark.parametrize("C", [4, 24, 64, 132, 256, 520])
+def test_seg_reduce_vs_fp64(U, C):
+    from twowl_b200 import ops
+    rng = np.random.default_rng(C)
+    M, nnz = 3000, 40000
+    M += M % 2
+    rows = np.minimum((rng.pareto(1.0, size=nnz) * 40).astype(np.int64), M - 1)
+    cols = rng.integers(0, M, size=nnz)
+    ptr, col = _csr_from(rows, cols, M)
+    X = torch.randn(M, C, dtype=torch.float64)
+    sc = torch.rand(M, dtype=torch.float64) + 0.1
+    bias = torch.randn(C, dtype=torch.float64)
+    mask = rng.random(M) < 0.2
+    order = np.argsort(rows, kind="stable")
+    r_s, c_s = torch.from_numpy(rows[order]), torch.from_numpy(cols[order])
+    for flip, row_flip in [(0, 0), (1, 0), (0, 1)]:
+        tgt = r_s ^ row_flip
+        s = c_s ^ flip
+        keep = (s != tgt) & ~torch.from_numpy(mask)[c_s]
+        ref = torch.zeros(M, C, dtype=torch.float64).index_add_(0, tgt[keep], sc[s[keep]].unsqueeze(1) * X[s[keep]])
+        ref = sc.unsqueeze(1) * ref + (sc ** 2).unsqueeze(1) * X + bias
+        got = ops.seg_reduce(ptr, col, M, X.float().cuda(), flip=flip, row_flip=row_flip, src_scale=sc.float().cuda(),
+                             dst_scale=sc.float().cuda(), skip_self=True, self_mode=1, bias=bias.float().cuda(),
+                             skip_mask=dev(mask.astype(np.uint8)))
+        assert_close(got, ref, rtol=1e-5, atol=2e-4, what=f"seg_reduce C={C} flip={flip} row_flip={row_flip}")
+        # dinv: exact integer degree
+        d = ops.gcn_dinv(ptr, col, M, flip=flip, row_flip=row_flip, skip_mask=dev(mask.astype(np.uint8)))
+        deg = torch.bincount(tgt[keep], minlength=M).double() + 1
+        assert_close(d, deg.pow(-0.5), rtol=2e-7, atol=0, what="gcn_dinv")
+
+
+@pytest.mark.parametrize("M,C,p,relu", [(1, 4, 0.0, True), (620, 64, 0.0, False), (6576, 24, 0.0, True),
+                                        (100003, 128, 0.0, True), (5000, 32, 0.5, True), (777, 1024, 0.0, True)])
+def test_graphnorm_fwd_bwd(U, M, C, p, relu):
+    from twowl_b200 import functional as F2
+    torch.manual_seed(M + C)
+    x = (torch.randn(M, C, dtype=torch.float64) * 2 + 3).requires_grad_(True)
+    w = (torch.rand(C, dtype=torch.float64) + 0.5).requires_grad_(True)
+    b = torch.randn(C, dtype=torch.float64).requires_grad_(True)
+    a = (torch.rand(C, dtype=torch.float64) + 0.5).requires_grad_(True)
+    add = torch.randn(M, C, dtype=torch.float64).requires_grad_(True)
+    gx, gw, gb, ga, gadd = [t.detach().float().cuda().requires_grad_(True) for t in (x, w, b, a, add)]
+    out, _ = F2.graphnorm_act(gx, gw, gb, ga, gadd, 1e-5, p, 1234, relu)
+    gout = torch.randn(M, C, dtype=torch.float64)
+    out.backward(gout.float().cuda())
+    if p == 0.0:
+        ref = O.graph_norm(x, w, b, a)
+        ref = (torch.relu(ref) if relu else ref) + add
+        ref.backward(gout)
+        assert_close(out, ref, atol=1e-5, what="graphnorm out")
+        scale = lambda t: float(t.abs().max())
+        for name, g, r in (("dx", gx, x), ("dw", gw, w), ("db", gb, b), ("dms", ga, a), ("dadd", gadd, add)):
+            assert_close(g.grad, r.grad, rtol=1e-5, atol=1e-5 * max(scale(r.grad), 1.0), what="graphnorm " + name)
+    else:
+        y = O.graph_norm(x, w, b, a).detach()
+        o = (out - gadd).detach().cpu().double()
+        kept = o != 0
+        frac = float(kept.double().mean()) / float((y > 0).double().mean())
+        assert abs(frac - (1 - p)) < 0.02, frac                                # keep rate
+        assert_close(o[kept], (torch.relu(y) / (1 - p))[kept], atol=1e-5, what="dropout scaling")
+        dropped = ~kept & (y > 0.1)                                             # dropped elements pass no gradient
+        ref_dx = torch.autograd.grad(O.graph_norm(x, w, b, a), x, gout * kept / (1 - p))[0]
+        assert_close(gx.grad, ref_dx, rtol=1e-5, atol=1e-5 * float(ref_dx.abs().max()), what="dropout dx")
+        assert int(dropped.sum()) > 0
+        # same seed -> same mask; different seed -> different mask
+        out2, _ = F2.graphnorm_act(gx, gw, gb, ga, gadd, 1e-5, p, 1234, relu)
+        out3, _ = F2.graphnorm_act(gx, gw, gb, ga, gadd, 1e-5, p, 99, relu)
+        assert torch.equal(out, out2) and not torch.equal(out, out3)
+
+
+@pytest.mark.parametrize("M,Ci,Co", [(1, 4, 4), (620, 64, 24), (6576, 24, 24), (4097, 128, 128), (1000, 256, 36),
+                                     (50000, 64, 64)])
+def test_linear_fwd_bwd(U, M, Ci, Co):
+    from twowl_b200 import functional as F2
+    torch.manual_seed(M)
+    x = torch.randn(M, Ci, dtype=torch.float64).requires_grad_(True)
+    w = torch.randn(Co, Ci, dtype=torch.float64).requires_grad_(True)
+    g = torch.randn(M, Co, dtype=torch.float64)
+    (x @ w.t()).backward(g)
+    gx, gw = x.detach().float().cuda().requires_grad_(True), w.detach().float().cuda().requires_grad_(True)
+    z = F2.linear(gx, gw)
+    z.backward(g.float().cuda())
+    k = lambda t: 1e-6 * float(t.abs().max()) * 4
+    assert_close(z, (x @ w.t()).detach(), atol=k(x @ w.t()), what="linear fwd")
+    assert_close(gx.grad, x.grad, atol=k(x.grad), what="linear dX")
+    assert_close(gw.grad, w.grad, atol=k(w.grad), what="linear dW")
+
+
+def test_pair_init_readout_embedding(U):
+    from twowl_b200 import functional as F2
+    from twowl_b200 import graph as G
+    torch.manual_seed(3)
+    N, R, C, V, L = 500, 4000, 24, 37, 300
+    X = torch.randn(N, C, dtype=torch.float64).requires_grad_(True)
+    pos = torch.randint(0, N, (R, 2))
+    idx = torch.randint(0, R, (2 * L,))
+    idx[5] = idx[4]
+    idx[10] = idx[2]                                   # duplicates: gradients must add up
+    w = torch.randn(1, C, dtype=torch.float64).requires_grad_(True)
+    b = torch.randn(1, dtype=torch.float64).requires_grad_(True)
+    emb = torch.randn(V, C, dtype=torch.float64).requires_grad_(True)
+    deg = torch.randint(0, V, (N,))
+    h0 = emb[deg] + X
+    H = h0[pos[:, 0]] * h0[pos[:, 1]]
+    h = H[idx]
+    ref = (h[0::2] * h[1::2]) @ w.t() + b
+    gout = torch.randn(L, 1, dtype=torch.float64)
+    ref.backward(gout)
+
+    c = lambda t: t.detach().float().cuda().requires_grad_(True)
+    gX, gw, gb, gemb = c(X), c(w), c(b), c(emb)
+    pt = G.pair_table(pos.cuda(), N)
+    g0 = F2.embedding(gemb, deg.cuda()) + gX
+    gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.ptr_d, pt.ids_d)
+    out = F2.readout(gH, idx.cuda(), gw, gb)
+    out.backward(gout.float().cuda())
+    assert_close(out, ref.detach(), atol=1e-4, what="readout fwd")
+    for name, g, r in (("dX", gX, X), ("dw", gw, w), ("db", gb, b), ("demb", gemb, emb)):
+        assert_close(g.grad, r.grad, atol=1e-5 * max(float(r.grad.abs().max()), 1.0), what=name)
