@@ -1,0 +1,408 @@
+"""bench.py - TwoWL forward+backward target-links/s on synthetic graphs (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rmat|collab|cora] [--hidden H]
+                    [--impl ours|reference]
+
+One *step* = LocalWLNet.forward + binary_cross_entropy_with_logits + backward on one batch
+(reference TwoWL/model/train.py:36-38) through the drop-in API of link-prediction-gnn_b200/TwoWL.
+`value`  : whole-job target links/s with every input already resident in HBM (device-timed, CUDA events).
+`e2e`    : the same through the reference-facing call sequence of train.py:18-38 starting from HOST
+           buffers: pinned-host batch ids/labels -> H2D -> double / sample_block -> forward -> loss ->
+           backward -> D2H of the loss, all inside the timed region.
+`roofline`: the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle port of the reference path (oracle/twowl_oracle.py) on a bounded sample.
+`--impl reference` times that CPU path alone (the reference is pure Python/torch-CPU; its hot loop is
+restated 1:1 by the oracle, which is pinned to the reference by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "link-prediction-gnn_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (rmat scale, edge samples, (a,b,c,d), default hidden)
+    "rmat": (20, 16_000_000, (0.57, 0.19, 0.19, 0.05), 64),     # configs[3]: R-MAT 1M nodes / 16M edges
+    "collab": (18, 1_300_000, (0.57, 0.19, 0.19, 0.05), 128),   # configs[2]: ogbl-collab scale
+    "cora": (None, 5278, None, 64),                             # configs[1]: 2708 nodes, uniform
+}
+
+
+# ------------------------------------------------------------------------------ synthetic graphs (input generation)
+
+def rmat_undirected(scale, samples, abcd, seed, device):
+    """Seeded R-MAT edge samples with a random vertex relabelling -> canonical (r<c) unique edge keys."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    a, b, c, _ = abcd
+    src = torch.zeros(samples, dtype=torch.int64, device=device)
+    dst = torch.zeros(samples, dtype=torch.int64, device=device)
+    for _ in range(scale):
+        r = torch.rand(samples, generator=g, device=device)
+        src = src * 2 + (r >= a + b).to(torch.int64)
+        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+    n = 1 << scale
+    perm = torch.randperm(n, generator=g, device=device)
+    return perm[src], perm[dst], n
+
+
+def make_graph(workload, seed, device, scale_override=None, samples_override=None):
+    """-> dict(n, pos [2,E], pred [2,P], pos1 [R,2]) in the reference's doubled layout."""
+    from TwoWL.utils import double
+    scale, samples, abcd, _ = WORKLOADS[workload]
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    if workload == "cora":
+        n = 2708
+        s = torch.randint(0, n, (samples,), generator=g, device=device)
+        d = torch.randint(0, n, (samples,), generator=g, device=device)
+    else:
+        s, d, n = rmat_undirected(scale_override or scale, samples_override or samples, abcd, seed, device)
+    lo, hi = torch.minimum(s, d), torch.maximum(s, d)
+    keys = torch.unique((lo * n + hi)[lo != hi])
+    m = keys.numel()
+    keys = keys[torch.randperm(m, generator=g, device=device)]
+    skeys = torch.sort(keys).values
+    neg = torch.empty(0, dtype=torch.int64, device=device)
+    while neg.numel() < m:                       # one uniform non-edge per positive
+        k = int(1.2 * (m - neg.numel())) + 64
+        r = torch.randint(0, n, (k,), generator=g, device=device)
+        c = torch.randint(0, n, (k,), generator=g, device=device)
+        lo, hi = torch.minimum(r, c), torch.maximum(r, c)
+        cand = (lo * n + hi)[lo != hi]
+        p = torch.searchsorted(skeys, cand).clamp_(max=m - 1)
+        neg = torch.unique(torch.cat((neg, cand[skeys[p] != cand])))
+    neg = neg[torch.randperm(neg.numel(), generator=g, device=device)[:m]]
+    pos = double(torch.stack((keys // n, keys % n)))
+    pred = double(torch.stack((neg // n, neg % n)))
+    pos1 = torch.cat((pos.t(), pred.t()), dim=0).contiguous()
+    return dict(n=n, pos=pos, pred=pred, pos1=pos1, und=m)
+
+
+def draw_batch(und, n_pred_und, nb, seed):
+    """Host-side batch draw, as train.py:18-23: nb positive + nb negative undirected ids (pinned)."""
+    rng = np.random.default_rng(seed)
+    i1 = torch.from_numpy(rng.choice(und, size=nb, replace=False).astype(np.int64)).pin_memory()
+    i2 = torch.from_numpy(rng.choice(n_pred_und, size=nb, replace=False).astype(np.int64)).pin_memory()
+    y = torch.cat((torch.ones(nb), torch.zeros(nb))).unsqueeze(-1).pin_memory()
+    return i1, i2, y
+
+
+# ------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]),
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline (oracle port)
+
+def cpu_baseline_sample(workload, hidden, seed=0, steps=2, budget_s=25.0):
+    """The reference CPU path (oracle port: vectorised get_ei2/sample_block + LocalWLNet fwd/BCE/bwd with
+    PyG semantics, torch CPU, all host threads) on a bounded sample of the same workload family."""
+    from oracle import twowl_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(seed)
+    if workload == "cora":
+        n, und = 2708, rng.integers(0, 2708, size=(2, 5278))
+        desc = "full cora-scale graph (2708 nodes, 5278 edge samples)"
+    else:
+        scale = 11 if workload == "rmat" else 12
+        ef = 16 if workload == "rmat" else 5
+        n = 1 << scale
+        a, b, c, _ = WORKLOADS[workload][2]
+        s = np.zeros(n * ef, dtype=np.int64)
+        d = np.zeros(n * ef, dtype=np.int64)
+        for _ in range(scale):
+            r = rng.random(n * ef)
+            s = s * 2 + (r >= a + b)
+            d = d * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c))
+        perm = rng.permutation(n)
+        und = np.stack([perm[s], perm[d]])
+        desc = f"R-MAT scale {scale} (same a,b,c,d; {n} nodes, {n * ef} edge samples) - the explicit [2,T] index the " \
+               f"reference needs does not fit host RAM at the full size"
+    pos, pred = O.synthetic_split(n, und, seed)
+    E = pos.shape[1]
+    nb = max(2, (E // 2) // 10)
+    idx1 = O.double(rng.permutation(E // 2)[:nb], for_index=True)
+    idx2 = O.double(rng.permutation(pred.shape[1] // 2)[:nb], for_index=True) + E
+    pos1 = torch.from_numpy(np.concatenate([pos.T, pred.T]))
+    y = torch.cat((torch.ones(nb), torch.zeros(nb))).unsqueeze(-1)
+    ei2 = O.get_ei2(n, pos, pred)
+    sd = O.init_state_dict(int(O.degree(pos, n).max()), hidden, hidden, 1, 1, seed=0)
+    times, sb_times = [], []
+    t_all = time.perf_counter()
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        ei_new, x_new, ei2_new = O.sample_block(idx1, n, pos, ei2)
+        t1 = time.perf_counter()
+        O.fwd_bwd(sd, torch.from_numpy(x_new), torch.from_numpy(ei_new), pos1, torch.from_numpy(np.concatenate([idx1, idx2])),
+                  ei2_new, y)
+        t2 = time.perf_counter()
+        if it > 0:                      # first iteration = warm-up
+            times.append(t2 - t1)
+            sb_times.append(t1 - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    med = statistics.median(times)
+    return {"value": 2 * nb / med, "unit": "target-links/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{desc}; T={ei2.shape[1]} wedges, {2 * nb} target links/step, hidden {hidden}, "
+                      f"fwd+bwd median of {len(times)} = {med * 1e3:.1f} ms (+ sample_block {statistics.median(sb_times) * 1e3:.1f} ms)",
+            "ms_per_step": med * 1e3, "links_per_step": 2 * nb}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, _, _, dh = WORKLOADS[args.workload]
+    hidden = args.hidden or dh
+    cb = cpu_baseline_sample(args.workload, hidden, steps=max(args.steps, 1), budget_s=120.0)
+    line = {"impl": "reference", "metric": "twowl_fwd_bwd_target_links_per_s", "value": cb["value"], "unit": "target-links/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "hidden": hidden, "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "target-links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rmat", choices=list(WORKLOADS))
+    ap.add_argument("--hidden", type=int, default=0)
+    ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale (debug)")
+    ap.add_argument("--samples", type=int, default=0, help="override the R-MAT edge samples (debug)")
+    ap.add_argument("--pair-path", default="auto", choices=["auto", "structured", "explicit"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from twowl_b200 import ops
+    import TwoWL.model.model as model
+    import TwoWL.utils as U
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hidden = args.hidden or WORKLOADS[args.workload][3]
+    args.warmup = max(args.warmup, 3)
+
+    # ---- dataset (resident, like the reference's `dataset` object after .to(device)) ----
+    g = make_graph(args.workload, 0, dev, args.scale or None, args.samples or None)
+    n, pos, pred, pos1 = g["n"], g["pos"], g["pred"], g["pos1"]
+    E, P = pos.shape[1], pred.shape[1]
+    x_full = U.degree(pos, n)
+    max_x = int(x_full.max().item())
+    explicit = args.pair_path == "explicit"
+    ei2 = U.get_ei2(n, pos, pred) if explicit else U.get_ei2_implicit(n, pos, pred)
+    nb = max(2, g["und"] // 10)
+    L = 2 * nb
+
+    torch.manual_seed(0)
+    mod = model.LocalWLNet(max_x, False, None, hidden, hidden, 1, 1, 0., 0., 0., 0., 0., 0.).to(dev).train()
+    mod.pair_path = args.pair_path
+
+    # every rank runs the same model on its own batches (replicated graph, data-parallel over target-link
+    # batches, gradients all-reduced): see DESIGN.md "Multi-GPU"
+    def sync_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in mod.parameters() if p.grad is not None])
+            dist.all_reduce(flat)
+
+    def prepare(batch):
+        i1, i2, y = (t.to(dev, non_blocking=True) for t in batch)
+        idx1 = U.double(i1, for_index=True)
+        idx2 = U.double(i2, for_index=True) + E
+        ei_new, x_new, ei2_new = U.sample_block(idx1, n, pos, ei2)
+        return x_new, ei_new, torch.cat((idx1, idx2)), ei2_new, y
+
+    def fwd_bwd(inp):
+        x_new, ei_new, idx, ei2_new, y = inp
+        for p_ in mod.parameters():
+            p_.grad = None
+        out = mod(x_new, ei_new, pos1, idx, ei2_new)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+        loss.backward()
+        sync_grads()
+        return loss
+
+    batches = [draw_batch(g["und"], P // 2, nb, 1000 + rank * 100 + i) for i in range(args.steps + args.warmup)]
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps of fwd+bwd, inputs prepared beforehand ----
+    inputs = [prepare(b) for b in batches]
+    for i in range(args.warmup):
+        fwd_bwd(inputs[i])
+    barrier()
+    ops.profile_start()
+    launches0 = ops.launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        for i in range(args.steps):
+            l2_flush.fill_(i & 255)     # evict L2 between timed steps (inputs also exceed L2 at rmat/collab size)
+            ev[i][0].record()
+            fwd_bwd(inputs[args.warmup + i])
+            ev[i][1].record()
+        barrier()
+    prof = ops.profile_stop()
+    launches = ops.launches() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    del inputs
+
+    # ---- sample_block alone (per-step, on the path; reported separately as SURVEY 8(d) asks) ----
+    sb_ev = []
+    for i in range(min(5, args.steps)):
+        i1, i2, y = (t.to(dev) for t in batches[i])
+        idx1 = U.double(i1, for_index=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        U.sample_block(idx1, n, pos, ei2)
+        b.record()
+        sb_ev.append((a, b))
+    torch.cuda.synchronize()
+    sb_ms = statistics.median(a.elapsed_time(b) for a, b in sb_ev)
+
+    # ---- end to end from host buffers: H2D batch -> sample_block -> fwd -> loss -> bwd -> D2H loss ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    e0.record()
+    for i in range(args.steps):
+        loss = fwd_bwd(prepare(batches[args.warmup + i]))
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the reference reads loss.item() every step (train.py:47)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    h2d = sum(t.numel() * t.element_size() for t in batches[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    by_op = {}
+    for name, nbytes, ms in prof:
+        d = by_op.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += nbytes
+        d[2] += ms
+    tot_kernel_ms = sum(d[2] for d in by_op.values()) or 1.0
+    top = max(by_op.items(), key=lambda kv: kv[1][2]) if by_op else ("none", [1, 0.0, 1.0])
+    tname, (tcnt, tbytes, tms) = top[0], top[1]
+    achieved = (tbytes / tcnt) / (tms / tcnt * 1e-3) / 1e9 if tms > 0 else 0.0
+    agg_bytes = sum(d[1] for d in by_op.values())
+    roofline = {"bound": "hbm", "kernel": tname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches": tcnt, "avg_ms": round(tms / tcnt, 4), "share_of_kernel_time": round(tms / tot_kernel_ms, 4),
+                "algorithmic_bytes_per_launch": int(tbytes / tcnt),
+                "all_kernels_algorithmic_GBps": round(agg_bytes / (tot_kernel_ms * 1e-3) / 1e9, 1),
+                "per_op": {k: {"n": v[0], "ms": round(v[2], 3), "GBps": round(v[1] / (v[2] * 1e-3) / 1e9, 1) if v[2] > 0 else None}
+                           for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][2])}}
+
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline_sample(args.workload, hidden)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    links = L * world * args.steps
+    line = {
+        "metric": "twowl_fwd_bwd_target_links_per_s", "value": links / (total_ms * 1e-3), "unit": "target-links/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "nodes": n, "undirected_edges": g["und"], "E": E, "R": E + P,
+                   "hidden": hidden, "depth1": 1, "depth2": 1, "target_links_per_step": L, "pair_path": args.pair_path,
+                   "wedges_T": ei2.shape[1] if explicit else None, "l2": "256 MiB flush write between timed steps; "
+                   "activations exceed L2", "parallelism": f"dp{world}: replicated graph, one batch per rank, grad all-reduce"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": links / (e2e_ms * 1e-3), "unit": "target-links/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "includes": "H2D batch ids+labels, double, "
+                "sample_block, forward, BCE, backward, D2H loss"},
+        "sample_block_ms": sb_ms,
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,41 @@ def launches() -> int:
     return _launches
 
 
+# ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream around each op ----
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> [(op name, algorithmic bytes, milliseconds)] for every op issued since profile_start()."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [(name, nbytes, a.elapsed_time(b)) for name, nbytes, a, b in rec]
+
+
+class _P:
+    __slots__ = ("name", "nbytes", "a")
+
+    def __init__(self, name, nbytes):
+        self.name, self.nbytes = name, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _prof.append((self.name, self.nbytes, self.a, b))
+
+
 def _count(n: int = 1):
     global _launches
     _launches += n
@@ -72,8 +107,9 @@ def csr_build(keys: torch.Tensor, num_keys: int, key_xor: int = 0, want_ptr: boo
     nb = lib.twowl_csr_build_workspace_bytes(n, int(num_keys))
     ws = _ws(nb, dev)
     p, s = _row(keys)
-    check(lib.twowl_csr_build(p, s, n, int(key_xor), int(num_keys), _p(ptr), ids.data_ptr(), ws.data_ptr(), nb,
-                              _stream()), "csr_build")
+    with _P("csr_build", n * 8 + n * 16 * 4):
+        check(lib.twowl_csr_build(p, s, n, int(key_xor), int(num_keys), _p(ptr), ids.data_ptr(), ws.data_ptr(), nb,
+                                  _stream()), "csr_build")
     _count(4 + 3 * 4)
     return ptr, ids
 
@@ -238,7 +274,8 @@ def seg_reduce(ptr, col, M: int, X, *, flip=0, row_flip=0, src_scale=None, skip_
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
                 mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate))
-    check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
+    with _P("seg_reduce", (col.numel() + M) * (4 * C + 8)):
+        check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
     _count()
     return out
 
@@ -248,8 +285,9 @@ def gather_rows(W: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     idx = idx.reshape(-1)
     out = torch.empty((idx.numel(), W.shape[1]), dtype=torch.float32, device=W.device)
     p, s = _row(idx)
-    check(lib.twowl_gather_rows(W.data_ptr(), W.shape[0], p, s, idx.numel(), W.shape[1], out.data_ptr(), _stream()),
-          "gather_rows")
+    with _P("gather_rows", idx.numel() * (8 * W.shape[1] + 8)):
+        check(lib.twowl_gather_rows(W.data_ptr(), W.shape[0], p, s, idx.numel(), W.shape[1], out.data_ptr(), _stream()),
+              "gather_rows")
     _count()
     return out
 
@@ -258,8 +296,9 @@ def pair_init_fwd(X, src32, dst32) -> torch.Tensor:
     _need_cuda(X, src32, dst32)
     R = src32.numel()
     out = torch.empty((R, X.shape[1]), dtype=torch.float32, device=X.device)
-    check(lib.twowl_pair_init_fwd(X.data_ptr(), src32.data_ptr(), dst32.data_ptr(), R, X.shape[1], out.data_ptr(),
-                                  _stream()), "pair_init_fwd")
+    with _P("pair_init_fwd", R * (12 * X.shape[1] + 8)):
+        check(lib.twowl_pair_init_fwd(X.data_ptr(), src32.data_ptr(), dst32.data_ptr(), R, X.shape[1], out.data_ptr(),
+                                      _stream()), "pair_init_fwd")
     _count()
     return out
 
@@ -270,8 +309,9 @@ def readout_fwd(H, idx, w, b) -> torch.Tensor:
     L = idx.numel() // 2
     pred = torch.empty((L, 1), dtype=torch.float32, device=H.device)
     p, s = _row(idx)
-    check(lib.twowl_readout_fwd(H.data_ptr(), p, s, L, H.shape[1], w.data_ptr(), b.data_ptr(), pred.data_ptr(),
-                                _stream()), "readout_fwd")
+    with _P("readout_fwd", L * (8 * H.shape[1] + 20)):
+        check(lib.twowl_readout_fwd(H.data_ptr(), p, s, L, H.shape[1], w.data_ptr(), b.data_ptr(), pred.data_ptr(),
+                                    _stream()), "readout_fwd")
     _count()
     return pred
 
@@ -289,8 +329,9 @@ def readout_bwd(H, idx, w, dpred):
     ws = _ws(nb, dev)
     p, s = _row(idx)
     dpred = dpred.contiguous()
-    check(lib.twowl_readout_bwd(H.data_ptr(), p, s, L, C, w.data_ptr(), dpred.data_ptr(), order.data_ptr(),
-                                dH.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, _stream()), "readout_bwd")
+    with _P("readout_bwd", H.numel() * 4 + L * (28 * C + 24)):
+        check(lib.twowl_readout_bwd(H.data_ptr(), p, s, L, C, w.data_ptr(), dpred.data_ptr(), order.data_ptr(),
+                                    dH.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, _stream()), "readout_bwd")
     _count(6)
     return dH, dw, db
 
@@ -303,8 +344,9 @@ def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
     stats = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     nb = lib.twowl_graphnorm_stats_workspace_bytes(M, C)
     ws = _ws(nb, x.device)
-    check(lib.twowl_graphnorm_stats(x.data_ptr(), M, C, mean_scale.data_ptr(), float(eps), stats.data_ptr(),
-                                    ws.data_ptr(), nb, _stream()), "graphnorm_stats")
+    with _P("graphnorm_stats", M * C * 4):
+        check(lib.twowl_graphnorm_stats(x.data_ptr(), M, C, mean_scale.data_ptr(), float(eps), stats.data_ptr(),
+                                        ws.data_ptr(), nb, _stream()), "graphnorm_stats")
     _count(2)
     return stats
 
@@ -312,9 +354,10 @@ def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
 def graphnorm_apply(x, stats, weight, bias, mean_scale, p_drop: float, seed: int, relu: bool, addend=None):
     M, C = x.shape
     out = torch.empty_like(x)
-    check(lib.twowl_graphnorm_apply(x.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(), bias.data_ptr(),
-                                    mean_scale.data_ptr(), float(p_drop), int(seed), int(relu), _p(addend),
-                                    out.data_ptr(), _stream()), "graphnorm_apply")
+    with _P("graphnorm_apply", M * C * 4 * (2 if addend is None else 3)):
+        check(lib.twowl_graphnorm_apply(x.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                        mean_scale.data_ptr(), float(p_drop), int(seed), int(relu), _p(addend),
+                                        out.data_ptr(), _stream()), "graphnorm_apply")
     _count()
     return out
 
@@ -325,9 +368,10 @@ def graphnorm_bwd(x, dout, stats, weight, bias, mean_scale, p_drop: float, seed:
     dparams = torch.empty(3 * C, dtype=torch.float32, device=x.device)
     nb = lib.twowl_graphnorm_bwd_workspace_bytes(M, C)
     ws = _ws(nb, x.device)
-    check(lib.twowl_graphnorm_bwd(x.data_ptr(), dout.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(),
-                                  bias.data_ptr(), mean_scale.data_ptr(), float(p_drop), int(seed), int(relu),
-                                  dx.data_ptr(), dparams.data_ptr(), ws.data_ptr(), nb, _stream()), "graphnorm_bwd")
+    with _P("graphnorm_bwd", M * C * 4 * 5):
+        check(lib.twowl_graphnorm_bwd(x.data_ptr(), dout.data_ptr(), M, C, stats.data_ptr(), weight.data_ptr(),
+                                      bias.data_ptr(), mean_scale.data_ptr(), float(p_drop), int(seed), int(relu),
+                                      dx.data_ptr(), dparams.data_ptr(), ws.data_ptr(), nb, _stream()), "graphnorm_bwd")
     _count(3)
     return dx, dparams
 
@@ -337,7 +381,8 @@ def colsum(x) -> torch.Tensor:
     out = torch.empty(C, dtype=torch.float32, device=x.device)
     nb = lib.twowl_colsum_workspace_bytes(M, C)
     ws = _ws(nb, x.device)
-    check(lib.twowl_colsum(x.data_ptr(), M, C, out.data_ptr(), ws.data_ptr(), nb, _stream()), "colsum")
+    with _P("colsum", M * C * 4):
+        check(lib.twowl_colsum(x.data_ptr(), M, C, out.data_ptr(), ws.data_ptr(), nb, _stream()), "colsum")
     _count(2)
     return out
 
@@ -349,7 +394,8 @@ def linear_fwd(X, W, impl: int = 0) -> torch.Tensor:
     M, Ci = X.shape
     Co = W.shape[0]
     Z = torch.empty((M, Co), dtype=torch.float32, device=X.device)
-    check(lib.twowl_linear_fwd(X.data_ptr(), W.data_ptr(), M, Ci, Co, Z.data_ptr(), impl, _stream()), "linear_fwd")
+    with _P("linear_fwd", 4 * M * (Ci + Co)):
+        check(lib.twowl_linear_fwd(X.data_ptr(), W.data_ptr(), M, Ci, Co, Z.data_ptr(), impl, _stream()), "linear_fwd")
     _count()
     return Z
 
@@ -358,8 +404,9 @@ def linear_bwd_input(dZ, W, impl: int = 0) -> torch.Tensor:
     M, Co = dZ.shape
     Ci = W.shape[1]
     dX = torch.empty((M, Ci), dtype=torch.float32, device=dZ.device)
-    check(lib.twowl_linear_bwd_input(dZ.data_ptr(), W.data_ptr(), M, Ci, Co, dX.data_ptr(), impl, _stream()),
-          "linear_bwd_input")
+    with _P("linear_bwd_input", 4 * M * (Ci + Co)):
+        check(lib.twowl_linear_bwd_input(dZ.data_ptr(), W.data_ptr(), M, Ci, Co, dX.data_ptr(), impl, _stream()),
+              "linear_bwd_input")
     _count()
     return dX
 
@@ -370,8 +417,9 @@ def linear_bwd_weight(dZ, X) -> torch.Tensor:
     dW = torch.empty((Co, Ci), dtype=torch.float32, device=dZ.device)
     nb = lib.twowl_linear_bwd_weight_workspace_bytes(M, Ci, Co)
     ws = _ws(nb, dZ.device)
-    check(lib.twowl_linear_bwd_weight(dZ.data_ptr(), X.data_ptr(), M, Ci, Co, dW.data_ptr(), ws.data_ptr(), nb,
-                                      _stream()), "linear_bwd_weight")
+    with _P("linear_bwd_weight", 4 * M * (Ci + Co)):
+        check(lib.twowl_linear_bwd_weight(dZ.data_ptr(), X.data_ptr(), M, Ci, Co, dW.data_ptr(), ws.data_ptr(), nb,
+                                          _stream()), "linear_bwd_weight")
     _count(2)
     return dW
 
@@ -394,8 +442,9 @@ def wedge_prepare(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr):
 def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
     R, C = Z.shape
     out = torch.empty_like(Z)
-    check(lib.twowl_wedge_apply_fwd(S.data_ptr(), Z.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(),
-                                    _p(bias), R, C, out.data_ptr(), _stream()), "wedge_apply_fwd")
+    with _P("wedge_apply_fwd", R * (12 * C + 12)):
+        check(lib.twowl_wedge_apply_fwd(S.data_ptr(), Z.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(),
+                                        _p(bias), R, C, out.data_ptr(), _stream()), "wedge_apply_fwd")
     _count()
     return out
 
@@ -403,8 +452,9 @@ def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
 def wedge_apply_bwd(dS, dO, dst_e32, blocked, E: int, N: int, dinv, selfw, direction: int) -> torch.Tensor:
     R, C = dO.shape
     dZ = torch.empty_like(dO)
-    check(lib.twowl_wedge_apply_bwd(dS.data_ptr(), dO.data_ptr(), dst_e32.data_ptr(), _p(blocked), E, N,
-                                    dinv.data_ptr(), selfw.data_ptr(), direction, R, C, dZ.data_ptr(), _stream()),
-          "wedge_apply_bwd")
+    with _P("wedge_apply_bwd", R * (12 * C + 12)):
+        check(lib.twowl_wedge_apply_bwd(dS.data_ptr(), dO.data_ptr(), dst_e32.data_ptr(), _p(blocked), E, N,
+                                        dinv.data_ptr(), selfw.data_ptr(), direction, R, C, dZ.data_ptr(), _stream()),
+              "wedge_apply_bwd")
     _count()
     return dZ
