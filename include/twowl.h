@@ -151,8 +151,27 @@ typedef struct twowl_seg_args {
   const int32_t* mul_idx;        /* row of X2 = mul_idx[col[k]] */
   float* out;                    /* [M, C] */
   int32_t accumulate;
+  /* optional long-row plan of this CSR (twowl_seg_plan); all NULL / 0 = every row handled by one lane group */
+  const int32_t* plan_counts;    /* int32[2]: number of long rows, number of chunks */
+  const int32_t* long_row;       /* int32[long_cap] */
+  const int32_t* long_base;      /* int32[long_cap] */
+  const int32_t* chunk_owner;    /* int32[chunk_cap] */
+  float* partial;                /* fp32 [chunk_cap, C] scratch */
+  int64_t chunk_cap;
+  int64_t long_cap;
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
+
+/* Load balance for power-law degree: rows of a CSR longer than TWOWL_LONG_ROW entries are listed (order free)
+ * and cut into chunks of TWOWL_ROW_CHUNK entries; twowl_seg_reduce then reduces the chunks with separate lane
+ * groups and adds each row's partial sums in chunk order (deterministic). Built once per CSR.
+ * Capacities depend on nnz only, so no device->host read is needed. */
+#define TWOWL_LONG_ROW 512
+#define TWOWL_ROW_CHUNK 256
+int64_t twowl_seg_plan_long_cap(int64_t nnz);
+int64_t twowl_seg_plan_chunk_cap(int64_t nnz);
+int twowl_seg_plan(const int64_t* ptr, int64_t M, int64_t nnz, int32_t* counts /*[2]*/, int32_t* long_row,
+                   int32_t* long_base, int32_t* chunk_owner, void* stream);
 
 /* nn.Embedding forward / any row gather: out[r] = W[idx[r*stride]]  ([n, C]). */
 int twowl_gather_rows(const float* W, int64_t rows_w, const int64_t* idx, int64_t stride, int64_t n, int32_t C,

@@ -49,19 +49,19 @@ class GCNConv(nn.Module):
     def forward(self, x, edge_index):
         g = G.node_graph(edge_index, x.shape[0])
         z = self.lin(x)
-        return F2.gcn_aggregate(z, self.bias, g.dinv, g.ptr, g.col, g.tptr, g.tcol, None, 0, 0)
+        return F2.gcn_aggregate(z, self.bias, g.dinv, g.ptr, g.col, g.plan, g.tptr, g.tcol, g.tplan, None, 0, 0)
 
     def forward_pairs(self, x, wedges, direction: int):
         """The pair-level call of model.py:77: direction 0 = conv(x, edge2), 1 = conv_r(x, edge2_r)."""
         z = self.lin(x)
         if isinstance(wedges, G.WedgeStruct):
             _, centre, dinv, selfw = wedges.prepared()
-            return F2.wedge_aggregate(z, self.bias, wedges.in_ptr, wedges.in_ids, wedges.out_ptr, wedges.out_ids,
-                                      centre[direction], dinv[direction], selfw[direction], wedges.dst_e,
+            return F2.wedge_aggregate(z, self.bias, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr,
+                                      wedges.out_ids, wedges.out_plan, centre[direction], dinv[direction], selfw[direction], wedges.dst_e,
                                       wedges.blocked, wedges.E, wedges.n_node, direction)
         flip, row_flip = (1, 0) if direction == 0 else (0, 1)
-        return F2.gcn_aggregate(z, self.bias, wedges.dinv[direction], wedges.ptr_b, wedges.col_b, wedges.ptr_a,
-                                wedges.col_a, None, flip, row_flip)
+        return F2.gcn_aggregate(z, self.bias, wedges.dinv[direction], wedges.ptr_b, wedges.col_b, wedges.plan_b,
+                                wedges.ptr_a, wedges.col_a, wedges.plan_a, None, flip, row_flip)
 
 
 class GraphNorm(nn.Module):
@@ -209,7 +209,7 @@ class LocalWLNet(nn.Module):
             x = conv1(x, edge1)
 
         pt = G.pair_table(pos, x.shape[0])
-        x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.ptr_d, pt.ids_d)
+        x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d)
         if len(self.conv2s):
             wedges = self._wedges(ei2, pt.R)
             for i in range(len(self.conv2s)):

@@ -8,7 +8,12 @@
 // A row is owned by a group of G lanes (G = pow2 >= C/4, <= 32); each lane keeps VEC float4 accumulators.
 // The group loads G col entries at once (coalesced), then broadcasts them one by one with shuffles and
 // issues the 128-bit row gathers 4 deep. Sums run in CSR order (= the reference's column order, because the
-// CSR is built by a STABLE sort) in registers: deterministic, no atomics.
+// CSR is built by a STABLE sort) in registers: deterministic, no atomics on data.
+//
+// Power-law load balance: rows longer than TWOWL_LONG_ROW entries (hubs: max degree 62 745 on R-MAT 1M/16M)
+// are listed once per CSR by twowl_seg_plan; they are cut into chunks of TWOWL_ROW_CHUNK entries that
+// separate groups reduce into a partial buffer, and a third pass adds each row's partials in chunk order.
+// The order in which long rows were listed (an integer atomic counter) never influences a result.
 #include "common.cuh"
 
 namespace twowl {
@@ -34,86 +39,192 @@ struct SegParams {
   const int32_t* mul_idx;
   float* out;
   int accumulate;
+  // long-row plan (all NULL/0 when the CSR has no plan)
+  const int32_t* plan_counts;  // [0] = number of long rows, [1] = number of chunks
+  const int32_t* long_row;     // CSR row of each long row
+  const int32_t* long_base;    // first chunk slot of each long row
+  const int32_t* chunk_owner;  // long-row slot of each chunk
+  float* partial;              // [chunks, C]
 };
 
+template <int G>
+struct GroupCtx {
+  int gl, gbase, cv;
+  unsigned gmask;
+  __device__ GroupCtx(int C) {
+    const int lane = threadIdx.x & 31;
+    gl = threadIdx.x % G;
+    gbase = lane - gl;
+    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    cv = C >> 2;
+  }
+};
+
+// acc += sum over entries [kb, ke) of the CSR feeding output row m
 template <int G, int VEC>
-__global__ void __launch_bounds__(kAggThreads) k_seg_reduce(const SegParams p) {
-  constexpr int kGroupsPerCta = kAggThreads / G;
-  const int lane = threadIdx.x & 31;
-  const int gl = threadIdx.x % G;                       // lane inside the group
-  const int gbase = lane - gl;                          // first warp lane of the group
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
-  const int cv = p.C >> 2;                              // float4 per row
-  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
-  const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
+__device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCtx<G>& g, int64_t m, int64_t kb, int64_t ke,
+                                               float4 (&acc)[VEC]) {
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
+  for (int64_t k0 = kb; k0 < ke; k0 += G) {
+    // stage G entries: source row (or -1 = dropped), its scale, optional second-factor row
+    int s_mine = -1, m2_mine = 0;
+    float w_mine = 0.f;
+    if (k0 + g.gl < ke) {
+      const int c = __ldg(p.col + k0 + g.gl);
+      const int s = c ^ p.flip;
+      const bool keep = !(p.skip_self && (int64_t)s == m) && !(p.skip_mask && p.skip_mask[c]);
+      if (keep) {
+        s_mine = s;
+        w_mine = p.src_scale ? __ldg(p.src_scale + s) : 1.f;
+        if (p.X2) m2_mine = __ldg(p.mul_idx + c);
+      }
+    }
+    const int cnt = (ke - k0 < G) ? (int)(ke - k0) : G;
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const int s = __shfl_sync(g.gmask, s_mine, g.gbase + j);
+      const float w = __shfl_sync(g.gmask, w_mine, g.gbase + j);
+      const int m2 = __shfl_sync(g.gmask, m2_mine, g.gbase + j);
+      if (s >= 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int c4 = g.gl + v * G;
+          if (c4 < g.cv) {
+            float4 x = ldg_cached(X4 + (int64_t)s * g.cv + c4);
+            if (p.X2) x = f4_mul(x, ldg_cached(X24 + (int64_t)m2 * g.cv + c4));
+            f4_fma(acc[v], w, x);
+          }
+        }
+      }
+    }
+  }
+}
 
-  // rows are dealt round-robin to groups: neighbouring hub rows land on different warps
+// out[m] = dst_scale*acc (+ self-loop term) (+ bias) (+ previous out)
+template <int G, int VEC>
+__device__ __forceinline__ void seg_finalize(const SegParams& p, const GroupCtx<G>& g, int64_t m, const float4 (&acc)[VEC]) {
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  const float ds = p.dst_scale ? p.dst_scale[m] : 1.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c4 = g.gl + v * G;
+    if (c4 < g.cv) {
+      float4 o = make_float4(ds * acc[v].x, ds * acc[v].y, ds * acc[v].z, ds * acc[v].w);
+      if (p.self_mode == 1) f4_fma(o, ds * ds, ldg_cached(X4 + m * g.cv + c4));
+      if (p.bias) f4_add(o, __ldg(reinterpret_cast<const float4*>(p.bias) + c4));
+      float4* dst = reinterpret_cast<float4*>(p.out) + m * g.cv + c4;
+      if (p.accumulate) f4_add(o, *dst);
+      *dst = o;
+    }
+  }
+}
+
+// pass 1: one group per row, rows dealt round-robin to groups; long rows (if planned) are left to pass 2/3
+template <int G, int VEC>
+__global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
+  constexpr int kGroupsPerCta = kAggThreads / G;
+  const GroupCtx<G> g(p.C);
+  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
+  const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
   for (int64_t m = group0; m < p.M; m += ngroups) {
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
     const int64_t r = m ^ (int64_t)p.row_flip;
     int64_t kb = 0, ke = 0;
-    if (r < p.M && !(p.row_skip_mask && p.row_skip_mask[r])) {
+    if (r < p.M) {
       kb = p.ptr[r];
       ke = p.ptr[r + 1];
+      if (p.plan_counts && ke - kb > TWOWL_LONG_ROW) continue;  // handled by k_seg_chunks + k_seg_long
+      if (p.row_skip_mask && p.row_skip_mask[r]) ke = kb;
     }
-    for (int64_t k0 = kb; k0 < ke; k0 += G) {
-      // stage G entries: source row (or -1 = dropped), its scale, optional second-factor row
-      int s_mine = -1, m2_mine = 0;
-      float w_mine = 0.f;
-      if (k0 + gl < ke) {
-        const int c = __ldg(p.col + k0 + gl);
-        const int s = c ^ p.flip;
-        const bool keep = !(p.skip_self && (int64_t)s == m) && !(p.skip_mask && p.skip_mask[c]);
-        if (keep) {
-          s_mine = s;
-          w_mine = p.src_scale ? __ldg(p.src_scale + s) : 1.f;
-          if (p.X2) m2_mine = __ldg(p.mul_idx + c);
-        }
-      }
-      const int cnt = (ke - k0 < G) ? (int)(ke - k0) : G;
-#pragma unroll 4
-      for (int j = 0; j < cnt; ++j) {
-        const int s = __shfl_sync(gmask, s_mine, gbase + j);
-        const float w = __shfl_sync(gmask, w_mine, gbase + j);
-        const int m2 = __shfl_sync(gmask, m2_mine, gbase + j);
-        if (s >= 0) {
+    seg_accumulate<G, VEC>(p, g, m, kb, ke, acc);
+    seg_finalize<G, VEC>(p, g, m, acc);
+  }
+}
+
+// pass 2: one group per chunk of a long row -> raw partial sums
+template <int G, int VEC>
+__global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
+  constexpr int kGroupsPerCta = kAggThreads / G;
+  const GroupCtx<G> g(p.C);
+  const int nchunks = p.plan_counts[1];
+  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
+  const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
+  for (int64_t ch = group0; ch < nchunks; ch += ngroups) {
+    const int slot = p.chunk_owner[ch];
+    const int64_t r = p.long_row[slot];
+    const int64_t m = r ^ (int64_t)p.row_flip;
+    const int64_t c = ch - p.long_base[slot];
+    int64_t kb = p.ptr[r] + c * TWOWL_ROW_CHUNK;
+    int64_t ke = kb + TWOWL_ROW_CHUNK < p.ptr[r + 1] ? kb + TWOWL_ROW_CHUNK : p.ptr[r + 1];
+    if (p.row_skip_mask && p.row_skip_mask[r]) ke = kb;
+    float4 acc[VEC];
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const int c4 = gl + v * G;
-            if (c4 < cv) {
-              float4 x = ldg_cached(X4 + (int64_t)s * cv + c4);
-              if (p.X2) x = f4_mul(x, ldg_cached(X24 + (int64_t)m2 * cv + c4));
-              f4_fma(acc[v], w, x);
-            }
-          }
-        }
-      }
-    }
-    const float ds = p.dst_scale ? p.dst_scale[m] : 1.f;
+    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+    seg_accumulate<G, VEC>(p, g, m, kb, ke, acc);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const int c4 = gl + v * G;
-      if (c4 < cv) {
-        float4 o = make_float4(ds * acc[v].x, ds * acc[v].y, ds * acc[v].z, ds * acc[v].w);
-        if (p.self_mode == 1) f4_fma(o, ds * ds, ldg_cached(X4 + m * cv + c4));
-        if (p.bias) f4_add(o, __ldg(reinterpret_cast<const float4*>(p.bias) + c4));
-        float4* dst = reinterpret_cast<float4*>(p.out) + m * cv + c4;
-        if (p.accumulate) f4_add(o, *dst);
-        *dst = o;
-      }
+      const int c4 = g.gl + v * G;
+      if (c4 < g.cv) reinterpret_cast<float4*>(p.partial)[ch * g.cv + c4] = acc[v];
     }
   }
 }
 
+// pass 3: one group per long row: partials added in chunk order, then the usual epilogue
 template <int G, int VEC>
-static void launch_seg(const SegParams& p, cudaStream_t s) {
+__global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
-  const int grid = grid_for(p.M, kGroupsPerCta, 8);
-  k_seg_reduce<G, VEC><<<grid, kAggThreads, 0, s>>>(p);
+  const GroupCtx<G> g(p.C);
+  const int nlong = p.plan_counts[0];
+  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
+  const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
+  for (int64_t slot = group0; slot < nlong; slot += ngroups) {
+    const int64_t r = p.long_row[slot];
+    const int64_t m = r ^ (int64_t)p.row_flip;
+    const int64_t len = p.ptr[r + 1] - p.ptr[r];
+    const int64_t nch = (len + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK;
+    const int64_t base = p.long_base[slot];
+    float4 acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+    for (int64_t c = 0; c < nch; ++c) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int c4 = g.gl + v * G;
+        if (c4 < g.cv) f4_add(acc[v], reinterpret_cast<const float4*>(p.partial)[(base + c) * g.cv + c4]);
+      }
+    }
+    seg_finalize<G, VEC>(p, g, m, acc);
+  }
+}
+
+template <int G, int VEC>
+static void launch_seg(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
+  constexpr int kGroupsPerCta = kAggThreads / G;
+  k_seg_rows<G, VEC><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+  if (p.plan_counts && chunk_cap > 0) {
+    k_seg_chunks<G, VEC><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+    k_seg_long<G, VEC><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+  }
+}
+
+// ---------------------------------------------------------------- long-row plan ------------------
+__global__ void __launch_bounds__(kAggThreads) k_plan_long(const int64_t* __restrict__ ptr, int64_t M, int32_t* __restrict__ counts,
+                                                           int32_t* __restrict__ long_row, int32_t* __restrict__ long_base,
+                                                           int32_t* __restrict__ chunk_owner) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t len = ptr[r + 1] - ptr[r];
+    if (len > TWOWL_LONG_ROW) {
+      const int nch = (int)((len + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK);
+      const int slot = atomicAdd(&counts[0], 1);   // listing order is free: results never depend on it
+      const int base = atomicAdd(&counts[1], nch);
+      long_row[slot] = (int32_t)r;
+      long_base[slot] = base;
+      for (int c = 0; c < nch; ++c) chunk_owner[base + c] = slot;
+    }
+  }
 }
 
 // deg[m] = 1 + #{k in row (m^row_flip) : (col[k]^flip) != m, !skip_mask[col[k]]}  ->  dinv = deg^-1/2
@@ -160,29 +271,50 @@ extern "C" int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M,
   return 0;
 }
 
+extern "C" int64_t twowl_seg_plan_long_cap(int64_t nnz) { return nnz / TWOWL_LONG_ROW + 1; }
+extern "C" int64_t twowl_seg_plan_chunk_cap(int64_t nnz) { return nnz / TWOWL_ROW_CHUNK + nnz / TWOWL_LONG_ROW + 2; }
+
+extern "C" int twowl_seg_plan(const int64_t* ptr, int64_t M, int64_t nnz, int32_t* counts, int32_t* long_row, int32_t* long_base,
+                              int32_t* chunk_owner, void* stream) {
+  TW_CHECK_ARG(M >= 0 && nnz >= 0 && nnz < 0x7fffffffLL && M < 0x7fffffffLL, "seg_plan: sizes out of int32 range");
+  cudaStream_t s = (cudaStream_t)stream;
+  TW_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
+  if (M > 0) {
+    k_plan_long<<<grid_for(M, kAggThreads), kAggThreads, 0, s>>>(ptr, M, counts, long_row, long_base, chunk_owner);
+    TW_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   TW_CHECK_ARG(a != nullptr, "seg_reduce: null args");
   TW_CHECK_ARG(a->M >= 0 && a->C > 0 && (a->C & 3) == 0 && a->C <= 1024, "seg_reduce: C=%d must be a multiple of 4 in [4,1024]",
                a->C);
-  TW_CHECK_ARG(aligned16(a->X) && aligned16(a->out) && aligned16(a->bias) && aligned16(a->X2),
+  TW_CHECK_ARG(aligned16(a->X) && aligned16(a->out) && aligned16(a->bias) && aligned16(a->X2) && aligned16(a->partial),
                "seg_reduce: feature pointers must be 16-byte aligned");
   TW_CHECK_ARG(!(a->row_flip && (a->M & 1)), "seg_reduce: row_flip needs an even row count");
   TW_CHECK_ARG((a->X2 == nullptr) == (a->mul_idx == nullptr), "seg_reduce: X2 and mul_idx go together");
+  const bool planned = a->plan_counts != nullptr;
+  TW_CHECK_ARG(!planned || (a->long_row && a->long_base && a->chunk_owner && (a->partial || a->chunk_cap == 0)),
+               "seg_reduce: incomplete long-row plan");
   if (a->M == 0) return 0;
   SegParams p;
   p.ptr = a->ptr, p.col = a->col, p.M = a->M, p.X = a->X, p.C = a->C, p.flip = a->flip, p.row_flip = a->row_flip;
   p.src_scale = a->src_scale, p.skip_mask = a->skip_mask, p.row_skip_mask = a->row_skip_mask;
   p.skip_self = a->skip_self, p.self_mode = a->self_mode, p.dst_scale = a->dst_scale, p.bias = a->bias;
   p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate;
+  p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
+  p.partial = a->partial;
   cudaStream_t s = (cudaStream_t)stream;
   const int cv = a->C >> 2;
-  if (cv <= 4) launch_seg<4, 1>(p, s);
-  else if (cv <= 8) launch_seg<8, 1>(p, s);
-  else if (cv <= 16) launch_seg<16, 1>(p, s);
-  else if (cv <= 32) launch_seg<32, 1>(p, s);
-  else if (cv <= 64) launch_seg<32, 2>(p, s);
-  else if (cv <= 128) launch_seg<32, 4>(p, s);
-  else launch_seg<32, 8>(p, s);
+  const int64_t cc = a->chunk_cap, lc = a->long_cap;
+  if (cv <= 4) launch_seg<4, 1>(p, cc, lc, s);
+  else if (cv <= 8) launch_seg<8, 1>(p, cc, lc, s);
+  else if (cv <= 16) launch_seg<16, 1>(p, cc, lc, s);
+  else if (cv <= 32) launch_seg<32, 1>(p, cc, lc, s);
+  else if (cv <= 64) launch_seg<32, 2>(p, cc, lc, s);
+  else if (cv <= 128) launch_seg<32, 4>(p, cc, lc, s);
+  else launch_seg<32, 8>(p, cc, lc, s);
   TW_LAUNCH_CHECK();
   return 0;
 }

@@ -30,6 +30,9 @@ class SegArgs(ctypes.Structure):
         ("skip_self", ctypes.c_int32), ("self_mode", ctypes.c_int32),
         ("dst_scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("X2", ctypes.c_void_p),
         ("mul_idx", ctypes.c_void_p), ("out", ctypes.c_void_p), ("accumulate", ctypes.c_int32),
+        ("plan_counts", ctypes.c_void_p), ("long_row", ctypes.c_void_p), ("long_base", ctypes.c_void_p),
+        ("chunk_owner", ctypes.c_void_p), ("partial", ctypes.c_void_p), ("chunk_cap", ctypes.c_int64),
+        ("long_cap", ctypes.c_int64),
     ]
 
 

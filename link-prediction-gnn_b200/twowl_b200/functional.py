@@ -47,36 +47,36 @@ linear.register_autograd(_linear_bwd, setup_context=_linear_setup)
 
 
 @torch.library.custom_op("twowl::gcn_aggregate", mutates_args=())
-def gcn_aggregate(z: Tensor, bias: Tensor, dinv: Tensor, ptr: Tensor, col: Tensor, tptr: Tensor, tcol: Tensor,
-                  mask: Optional[Tensor], flip: int, row_flip: int) -> Tensor:
+def gcn_aggregate(z: Tensor, bias: Tensor, dinv: Tensor, ptr: Tensor, col: Tensor, plan: Optional[Tensor], tptr: Tensor,
+                  tcol: Tensor, tplan: Optional[Tensor], mask: Optional[Tensor], flip: int, row_flip: int) -> Tensor:
     """out[m] = dinv[m] * sum_{k in row m^row_flip, s=col[k]^flip != m, !mask[col[k]]} dinv[s] z[s]
                + dinv[m]^2 z[m] + bias   (PyG GCNConv.propagate with gcn_norm)."""
-    return ops.seg_reduce(ptr, col, z.shape[0], z.contiguous(), flip=flip, row_flip=row_flip, src_scale=dinv,
+    return ops.seg_reduce(ptr, col, z.shape[0], z.contiguous(), plan=plan, flip=flip, row_flip=row_flip, src_scale=dinv,
                           dst_scale=dinv, skip_self=True, self_mode=1, bias=bias, skip_mask=mask)
 
 
 @gcn_aggregate.register_fake
-def _(z, bias, dinv, ptr, col, tptr, tcol, mask, flip, row_flip):
+def _(z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip):
     return torch.empty_like(z)
 
 
 def _gcn_setup(ctx, inputs, output):
-    z, bias, dinv, ptr, col, tptr, tcol, mask, flip, row_flip = inputs
-    ctx.save_for_backward(dinv, tptr, tcol, mask)
+    z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip = inputs
+    ctx.save_for_backward(dinv, tptr, tcol, tplan, mask)
     ctx.flip, ctx.row_flip = flip, row_flip
 
 
 def _gcn_bwd(ctx, g):
-    dinv, tptr, tcol, mask = ctx.saved_tensors
+    dinv, tptr, tcol, tplan, mask = ctx.saved_tensors
     g = g.contiguous()
     dz = dbias = None
     if ctx.needs_input_grad[0]:
         # transpose: rows by SOURCE; the roles of flip / row_flip swap; the column mask becomes a row mask
-        dz = ops.seg_reduce(tptr, tcol, g.shape[0], g, flip=ctx.row_flip, row_flip=ctx.flip, src_scale=dinv,
+        dz = ops.seg_reduce(tptr, tcol, g.shape[0], g, plan=tplan, flip=ctx.row_flip, row_flip=ctx.flip, src_scale=dinv,
                             dst_scale=dinv, skip_self=True, self_mode=1, row_skip_mask=mask)
     if ctx.needs_input_grad[1]:
         dbias = ops.colsum(g)
-    return dz, dbias, None, None, None, None, None, None, None, None
+    return (dz, dbias) + (None,) * 10
 
 
 gcn_aggregate.register_autograd(_gcn_bwd, setup_context=_gcn_setup)
@@ -85,39 +85,41 @@ gcn_aggregate.register_autograd(_gcn_bwd, setup_context=_gcn_setup)
 
 
 @torch.library.custom_op("twowl::wedge_aggregate", mutates_args=())
-def wedge_aggregate(z: Tensor, bias: Tensor, in_ptr: Tensor, in_ids: Tensor, out_ptr: Tensor, out_ids: Tensor,
-                    centre: Tensor, dinv: Tensor, selfw: Tensor, dst_e: Tensor, blocked: Optional[Tensor], n_edge: int,
+def wedge_aggregate(z: Tensor, bias: Tensor, in_ptr: Tensor, in_ids: Tensor, in_plan: Optional[Tensor], out_ptr: Tensor,
+                    out_ids: Tensor, out_plan: Optional[Tensor], centre: Tensor, dinv: Tensor, selfw: Tensor, dst_e: Tensor, blocked: Optional[Tensor], n_edge: int,
                     n_node: int, direction: int) -> Tensor:
     """Pair-level GCNConv for a wedge index that is the full join of get_ei2 minus blocked source edges:
     S[i] = sum over unblocked in-edges of i; out[b] = dinv[b] S[centre[b]] + selfw[b] z[b] + bias
     (DESIGN.md 'Factorised pair aggregation'). direction 0 = edge2, 1 = edge2_r of utils.py:71-78."""
     z = z.contiguous()
-    S = ops.seg_reduce(in_ptr, in_ids, n_node, z, flip=1 - direction, src_scale=dinv, skip_mask=blocked)
+    S = ops.seg_reduce(in_ptr, in_ids, n_node, z, plan=in_plan, flip=1 - direction, src_scale=dinv, skip_mask=blocked)
     return ops.wedge_apply_fwd(S, z, centre, dinv, selfw, bias)
 
 
 @wedge_aggregate.register_fake
-def _(z, bias, in_ptr, in_ids, out_ptr, out_ids, centre, dinv, selfw, dst_e, blocked, n_edge, n_node, direction):
+def _(z, bias, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre, dinv, selfw, dst_e, blocked, n_edge, n_node,
+      direction):
     return torch.empty_like(z)
 
 
 def _wedge_setup(ctx, inputs, output):
-    (z, bias, in_ptr, in_ids, out_ptr, out_ids, centre, dinv, selfw, dst_e, blocked, n_edge, n_node, direction) = inputs
-    ctx.save_for_backward(out_ptr, out_ids, dinv, selfw, dst_e, blocked)
+    (z, bias, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre, dinv, selfw, dst_e, blocked, n_edge, n_node,
+     direction) = inputs
+    ctx.save_for_backward(out_ptr, out_ids, out_plan, dinv, selfw, dst_e, blocked)
     ctx.meta = (n_edge, n_node, direction)
 
 
 def _wedge_bwd(ctx, g):
-    out_ptr, out_ids, dinv, selfw, dst_e, blocked = ctx.saved_tensors
+    out_ptr, out_ids, out_plan, dinv, selfw, dst_e, blocked = ctx.saved_tensors
     n_edge, n_node, direction = ctx.meta
     g = g.contiguous()
     dz = dbias = None
     if ctx.needs_input_grad[0]:
-        dS = ops.seg_reduce(out_ptr, out_ids, n_node, g, flip=direction, src_scale=dinv)
+        dS = ops.seg_reduce(out_ptr, out_ids, n_node, g, plan=out_plan, flip=direction, src_scale=dinv)
         dz = ops.wedge_apply_bwd(dS, g, dst_e, blocked, n_edge, n_node, dinv, selfw, direction)
     if ctx.needs_input_grad[1]:
         dbias = ops.colsum(g)
-    return (dz, dbias) + (None,) * 12
+    return (dz, dbias) + (None,) * 14
 
 
 wedge_aggregate.register_autograd(_wedge_bwd, setup_context=_wedge_setup)
@@ -180,8 +182,9 @@ def _emb_setup(ctx, inputs, output):
 
 def _emb_bwd(ctx, g):
     (x,) = ctx.saved_tensors
-    ptr, ids = ops.csr_build(x.reshape(-1), ctx.rows)
-    return ops.seg_reduce(ptr, ids, ctx.rows, g.contiguous()), None
+    ptr, ids = ops.csr_build(x.reshape(-1), ctx.rows)   # rows = degree values: extremely skewed, so plan it
+    plan = ops.seg_plan(ptr, ctx.rows, ids.numel())
+    return ops.seg_reduce(ptr, ids, ctx.rows, g.contiguous(), plan=plan), None
 
 
 embedding.register_autograd(_emb_bwd, setup_context=_emb_setup)
@@ -190,14 +193,15 @@ embedding.register_autograd(_emb_bwd, setup_context=_emb_setup)
 
 
 @torch.library.custom_op("twowl::pair_init", mutates_args=())
-def pair_init(x: Tensor, src: Tensor, dst: Tensor, ptr_s: Tensor, ids_s: Tensor, ptr_d: Tensor, ids_d: Tensor) -> Tensor:
+def pair_init(x: Tensor, src: Tensor, dst: Tensor, ptr_s: Tensor, ids_s: Tensor, plan_s: Optional[Tensor], ptr_d: Tensor,
+              ids_d: Tensor, plan_d: Optional[Tensor]) -> Tensor:
     """H[p] = x[src[p]] * x[dst[p]] (model.py:75); (ptr_s, ids_s) / (ptr_d, ids_d) = pair rows grouped by
     src / dst node, used by the backward."""
     return ops.pair_init_fwd(x.contiguous(), src, dst)
 
 
 @pair_init.register_fake
-def _(x, src, dst, ptr_s, ids_s, ptr_d, ids_d):
+def _(x, src, dst, ptr_s, ids_s, plan_s, ptr_d, ids_d, plan_d):
     return x.new_empty((src.numel(), x.shape[1]))
 
 
@@ -206,13 +210,13 @@ def _pi_setup(ctx, inputs, output):
 
 
 def _pi_bwd(ctx, g):
-    x, src, dst, ptr_s, ids_s, ptr_d, ids_d = ctx.saved_tensors
+    x, src, dst, ptr_s, ids_s, plan_s, ptr_d, ids_d, plan_d = ctx.saved_tensors
     g = g.contiguous()
     N = x.shape[0]
     # dx[n] = sum_{p: src[p]=n} g[p]*x[dst[p]] + sum_{p: dst[p]=n} g[p]*x[src[p]]
-    dx = ops.seg_reduce(ptr_s, ids_s, N, g, X2=x, mul_idx=dst)
-    ops.seg_reduce(ptr_d, ids_d, N, g, X2=x, mul_idx=src, out=dx, accumulate=True)
-    return dx, None, None, None, None, None, None
+    dx = ops.seg_reduce(ptr_s, ids_s, N, g, plan=plan_s, X2=x, mul_idx=dst)
+    ops.seg_reduce(ptr_d, ids_d, N, g, plan=plan_d, X2=x, mul_idx=src, out=dx, accumulate=True)
+    return (dx,) + (None,) * 8
 
 
 pair_init.register_autograd(_pi_bwd, setup_context=_pi_setup)

@@ -65,6 +65,8 @@ class NodeGraph:
     tptr: torch.Tensor   # CSR by source: rows = ei[0], col = ei[1]
     tcol: torch.Tensor
     dinv: torch.Tensor   # (1 + in-degree without self-loops)^-1/2
+    plan: torch.Tensor   # long-row plans (ops.seg_plan) of the two CSRs
+    tplan: torch.Tensor
 
 
 def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
@@ -74,7 +76,9 @@ def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
         col = ops.gather_cols(ids, ei[0])
         tptr, tids = ops.csr_build(ei[0], n)
         tcol = ops.gather_cols(tids, ei[1])
-        return NodeGraph(n, ptr, col, tptr, tcol, ops.gcn_dinv(ptr, col, n))
+        m = ei.shape[1]
+        return NodeGraph(n, ptr, col, tptr, tcol, ops.gcn_dinv(ptr, col, n), ops.seg_plan(ptr, n, m),
+                         ops.seg_plan(tptr, n, m))
     return _cache.get(edge1, ("node", n), build)
 
 
@@ -90,6 +94,8 @@ class PairTable:
     ids_s: torch.Tensor
     ptr_d: torch.Tensor  # pair rows grouped by dst node
     ids_d: torch.Tensor
+    plan_s: torch.Tensor
+    plan_d: torch.Tensor
 
 
 def pair_table(pos: torch.Tensor, n: int) -> PairTable:
@@ -97,7 +103,9 @@ def pair_table(pos: torch.Tensor, n: int) -> PairTable:
         p = _i64(pos)
         ptr_s, ids_s = ops.csr_build(p[:, 0], n)
         ptr_d, ids_d = ops.csr_build(p[:, 1], n)
-        return PairTable(n, p.shape[0], ops.narrow_i32(p[:, 0]), ops.narrow_i32(p[:, 1]), ptr_s, ids_s, ptr_d, ids_d)
+        R = p.shape[0]
+        return PairTable(n, R, ops.narrow_i32(p[:, 0]), ops.narrow_i32(p[:, 1]), ptr_s, ids_s, ptr_d, ids_d,
+                         ops.seg_plan(ptr_s, n, R), ops.seg_plan(ptr_d, n, R))
     return _cache.get(pos, ("pos", n), build)
 
 
@@ -111,6 +119,8 @@ class ExplicitWedges:
     ptr_a: torch.Tensor   # CSR by source edge a, col = target pair b
     col_a: torch.Tensor
     dinv: tuple           # (dinv for edge2 = [a^1; b], dinv for edge2_r = [a; b^1])
+    plan_b: torch.Tensor
+    plan_a: torch.Tensor
 
 
 def explicit_wedges(ei2: torch.Tensor, R: int) -> ExplicitWedges:
@@ -127,7 +137,8 @@ def explicit_wedges(ei2: torch.Tensor, R: int) -> ExplicitWedges:
         col_a = ops.gather_cols(ids_a, e[1])
         d0 = ops.gcn_dinv(ptr_b, col_b, R, flip=1, row_flip=0)
         d1 = ops.gcn_dinv(ptr_b, col_b, R, flip=0, row_flip=1)
-        return ExplicitWedges(R, ptr_b, col_b, ptr_a, col_a, (d0, d1))
+        T = e.shape[1]
+        return ExplicitWedges(R, ptr_b, col_b, ptr_a, col_a, (d0, d1), ops.seg_plan(ptr_b, R, T), ops.seg_plan(ptr_a, R, T))
     return _cache.get(ei2, ("ei2", R), build)
 
 
@@ -147,6 +158,8 @@ class WedgeStruct:
     in_ids: torch.Tensor
     out_ptr: torch.Tensor  # int64 [n+1], out_ids int32: pair rows grouped by source node (ascending id)
     out_ids: torch.Tensor
+    in_plan: torch.Tensor  # long-row plans of the two lists (hubs)
+    out_plan: torch.Tensor
     blocked: Optional[torch.Tensor] = None
     _prep: Optional[tuple] = field(default=None, repr=False)
 
@@ -154,7 +167,7 @@ class WedgeStruct:
         if self.blocked is not None:
             blocked = torch.maximum(blocked, self.blocked)
         return WedgeStruct(self.n_node, self.E, self.R, self.src, self.dst_e, self.in_ptr, self.in_ids, self.out_ptr,
-                           self.out_ids, blocked)
+                           self.out_ids, self.in_plan, self.out_plan, blocked)
 
     def prepared(self):
         """(cnt[N], centre[2,R], dinv[2,R], selfw[2,R]) - per-row constants of both directions."""
@@ -178,7 +191,7 @@ def build_wedge_struct(n_node: int, pos_edge: torch.Tensor, pred_edge: torch.Ten
     in_ptr, in_ids = ops.csr_build(pos_edge[1], n_node)
     out_ptr, out_ids = ops.csr_build(src_all, n_node)
     return WedgeStruct(int(n_node), E, E + P, ops.narrow_i32(src_all), ops.narrow_i32(pos_edge[1]), in_ptr, in_ids,
-                       out_ptr, out_ids)
+                       out_ptr, out_ids, ops.seg_plan(in_ptr, int(n_node), E), ops.seg_plan(out_ptr, int(n_node), E + P))
 
 
 class WedgeIndex:

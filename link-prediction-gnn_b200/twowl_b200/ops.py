@@ -262,9 +262,22 @@ def gcn_dinv(ptr, col, M: int, flip: int = 0, row_flip: int = 0, skip_mask=None,
     return dinv
 
 
-def seg_reduce(ptr, col, M: int, X, *, flip=0, row_flip=0, src_scale=None, skip_mask=None, row_skip_mask=None,
-               skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None, out=None,
-               accumulate=False) -> torch.Tensor:
+def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
+    """Long-row plan of a CSR as ONE int32 tensor: [counts(2) | long_row(lc) | long_base(lc) | chunk_owner(cc)],
+    lc / cc being the capacities twowl_seg_plan_{long,chunk}_cap give for nnz (no host read needed)."""
+    _need_cuda(ptr)
+    lc, cc = lib.twowl_seg_plan_long_cap(nnz), lib.twowl_seg_plan_chunk_cap(nnz)
+    plan = torch.empty(2 + 2 * lc + cc, dtype=torch.int32, device=ptr.device)
+    base = plan.data_ptr()
+    check(lib.twowl_seg_plan(ptr.data_ptr(), M, nnz, base, base + 8, base + 8 + 4 * lc, base + 8 + 8 * lc, _stream()),
+          "seg_plan")
+    _count()
+    return plan
+
+
+def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
+               row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
+               out=None, accumulate=False) -> torch.Tensor:
     _need_cuda(ptr, col, X)
     assert X.dtype == torch.float32 and X.is_contiguous()
     C = X.shape[1]
@@ -274,9 +287,18 @@ def seg_reduce(ptr, col, M: int, X, *, flip=0, row_flip=0, src_scale=None, skip_
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
                 mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate))
+    partial = None
+    if plan is not None:
+        nnz = col.numel()
+        lc, cc = lib.twowl_seg_plan_long_cap(nnz), lib.twowl_seg_plan_chunk_cap(nnz)
+        assert plan.numel() == 2 + 2 * lc + cc, "plan does not belong to this CSR"
+        partial = torch.empty((cc, C), dtype=torch.float32, device=X.device)
+        base = plan.data_ptr()
+        a.plan_counts, a.long_row, a.long_base, a.chunk_owner = base, base + 8, base + 8 + 4 * lc, base + 8 + 8 * lc
+        a.partial, a.chunk_cap, a.long_cap = partial.data_ptr(), cc, lc
     with _P("seg_reduce", (col.numel() + M) * (4 * C + 8)):
         check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
-    _count()
+    _count(1 if plan is None else 3)
     return out
 
 

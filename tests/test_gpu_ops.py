@@ -198,10 +198,16 @@ def test_seg_reduce_vs_fp64(U, C):
         keep = (s != tgt) & ~torch.from_numpy(mask)[c_s]
         ref = torch.zeros(M, C, dtype=torch.float64).index_add_(0, tgt[keep], sc[s[keep]].unsqueeze(1) * X[s[keep]])
         ref = sc.unsqueeze(1) * ref + (sc ** 2).unsqueeze(1) * X + bias
-        got = ops.seg_reduce(ptr, col, M, X.float().cuda(), flip=flip, row_flip=row_flip, src_scale=sc.float().cuda(),
-                             dst_scale=sc.float().cuda(), skip_self=True, self_mode=1, bias=bias.float().cuda(),
-                             skip_mask=dev(mask.astype(np.uint8)))
+        kw = dict(flip=flip, row_flip=row_flip, src_scale=sc.float().cuda(), dst_scale=sc.float().cuda(), skip_self=True,
+                  self_mode=1, bias=bias.float().cuda(), skip_mask=dev(mask.astype(np.uint8)))
+        got = ops.seg_reduce(ptr, col, M, X.float().cuda(), **kw)
         assert_close(got, ref, rtol=1e-5, atol=2e-4, what=f"seg_reduce C={C} flip={flip} row_flip={row_flip}")
+        # with the long-row plan (rows > TWOWL_LONG_ROW entries are cut into chunks): same values, and repeatable
+        plan = ops.seg_plan(ptr, M, nnz)
+        assert int(plan[0]) >= 1, "the test graph must contain long rows"
+        got2 = ops.seg_reduce(ptr, col, M, X.float().cuda(), plan=plan, **kw)
+        assert_close(got2, ref, rtol=1e-5, atol=2e-4, what=f"seg_reduce planned C={C}")
+        assert torch.equal(got2, ops.seg_reduce(ptr, col, M, X.float().cuda(), plan=ops.seg_plan(ptr, M, nnz), **kw))
         # dinv: exact integer degree
         d = ops.gcn_dinv(ptr, col, M, flip=flip, row_flip=row_flip, skip_mask=dev(mask.astype(np.uint8)))
         deg = torch.bincount(tgt[keep], minlength=M).double() + 1
@@ -290,7 +296,7 @@ def test_pair_init_readout_embedding(U):
     gX, gw, gb, gemb = c(X), c(w), c(b), c(emb)
     pt = G.pair_table(pos.cuda(), N)
     g0 = F2.embedding(gemb, deg.cuda()) + gX
-    gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.ptr_d, pt.ids_d)
+    gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d)
     out = F2.readout(gH, idx.cuda(), gw, gb)
     out.backward(gout.float().cuda())
     assert_close(out, ref.detach(), atol=1e-4, what="readout fwd")
