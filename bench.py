@@ -20,7 +20,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -102,39 +101,59 @@ def draw_batch(und, n_pred_und, nb, seed):
 # ------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region, in-process through NVML (pynvml) every
+    50 ms - forking nvidia-smi from a process with a CUDA context stalls the launching thread for tens of ms."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
 
     def _run(self):
+        nv = self.nv
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((clk, rs))
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
-        self.t.start()
+        if self.h is not None:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.h is not None:
+            self.t.join(timeout=2)
 
     def summary(self):
-        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        if not rows:
+        if self.h is None or not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]),
-                "reasons": reasons, "samples": len(rows)}
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = [k for k, b in bits.items() if any(r & b for _, r in self.rows)]
+        return {"sm_mhz": statistics.median(c for c, _ in self.rows), "sm_max_mhz": int(self.max), "reasons": reasons,
+                "samples": len(self.rows), "how": "pynvml, 50 ms period, timed region only"}
 
 
 # ------------------------------------------------------------------------------ CPU baseline (oracle port)
