@@ -225,7 +225,9 @@ int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, siz
 /* ------------------------------------------------------------------ dense linear layers --------- */
 
 /* PyG Linear without bias (GCNConv.lin, model.py:37): Z[M,Co] = X[M,Ci] * W[Co,Ci]^T, fp32 in/out.
- * impl 0: SIMT FFMA tiles (exact fp32 accumulation).
+ * impl 0: SIMT FFMA tiles (exact fp32 accumulation).  impl 1: tcgen05.mma kind::tf32 with 3xTF32 split operands,
+ * accumulator in TMEM (fp32-accurate to ~1e-6 relative; needs K % 32 == 0, K <= 128, N % 16 == 0, N <= 256 and the
+ * split weight + one 128-row tile to fit shared memory, else TWOWL_EINVAL).  impl 2: 1 where supported, else 0.
  * bwd_input: dX[M,Ci] = dZ[M,Co] * W[Co,Ci].   bwd_weight: dW[Co,Ci] = dZ^T X (split over M, fixed order). */
 int twowl_linear_fwd(const float* X, const float* W, int64_t M, int32_t Ci, int32_t Co, float* Z, int32_t impl,
                      void* stream);

@@ -81,20 +81,39 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
       }
     }
     const int cnt = (ke - k0 < G) ? (int)(ke - k0) : G;
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      const int s = __shfl_sync(g.gmask, s_mine, g.gbase + j);
-      const float w = __shfl_sync(g.gmask, w_mine, g.gbase + j);
-      const int m2 = __shfl_sync(g.gmask, m2_mine, g.gbase + j);
-      if (s >= 0) {
+    // UNR gathered rows are requested back to back (predicated 128-bit loads, no branches in between) before
+    // any of them is consumed: the kernel lives on memory-level parallelism, not on occupancy
+    constexpr int UNR = (VEC >= 8) ? 1 : (8 / VEC > G ? G : 8 / VEC);
+    for (int j0 = 0; j0 < cnt; j0 += UNR) {
+      int sj[UNR], m2j[UNR];
+      float wj[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int src_lane = g.gbase + ((j0 + u) & (G - 1));
+        sj[u] = __shfl_sync(g.gmask, s_mine, src_lane);
+        wj[u] = __shfl_sync(g.gmask, w_mine, src_lane);
+        m2j[u] = __shfl_sync(g.gmask, m2_mine, src_lane);
+        if (j0 + u >= cnt) sj[u] = -1;
+      }
+      float4 x[UNR][VEC];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           const int c4 = g.gl + v * G;
-          if (c4 < g.cv) {
-            float4 x = ldg_cached(X4 + (int64_t)s * g.cv + c4);
-            if (p.X2) x = f4_mul(x, ldg_cached(X24 + (int64_t)m2 * g.cv + c4));
-            f4_fma(acc[v], w, x);
+          const bool on = sj[u] >= 0 && c4 < g.cv;
+          x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
+          if (p.X2) {
+            const float4 y = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
+            x[u][v] = f4_mul(x[u][v], y);
           }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (sj[u] >= 0) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) f4_fma(acc[v], wj[u], x[u][v]);
         }
       }
     }

@@ -130,4 +130,9 @@ size_t radix_workspace_bytes(int64_t n);
 int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int64_t n,
                      int bits, void* ws, cudaStream_t s);
 
+// ---- tensor-core linear layer implemented in linear_tc.cu ----------------------------------------
+// C[M,Nd] = A[M,Kd] * B^T with B[n][k] = W[n*Kd+k] (w_kn = 0) or W[k*Nd+n] (w_kn = 1); tcgen05 kind::tf32, 3xTF32.
+bool linear_tc_supported(int Kd, int Nd);
+int linear_tc(const float* A, const float* W, float* C, int64_t M, int Kd, int Nd, int w_kn, cudaStream_t s);
+
 }  // namespace twowl

@@ -157,8 +157,9 @@ extern "C" int twowl_linear_fwd(const float* X, const float* W, int64_t M, int32
                                 void* stream) {
   if (int rc = check_lin("linear_fwd", M, Ci, Co)) return rc;
   TW_CHECK_ARG(aligned16(X) && aligned16(W) && aligned16(Z), "linear_fwd: 16-byte alignment required");
-  TW_CHECK_ARG(impl == 0, "linear_fwd: impl %d not available (0 = SIMT FFMA)", impl);
+  TW_CHECK_ARG(impl >= 0 && impl <= 2, "linear_fwd: impl %d unknown (0 = SIMT FFMA, 1 = tcgen05 3xTF32, 2 = auto)", impl);
   if (M == 0) return 0;
+  if (impl == 1 || (impl == 2 && linear_tc_supported(Ci, Co))) return linear_tc(X, W, Z, M, Ci, Co, 0, (cudaStream_t)stream);
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Co, BN));
   k_gemm_rows<true><<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(X, W, Z, M, Co, Ci);
   TW_LAUNCH_CHECK();
@@ -169,8 +170,9 @@ extern "C" int twowl_linear_bwd_input(const float* dZ, const float* W, int64_t M
                                       int32_t impl, void* stream) {
   if (int rc = check_lin("linear_bwd_input", M, Ci, Co)) return rc;
   TW_CHECK_ARG(aligned16(dZ) && aligned16(W) && aligned16(dX), "linear_bwd_input: 16-byte alignment required");
-  TW_CHECK_ARG(impl == 0, "linear_bwd_input: impl %d not available (0 = SIMT FFMA)", impl);
+  TW_CHECK_ARG(impl >= 0 && impl <= 2, "linear_bwd_input: impl %d unknown (0 = SIMT FFMA, 1 = tcgen05 3xTF32, 2 = auto)", impl);
   if (M == 0) return 0;
+  if (impl == 1 || (impl == 2 && linear_tc_supported(Co, Ci))) return linear_tc(dZ, W, dX, M, Co, Ci, 1, (cudaStream_t)stream);
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Ci, BN));
   k_gemm_rows<false><<<grid, kGemmThreads, 0, (cudaStream_t)stream>>>(dZ, W, dX, M, Ci, Co);
   TW_LAUNCH_CHECK();

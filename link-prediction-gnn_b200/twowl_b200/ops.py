@@ -8,6 +8,7 @@ exactly where the reference's own torch ops (cat / boolean indexing) synchronise
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -411,21 +412,27 @@ def colsum(x) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------ linear
 
-def linear_fwd(X, W, impl: int = 0) -> torch.Tensor:
+# 0 = SIMT FFMA (exact fp32), 1 = tcgen05 3xTF32 (error when the shape is unsupported), 2 = tcgen05 where supported
+LINEAR_IMPL = int(os.environ.get("TWOWL_LINEAR_IMPL", "2"))
+
+
+def linear_fwd(X, W, impl: int = -1) -> torch.Tensor:
     _need_cuda(X, W)
     M, Ci = X.shape
     Co = W.shape[0]
     Z = torch.empty((M, Co), dtype=torch.float32, device=X.device)
+    impl = LINEAR_IMPL if impl < 0 else impl
     with _P("linear_fwd", 4 * M * (Ci + Co)):
         check(lib.twowl_linear_fwd(X.data_ptr(), W.data_ptr(), M, Ci, Co, Z.data_ptr(), impl, _stream()), "linear_fwd")
     _count()
     return Z
 
 
-def linear_bwd_input(dZ, W, impl: int = 0) -> torch.Tensor:
+def linear_bwd_input(dZ, W, impl: int = -1) -> torch.Tensor:
     M, Co = dZ.shape
     Ci = W.shape[1]
     dX = torch.empty((M, Ci), dtype=torch.float32, device=dZ.device)
+    impl = LINEAR_IMPL if impl < 0 else impl
     with _P("linear_bwd_input", 4 * M * (Ci + Co)):
         check(lib.twowl_linear_bwd_input(dZ.data_ptr(), W.data_ptr(), M, Ci, Co, dX.data_ptr(), impl, _stream()),
               "linear_bwd_input")

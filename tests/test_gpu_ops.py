@@ -254,9 +254,13 @@ def test_graphnorm_fwd_bwd(U, M, C, p, relu):
 
 
 @pytest.mark.parametrize("M,Ci,Co", [(1, 4, 4), (620, 64, 24), (6576, 24, 24), (4097, 128, 128), (1000, 256, 36),
-                                     (50000, 64, 64)])
-def test_linear_fwd_bwd(U, M, Ci, Co):
+                                     (50000, 64, 64), (129, 32, 32), (70001, 64, 128), (3000, 128, 64), (257, 96, 48)])
+@pytest.mark.parametrize("impl", [0, 2])
+def test_linear_fwd_bwd(U, M, Ci, Co, impl, monkeypatch):
+    """impl 0 = SIMT FFMA tiles; impl 2 = tcgen05 3xTF32 where the shape is supported (64x64, 128x128->SIMT, ...)."""
     from twowl_b200 import functional as F2
+    from twowl_b200 import ops
+    monkeypatch.setattr(ops, "LINEAR_IMPL", impl)
     torch.manual_seed(M)
     x = torch.randn(M, Ci, dtype=torch.float64).requires_grad_(True)
     w = torch.randn(Co, Ci, dtype=torch.float64).requires_grad_(True)
