@@ -211,7 +211,8 @@ int twowl_graphnorm_apply(const float* x, int64_t M, int32_t C, const float* sta
                           const float* addend, float* out, void* stream);
 
 /* Backward of the fused GraphNorm+Dropout+ReLU. Given dout (gradient w.r.t. the fused output) and the saved
- * input x + stats:  dx[M,C] and dparams[3C] = (dweight, dbias, dmean_scale) are written. */
+ * input x + stats:  dx[M,C] and dparams[4C] = (dweight, dbias, dmean_scale, column sums of dx) are written; the
+ * last block is the gradient of the bias of the GCNConv that produced x, obtained without another pass. */
 size_t twowl_graphnorm_bwd_workspace_bytes(int64_t M, int32_t C);
 int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M, int32_t C, const float* stats,
                         const float* weight, const float* bias, const float* mean_scale, float p_drop,
@@ -236,6 +237,38 @@ int twowl_linear_bwd_input(const float* dZ, const float* W, int64_t M, int32_t C
 size_t twowl_linear_bwd_weight_workspace_bytes(int64_t M, int32_t Ci, int32_t Co);
 int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t M, int32_t Ci, int32_t Co, float* dW,
                             void* ws, size_t ws_bytes, void* stream);
+/* same with dZ rows scaled on the fly: dW = (row_scale * dZ)^T X */
+int twowl_linear_bwd_weight_scaled(const float* dZ, const float* row_scale, const float* X, int64_t M, int32_t Ci,
+                                   int32_t Co, float* dW, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ fused tensor-core pair layer -- */
+
+/* out[r,:] = sum_{s<nsrc} (row_scale_s[r] * A_s[r,:]) * B_s^T + sum_{g<ngather} tcoef_g[r] * T_g[tidx_g[r],:] + bias
+ * with B_s[n][k] = W_s[n*Kd+k] (w_kn=0) or W_s[k*Nd+n] (w_kn=1), on tcgen05.mma kind::tf32 (3xTF32, TMEM accumulator),
+ * one persistent warp-specialised CTA per SM. tidx < 0 = no term for that row. When `stats` is given the kernel
+ * also reduces the column (sum, sum of squares) of `out` and writes GraphNorm's (mean[Nd], inv_std[Nd]) for
+ * mean_scale/eps - the statistics pass of the GraphNorm that follows costs no extra read of `out`.
+ * Forward of the structured pair-level GCNConv (model.py:77): A=H, row_scale=selfw, W=lin.weight, gather
+ * (S W^T, centre, dinv), bias. Backward w.r.t. H: nsrc=2 over (dO_f, dO_r) with w_kn=1. */
+typedef struct twowl_conv_args {
+  int32_t nsrc, ngather, Kd, Nd;
+  int64_t M;
+  const float* A[2];          /* [M, Kd] */
+  const float* row_scale[2];  /* [M] or NULL */
+  const float* W[2];
+  int32_t w_kn[2];
+  const float* T[2];          /* [rows_T, Nd] */
+  const int32_t* tidx[2];     /* [M] */
+  const float* tcoef[2];      /* [M] */
+  const float* bias;          /* [Nd] or NULL */
+  float* out;                 /* [M, Nd] */
+  float* stats;               /* [2*Nd] or NULL */
+  const float* mean_scale;    /* [Nd], needed with stats */
+  float eps;
+} twowl_conv_args;
+int twowl_pair_conv_supported(int32_t Kd, int32_t Nd, int32_t nsrc);
+size_t twowl_pair_conv_workspace_bytes(int64_t M, int32_t Nd);
+int twowl_pair_conv(const twowl_conv_args* h_args, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ structured wedge path ------- */
 
@@ -248,7 +281,8 @@ int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t M, int32_t 
  * cnt[i] = number of unblocked observed edges with target i (int32[N]). */
 int twowl_wedge_prepare(const int32_t* src /*[R]*/, const int32_t* dst_e /*[E]*/, int64_t E, int64_t R, int64_t N,
                         const uint8_t* blocked /*[E] or NULL*/, const int64_t* in_ptr /*[N+1]*/, int32_t* cnt /*[N]*/,
-                        int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/, void* stream);
+                        int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/,
+                        int32_t* bnode /*[2,R]: node whose S row r feeds (backward gather), -1 if none*/, void* stream);
 /* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias   (centre < 0: no S term) */
 int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,
                           const float* selfw, const float* bias, int64_t R, int32_t C, float* out, void* stream);

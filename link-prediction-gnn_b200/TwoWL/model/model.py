@@ -55,7 +55,7 @@ class GCNConv(nn.Module):
         """The pair-level call of model.py:77: direction 0 = conv(x, edge2), 1 = conv_r(x, edge2_r)."""
         z = self.lin(x)
         if isinstance(wedges, G.WedgeStruct):
-            _, centre, dinv, selfw = wedges.prepared()
+            _, centre, dinv, selfw, _ = wedges.prepared()
             return F2.wedge_aggregate(z, self.bias, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr,
                                       wedges.out_ids, wedges.out_plan, centre[direction], dinv[direction], selfw[direction], wedges.dst_e,
                                       wedges.blocked, wedges.E, wedges.n_node, direction)
@@ -157,6 +157,9 @@ class LocalWLNet(nn.Module):
         self.node_feat = node_feat
         # "structured" | "explicit" | "auto": how the pair-level GCNConv consumes ei2 (see forward)
         self.pair_path = "auto"
+        # one fused custom op per pair layer (tcgen05 GEMM + structured aggregation + GraphNorm statistics) when the
+        # wedges are structured and the widths are supported; False = the op-by-op path
+        self.fused_pair_layer = True
 
         if use_node_feat:
             self.lin1 = nn.Sequential(
@@ -213,6 +216,9 @@ class LocalWLNet(nn.Module):
         if len(self.conv2s):
             wedges = self._wedges(ei2, pt.R)
             for i in range(len(self.conv2s)):
-                a = self.conv2s[i].forward_pairs(x, wedges, 0)
-                x = self.conv2s_r[i].forward_pairs(x, wedges, 1, addend=a)
+                if self.fused_pair_layer and F2.pair_layer_supported(wedges, x.shape[1], self.conv2s[i], self.conv2s_r[i]):
+                    x = F2.pair_layer_apply(x, wedges, self.conv2s[i], self.conv2s_r[i], self.training)
+                else:
+                    a = self.conv2s[i].forward_pairs(x, wedges, 0)
+                    x = self.conv2s_r[i].forward_pairs(x, wedges, 1, addend=a)
         return F2.readout(x, idx, self.pred.weight, self.pred.bias)

@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_rows(const float* __restr
 // dW[Co,Ci] = sum_m dZ[m,co] * X[m,ci]: 64x64 output tile per CTA, split over M; each split writes its
 // partial tile to part[split][Co][Ci]; k_dw_final adds the splits in order (deterministic).
 constexpr int WT = 64, WK = 16;
-__global__ void __launch_bounds__(kGemmThreads) k_dw_partial(const float* __restrict__ dZ, const float* __restrict__ X, int64_t M,
-                                                             int Ci, int Co, int64_t rows_per_split, float* __restrict__ part) {
+__global__ void __launch_bounds__(kGemmThreads) k_dw_partial(const float* __restrict__ dZ, const float* __restrict__ rs,
+                                                             const float* __restrict__ X, int64_t M, int Ci, int Co,
+                                                             int64_t rows_per_split, float* __restrict__ part) {
   __shared__ __align__(16) float As[WK][WT];
   __shared__ __align__(16) float Bs[WK][WT];
   const int tid = threadIdx.x;
@@ -98,7 +99,13 @@ __global__ void __launch_bounds__(kGemmThreads) k_dw_partial(const float* __rest
   for (int64_t m0 = mb; m0 < me; m0 += WK) {
     float4 a = f4_zero(), b = f4_zero();
     if (m0 + lr < me) {
-      if (co0 + lq * 4 < Co) a = ldg_stream(reinterpret_cast<const float4*>(dZ + (m0 + lr) * Co + co0 + lq * 4));
+      if (co0 + lq * 4 < Co) {
+        a = ldg_stream(reinterpret_cast<const float4*>(dZ + (m0 + lr) * Co + co0 + lq * 4));
+        if (rs) {
+          const float sc = __ldg(rs + m0 + lr);
+          a.x *= sc, a.y *= sc, a.z *= sc, a.w *= sc;
+        }
+      }
       if (ci0 + lq * 4 < Ci) b = ldg_stream(reinterpret_cast<const float4*>(X + (m0 + lr) * Ci + ci0 + lq * 4));
     }
     *reinterpret_cast<float4*>(&As[lr][lq * 4]) = a;
@@ -183,8 +190,15 @@ extern "C" size_t twowl_linear_bwd_weight_workspace_bytes(int64_t M, int32_t Ci,
   return align_up((size_t)dw_splits(M > 0 ? M : 1, Ci, Co) * (size_t)Ci * Co * sizeof(float));
 }
 
+extern "C" int twowl_linear_bwd_weight_scaled(const float* dZ, const float* row_scale, const float* X, int64_t M, int32_t Ci,
+                                              int32_t Co, float* dW, void* ws, size_t ws_bytes, void* stream);
 extern "C" int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t M, int32_t Ci, int32_t Co, float* dW, void* ws,
                                        size_t ws_bytes, void* stream) {
+  return twowl_linear_bwd_weight_scaled(dZ, nullptr, X, M, Ci, Co, dW, ws, ws_bytes, stream);
+}
+
+extern "C" int twowl_linear_bwd_weight_scaled(const float* dZ, const float* row_scale, const float* X, int64_t M, int32_t Ci,
+                                              int32_t Co, float* dW, void* ws, size_t ws_bytes, void* stream) {
   if (int rc = check_lin("linear_bwd_weight", M, Ci, Co)) return rc;
   TW_CHECK_ARG(aligned16(dZ) && aligned16(X) && aligned16(dW), "linear_bwd_weight: 16-byte alignment required");
   TW_CHECK_WS(ws_bytes, twowl_linear_bwd_weight_workspace_bytes(M, Ci, Co));
@@ -197,7 +211,7 @@ extern "C" int twowl_linear_bwd_weight(const float* dZ, const float* X, int64_t 
   int64_t rows_per_split = cdiv(M, splits);
   rows_per_split = cdiv(rows_per_split, WK) * WK;
   dim3 grid((unsigned)cdiv(Ci, WT), (unsigned)cdiv(Co, WT), (unsigned)splits);
-  k_dw_partial<<<grid, kGemmThreads, 0, s>>>(dZ, X, M, Ci, Co, rows_per_split, (float*)ws);
+  k_dw_partial<<<grid, kGemmThreads, 0, s>>>(dZ, row_scale, X, M, Ci, Co, rows_per_split, (float*)ws);
   k_dw_final<<<(int)cdiv((int64_t)Ci * Co, 256), 256, 0, s>>>((const float*)ws, splits, Ci * Co, dW);
   TW_LAUNCH_CHECK();
   return 0;

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
 }
 
 // sums[0:C] = A = sum g_y, sums[C:2C] = B = sum g_y*n, sums[2C:3C] = (alpha/M) * sum g_o   (fp32, for pass 2)
-// dparams[0:C] = dweight = B, [C:2C] = dbias = A, [2C:3C] = dmean_scale = -mean * sum g_o
+// dparams[0:C] = dweight = B, [C:2C] = dbias = A, [2C:3C] = dmean_scale = -mean * sum g_o, [3C:4C] = colsum(dx)
 __global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int64_t M, int C, const float* __restrict__ stats,
                                const float* __restrict__ weight, const float* __restrict__ mean_scale, float* __restrict__ sums,
                                float* __restrict__ dparams) {
@@ -224,6 +224,7 @@ __global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int6
   dparams[c] = (float)B;
   dparams[C + c] = (float)A;
   dparams[2 * C + c] = (float)(-mean * sum_go);
+  dparams[3 * C + c] = (float)((1.0 - a) * sum_go);  // sum over rows of dx = sum g_o - a * sum g_o
 }
 
 __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_dx(const float* __restrict__ x, const float* __restrict__ dout, int64_t M,

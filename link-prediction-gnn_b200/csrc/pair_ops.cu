@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_cnt_block(const int32_t* 
 __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __restrict__ src, const int32_t* __restrict__ dst_e,
                                                             int64_t E, int64_t R, int64_t N, const uint8_t* __restrict__ blocked,
                                                             const int32_t* __restrict__ cnt, int32_t* __restrict__ centre,
-                                                            float* __restrict__ dinv, float* __restrict__ selfw) {
+                                                            float* __restrict__ dinv, float* __restrict__ selfw,
+                                                            int32_t* __restrict__ bnode) {
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < R; b += (int64_t)gridDim.x * blockDim.x) {
     // direction 0 (edge2 = [a^1; b]): row b is fed by the in-list of src[b]; its id-self-loop is a = b^1
     // direction 1 (edge2_r = [a; b^1]): row b is fed by the in-list of src[b^1]; its id-self-loop is a = b
@@ -172,6 +173,18 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __res
     dinv[R + b] = d1;
     selfw[b] = self0 ? 0.f : d0 * d0;
     selfw[R + b] = self1 ? 0.f : d1 * d1;
+    // backward: row b is a source of S_d[node] iff its feeding edge (b^1 for direction 0, b for direction 1) is live
+    int32_t n0b = -1, n1b = -1;
+    if (mate < E && !(blocked && blocked[mate])) {
+      const int32_t nd = dst_e[mate];
+      if (nd >= 0 && nd < N) n0b = nd;
+    }
+    if (b < E && !(blocked && blocked[b])) {
+      const int32_t nd = dst_e[b];
+      if (nd >= 0 && nd < N) n1b = nd;
+    }
+    bnode[b] = n0b;
+    bnode[R + b] = n1b;
   }
 }
 
@@ -296,12 +309,12 @@ extern "C" int twowl_readout_bwd(const float* H, const int64_t* idx, int64_t sid
 
 extern "C" int twowl_wedge_prepare(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N,
                                    const uint8_t* blocked, const int64_t* in_ptr, int32_t* cnt, int32_t* centre, float* dinv,
-                                   float* selfw, void* stream) {
+                                   float* selfw, int32_t* bnode, void* stream) {
   TW_CHECK_ARG(E >= 0 && R >= E && N >= 0, "wedge_prepare: need 0 <= E <= R and N >= 0");
   cudaStream_t s = (cudaStream_t)stream;
   if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
   if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
-  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, centre, dinv, selfw);
+  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, centre, dinv, selfw, bnode);
   TW_LAUNCH_CHECK();
   return 0;
 }

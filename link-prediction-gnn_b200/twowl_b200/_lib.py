@@ -36,6 +36,17 @@ class SegArgs(ctypes.Structure):
     ]
 
 
+class ConvArgs(ctypes.Structure):
+    """``twowl_conv_args`` of include/twowl.h (field order must match)."""
+    _fields_ = [
+        ("nsrc", ctypes.c_int32), ("ngather", ctypes.c_int32), ("Kd", ctypes.c_int32), ("Nd", ctypes.c_int32),
+        ("M", ctypes.c_int64), ("A", ctypes.c_void_p * 2), ("row_scale", ctypes.c_void_p * 2),
+        ("W", ctypes.c_void_p * 2), ("w_kn", ctypes.c_int32 * 2), ("T", ctypes.c_void_p * 2),
+        ("tidx", ctypes.c_void_p * 2), ("tcoef", ctypes.c_void_p * 2), ("bias", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("mean_scale", ctypes.c_void_p), ("eps", ctypes.c_float),
+    ]
+
+
 def parse_header(path: str = HEADER_PATH):
     """-> {name: (restype_str, [argtype_str, ...])} for every function the header declares."""
     text = open(path).read()

@@ -246,3 +246,101 @@ def _ro_bwd(ctx, g):
 
 
 readout.register_autograd(_ro_bwd, setup_context=_ro_setup)
+
+
+# ------------------------------------------------------------------------------ fused structured pair layer
+#
+# One custom op for  x <- relu(drop(GN_f(conv_f(x, edge2)))) + relu(drop(GN_r(conv_r(x, edge2_r))))  (model.py:77)
+# on the structured wedge path: per direction d
+#   SH_d = per-node sum of dinv_d * H over the unblocked in-edges          (seg_reduce, N rows)
+#   O_d  = selfw_d * (H W_d^T) + dinv_d * (SH_d W_d^T)[centre_d] + bias_d   (tcgen05 GEMM, fused epilogue + GN statistics)
+# and the two GraphNorm(+Dropout+ReLU) applications summed. The backward is hand-written from the same pieces.
+
+
+@torch.library.custom_op("twowl::pair_layer", mutates_args=())
+def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf: Tensor, wr: Tensor, br: Tensor, gwr: Tensor,
+               gbr: Tensor, gmr: Tensor, in_ptr: Tensor, in_ids: Tensor, in_plan: Tensor, out_ptr: Tensor, out_ids: Tensor,
+               out_plan: Tensor, centre: Tensor, dinv: Tensor, selfw: Tensor, bnode: Tensor, blocked: Optional[Tensor],
+               n_node: int, eps: float, p_drop: float, seed_f: int, seed_r: int
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (h_next, O_f, O_r, stats_f, stats_r, SH_f, SH_r); only h_next is differentiable, the rest is saved state."""
+    h = h.contiguous()
+    outs = []
+    for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
+        SH = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, flip=1 - d, src_scale=dinv[d], skip_mask=blocked)
+        S = ops.linear_fwd(SH, w)
+        O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
+                              stats_mean_scale=gm, eps=eps)
+        outs.append((O, st, SH))
+    a = ops.graphnorm_apply(outs[0][0], outs[0][1], gwf, gbf, gmf, p_drop, seed_f, True)
+    hn = ops.graphnorm_apply(outs[1][0], outs[1][1], gwr, gbr, gmr, p_drop, seed_r, True, addend=a)
+    return hn, outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2]
+
+
+@pair_layer.register_fake
+def _(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre, dinv,
+      selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r):
+    C = wf.shape[0]
+    o = h.new_empty((h.shape[0], C))
+    return (o, torch.empty_like(o), torch.empty_like(o), h.new_empty((2 * C,)), h.new_empty((2 * C,)),
+            h.new_empty((n_node, h.shape[1])), h.new_empty((n_node, h.shape[1])))
+
+
+def _pl_setup(ctx, inputs, output):
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre, dinv,
+     selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r) = inputs
+    hn, Of, Or, sf, sr, SHf, SHr = output
+    ctx.save_for_backward(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, out_ptr, out_ids, out_plan, dinv, selfw, bnode,
+                          Of, Or, sf, sr, SHf, SHr)
+    ctx.meta = (n_node, p_drop, seed_f, seed_r)
+    ctx.mark_non_differentiable(Of, Or, sf, sr, SHf, SHr)
+
+
+def _pl_bwd(ctx, g, *_unused):
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr, SHf,
+     SHr) = ctx.saved_tensors
+    n_node, p_drop, seed_f, seed_r = ctx.meta
+    g = g.contiguous()
+    C = wf.shape[0]
+    res = []
+    dOs, dSWs = [], []
+    for d, (w, b, gw, gb, gm, O, st, SH, seed) in enumerate(((wf, bf, gwf, gbf, gmf, Of, sf, SHf, seed_f),
+                                                            (wr, br, gwr, gbr, gmr, Or, sr, SHr, seed_r))):
+        dO, dpar = ops.graphnorm_bwd(O, g, st, gw, gb, gm, p_drop, seed, True)
+        dS = ops.seg_reduce(out_ptr, out_ids, n_node, dO, plan=out_plan, flip=d, src_scale=dinv[d])
+        # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
+        dW = ops.linear_bwd_weight(dO, h, row_scale=selfw[d]) + ops.linear_bwd_weight(dS, SH)
+        dSWs.append(ops.linear_bwd_input(dS, w))
+        dOs.append(dO)
+        res.append((dW, dpar[3 * C:], dpar[:C], dpar[C:2 * C], dpar[2 * C:3 * C]))
+    dh = ops.pair_conv(dOs, [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
+                       gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])])
+    return (dh,) + res[0] + res[1] + (None,) * 16
+
+
+pair_layer.register_autograd(_pl_bwd, setup_context=_pl_setup)
+
+
+def pair_layer_supported(wedges, C: int, seq_f, seq_r) -> bool:
+    """Structured wedges, equal in/out width, a width the tensor-core kernel covers, ReLU blocks (model.py:62-65)."""
+    from .graph import WedgeStruct
+    if not isinstance(wedges, WedgeStruct):
+        return False
+    convf = seq_f.modlist[0]
+    if convf.in_channels != C or convf.out_channels != C or seq_r.modlist[0].out_channels != C:
+        return False
+    if not (isinstance(seq_f.modlist[3], torch.nn.ReLU) and isinstance(seq_r.modlist[3], torch.nn.ReLU)):
+        return False
+    return ops.pair_conv_supported(C, C, 2) and ops.LINEAR_IMPL != 0
+
+
+def pair_layer_apply(x, wedges, seq_f, seq_r, training: bool):
+    cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
+    cr, gr = seq_r.modlist[0], seq_r.modlist[1]
+    p = dpf.p if (training and dpf.p > 0.0) else 0.0
+    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(2)] if p > 0.0 else [0, 0]
+    _, centre, dinv, selfw, bnode = wedges.prepared()
+    out = pair_layer(x, cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight, gr.bias,
+                     gr.mean_scale, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr, wedges.out_ids,
+                     wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked, wedges.n_node, gf.eps, p, seeds[0], seeds[1])
+    return out[0]

@@ -170,7 +170,7 @@ class WedgeStruct:
                            self.out_ids, self.in_plan, self.out_plan, blocked)
 
     def prepared(self):
-        """(cnt[N], centre[2,R], dinv[2,R], selfw[2,R]) - per-row constants of both directions."""
+        """(cnt[N], centre[2,R], dinv[2,R], selfw[2,R], bnode[2,R]) - per-row constants of both directions."""
         if self._prep is None:
             if self.E % 2 or self.R % 2:
                 raise RuntimeError("structured wedge path needs the doubled layout (even E and R)")

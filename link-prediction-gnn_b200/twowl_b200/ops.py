@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import SegArgs, check, lib
+from ._lib import ConvArgs, SegArgs, check, lib
 
 SELECT_TILE = 2048
 _launches = 0  # number of C-ABI compute calls issued (bench.py reports kernels through this)
@@ -388,7 +388,7 @@ def graphnorm_apply(x, stats, weight, bias, mean_scale, p_drop: float, seed: int
 def graphnorm_bwd(x, dout, stats, weight, bias, mean_scale, p_drop: float, seed: int, relu: bool):
     M, C = x.shape
     dx = torch.empty_like(x)
-    dparams = torch.empty(3 * C, dtype=torch.float32, device=x.device)
+    dparams = torch.empty(4 * C, dtype=torch.float32, device=x.device)
     nb = lib.twowl_graphnorm_bwd_workspace_bytes(M, C)
     ws = _ws(nb, x.device)
     with _P("graphnorm_bwd", M * C * 4 * 5):
@@ -440,15 +440,15 @@ def linear_bwd_input(dZ, W, impl: int = -1) -> torch.Tensor:
     return dX
 
 
-def linear_bwd_weight(dZ, X) -> torch.Tensor:
+def linear_bwd_weight(dZ, X, row_scale=None) -> torch.Tensor:
     M, Co = dZ.shape
     Ci = X.shape[1]
     dW = torch.empty((Co, Ci), dtype=torch.float32, device=dZ.device)
     nb = lib.twowl_linear_bwd_weight_workspace_bytes(M, Ci, Co)
     ws = _ws(nb, dZ.device)
     with _P("linear_bwd_weight", 4 * M * (Ci + Co)):
-        check(lib.twowl_linear_bwd_weight(dZ.data_ptr(), X.data_ptr(), M, Ci, Co, dW.data_ptr(), ws.data_ptr(), nb,
-                                          _stream()), "linear_bwd_weight")
+        check(lib.twowl_linear_bwd_weight_scaled(dZ.data_ptr(), _p(row_scale), X.data_ptr(), M, Ci, Co, dW.data_ptr(),
+                                                 ws.data_ptr(), nb, _stream()), "linear_bwd_weight")
     _count(2)
     return dW
 
@@ -461,11 +461,12 @@ def wedge_prepare(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr):
     centre = torch.empty((2, R), dtype=torch.int32, device=dev)
     dinv = torch.empty((2, R), dtype=torch.float32, device=dev)
     selfw = torch.empty((2, R), dtype=torch.float32, device=dev)
+    bnode = torch.empty((2, R), dtype=torch.int32, device=dev)
     check(lib.twowl_wedge_prepare(src32.data_ptr(), dst_e32.data_ptr(), E, R, N, _p(blocked), in_ptr.data_ptr(),
-                                  cnt.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(), _stream()),
-          "wedge_prepare")
+                                  cnt.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(), bnode.data_ptr(),
+                                  _stream()), "wedge_prepare")
     _count(3)
-    return cnt, centre, dinv, selfw
+    return cnt, centre, dinv, selfw, bnode
 
 
 def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
@@ -487,3 +488,41 @@ def wedge_apply_bwd(dS, dO, dst_e32, blocked, E: int, N: int, dinv, selfw, direc
               "wedge_apply_bwd")
     _count()
     return dZ
+
+
+# ------------------------------------------------------------------------------ fused tensor-core pair layer
+
+def pair_conv_supported(Kd: int, Nd: int, nsrc: int) -> bool:
+    return bool(lib.twowl_pair_conv_supported(Kd, Nd, nsrc))
+
+
+def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_scale=None, eps: float = 1e-5):
+    """out = sum_s (row_scale_s * A_s) B_s^T + sum_g coef_g * T_g[idx_g] + bias on tcgen05 (3xTF32).
+    A, W, w_kn, row_scale: sequences of length nsrc; gathers: sequence of (T, idx int32, coef).
+    Returns out, or (out, stats[2*Nd]) when stats_mean_scale is given (GraphNorm mean / inv_std of out)."""
+    nsrc = len(A)
+    M, Kd = A[0].shape
+    Nd = W[0].shape[1] if w_kn[0] else W[0].shape[0]
+    dev = A[0].device
+    _need_cuda(*A, *W)
+    out = torch.empty((M, Nd), dtype=torch.float32, device=dev)
+    a = ConvArgs(nsrc=nsrc, ngather=len(gathers), Kd=Kd, Nd=Nd, M=M, bias=_p(bias), out=out.data_ptr(), eps=float(eps))
+    keep = []
+    for s in range(nsrc):
+        x = A[s].contiguous()
+        keep.append(x)
+        a.A[s], a.W[s], a.w_kn[s] = x.data_ptr(), W[s].data_ptr(), int(w_kn[s])
+        a.row_scale[s] = _p(row_scale[s]) if row_scale is not None else None
+    for g, (T, idx, coef) in enumerate(gathers):
+        a.T[g], a.tidx[g], a.tcoef[g] = T.data_ptr(), idx.data_ptr(), coef.data_ptr()
+    stats, ws, nb = None, None, 0
+    if stats_mean_scale is not None:
+        stats = torch.empty(2 * Nd, dtype=torch.float32, device=dev)
+        nb = lib.twowl_pair_conv_workspace_bytes(M, Nd)
+        ws = _ws(nb, dev)
+        a.stats, a.mean_scale = stats.data_ptr(), stats_mean_scale.data_ptr()
+    nbytes = M * (4 * Kd * nsrc + 4 * Nd + 8 * len(gathers) + (4 * Nd + 8) * len(gathers))
+    with _P("pair_conv", nbytes):
+        check(lib.twowl_pair_conv(ctypes.byref(a), _p(ws), nb, _stream()), "pair_conv")
+    _count(1 if stats is None else 2)
+    return out if stats is None else (out, stats)

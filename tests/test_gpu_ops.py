@@ -306,3 +306,44 @@ def test_pair_init_readout_embedding(U):
     assert_close(out, ref.detach(), atol=1e-4, what="readout fwd")
     for name, g, r in (("dX", gX, X), ("dw", gw, w), ("db", gb, b), ("demb", gemb, emb)):
         assert_close(g.grad, r.grad, atol=1e-5 * max(float(r.grad.abs().max()), 1.0), what=name)
+
+
+@pytest.mark.parametrize("M,Kd,Nd,nsrc,ngather,stats", [
+    (1, 64, 64, 1, 0, False), (127, 32, 32, 1, 1, True), (128, 64, 64, 2, 2, False), (129, 64, 32, 1, 1, True),
+    (1000, 32, 64, 2, 1, False), (40001, 64, 64, 1, 1, True), (40001, 64, 64, 2, 2, False), (5000, 64, 128, 1, 2, True),
+    (300000, 64, 64, 1, 1, True),
+])
+def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
+    """The fused tensor-core kernel (3xTF32 GEMM + row scale + gathered-row epilogue + GraphNorm statistics)."""
+    from twowl_b200 import ops
+    if not ops.pair_conv_supported(Kd, Nd, nsrc):
+        pytest.skip("shape not covered by the tcgen05 kernel")
+    torch.manual_seed(M + Kd + Nd)
+    NT = 777
+    A = [torch.randn(M, Kd, dtype=torch.float64) for _ in range(nsrc)]
+    rs = [torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3) for _ in range(nsrc)]   # zeros occur (selfw = 0 rows)
+    W = [torch.randn(Kd, Nd, dtype=torch.float64) / Kd ** 0.5 for _ in range(nsrc)]          # stored [Kd, Nd]: w_kn = 1
+    T = [torch.randn(NT, Nd, dtype=torch.float64) for _ in range(ngather)]
+    idx = [torch.randint(-1, NT, (M,)) for _ in range(ngather)]
+    coef = [torch.rand(M, dtype=torch.float64) for _ in range(ngather)]
+    bias = torch.randn(Nd, dtype=torch.float64)
+    ref = bias.expand(M, Nd).clone()
+    for s in range(nsrc):
+        ref += (rs[s].unsqueeze(1) * A[s]) @ W[s]
+    for g in range(ngather):
+        ok = idx[g] >= 0
+        ref[ok] += coef[g][ok].unsqueeze(1) * T[g][idx[g][ok]]
+    c = lambda t: t.float().cuda().contiguous()
+    for w_kn in (1, 0):
+        Wd = [c(w) if w_kn else c(w.t()) for w in W]
+        ms = torch.rand(Nd) + 0.5
+        res = ops.pair_conv([c(a) for a in A], Wd, [w_kn] * nsrc, row_scale=[c(r) for r in rs],
+                            gathers=[(c(T[g]), idx[g].int().cuda(), c(coef[g])) for g in range(ngather)], bias=c(bias),
+                            stats_mean_scale=ms.cuda() if stats else None, eps=1e-5)
+        out = res[0] if stats else res
+        assert_close(out, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()), what=f"pair_conv out w_kn={w_kn}")
+        if stats:
+            mean = ref.mean(0)
+            var = ((ref - mean * ms.double()) ** 2).mean(0)
+            assert_close(res[1][:Nd], mean, rtol=1e-5, atol=1e-5, what="pair_conv mean")
+            assert_close(res[1][Nd:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what="pair_conv inv_std")
