@@ -157,7 +157,7 @@ def _gn_bwd(ctx, g, _g_stats):
     g = g.contiguous()
     dx, dparams = ops.graphnorm_bwd(x.contiguous(), g, stats, weight, bias, mean_scale, p_drop, seed, relu)
     C = x.shape[1]
-    return (dx, dparams[:C], dparams[C:2 * C], dparams[2 * C:], g if ctx.has_addend else None, None, None, None, None)
+    return (dx, dparams[:C], dparams[C:2 * C], dparams[2 * C:3 * C], g if ctx.has_addend else None, None, None, None, None)
 
 
 graphnorm_act.register_autograd(_gn_bwd, setup_context=_gn_setup)
