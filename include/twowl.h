@@ -270,6 +270,13 @@ int twowl_pair_conv_supported(int32_t Kd, int32_t Nd, int32_t nsrc);
 size_t twowl_pair_conv_workspace_bytes(int64_t M, int32_t Nd);
 int twowl_pair_conv(const twowl_conv_args* h_args, void* ws, size_t ws_bytes, void* stream);
 
+/* Weight gradients of both pair-level linear layers in one pass over the rows (tcgen05 kind::tf32, 3xTF32, MN-major
+ * operands): dWf[C,C] = (rsf * dOf)^T H, dWr[C,C] = (rsr * dOr)^T H. H is read once. C in {32, 64}. */
+int twowl_pair_dw_supported(int32_t C);
+size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C);
+int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
+                  int32_t C, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ structured wedge path ------- */
 
 /* When ei2 is the full wedge join of (pos_edge, pred_edge) minus the wedges whose source edge is blocked

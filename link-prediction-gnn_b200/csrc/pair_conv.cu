@@ -290,21 +290,37 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
           const int col = c0 + lchunk * 4;
           float4 bsum = f4_zero(), bsq = f4_zero();
           const float4 bias4 = (p.bias && col < Nd) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
+          // phase 1: every index / coefficient, phase 2: every gathered row, phase 3: math + stores. Kept apart on
+          // purpose: the streaming store is an asm with a memory clobber, loads must not queue up behind it.
+          int ix[2][8];
+          float cf[2][8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = wrow0 + i * 4 + lrow;
+            const bool ok = row < p.M && col < Nd;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              ix[g][i] = (ok && g < p.ngather) ? __ldg(p.tidx[g] + row) : -1;
+              cf[g][i] = (ok && g < p.ngather) ? __ldg(p.tcoef[g] + row) : 0.f;
+            }
+          }
+          float4 gv[2][8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              gv[g][i] = (ix[g][i] >= 0) ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rl = i * 4 + lrow;
             const int64_t row = wrow0 + rl;
             float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(Et) + rl * 128 + ((lchunk ^ (rl & 7)) << 4));
             if (row < p.M && col < Nd) {
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                if (g < p.ngather) {
-                  const int ix = __ldg(p.tidx[g] + row);
-                  if (ix >= 0) f4_fma(o, __ldg(p.tcoef[g] + row), ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix * Nd + col)));
-                }
-              }
+              f4_fma(o, cf[0][i], gv[0][i]);
+              f4_fma(o, cf[1][i], gv[1][i]);
               f4_add(o, bias4);
-              stg_stream(reinterpret_cast<float4*>(p.out + row * Nd + col), o);
+              *reinterpret_cast<float4*>(p.out + row * Nd + col) = o;
               f4_add(bsum, o);
               bsq.x = fmaf(o.x, o.x, bsq.x), bsq.y = fmaf(o.y, o.y, bsq.y), bsq.z = fmaf(o.z, o.z, bsq.z), bsq.w = fmaf(o.w, o.w, bsq.w);
             }

@@ -302,16 +302,22 @@ def _pl_bwd(ctx, g, *_unused):
     n_node, p_drop, seed_f, seed_r = ctx.meta
     g = g.contiguous()
     C = wf.shape[0]
-    res = []
-    dOs, dSWs = [], []
-    for d, (w, b, gw, gb, gm, O, st, SH, seed) in enumerate(((wf, bf, gwf, gbf, gmf, Of, sf, SHf, seed_f),
-                                                            (wr, br, gwr, gbr, gmr, Or, sr, SHr, seed_r))):
+    dOs, dSs, dpars = [], [], []
+    for d, (gw, gb, gm, O, st, seed) in enumerate(((gwf, gbf, gmf, Of, sf, seed_f), (gwr, gbr, gmr, Or, sr, seed_r))):
         dO, dpar = ops.graphnorm_bwd(O, g, st, gw, gb, gm, p_drop, seed, True)
-        dS = ops.seg_reduce(out_ptr, out_ids, n_node, dO, plan=out_plan, flip=d, src_scale=dinv[d])
-        # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
-        dW = ops.linear_bwd_weight(dO, h, row_scale=selfw[d]) + ops.linear_bwd_weight(dS, SH)
-        dSWs.append(ops.linear_bwd_input(dS, w))
         dOs.append(dO)
+        dpars.append(dpar)
+        dSs.append(ops.seg_reduce(out_ptr, out_ids, n_node, dO, plan=out_plan, flip=d, src_scale=dinv[d]))
+    # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
+    if ops.pair_dw_supported(C) and h.shape[1] == C:
+        dWs = list(ops.pair_dw(dOs[0], dOs[1], selfw[0], selfw[1], h))
+    else:
+        dWs = [ops.linear_bwd_weight(dOs[d], h, row_scale=selfw[d]) for d in range(2)]
+    res, dSWs = [], []
+    for d, (w, SH) in enumerate(((wf, SHf), (wr, SHr))):
+        dW = dWs[d] + ops.linear_bwd_weight(dSs[d], SH)
+        dSWs.append(ops.linear_bwd_input(dSs[d], w))
+        dpar = dpars[d]
         res.append((dW, dpar[3 * C:], dpar[:C], dpar[C:2 * C], dpar[2 * C:3 * C]))
     dh = ops.pair_conv(dOs, [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
                        gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])])

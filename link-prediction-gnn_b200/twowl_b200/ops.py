@@ -526,3 +526,22 @@ def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_s
         check(lib.twowl_pair_conv(ctypes.byref(a), _p(ws), nb, _stream()), "pair_conv")
     _count(1 if stats is None else 2)
     return out if stats is None else (out, stats)
+
+
+def pair_dw_supported(C: int) -> bool:
+    return bool(lib.twowl_pair_dw_supported(C))
+
+
+def pair_dw(dOf, dOr, rsf, rsr, H):
+    """(dWf, dWr) = ((rsf*dOf)^T H, (rsr*dOr)^T H) in one pass on tcgen05 (3xTF32)."""
+    _need_cuda(dOf, dOr, H)
+    M, C = H.shape
+    dWf = torch.empty((C, C), dtype=torch.float32, device=H.device)
+    dWr = torch.empty((C, C), dtype=torch.float32, device=H.device)
+    nb = lib.twowl_pair_dw_workspace_bytes(M, C)
+    ws = _ws(nb, H.device)
+    with _P("pair_dw", 12 * M * C + 8 * M):
+        check(lib.twowl_pair_dw(dOf.data_ptr(), dOr.data_ptr(), rsf.data_ptr(), rsr.data_ptr(), H.data_ptr(), M, C,
+                                dWf.data_ptr(), dWr.data_ptr(), ws.data_ptr(), nb, _stream()), "pair_dw")
+    _count(2)
+    return dWf, dWr

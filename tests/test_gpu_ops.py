@@ -347,3 +347,22 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
             var = ((ref - mean * ms.double()) ** 2).mean(0)
             assert_close(res[1][:Nd], mean, rtol=1e-5, atol=1e-5, what="pair_conv mean")
             assert_close(res[1][Nd:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what="pair_conv inv_std")
+
+
+@pytest.mark.parametrize("M,C", [(1, 64), (63, 32), (64, 64), (65, 64), (5000, 32), (70001, 64), (400000, 64)])
+def test_pair_dw_tcgen05_vs_fp64(U, M, C):
+    """[dW_f; dW_r] = [selfw_f*dO_f | selfw_r*dO_r]^T H with MN-major tcgen05 operands."""
+    from twowl_b200 import ops
+    torch.manual_seed(M + C)
+    dOf, dOr, H = (torch.randn(M, C, dtype=torch.float64) for _ in range(3))
+    rsf = torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3)
+    rsr = torch.rand(M, dtype=torch.float64)
+    ref_f = (rsf.unsqueeze(1) * dOf).t() @ H
+    ref_r = (rsr.unsqueeze(1) * dOr).t() @ H
+    c = lambda t: t.float().cuda().contiguous()
+    gf, gr = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
+    tol = 4e-6 * max(float(ref_f.abs().max()), float(ref_r.abs().max()), 1.0)
+    assert_close(gf, ref_f, rtol=1e-5, atol=tol, what="pair_dw f")
+    assert_close(gr, ref_r, rtol=1e-5, atol=tol, what="pair_dw r")
+    gf2, gr2 = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
+    assert torch.equal(gf, gf2) and torch.equal(gr, gr2)      # deterministic
