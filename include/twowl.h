@@ -219,6 +219,20 @@ int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M, int32_t C,
                         uint64_t seed, int32_t relu, float* dx, float* dparams, void* ws, size_t ws_bytes,
                         void* stream);
 
+/* Both GraphNorm branches of one pair layer in one pass (they share the output / the incoming gradient):
+ *   apply2: out = act(drop(GN_f(xf))) + act(drop(GN_r(xr)))     - the conv2s[i](x) + conv2s_r[i](x) of model.py:77
+ *   bwd2:   dxf, dxr and dparams_f[4C], dparams_r[4C] from one dout. */
+int twowl_graphnorm_apply2(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                           const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                           const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                           int32_t relu, float* out, void* stream);
+size_t twowl_graphnorm_bwd2_workspace_bytes(int64_t M, int32_t C);
+int twowl_graphnorm_bwd2(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C,
+                         const float* stats_f, const float* stats_r, const float* wf, const float* bf, const float* mf,
+                         const float* wr, const float* br, const float* mr, float p_drop, uint64_t seed_f,
+                         uint64_t seed_r, int32_t relu, float* dxf, float* dxr, float* dparams_f, float* dparams_r,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* out[c] = sum_m x[m,c] (bias gradients). Deterministic two-level sum. */
 size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C);
 int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream);

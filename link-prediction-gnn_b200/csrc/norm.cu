@@ -205,15 +205,15 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
 
 // sums[0:C] = A = sum g_y, sums[C:2C] = B = sum g_y*n, sums[2C:3C] = (alpha/M) * sum g_o   (fp32, for pass 2)
 // dparams[0:C] = dweight = B, [C:2C] = dbias = A, [2C:3C] = dmean_scale = -mean * sum g_o, [3C:4C] = colsum(dx)
-__global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int64_t M, int C, const float* __restrict__ stats,
-                               const float* __restrict__ weight, const float* __restrict__ mean_scale, float* __restrict__ sums,
-                               float* __restrict__ dparams) {
+__global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int nv, int voff, int64_t M, int C,
+                               const float* __restrict__ stats, const float* __restrict__ weight,
+                               const float* __restrict__ mean_scale, float* __restrict__ sums, float* __restrict__ dparams) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double A = 0, B = 0;
   for (int b = 0; b < nparts; ++b) {
-    A += part[((size_t)b * 2 + 0) * C + c];
-    B += part[((size_t)b * 2 + 1) * C + c];
+    A += part[((size_t)b * nv + voff + 0) * C + c];
+    B += part[((size_t)b * nv + voff + 1) * C + c];
   }
   const double mean = stats[c], inv = stats[C + c], w = weight[c], a = mean_scale[c];
   // sum_rows n = inv * M * mean * (1 - a);  sum g_o = inv*w*(A - (B/M) * sum n)
@@ -252,6 +252,114 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_dx(const float* __restr
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = cc.sc[i] * (gy[i] - n[i] * bm[i]) - corr[i];
     o4[e] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------- two branches sharing dout ------
+// out = act(drop(GN_f(xf))) + act(drop(GN_r(xr)))  - the conv2s[i](x) + conv2s_r[i](x) sum of model.py:77 in one pass
+__global__ void __launch_bounds__(kNormThreads) k_gn_apply2(const float* __restrict__ xf, const float* __restrict__ xr, int64_t M,
+                                                            int C, const float* __restrict__ stf, const float* __restrict__ str_,
+                                                            const float* __restrict__ wf, const float* __restrict__ bf,
+                                                            const float* __restrict__ mf, const float* __restrict__ wr,
+                                                            const float* __restrict__ br, const float* __restrict__ mr,
+                                                            uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                            int relu, float* __restrict__ out) {
+  const RowMap rm(C);
+  if (rm.slot < 0) return;
+  const int c0 = rm.c4 * 4;
+  const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
+  const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+  const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+    const int64_t e = r * rm.cv + rm.c4;
+    const float4 a = ldg_stream(xf4 + e), b = ldg_stream(xr4 + e);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float yf = fmaf(cf.sc[i], av[i], cf.of[i]), yr = fmaf(cr.sc[i], bv[i], cr.of[i]);
+      if (thresh) {
+        yf *= drop_scale(seed_f, (uint64_t)e * 4 + i, thresh, inv_keep);
+        yr *= drop_scale(seed_r, (uint64_t)e * 4 + i, thresh, inv_keep);
+      }
+      if (relu) yf = fmaxf(yf, 0.f), yr = fmaxf(yr, 0.f);
+      o[i] = yf + yr;
+    }
+    o4[e] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_partial(const float* __restrict__ xf, const float* __restrict__ xr,
+                                                                  const float* __restrict__ dout, int64_t M, int C,
+                                                                  const float* __restrict__ stf, const float* __restrict__ str_,
+                                                                  const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                  const float* __restrict__ mf, const float* __restrict__ wr,
+                                                                  const float* __restrict__ br, const float* __restrict__ mr,
+                                                                  uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                                  int relu, double* __restrict__ part) {
+  const RowMap rm(C);
+  float4 v[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+  if (rm.slot >= 0) {
+    const int c0 = rm.c4 * 4;
+    const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
+    const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+    const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dout);
+    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+      const int64_t e = r * rm.cv + rm.c4;
+      const float4 d = ldg_cached(d4 + e);
+      float gy[4], n[4];
+      gn_gy(ldg_cached(xf4 + e), d, cf.sc, cf.of, cf.nm, cf.ni, thresh, inv_keep, seed_f, (uint64_t)e, relu, gy, n);
+      v[0].x += gy[0], v[0].y += gy[1], v[0].z += gy[2], v[0].w += gy[3];
+      v[1].x = fmaf(gy[0], n[0], v[1].x), v[1].y = fmaf(gy[1], n[1], v[1].y);
+      v[1].z = fmaf(gy[2], n[2], v[1].z), v[1].w = fmaf(gy[3], n[3], v[1].w);
+      gn_gy(ldg_cached(xr4 + e), d, cr.sc, cr.of, cr.nm, cr.ni, thresh, inv_keep, seed_r, (uint64_t)e, relu, gy, n);
+      v[2].x += gy[0], v[2].y += gy[1], v[2].z += gy[2], v[2].w += gy[3];
+      v[3].x = fmaf(gy[0], n[0], v[3].x), v[3].y = fmaf(gy[1], n[1], v[3].y);
+      v[3].z = fmaf(gy[2], n[2], v[3].z), v[3].w = fmaf(gy[3], n[3], v[3].w);
+    }
+  }
+  cta_col_reduce<4>(rm, v, part, C);
+}
+
+__global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx(const float* __restrict__ xf, const float* __restrict__ xr,
+                                                             const float* __restrict__ dout, int64_t M, int C,
+                                                             const float* __restrict__ stf, const float* __restrict__ str_,
+                                                             const float* __restrict__ wf, const float* __restrict__ bf,
+                                                             const float* __restrict__ mf, const float* __restrict__ wr,
+                                                             const float* __restrict__ br, const float* __restrict__ mr,
+                                                             uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                             int relu, const float* __restrict__ sums_f,
+                                                             const float* __restrict__ sums_r, float* __restrict__ dxf,
+                                                             float* __restrict__ dxr) {
+  const RowMap rm(C);
+  if (rm.slot < 0) return;
+  const int c0 = rm.c4 * 4;
+  const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
+  float bmf[4], cof[4], bmr[4], cor[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bmf[i] = sums_f[C + c0 + i], cof[i] = sums_f[2 * C + c0 + i];
+    bmr[i] = sums_r[C + c0 + i], cor[i] = sums_r[2 * C + c0 + i];
+  }
+  const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+  const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+  const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dout);
+  float4* __restrict__ of4 = reinterpret_cast<float4*>(dxf);
+  float4* __restrict__ or4 = reinterpret_cast<float4*>(dxr);
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+    const int64_t e = r * rm.cv + rm.c4;
+    const float4 d = ldg_stream(d4 + e), a = ldg_stream(xf4 + e), b = ldg_stream(xr4 + e);
+    float gy[4], n[4], o[4];
+    gn_gy(a, d, cf.sc, cf.of, cf.nm, cf.ni, thresh, inv_keep, seed_f, (uint64_t)e, relu, gy, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = cf.sc[i] * (gy[i] - n[i] * bmf[i]) - cof[i];
+    of4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    gn_gy(b, d, cr.sc, cr.of, cr.nm, cr.ni, thresh, inv_keep, seed_r, (uint64_t)e, relu, gy, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = cr.sc[i] * (gy[i] - n[i] * bmr[i]) - cor[i];
+    or4[e] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -348,7 +456,7 @@ extern "C" int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M,
   const int grid = norm_grid(M, C);
   k_gn_bwd_partial<<<grid, kNormThreads, red_smem(C, 2), s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep,
                                                               seed, relu, part);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, M, C, stats, weight, mean_scale, sums, dparams);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 2, 0, M, C, stats, weight, mean_scale, sums, dparams);
   k_gn_bwd_dx<<<grid, kNormThreads, 0, s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep, seed, relu, sums,
                                             dx);
   TW_LAUNCH_CHECK();
@@ -372,6 +480,55 @@ extern "C" int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, vo
   const int grid = norm_grid(M, C);
   k_colsum_partial<<<grid, kNormThreads, red_smem(C, 1), s>>>(x, M, C, (double*)ws);
   k_colsum_final<<<(int)cdiv(C, 128), 128, 0, s>>>((const double*)ws, grid, C, out);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_graphnorm_apply2(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                      const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                      const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                      int32_t relu, float* out, void* stream) {
+  if (int rc = check_mc("graphnorm_apply2", M, C)) return rc;
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(out), "graphnorm_apply2: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_apply2: dropout p=%f outside [0,1)", p_drop);
+  if (M == 0) return 0;
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  k_gn_apply2<<<norm_grid(M, C), kNormThreads, 0, (cudaStream_t)stream>>>(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr,
+                                                                         thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, out);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_graphnorm_bwd2_workspace_bytes(int64_t M, int32_t C) {
+  (void)M;
+  return align_up((size_t)kNormMaxCtas * 4 * (size_t)C * sizeof(double)) + 2 * align_up(3 * (size_t)C * sizeof(float));
+}
+
+extern "C" int twowl_graphnorm_bwd2(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C,
+                                    const float* stats_f, const float* stats_r, const float* wf, const float* bf, const float* mf,
+                                    const float* wr, const float* br, const float* mr, float p_drop, uint64_t seed_f,
+                                    uint64_t seed_r, int32_t relu, float* dxf, float* dxr, float* dparams_f, float* dparams_r,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("graphnorm_bwd2", M, C)) return rc;
+  TW_CHECK_ARG(M > 0, "graphnorm_bwd2: needs at least one row");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(dout) && aligned16(dxf) && aligned16(dxr),
+               "graphnorm_bwd2: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_bwd2: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_graphnorm_bwd2_workspace_bytes(M, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver c(ws);
+  double* part = c.take<double>((size_t)kNormMaxCtas * 4 * C);
+  float* sums_f = c.take<float>(3 * (size_t)C);
+  float* sums_r = c.take<float>(3 * (size_t)C);
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  const int grid = norm_grid(M, C);
+  k_gn_bwd2_partial<<<grid, kNormThreads, red_smem(C, 4), s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
+                                                               inv_keep, seed_f, seed_r, relu, part);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 4, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 4, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_gn_bwd2_dx<<<grid, kNormThreads, 0, s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep, seed_f,
+                                             seed_r, relu, sums_f, sums_r, dxf, dxr);
   TW_LAUNCH_CHECK();
   return 0;
 }

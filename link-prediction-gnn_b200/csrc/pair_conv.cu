@@ -10,20 +10,21 @@
 //   plain linear             :  nsrc = 1, no scale, no gather
 //
 // One persistent CTA per SM, 13 warps, warp-specialised:
-//   warps 0-7  producers : coalesced 128-bit global loads of a 128-row tile (two register sets = two tiles in
-//                          flight), row scale, 3xTF32 hi/lo split, swizzled st.shared into a 2-stage ring
+//   warps 0-3  producers : coalesced 128-bit global loads of a 128-row tile (the next tile's loads are in flight
+//                          while the current one is staged), row scale, 3xTF32 hi/lo split, swizzled st.shared into a 2-stage ring
 //                          (UMMA canonical K-major SWIZZLE_128B), fence.proxy.async, mbarrier arrive
 //   warp  12   MMA issuer: one lane issues 3 x Kd/8 tcgen05.mma kind::tf32 per source into one of two TMEM
 //                          accumulators; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 8-11 epilogue  : tcgen05.ld -> per-warp smem transpose -> coalesced 128-byte row segments: gather terms,
+//   warps 4-11 epilogue  : (4 TMEM lane quarters x 2 column halves) gathered rows requested before the accumulator
+//                          is waited for; tcgen05.ld -> per-warp smem transpose -> coalesced 128-byte row segments: gather terms,
 //                          bias, store, column sums (fp32 per tile -> double per CTA, fixed order)
 // HBM-bound by design: 4*M*(nsrc*Kd + Nd) bytes + gathers for 6*M*Kd*Nd*nsrc tensor flop.
 #include "common.cuh"
 
 namespace twowl {
 
-constexpr int kPcProducerWarps = 8;
-constexpr int kPcEpilogueWarps = 4;
+constexpr int kPcProducerWarps = 4;
+constexpr int kPcEpilogueWarps = 8;
 constexpr int kPcThreads = (kPcProducerWarps + kPcEpilogueWarps + 1) * 32;  // 416
 constexpr int kPcTileM = 128;
 constexpr int kPcStages = 2;
@@ -103,7 +104,7 @@ __device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo
   lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
 }
 
-template <int KD>
+template <int KD, int NG>
 __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p) {
   constexpr int KB = KD / 32;
   constexpr int K4 = KD / 4;
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
       *reinterpret_cast<float4*>(Blo + off) = lo;
     }
   }
-  for (int i = tid; i < kPcEpilogueWarps * 2 * Nd; i += kPcThreads) red[i] = 0.0;
+  if (p.stats_part)
+    for (int i = tid; i < kPcEpilogueWarps * 2 * Nd; i += kPcThreads) red[i] = 0.0;
   pc_proxy_fence();
   pc_fence_before();
   __syncthreads();
@@ -176,11 +178,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
 
   if (warp < kPcProducerWarps) {
     // ===================================================== producers
-    const int ptid = tid;  // 0..255
-    float4 regs[2][kChunks];
+    const int ptid = tid;  // 0..127
+    float4 regs[kChunks];
     const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t nit = my_tiles * p.nsrc;  // stage uses, in order (tile, src)
-    auto issue = [&](int64_t it, float4 (&r)[kChunks]) {
+    auto issue = [&](int64_t it) {
       const int64_t tile = blockIdx.x + (it / p.nsrc) * gridDim.x;
       const int s = (int)(it % p.nsrc);
       const float4* __restrict__ A4 = reinterpret_cast<const float4*>(s == 0 ? p.A[0] : p.A[1]) + tile * kPcTileM * K4;
@@ -188,10 +190,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
 #pragma unroll
       for (int j = 0; j < kChunks; ++j) {
         const int idx = j * (kPcProducerWarps * 32) + ptid;
-        r[j] = (idx / K4 < rows_left) ? ldg_stream(A4 + idx) : f4_zero();
+        regs[j] = (idx / K4 < rows_left) ? ldg_stream(A4 + idx) : f4_zero();
       }
     };
-    auto stage = [&](int64_t it, float4 (&r)[kChunks]) {
+    auto stage = [&](int64_t it) {
       const int64_t tile = blockIdx.x + (it / p.nsrc) * gridDim.x;
       const int s = (int)(it % p.nsrc);
       const int st = (int)(it % kPcStages);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
       for (int j = 0; j < kChunks; ++j) {
         const int idx = j * (kPcProducerWarps * 32) + ptid;
         const int rr = idx / K4, k4 = idx % K4;
-        float4 v = r[j];
+        float4 v = regs[j];
         if (rsv) {
           const float sc = (row0 + rr < p.M) ? __ldg(rsv + row0 + rr) : 0.f;
           v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
@@ -219,12 +221,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
       pc_proxy_fence();
       pc_mbar_arrive(&full[st]);
     };
-    if (nit > 0) issue(0, regs[0]);
-    for (int64_t it = 0; it < nit; it += 2) {
-      if (it + 1 < nit) issue(it + 1, regs[1]);
-      stage(it, regs[0]);
-      if (it + 2 < nit) issue(it + 2, regs[0]);
-      if (it + 1 < nit) stage(it + 1, regs[1]);
+    // the loads of use it+1 are in flight while use it is staged and while the wait for its smem slot lasts
+    if (nit > 0) issue(0);
+    for (int64_t it = 0; it < nit; ++it) {
+      stage(it);
+      if (it + 1 < nit) issue(it + 1);
     }
   } else if (warp == 12) {
     // ===================================================== MMA issuer
@@ -266,87 +267,106 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue (warps 8..11 <-> TMEM lanes 0..127)
+    // ===================================================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves
     const int ew = warp - kPcProducerWarps;
-    float* Et = reinterpret_cast<float*>(Es + ew * 4096);
+    const int quarter = ew & 3, half = ew >> 2;
+    uint8_t* Et = Es + ew * 4096;
     const int lrow = lane >> 3, lchunk = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 bytes per pass
+    constexpr int NGA = NG > 0 ? NG : 1;
+    int ix[NGA][8], ixn[NGA][8];
+    float cf[NGA][8], cfn[NGA][8];
+    auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = tile_ * kPcTileM + quarter * 32 + i * 4 + lrow;
+#pragma unroll
+        for (int g = 0; g < NGA; ++g) {
+          const bool ok = g < NG && row < p.M;
+          ixx[g][i] = ok ? __ldg(p.tidx[g] + row) : -1;
+          cff[g][i] = ok ? __ldg(p.tcoef[g] + row) : 0.f;
+        }
+      }
+    };
+    if (NG > 0 && blockIdx.x < ntiles) load_idx(blockIdx.x, ix, cf);
     int64_t ti = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int a = (int)(ti & 1);
-      pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
-      pc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1)) + ((uint32_t)(ew * 32) << 16);
-      const int64_t wrow0 = tile * kPcTileM + ew * 32;
-      for (int c0 = 0; c0 < Nd; c0 += 32) {
-        {
-          uint32_t v[32];
-          pc_tmem_ld32(taddr + c0, v);
-          // transpose through smem: lane = row; 16-byte chunk q of row `lane` goes to chunk q ^ (lane & 7)
+      const uint32_t taddr = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
+      const int64_t wrow0 = tile * kPcTileM + quarter * 32;
+      bool waited = false;
+      for (int c0 = half * 32; c0 < Nd; c0 += 64) {
+        const int col = c0 + lchunk * 4;
+        // gathered rows first: they do not depend on the accumulator, so their latency hides behind the wait for it
+        float4 gv[NGA][8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Et) + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          __syncwarp();
-          const int col = c0 + lchunk * 4;
-          float4 bsum = f4_zero(), bsq = f4_zero();
-          const float4 bias4 = (p.bias && col < Nd) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
-          // phase 1: every index / coefficient, phase 2: every gathered row, phase 3: math + stores. Kept apart on
-          // purpose: the streaming store is an asm with a memory clobber, loads must not queue up behind it.
-          int ix[2][8];
-          float cf[2][8];
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t row = wrow0 + i * 4 + lrow;
-            const bool ok = row < p.M && col < Nd;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              ix[g][i] = (ok && g < p.ngather) ? __ldg(p.tidx[g] + row) : -1;
-              cf[g][i] = (ok && g < p.ngather) ? __ldg(p.tcoef[g] + row) : 0.f;
-            }
-          }
-          float4 gv[2][8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-              gv[g][i] = (ix[g][i] >= 0) ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + lrow;
-            const int64_t row = wrow0 + rl;
-            float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(Et) + rl * 128 + ((lchunk ^ (rl & 7)) << 4));
-            if (row < p.M && col < Nd) {
-              f4_fma(o, cf[0][i], gv[0][i]);
-              f4_fma(o, cf[1][i], gv[1][i]);
-              f4_add(o, bias4);
-              *reinterpret_cast<float4*>(p.out + row * Nd + col) = o;
-              f4_add(bsum, o);
-              bsq.x = fmaf(o.x, o.x, bsq.x), bsq.y = fmaf(o.y, o.y, bsq.y), bsq.z = fmaf(o.z, o.z, bsq.z), bsq.w = fmaf(o.w, o.w, bsq.w);
-            }
-          }
-          if (p.stats_part) {
-            // lanes with the same chunk (lane & 7) hold partial sums of the same 4 columns: fixed-order xor tree,
-            // then one lane per chunk adds the 32-row partial to this warp's double accumulators in smem
-            float ps[8] = {bsum.x, bsum.y, bsum.z, bsum.w, bsq.x, bsq.y, bsq.z, bsq.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);
-              ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16);
-            }
-            if (lrow == 0 && col < Nd) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                red[(ew * 2 + 0) * Nd + col + e] += (double)ps[e];
-                red[(ew * 2 + 1) * Nd + col + e] += (double)ps[4 + e];
-              }
-            }
-          }
-          __syncwarp();
+          for (int g = 0; g < NGA; ++g)
+            gv[g][i] = (NG > g && ix[g][i] >= 0 && col < Nd)
+                           ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
         }
+        if (!waited) {
+          // next tile's indices / coefficients (NG <= 1 only: register budget) - one more load latency off the chain
+          if (NG == 1 && tile + gridDim.x < ntiles) load_idx(tile + gridDim.x, ixn, cfn);
+          pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
+          pc_fence_after();
+          waited = true;
+        }
+        uint32_t v[32];
+        pc_tmem_ld32(taddr + c0, v);
+        // transpose through smem: lane = row; 16-byte chunk q of row `lane` goes to chunk q ^ (lane & 7)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(Et + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        __syncwarp();
+        float4 bsum = f4_zero(), bsq = f4_zero();
+        const float4 bias4 = (p.bias && col < Nd) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + lrow;
+          const int64_t row = wrow0 + rl;
+          float4 o = *reinterpret_cast<const float4*>(Et + rl * 128 + ((lchunk ^ (rl & 7)) << 4));
+          if (row < p.M && col < Nd) {
+#pragma unroll
+            for (int g = 0; g < NGA; ++g)
+              if (NG > g) f4_fma(o, cf[g][i], gv[g][i]);
+            f4_add(o, bias4);
+            *reinterpret_cast<float4*>(p.out + row * Nd + col) = o;
+            f4_add(bsum, o);
+            bsq.x = fmaf(o.x, o.x, bsq.x), bsq.y = fmaf(o.y, o.y, bsq.y), bsq.z = fmaf(o.z, o.z, bsq.z), bsq.w = fmaf(o.w, o.w, bsq.w);
+          }
+        }
+        if (p.stats_part) {
+          // lanes with the same chunk (lane & 7) hold partial sums of the same 4 columns: fixed-order xor tree,
+          // then one lane per chunk adds the 32-row partial to this warp's double accumulators in smem
+          float ps[8] = {bsum.x, bsum.y, bsum.z, bsum.w, bsq.x, bsq.y, bsq.z, bsq.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);
+            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16);
+          }
+          if (lrow == 0 && col < Nd) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              red[(ew * 2 + 0) * Nd + col + e] += (double)ps[e];
+              red[(ew * 2 + 1) * Nd + col + e] += (double)ps[4 + e];
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (!waited) {  // this warp has no column block (Nd <= 32 and half == 1): still take part in the handshake
+        pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
+        pc_fence_after();
       }
       pc_fence_before();
       pc_mbar_arrive(&tempty[a]);
+      if (NG == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ix[0][i] = ixn[0][i], cf[0][i] = cfn[0][i];
+      } else if (NG == 2 && tile + gridDim.x < ntiles) {
+        load_idx(tile + gridDim.x, ix, cf);
+      }
     }
   }
   pc_fence_before();
@@ -380,25 +400,30 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
   stats[C + c] = (float)(1.0 / sqrt(var + (1.0 - a) * (1.0 - a) * mean * mean + (double)eps));
 }
 
-static size_t pc_smem_bytes(int Kd, int Nd, int nsrc) {
+static size_t pc_smem_bytes(int Kd, int Nd, int nsrc, bool with_stats = true) {
   return (size_t)nsrc * 2 * Kd * Nd * 4 + (size_t)kPcStages * 2 * kPcTileM * Kd * 4 + kPcEpilogueWarps * 4096 + 10 * 8 +
-         (size_t)kPcEpilogueWarps * 2 * Nd * 8 + 1024;
+         (with_stats ? (size_t)kPcEpilogueWarps * 2 * Nd * 8 : 0) + 1024;
 }
 static bool pc_supported(int Kd, int Nd, int nsrc) {
-  return (Kd == 32 || Kd == 64) && Nd >= 16 && Nd <= 256 && (Nd % 16) == 0 && 2 * Nd <= 512 && pc_smem_bytes(Kd, Nd, nsrc) <= 227 * 1024;
+  return (Kd == 32 || Kd == 64) && Nd >= 16 && Nd <= 256 && (Nd % 16) == 0 && 2 * Nd <= 512 && pc_smem_bytes(Kd, Nd, nsrc, nsrc == 1) <= 227 * 1024;
 }
 static int pc_grid(int64_t M) {
   const int64_t ntiles = cdiv(M, kPcTileM);
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 
-template <int KD>
+template <int KD, int NG>
 static int pc_launch(const ConvParams& p, cudaStream_t s) {
-  const size_t smem = pc_smem_bytes(KD, p.Nd, p.nsrc);
-  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_conv<KD><<<pc_grid(p.M), kPcThreads, smem, s>>>(p);
+  const size_t smem = pc_smem_bytes(KD, p.Nd, p.nsrc, p.stats_part != nullptr);
+  TW_CHECK_ARG(smem <= 227 * 1024, "pair_conv: %zu bytes of shared memory needed (statistics only with one source)", smem);
+  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<KD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pair_conv<KD, NG><<<pc_grid(p.M), kPcThreads, smem, s>>>(p);
   TW_LAUNCH_CHECK();
   return 0;
+}
+template <int KD>
+static int pc_launch_ng(const ConvParams& p, cudaStream_t s) {
+  return p.ngather == 0 ? pc_launch<KD, 0>(p, s) : p.ngather == 1 ? pc_launch<KD, 1>(p, s) : pc_launch<KD, 2>(p, s);
 }
 
 }  // namespace twowl
@@ -440,7 +465,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     p.stats_part = (double*)ws;
   }
   if (a->M == 0) return 0;
-  int rc = (a->Kd == 32) ? pc_launch<32>(p, s) : pc_launch<64>(p, s);
+  int rc = (a->Kd == 32) ? pc_launch_ng<32>(p, s) : pc_launch_ng<64>(p, s);
   if (rc) return rc;
   if (want_stats) {
     k_pc_stats_final<<<(int)cdiv(a->Nd, 128), 128, 0, s>>>(p.stats_part, pc_grid(a->M), a->M, a->Nd, a->mean_scale, a->eps, a->stats);

@@ -272,8 +272,8 @@ def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf:
         O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
                               stats_mean_scale=gm, eps=eps)
         outs.append((O, st, SH))
-    a = ops.graphnorm_apply(outs[0][0], outs[0][1], gwf, gbf, gmf, p_drop, seed_f, True)
-    hn = ops.graphnorm_apply(outs[1][0], outs[1][1], gwr, gbr, gmr, p_drop, seed_r, True, addend=a)
+    hn = ops.graphnorm_apply2(outs[0][0], outs[1][0], outs[0][1], outs[1][1], (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f,
+                              seed_r, True)
     return hn, outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2]
 
 
@@ -302,12 +302,9 @@ def _pl_bwd(ctx, g, *_unused):
     n_node, p_drop, seed_f, seed_r = ctx.meta
     g = g.contiguous()
     C = wf.shape[0]
-    dOs, dSs, dpars = [], [], []
-    for d, (gw, gb, gm, O, st, seed) in enumerate(((gwf, gbf, gmf, Of, sf, seed_f), (gwr, gbr, gmr, Or, sr, seed_r))):
-        dO, dpar = ops.graphnorm_bwd(O, g, st, gw, gb, gm, p_drop, seed, True)
-        dOs.append(dO)
-        dpars.append(dpar)
-        dSs.append(ops.seg_reduce(out_ptr, out_ids, n_node, dO, plan=out_plan, flip=d, src_scale=dinv[d]))
+    dOf, dOr, dpf, dpr = ops.graphnorm_bwd2(Of, Or, g, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r, True)
+    dOs, dpars = [dOf, dOr], [dpf, dpr]
+    dSs = [ops.seg_reduce(out_ptr, out_ids, n_node, dOs[d], plan=out_plan, flip=d, src_scale=dinv[d]) for d in range(2)]
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
     if ops.pair_dw_supported(C) and h.shape[1] == C:
         dWs = list(ops.pair_dw(dOs[0], dOs[1], selfw[0], selfw[1], h))

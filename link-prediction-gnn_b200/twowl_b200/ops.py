@@ -545,3 +545,33 @@ def pair_dw(dOf, dOr, rsf, rsr, H):
                                 dWf.data_ptr(), dWr.data_ptr(), ws.data_ptr(), nb, _stream()), "pair_dw")
     _count(2)
     return dWf, dWr
+
+
+def graphnorm_apply2(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool):
+    """pf / pr = (weight, bias, mean_scale) of the two GraphNorms."""
+    M, C = xf.shape
+    out = torch.empty_like(xf)
+    with _P("graphnorm_apply2", M * C * 4 * 3):
+        check(lib.twowl_graphnorm_apply2(xf.data_ptr(), xr.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                         pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(),
+                                         pr[2].data_ptr(), float(p_drop), int(seed_f), int(seed_r), int(relu), out.data_ptr(),
+                                         _stream()), "graphnorm_apply2")
+    _count()
+    return out
+
+
+def graphnorm_bwd2(xf, xr, dout, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool):
+    M, C = xf.shape
+    dxf, dxr = torch.empty_like(xf), torch.empty_like(xr)
+    dpf = torch.empty(4 * C, dtype=torch.float32, device=xf.device)
+    dpr = torch.empty(4 * C, dtype=torch.float32, device=xf.device)
+    nb = lib.twowl_graphnorm_bwd2_workspace_bytes(M, C)
+    ws = _ws(nb, xf.device)
+    with _P("graphnorm_bwd2", M * C * 4 * 8):
+        check(lib.twowl_graphnorm_bwd2(xf.data_ptr(), xr.data_ptr(), dout.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(),
+                                       pf[0].data_ptr(), pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(),
+                                       pr[2].data_ptr(), float(p_drop), int(seed_f), int(seed_r), int(relu), dxf.data_ptr(),
+                                       dxr.data_ptr(), dpf.data_ptr(), dpr.data_ptr(), ws.data_ptr(), nb, _stream()),
+              "graphnorm_bwd2")
+    _count(4)
+    return dxf, dxr, dpf, dpr
