@@ -4,8 +4,9 @@
 //
 // (reference: autograd of GCNConv.lin at TwoWL/model/model.py:37 for conv2s[i] and conv2s_r[i], which share
 // their input H - model.py:77). The reduction runs over M = rows of the pair table, so both operands are used
-// in their natural row-major form as MN-MAJOR UMMA operands (SWIZZLE_128B): a 64-row tile of dO_f/dO_r is the
-// A operand [128 x 64k], the same rows of H are the B operand [C x 64k]; tcgen05.mma kind::tf32, 3xTF32 split.
+// in their natural row-major form as MN-MAJOR UMMA operands (SWIZZLE_128B_BASE32B, the one layout a transposed tf32
+// operand may use; a 16-byte chunk of a row is stored as loaded): a 64-row tile of dO_f/dO_r is the A operand [128 x 64k],
+// the same rows of H are the B operand [C x 64k]; tcgen05.mma kind::tf32, 3xTF32 split.
 // H is read once for both directions: 3 reads of [M,C] in total.
 //
 // One persistent warp-specialised CTA per SM (same roles as pair_conv.cu). Accuracy of the long reduction: the
@@ -32,10 +33,24 @@ struct DwParams {
 };
 
 __device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// MN-major SWIZZLE_128B: 32-float (128 B) slabs `lbo` bytes apart along M/N, 8-row atoms 1024 B apart along K
-__device__ __forceinline__ uint64_t dw_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)64 << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+// MN-major tf32 operands: on sm_100a the tensor core accepts ONLY layout type 1 (SWIZZLE_128B_BASE32B) for a transposed
+// tf32 operand - every other layout type makes tcgen05.mma write zeros (measured with tools/mma_probe.cu). The layout,
+// as the hardware reads it (same probe): element (mn, k) of an operand lives at byte
+//   (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + ((((mn % 32) / 8) ^ (k % 4)) * 32) + (mn % 8) * 4
+// i.e. 512-byte atoms of 4 k-rows x 32 mn-elements whose 32-byte units are XOR-swizzled by the k-row (Swizzle<2,5,2>).
+// A 16-byte chunk of a row-major global row is stored as loaded; 8 consecutive chunks of one row fill one 128-byte line,
+// so the staging stores of a quarter-warp are bank-conflict free.
+constexpr uint32_t kDwSbo = 512u;                                   // next group of 4 k-rows
+constexpr uint32_t kDwLbo = (kDwTileK / 4) * kDwSbo;                // next group of 32 mn-elements (8 KB)
+constexpr uint32_t kDwKStep = 2u * kDwSbo;                          // one tf32 MMA consumes 8 k-rows
+__device__ __forceinline__ uint64_t dw_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((kDwLbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((kDwSbo >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of the 16-byte chunk cc (mn elements 4cc..4cc+3) of k-row rr inside one operand buffer
+__device__ __forceinline__ uint32_t dw_off(int rr, int cc) {
+  return (uint32_t)(cc >> 3) * kDwLbo + (uint32_t)(rr >> 2) * kDwSbo + (uint32_t)(rr & 3) * 128u +
+         (uint32_t)((((cc & 7) >> 1) ^ (rr & 3)) << 5) + (uint32_t)((cc & 1) << 4);
 }
 __device__ __forceinline__ void dw_mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dw_smem_u32(bar)), "r"(count));
@@ -77,7 +92,6 @@ __device__ __forceinline__ void dw_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t dw_sw128(int r, int c) { return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4)); }
 __device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo) {
   hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
   hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -86,16 +100,14 @@ __device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo
   lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
 }
 
-// C = width of dO_f, dO_r and H (32 or 64). Shared-memory slabs are [kDwTileK rows][128 B], swizzled:
-//   A stage: 4 slabs hi + 4 slabs lo  (M = 128 = [f cols | r cols | zero padding when C = 32])
-//   B stage: C/32 slabs hi + C/32 slabs lo
+// C = width of dO_f, dO_r and H (32 or 64).
+//   A stage: 4 groups of 32 M-elements, hi then lo  (M = 128 = [f cols | r cols | zero padding when C = 32])
+//   B stage: C/32 groups hi + C/32 lo
 template <int C>
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
-  constexpr int SL = C / 32;                       // slabs per source
   constexpr int C4 = C / 4;                        // 16-byte chunks per row
-  constexpr uint32_t kSlab = kDwTileK * 128u;      // 8 KB
-  constexpr uint32_t kAHalf = 4u * kSlab;          // hi (or lo) part of the A stage
-  constexpr uint32_t kBHalf = (uint32_t)SL * kSlab;
+  constexpr uint32_t kAHalf = 4u * kDwLbo;         // hi (or lo) part of the A stage: 128 M elements = 4 groups
+  constexpr uint32_t kBHalf = (uint32_t)(C / 32) * kDwLbo;
   constexpr uint32_t kStage = 2u * kAHalf + 2u * kBHalf;
   constexpr int kChunksSrc = kDwTileK * C4 / (kDwProducerWarps * 32);  // chunks per producer thread per source
   extern __shared__ uint8_t dw_smem_raw[];
@@ -127,11 +139,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero the padding slabs of A (C = 32 only): written once, never touched by the producers
-  if (SL == 1) {
+  if (2 * C < 128) {
     for (int st = 0; st < kDwStages; ++st)
       for (int half = 0; half < 2; ++half) {
-        float4* z = reinterpret_cast<float4*>(smem + st * kStage + half * kAHalf + 2 * kSlab);
-        for (int i = tid; i < (int)(2 * kSlab / 16); i += kDwThreads) z[i] = f4_zero();
+        float4* z = reinterpret_cast<float4*>(smem + st * kStage + half * kAHalf + (2 * C / 32) * kDwLbo);
+        for (int i = tid; i < (int)((4 - 2 * C / 32) * kDwLbo / 16); i += kDwThreads) z[i] = f4_zero();
       }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
         const bool ok = row0 + rr < p.M;
         const float scf = ok ? __ldg(p.rsf + row0 + rr) : 0.f;
         const float scr = ok ? __ldg(p.rsr + row0 + rr) : 0.f;
-        const uint32_t off = (uint32_t)(c4 >> 3) * kSlab + dw_sw128(rr, c4 & 7);
+        const uint32_t off = dw_off(rr, c4), off_r = dw_off(rr, c4 + C4);
         float4 v = r[0][j], hi, lo;
         v.x *= scf, v.y *= scf, v.z *= scf, v.w *= scf;
         dw_split(v, hi, lo);
@@ -183,8 +195,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
         v = r[1][j];
         v.x *= scr, v.y *= scr, v.z *= scr, v.w *= scr;
         dw_split(v, hi, lo);
-        *reinterpret_cast<float4*>(Ahi + SL * kSlab + off) = hi;
-        *reinterpret_cast<float4*>(Alo + SL * kSlab + off) = lo;
+        *reinterpret_cast<float4*>(Ahi + off_r) = hi;
+        *reinterpret_cast<float4*>(Alo + off_r) = lo;
         dw_split(r[2][j], hi, lo);
         *reinterpret_cast<float4*>(Bhi + off) = hi;
         *reinterpret_cast<float4*>(Blo + off) = lo;
@@ -224,9 +236,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
           const uint8_t* Ap = (pass == 0) ? Alo : Ahi;
           const uint8_t* Bp = (pass == 1) ? Blo : Bhi;
 #pragma unroll
-          for (int k = 0; k < kDwTileK / 8; ++k) {  // one 8-row swizzle atom (1024 B) per K-step
-            dw_mma(tmem_base + (uint32_t)(a * 64), dw_desc(dw_smem_u32(Ap) + k * 1024, kSlab), dw_desc(dw_smem_u32(Bp) + k * 1024, kSlab),
-                   idesc, acc);
+          for (int k = 0; k < kDwTileK / 8; ++k) {  // one group of 8 k-rows per K-step
+            dw_mma(tmem_base + (uint32_t)(a * 64), dw_desc(dw_smem_u32(Ap) + k * kDwKStep), dw_desc(dw_smem_u32(Bp) + k * kDwKStep), idesc, acc);
             acc = 1;
           }
         }
@@ -282,7 +293,10 @@ static int dw_grid(int64_t M) {
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 template <int C>
-static size_t dw_smem() { return (size_t)kDwStages * (2 * 4 * kDwTileK * 128 + 2 * (C / 32) * kDwTileK * 128) + 128 + 1024; }
+static size_t dw_smem() {
+  const size_t stage = 2 * 4 * (size_t)kDwLbo + 2 * (C / 32) * (size_t)kDwLbo;
+  return (size_t)kDwStages * stage + 128 + 1024;
+}
 
 template <int C>
 static int dw_launch(const DwParams& p, cudaStream_t s) {
