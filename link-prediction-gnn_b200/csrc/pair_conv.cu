@@ -1,7 +1,7 @@
 // pair_conv.cu - the pair-level GCNConv of TwoWL/model/model.py:77 with its dense linear layer on tcgen05 tensor
-// cores and the structured ("factorised") aggregation fused into the GEMM's prologue / epilogue:
+// cores and the structured ("factorised") aggregation fused into the GEMM's epilogue:
 //
-//   out[r, :] = sum_{s < nsrc} (rs_s[r] * A_s[r, :]) * B_s^T  +  sum_{g < ngather} coef_g[r] * T_g[idx_g[r], :]  +  bias
+//   out[r, :] = sum_{s < nsrc} rs_s[r] * (A_s[r, :] * B_s^T)  +  sum_{g < ngather} coef_g[r] * T_g[idx_g[r], :]  +  bias
 //
 //   forward, one direction d :  A = H, rs = selfw_d, B = W_d, gather (S_d, centre_d, dinv_d), bias_d, + column
 //                               statistics of `out` for the GraphNorm that follows (no extra pass over out)
@@ -9,28 +9,35 @@
 //                               ((dS_f W_f), node_f, dinv_f) and ((dS_r W_r), node_r, dinv_r)
 //   plain linear             :  nsrc = 1, no scale, no gather
 //
-// One persistent CTA per SM, 13 warps, warp-specialised:
-//   warps 0-3  producers : coalesced 128-bit global loads of a 128-row tile (the next tile's loads are in flight
-//                          while the current one is staged), row scale, 3xTF32 hi/lo split, swizzled st.shared into a 2-stage ring
-//                          (UMMA canonical K-major SWIZZLE_128B), fence.proxy.async, mbarrier arrive
-//   warp  12   MMA issuer: one lane issues 3 x Kd/8 tcgen05.mma kind::tf32 per source into one of two TMEM
-//                          accumulators; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 4-11 epilogue  : (4 TMEM lane quarters x 2 column halves) gathered rows requested before the accumulator
-//                          is waited for; tcgen05.ld -> per-warp smem transpose -> coalesced 128-byte row segments: gather terms,
-//                          bias, store, column sums (fp32 per tile -> double per CTA, fixed order)
+// One persistent CTA per SM, 12 warps, warp-specialised:
+//   warp  0    TMA producer: one lane streams raw fp32 128-row tiles of A_s into a ring of shared-memory stages with
+//                            cp.async.bulk.tensor (SWIZZLE_128B tensor map = the UMMA canonical K-major layout, L2
+//                            evict-first), 2-3 tiles in flight per SM
+//   warps 2-3  split       : lo = x - trunc_tf32(x) of a landed tile into a second buffer (smem -> smem). The tensor
+//                            core TRUNCATES fp32 operands to tf32 (measured, tools/mma_probe.cu), so the raw tile IS
+//                            the `hi` operand of the 3xTF32 scheme and is never rewritten
+//   warp  1    MMA issuer  : one lane issues 3 x Kd/8 tcgen05.mma kind::tf32 per source (lo*hi, hi*lo, hi*hi) into that
+//                            source's TMEM accumulator (double buffered); tcgen05.commit releases the stages / publishes
+//   warps 4-11 epilogue    : (4 TMEM lane quarters x 2 column halves) gathered rows requested before the accumulator
+//                            is waited for; tcgen05.ld -> row scale, source sum -> per-warp smem transpose -> coalesced
+//                            128-byte row segments: gather terms, bias, store, column sums (fp32 per tile -> double per
+//                            CTA, fixed order)
 // HBM-bound by design: 4*M*(nsrc*Kd + Nd) bytes + gathers for 6*M*Kd*Nd*nsrc tensor flop.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace twowl {
 
-constexpr int kPcProducerWarps = 4;
+constexpr int kPcSplitWarps = 2;
 constexpr int kPcEpilogueWarps = 8;
-constexpr int kPcThreads = (kPcProducerWarps + kPcEpilogueWarps + 1) * 32;  // 416
+constexpr int kPcFirstSplit = 2;
+constexpr int kPcFirstEpi = kPcFirstSplit + kPcSplitWarps;                    // 4
+constexpr int kPcThreads = (kPcFirstEpi + kPcEpilogueWarps) * 32;            // 384: 12 warps -> up to 168 registers per thread
 constexpr int kPcTileM = 128;
-constexpr int kPcStages = 2;
+constexpr int kPcMaxStages = 4;
 
 struct ConvParams {
-  const float* A[2];
   const float* rs[2];
   const float* W[2];
   int w_kn[2];
@@ -45,6 +52,7 @@ struct ConvParams {
   float* out;
   double* stats_part;  // [gridDim.x][2][Nd] column (sum, sum of squares) of `out`, or NULL
   int tmem_cols;
+  int stages;          // raw-tile ring depth (2..kPcMaxStages)
 };
 
 __device__ __forceinline__ uint32_t pc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,6 +77,16 @@ __device__ __forceinline__ void pc_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void pc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pc_smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void pc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pc_tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          pc_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(pc_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void pc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(pc_smem_u32(bar)) : "memory");
 }
@@ -83,19 +101,15 @@ __device__ __forceinline__ void pc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void pc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void pc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void pc_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void pc_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void pc_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
+__device__ __forceinline__ void pc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pc_sw128(int r, int c) { return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4)); }
+__device__ __forceinline__ float pc_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo) {
   hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
   hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -105,44 +119,54 @@ __device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo
 }
 
 template <int KD, int NG>
-__global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p) {
+__global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
+                                                             const __grid_constant__ CUtensorMap tmA1) {
   constexpr int KB = KD / 32;
   constexpr int K4 = KD / 4;
-  constexpr int kChunks = kPcTileM * K4 / (kPcProducerWarps * 32);  // 16-byte chunks per producer thread per stage
-  constexpr uint32_t kAStage = 2u * kPcTileM * KD * 4u;             // hi + lo
+  constexpr uint32_t kTile = (uint32_t)kPcTileM * KD * 4u;  // one raw (or lo) tile
   extern __shared__ uint8_t pc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int Nd = p.Nd;
+  const int S = p.stages;
   const uint32_t kBMat = (uint32_t)KD * Nd * 4u;  // one of hi / lo of one source
   uint8_t* Bs = smem;                                   // [nsrc][hi, lo]
-  uint8_t* As = Bs + (size_t)p.nsrc * 2 * kBMat;        // [stage][hi, lo]
-  uint8_t* Es = As + (size_t)kPcStages * kAStage;       // [epilogue warp] 32 rows x 32 cols fp32 transpose buffer
+  uint8_t* As = Bs + (size_t)p.nsrc * 2 * kBMat;        // [S] raw tiles
+  uint8_t* Ls = As + (size_t)S * kTile;                 // lo tile
+  uint8_t* Es = Ls + kTile;                             // [epilogue warp] 32 rows x 32 cols fp32 transpose buffer
   uint64_t* bars = reinterpret_cast<uint64_t*>(Es + kPcEpilogueWarps * 4096);
-  uint64_t* full = bars;           // [stages]  producers -> MMA
-  uint64_t* empty = bars + 2;      // [stages]  MMA -> producers
-  uint64_t* tfull = bars + 4;      // [2]       MMA -> epilogue
-  uint64_t* tempty = bars + 6;     // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  double* red = reinterpret_cast<double*>(bars + 10);   // [epilogue warps][2][Nd] end-of-kernel reduction
+  uint64_t* raw_full = bars;                       // [S]  TMA -> split, MMA
+  uint64_t* raw_empty = bars + kPcMaxStages;       // [S]  MMA -> TMA
+  uint64_t* lo_full = bars + 2 * kPcMaxStages;     //      split -> MMA
+  uint64_t* lo_empty = lo_full + 1;                //      MMA -> split
+  uint64_t* tfull = lo_full + 2;                   // [2]  MMA -> epilogue
+  uint64_t* tempty = lo_full + 4;                  // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 6);
+  double* red = reinterpret_cast<double*>(lo_full + 8);   // [epilogue warps][2][Nd] end-of-kernel reduction
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (p.M + kPcTileM - 1) / kPcTileM;
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t nuse = my_tiles * p.nsrc;  // stage uses, in order (tile, src)
 
-  if (warp == 12) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pc_smem_u32(tmem_slot)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < kPcStages; ++s) {
-      pc_mbar_init(&full[s], kPcProducerWarps * 32);
-      pc_mbar_init(&empty[s], 1);
+    for (int s = 0; s < kPcMaxStages; ++s) {
+      pc_mbar_init(&raw_full[s], 1);
+      pc_mbar_init(&raw_empty[s], 1);
     }
+    pc_mbar_init(lo_full, kPcSplitWarps * 32);
+    pc_mbar_init(lo_empty, 1);
     for (int a = 0; a < 2; ++a) {
       pc_mbar_init(&tfull[a], 1);
       pc_mbar_init(&tempty[a], kPcEpilogueWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
+    if (p.nsrc > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA1)) : "memory");
   }
   // resident weights: hi/lo split in the canonical layout (slab = 32 k-values, Nd rows of 128 bytes)
   for (int s = 0; s < p.nsrc; ++s) {
@@ -176,76 +200,44 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
   pc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kPcProducerWarps) {
-    // ===================================================== producers
-    const int ptid = tid;  // 0..127
-    float4 regs[kChunks];
-    const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t nit = my_tiles * p.nsrc;  // stage uses, in order (tile, src)
-    auto issue = [&](int64_t it) {
-      const int64_t tile = blockIdx.x + (it / p.nsrc) * gridDim.x;
-      const int s = (int)(it % p.nsrc);
-      const float4* __restrict__ A4 = reinterpret_cast<const float4*>(s == 0 ? p.A[0] : p.A[1]) + tile * kPcTileM * K4;
-      const int64_t rows_left = p.M - tile * kPcTileM;
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      for (int64_t u = 0; u < nuse; ++u) {
+        const int64_t tile = blockIdx.x + (u / p.nsrc) * gridDim.x;
+        const int s = (int)(u % p.nsrc);
+        const int st = (int)(u % S);
+        pc_mbar_wait(&raw_empty[st], (uint32_t)(((u / S) & 1) ^ 1));
+        pc_mbar_expect_tx(&raw_full[st], kTile);
+        const CUtensorMap* tm = s ? &tmA1 : &tmA0;
+        uint8_t* dst = As + (size_t)st * kTile;
 #pragma unroll
-      for (int j = 0; j < kChunks; ++j) {
-        const int idx = j * (kPcProducerWarps * 32) + ptid;
-        regs[j] = (idx / K4 < rows_left) ? ldg_stream(A4 + idx) : f4_zero();
+        for (int kb = 0; kb < KB; ++kb) pc_tma_load_2d(dst + (size_t)kb * kPcTileM * 128, tm, kb * 32, (int)(tile * kPcTileM), &raw_full[st], policy);
       }
-    };
-    auto stage = [&](int64_t it) {
-      const int64_t tile = blockIdx.x + (it / p.nsrc) * gridDim.x;
-      const int s = (int)(it % p.nsrc);
-      const int st = (int)(it % kPcStages);
-      const uint32_t ph = (uint32_t)((it / kPcStages) & 1);
-      pc_mbar_wait(&empty[st], ph ^ 1u);
-      uint8_t* Ahi = As + (size_t)st * kAStage;
-      uint8_t* Alo = Ahi + kAStage / 2;
-      const float* __restrict__ rsv = (s == 0) ? p.rs[0] : p.rs[1];
-      const int64_t row0 = tile * kPcTileM;
-#pragma unroll
-      for (int j = 0; j < kChunks; ++j) {
-        const int idx = j * (kPcProducerWarps * 32) + ptid;
-        const int rr = idx / K4, k4 = idx % K4;
-        float4 v = regs[j];
-        if (rsv) {
-          const float sc = (row0 + rr < p.M) ? __ldg(rsv + row0 + rr) : 0.f;
-          v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-        }
-        float4 hi, lo;
-        pc_split(v, hi, lo);
-        const uint32_t off = (uint32_t)(k4 >> 3) * (kPcTileM * 128u) + pc_sw128(rr, k4 & 7);
-        *reinterpret_cast<float4*>(Ahi + off) = hi;
-        *reinterpret_cast<float4*>(Alo + off) = lo;
-      }
-      pc_proxy_fence();
-      pc_mbar_arrive(&full[st]);
-    };
-    // the loads of use it+1 are in flight while use it is staged and while the wait for its smem slot lasts
-    if (nit > 0) issue(0);
-    for (int64_t it = 0; it < nit; ++it) {
-      stage(it);
-      if (it + 1 < nit) issue(it + 1);
     }
-  } else if (warp == 12) {
+    __syncwarp();
+  } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nd >> 3) << 17) | ((uint32_t)(kPcTileM >> 4) << 24);
-      int64_t it = 0, ti = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      int64_t u = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
         const int a = (int)(ti & 1);
         pc_mbar_wait(&tempty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));
         pc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1));
-        uint32_t acc = 0;
-        for (int s = 0; s < p.nsrc; ++s, ++it) {
-          const int st = (int)(it % kPcStages);
-          pc_mbar_wait(&full[st], (uint32_t)((it / kPcStages) & 1));
+        for (int s = 0; s < p.nsrc; ++s, ++u) {
+          const int st = (int)(u % S);
+          const uint32_t tacc = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1) + s * Nd);
+          pc_mbar_wait(&raw_full[st], (uint32_t)((u / S) & 1));
+          pc_mbar_wait(lo_full, (uint32_t)(u & 1));
           pc_fence_after();
-          const uint8_t* Ahi = As + (size_t)st * kAStage;
-          const uint8_t* Alo = Ahi + kAStage / 2;
+          const uint8_t* Ahi = As + (size_t)st * kTile;
+          const uint8_t* Alo = Ls;
           const uint8_t* Bhi = Bs + (size_t)s * 2 * kBMat;
           const uint8_t* Blo = Bhi + kBMat;
+          uint32_t acc = 0;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {  // lo*hi, hi*lo, hi*hi: small terms first
             const uint8_t* Ap = (pass == 0) ? Alo : Ahi;
@@ -259,23 +251,53 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
                 acc = 1;
               }
             }
+            if (pass == 0) pc_commit(lo_empty);  // the lo tile is free once the first pass has read it
           }
-          pc_commit(&empty[st]);   // stage reusable once these MMAs have read it
+          pc_commit(&raw_empty[st]);  // stage reusable once these MMAs have read it
         }
-        pc_commit(&tfull[a]);      // accumulator complete
+        pc_commit(&tfull[a]);         // accumulators complete
       }
     }
     __syncwarp();
+  } else if (warp < kPcFirstEpi) {
+    // ===================================================== split: lo = x - trunc_tf32(x), same (swizzled) offsets
+    const int t = tid - kPcFirstSplit * 32;  // 0..63
+    constexpr int kSplitThreads = kPcSplitWarps * 32;
+    constexpr int kBatch = 16;                                       // float4 per thread per batch
+    constexpr int kBatches = (int)(kTile / 16u) / (kSplitThreads * kBatch);
+    for (int64_t u = 0; u < nuse; ++u) {
+      const int st = (int)(u % S);
+      pc_mbar_wait(&raw_full[st], (uint32_t)((u / S) & 1));
+      const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)st * kTile);
+      float4* __restrict__ dst = reinterpret_cast<float4*>(Ls);
+      float4 x[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) x[j] = src[j * kSplitThreads + t];
+      pc_mbar_wait(lo_empty, (uint32_t)((u & 1) ^ 1));
+#pragma unroll
+      for (int b = 0; b < kBatches; ++b) {
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+          dst[(b * kBatch + j) * kSplitThreads + t] = make_float4(pc_lo(x[j].x), pc_lo(x[j].y), pc_lo(x[j].z), pc_lo(x[j].w));
+        if (b + 1 < kBatches) {
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) x[j] = src[((b + 1) * kBatch + j) * kSplitThreads + t];
+        }
+      }
+      pc_proxy_fence();
+      pc_mbar_arrive(lo_full);
+    }
   } else {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves
-    const int ew = warp - kPcProducerWarps;
-    const int quarter = ew & 3, half = ew >> 2;
+    const int ew = warp - kPcFirstEpi;
+    const int quarter = warp & 3, half = ew >> 2;   // a warp may only touch TMEM lanes 32*(warp%4)..+31
     uint8_t* Et = Es + ew * 4096;
     const int lrow = lane >> 3, lchunk = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 bytes per pass
     constexpr int NGA = NG > 0 ? NG : 1;
     int ix[NGA][8], ixn[NGA][8];
     float cf[NGA][8], cfn[NGA][8];
-    auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8]) {
+    float rsc[2], rscn[2];
+    auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8], float (&rss)[2]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t row = tile_ * kPcTileM + quarter * 32 + i * 4 + lrow;
@@ -286,10 +308,16 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
           cff[g][i] = ok ? __ldg(p.tcoef[g] + row) : 0.f;
         }
       }
+      const int64_t myrow = tile_ * kPcTileM + quarter * 32 + lane;   // TMEM phase: lane = row
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* __restrict__ rsv = s ? p.rs[1] : p.rs[0];
+        rss[s] = (s < p.nsrc && rsv && myrow < p.M) ? __ldg(rsv + myrow) : 1.f;
+      }
     };
-    if (NG > 0 && blockIdx.x < ntiles) load_idx(blockIdx.x, ix, cf);
-    int64_t ti = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    if (blockIdx.x < ntiles) load_idx(blockIdx.x, ix, cf, rsc);
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int64_t tile = blockIdx.x + ti * gridDim.x;
       const int a = (int)(ti & 1);
       const uint32_t taddr = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
       const int64_t wrow0 = tile * kPcTileM + quarter * 32;
@@ -306,18 +334,30 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
                            ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
         }
         if (!waited) {
-          // next tile's indices / coefficients (NG <= 1 only: register budget) - one more load latency off the chain
-          if (NG == 1 && tile + gridDim.x < ntiles) load_idx(tile + gridDim.x, ixn, cfn);
+          // next tile's indices / coefficients / row scales - one more load latency off the chain (NG <= 1: registers)
+          if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + gridDim.x, ixn, cfn, rscn);
           pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
           pc_fence_after();
           waited = true;
         }
-        uint32_t v[32];
-        pc_tmem_ld32(taddr + c0, v);
-        // transpose through smem: lane = row; 16-byte chunk q of row `lane` goes to chunk q ^ (lane & 7)
+        // TMEM -> registers (lane = row), row scale and source sum, transpose through smem: 16-byte chunk q of row
+        // `lane` goes to chunk q ^ (lane & 7)
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(Et + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        for (int q2 = 0; q2 < 4; ++q2) {
+          uint32_t v0[8], v1[8];
+          pc_tmem_ld8(taddr + c0 + q2 * 8, v0);
+          if (p.nsrc > 1) pc_tmem_ld8(taddr + Nd + c0 + q2 * 8, v1);
+          pc_tmem_wait_ld();
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = rsc[0] * __uint_as_float(v0[e]);
+          if (p.nsrc > 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(rsc[1], __uint_as_float(v1[e]), o[e]);
+          }
+          *reinterpret_cast<float4*>(Et + lane * 128 + (((q2 * 2) ^ (lane & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(Et + lane * 128 + (((q2 * 2 + 1) ^ (lane & 7)) << 4)) = make_float4(o[4], o[5], o[6], o[7]);
+        }
         __syncwarp();
         float4 bsum = f4_zero(), bsq = f4_zero();
         const float4 bias4 = (p.bias && col < Nd) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
@@ -356,16 +396,18 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
         __syncwarp();
       }
       if (!waited) {  // this warp has no column block (Nd <= 32 and half == 1): still take part in the handshake
+        if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + gridDim.x, ixn, cfn, rscn);
         pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
         pc_fence_after();
       }
       pc_fence_before();
       pc_mbar_arrive(&tempty[a]);
-      if (NG == 1) {
+      if (NG <= 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) ix[0][i] = ixn[0][i], cf[0][i] = cfn[0][i];
-      } else if (NG == 2 && tile + gridDim.x < ntiles) {
-        load_idx(tile + gridDim.x, ix, cf);
+        rsc[0] = rscn[0], rsc[1] = rscn[1];
+      } else if (ti + 1 < my_tiles) {
+        load_idx(tile + gridDim.x, ix, cf, rsc);
       }
     }
   }
@@ -379,7 +421,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p)
       p.stats_part[((size_t)blockIdx.x * 2 + v) * Nd + c] = s;
     }
   }
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
 // mean / inv_std of GraphNorm from per-CTA (sum, sum of squares) double partials (norm.cu semantics)
@@ -400,30 +442,63 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
   stats[C + c] = (float)(1.0 / sqrt(var + (1.0 - a) * (1.0 - a) * mean * mean + (double)eps));
 }
 
-static size_t pc_smem_bytes(int Kd, int Nd, int nsrc, bool with_stats = true) {
-  return (size_t)nsrc * 2 * Kd * Nd * 4 + (size_t)kPcStages * 2 * kPcTileM * Kd * 4 + kPcEpilogueWarps * 4096 + 10 * 8 +
+static size_t pc_smem_bytes(int Kd, int Nd, int nsrc, bool with_stats, int stages) {
+  return (size_t)nsrc * 2 * Kd * Nd * 4 + (size_t)(stages + 1) * kPcTileM * Kd * 4 + kPcEpilogueWarps * 4096 + (2 * kPcMaxStages + 8) * 8 +
          (with_stats ? (size_t)kPcEpilogueWarps * 2 * Nd * 8 : 0) + 1024;
 }
+// deepest raw-tile ring (<= kPcMaxStages) that fits the 227 KB of shared memory, 0 if not even 2 stages fit
+static int pc_stages(int Kd, int Nd, int nsrc, bool with_stats) {
+  for (int st = kPcMaxStages; st >= 2; --st)
+    if (pc_smem_bytes(Kd, Nd, nsrc, with_stats, st) <= 227 * 1024) return st;
+  return 0;
+}
 static bool pc_supported(int Kd, int Nd, int nsrc) {
-  return (Kd == 32 || Kd == 64) && Nd >= 16 && Nd <= 256 && (Nd % 16) == 0 && 2 * Nd <= 512 && pc_smem_bytes(Kd, Nd, nsrc, nsrc == 1) <= 227 * 1024;
+  return (Kd == 32 || Kd == 64) && Nd >= 16 && Nd <= 256 && (Nd % 16) == 0 && 2 * nsrc * Nd <= 512 && pc_stages(Kd, Nd, nsrc, nsrc == 1) >= 2;
 }
 static int pc_grid(int64_t M) {
   const int64_t ntiles = cdiv(M, kPcTileM);
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not linked
+typedef CUresult (*pc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pc_encode_fn pc_encoder() {
+  static pc_encode_fn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<pc_encode_fn>(sym);
+  }
+  return fn;
+}
+// row-major fp32 [M, Kd] -> boxes of 32 columns x 128 rows, SWIZZLE_128B (the UMMA K-major canonical layout)
+static int pc_make_tmap(CUtensorMap* tm, const float* A, int64_t M, int Kd) {
+  pc_encode_fn enc = pc_encoder();
+  TW_CHECK_ARG(enc != nullptr, "pair_conv: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kd, (cuuint64_t)M};
+  const cuuint64_t gstr[1] = {(cuuint64_t)Kd * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kPcTileM};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TW_CHECK_ARG(r == CUDA_SUCCESS, "pair_conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <int KD, int NG>
-static int pc_launch(const ConvParams& p, cudaStream_t s) {
-  const size_t smem = pc_smem_bytes(KD, p.Nd, p.nsrc, p.stats_part != nullptr);
-  TW_CHECK_ARG(smem <= 227 * 1024, "pair_conv: %zu bytes of shared memory needed (statistics only with one source)", smem);
+static int pc_launch(const ConvParams& p, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
+  const size_t smem = pc_smem_bytes(KD, p.Nd, p.nsrc, p.stats_part != nullptr, p.stages);
   TW_CUDA(cudaFuncSetAttribute(k_pair_conv<KD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_conv<KD, NG><<<pc_grid(p.M), kPcThreads, smem, s>>>(p);
+  k_pair_conv<KD, NG><<<pc_grid(p.M), kPcThreads, smem, s>>>(p, t0, t1);
   TW_LAUNCH_CHECK();
   return 0;
 }
 template <int KD>
-static int pc_launch_ng(const ConvParams& p, cudaStream_t s) {
-  return p.ngather == 0 ? pc_launch<KD, 0>(p, s) : p.ngather == 1 ? pc_launch<KD, 1>(p, s) : pc_launch<KD, 2>(p, s);
+static int pc_launch_ng(const ConvParams& p, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
+  return p.ngather == 0 ? pc_launch<KD, 0>(p, t0, t1, s) : p.ngather == 1 ? pc_launch<KD, 1>(p, t0, t1, s) : pc_launch<KD, 2>(p, t0, t1, s);
 }
 
 }  // namespace twowl
@@ -446,7 +521,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < a->nsrc; ++s) {
     TW_CHECK_ARG(aligned16(a->A[s]) && aligned16(a->W[s]), "pair_conv: A/W must be 16-byte aligned");
-    p.A[s] = a->A[s], p.rs[s] = a->row_scale[s], p.W[s] = a->W[s], p.w_kn[s] = a->w_kn[s];
+    p.rs[s] = a->row_scale[s], p.W[s] = a->W[s], p.w_kn[s] = a->w_kn[s];
   }
   for (int g = 0; g < a->ngather; ++g) {
     TW_CHECK_ARG(a->T[g] && a->tidx[g] && a->tcoef[g] && aligned16(a->T[g]), "pair_conv: incomplete gather term %d", g);
@@ -455,7 +530,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
   TW_CHECK_ARG(aligned16(a->out) && aligned16(a->bias), "pair_conv: out/bias must be 16-byte aligned");
   p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
   int cols = 32;
-  while (cols < 2 * a->Nd) cols <<= 1;
+  while (cols < 2 * a->nsrc * a->Nd) cols <<= 1;
   p.tmem_cols = cols;
   cudaStream_t s = (cudaStream_t)stream;
   const bool want_stats = a->stats != nullptr;
@@ -465,7 +540,16 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     p.stats_part = (double*)ws;
   }
   if (a->M == 0) return 0;
-  int rc = (a->Kd == 32) ? pc_launch_ng<32>(p, s) : pc_launch_ng<64>(p, s);
+  p.stages = pc_stages(a->Kd, a->Nd, a->nsrc, want_stats);
+  TW_CHECK_ARG(p.stages >= 2, "pair_conv: shared memory does not hold Kd=%d Nd=%d nsrc=%d%s", a->Kd, a->Nd, a->nsrc,
+               want_stats ? " with statistics" : "");
+  CUtensorMap tm[2];
+  memset(tm, 0, sizeof(tm));
+  for (int i = 0; i < a->nsrc; ++i) {
+    const int rc_t = pc_make_tmap(&tm[i], a->A[i], a->M, a->Kd);
+    if (rc_t) return rc_t;
+  }
+  int rc = (a->Kd == 32) ? pc_launch_ng<32>(p, tm[0], tm[1], s) : pc_launch_ng<64>(p, tm[0], tm[1], s);
   if (rc) return rc;
   if (want_stats) {
     k_pc_stats_final<<<(int)cdiv(a->Nd, 128), 128, 0, s>>>(p.stats_part, pc_grid(a->M), a->M, a->Nd, a->mean_scale, a->eps, a->stats);

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(int test_b, uint32_t lbo, uint
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 16384 + 16);
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 49152; i += 128) T[i] = (float)(hi_code ? (i / 2047) + 1 : (i % 2047) + 1);
+  for (int i = tid; i < 49152; i += 128) T[i] = hi_code == 2 ? (1.0f + 0x1p-11f + 0x1p-12f) * ((i & 1) ? -1.f : 1.f) : (float)(hi_code ? (i / 2047) + 1 : (i % 2047) + 1);
   for (int i = tid; i < 4096; i += 128) I[i] = 0.f;
   __syncthreads();
   if (tid < 8) {
@@ -115,6 +115,13 @@ int main() {
       cudaMemcpy(pass ? h2.data() : h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
     }
     // D[m][n]: test A -> D[m][k<8] = A_hw(m,k);  test B -> D[k<8][n] = B_hw(n,k). Print the BYTE offset read for (mn,k).
+    if (v.test_b == 2) {
+      k_probe<<<1, 128, 216000>>>(v.test_b, v.lbo, v.sbo, v.layout, v.N, 2, d_out);
+      cudaDeviceSynchronize();
+      float t[8];
+      cudaMemcpy(t, d_out, sizeof(t), cudaMemcpyDeviceToHost);
+      printf("  operand 1+2^-11+2^-12 (0.75 ulp_tf32 above 1), sign alternating: D[0][0..3] = %.10f %.10f %.10f %.10f (1.0 = truncation, 1.0009765625 = rounding)\n", t[0], t[1], t[2], t[3]);
+    }
     int nz = 0; for (float x : h) nz += (x != 0.f);
     printf("  nonzeros in D: %d\n", nz);
     const int mns[] = {0, 1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 32, 33, 36, 63};
