@@ -233,6 +233,24 @@ int twowl_graphnorm_bwd2(const float* xf, const float* xr, const float* dout, in
                          uint64_t seed_r, int32_t relu, float* dxf, float* dxr, float* dparams_f, float* dparams_r,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* LAST pair layer + readout (model.py:77-83): when the output of conv2s[i](x) + conv2s_r[i](x) only feeds x[idx], the two
+ * GraphNorm(+Dropout+ReLU) branches are evaluated at the 2L rows idx selects, never for the whole pair table:
+ *   fwd: pred[l] = sum_c hn[idx[2l],c] * hn[idx[2l+1],c] * w[c] + b,   hn[r] = act(drop(GN_f(xf[r]))) + act(drop(GN_r(xr[r])))
+ *   bwd: from dpred[L]: dense dxf, dxr [M,C] (GraphNorm's statistics give every row a gradient), dparams_f / dparams_r [4C] as in
+ *        twowl_graphnorm_bwd2, dw[C], db[1]. The incoming gradient is zero outside the selected rows, so the column reductions
+ *        run over the 2L positions only and the dense pass reads xf, xr once. A row selected several times adds its positions in
+ *        ascending order (deterministic). */
+int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                          const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
+                          float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx, int64_t L,
+                          const float* w, const float* b, float* pred, void* stream);
+size_t twowl_gn2_readout_bwd_workspace_bytes(int64_t M, int64_t L, int32_t C);
+int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                          const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
+                          float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx, int64_t L,
+                          const float* w, const float* dpred, float* dxf, float* dxr, float* dparams_f, float* dparams_r, float* dw,
+                          float* db, void* ws, size_t ws_bytes, void* stream);
+
 /* out[c] = sum_m x[m,c] (bias gradients). Deterministic two-level sum. */
 size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C);
 int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream);

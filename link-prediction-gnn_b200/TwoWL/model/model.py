@@ -160,6 +160,9 @@ class LocalWLNet(nn.Module):
         # one fused custom op per pair layer (tcgen05 GEMM + structured aggregation + GraphNorm statistics) when the
         # wedges are structured and the widths are supported; False = the op-by-op path
         self.fused_pair_layer = True
+        # the LAST pair layer only feeds x[idx] (model.py:77-83): fuse it with the readout so its GraphNorm / ReLU run
+        # on the selected rows only (needs fused_pair_layer and an idx)
+        self.fused_readout = True
 
         if use_node_feat:
             self.lin1 = nn.Sequential(
@@ -215,8 +218,12 @@ class LocalWLNet(nn.Module):
         x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d)
         if len(self.conv2s):
             wedges = self._wedges(ei2, pt.R)
+            last = len(self.conv2s) - 1
             for i in range(len(self.conv2s)):
                 if self.fused_pair_layer and F2.pair_layer_supported(wedges, x.shape[1], self.conv2s[i], self.conv2s_r[i]):
+                    if i == last and self.fused_readout and idx is not None:
+                        return F2.pair_layer_readout_apply(x, wedges, self.conv2s[i], self.conv2s_r[i], self.training, idx,
+                                                           self.pred)
                     x = F2.pair_layer_apply(x, wedges, self.conv2s[i], self.conv2s_r[i], self.training)
                 else:
                     a = self.conv2s[i].forward_pairs(x, wedges, 0)

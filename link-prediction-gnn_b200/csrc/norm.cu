@@ -363,6 +363,201 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- last pair layer + readout -------
+// When a pair layer's output only feeds the readout x[idx] (model.py:77-83, the LAST conv2s/conv2s_r layer), the two
+// GraphNorm(+Dropout+ReLU) branches are evaluated at the 2L selected rows only, and the backward exploits that the
+// incoming gradient is zero outside those rows: column reductions over 2L positions, one dense pass for dxf / dxr.
+__device__ __forceinline__ float4 gn2_row(const float4& a, const float4& b, const GnCols& cf, const GnCols& cr, uint32_t thresh,
+                                          float inv_keep, uint64_t seed_f, uint64_t seed_r, int relu, uint64_t e) {
+  const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float yf = fmaf(cf.sc[i], av[i], cf.of[i]), yr = fmaf(cr.sc[i], bv[i], cr.of[i]);
+    if (thresh) {
+      yf *= drop_scale(seed_f, e * 4 + i, thresh, inv_keep);
+      yr *= drop_scale(seed_r, e * 4 + i, thresh, inv_keep);
+    }
+    if (relu) yf = fmaxf(yf, 0.f), yr = fmaxf(yr, 0.f);
+    o[i] = yf + yr;
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// one warp per target link l: pred[l] = sum_c hn[i0,c]*hn[i1,c]*w[c] + b   (xor-shuffle tree, fixed order)
+__global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* __restrict__ xf, const float* __restrict__ xr, int C,
+                                                                  const float* __restrict__ stf, const float* __restrict__ str_,
+                                                                  const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                  const float* __restrict__ mf, const float* __restrict__ wr,
+                                                                  const float* __restrict__ br, const float* __restrict__ mr,
+                                                                  uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                                  int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
+                                                                  const float* __restrict__ w, const float* __restrict__ b,
+                                                                  float* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int cv = C >> 2;
+  const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+  const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w);
+  const int64_t warp0 = ((int64_t)blockIdx.x * kNormThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kNormThreads) >> 5;
+  for (int64_t l = warp0; l < L; l += nwarps) {
+    const int64_t i0 = idx[(2 * l) * sidx], i1 = idx[(2 * l + 1) * sidx];
+    float acc = 0.f;
+    for (int c4 = lane; c4 < cv; c4 += 32) {
+      const GnCols cf(C, c4 * 4, stf, wf, bf, mf), cr(C, c4 * 4, str_, wr, br, mr);
+      const int64_t e0 = i0 * cv + c4, e1 = i1 * cv + c4;
+      const float4 h0 = gn2_row(ldg_cached(xf4 + e0), ldg_cached(xr4 + e0), cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)e0);
+      const float4 h1 = gn2_row(ldg_cached(xf4 + e1), ldg_cached(xr4 + e1), cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)e1);
+      const float4 ww = __ldg(w4 + c4);
+      acc = fmaf(h0.x * h1.x, ww.x, acc);
+      acc = fmaf(h0.y * h1.y, ww.y, acc);
+      acc = fmaf(h0.z * h1.z, ww.z, acc);
+      acc = fmaf(h0.w * h1.w, ww.w, acc);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) pred[l] = acc + b[0];
+  }
+}
+
+// per selected position j (row a = idx[j], partner row b = idx[j^1], link l = j/2):
+//   G[j] = dpred[l] * w * hn[b]   (gradient w.r.t. hn[a]),  and the column partial sums of both GraphNorm backwards
+//   (sum g_y, sum g_y*n per branch) plus dw = sum_l dpred[l] * hn[a]*hn[b] (even positions only).
+__global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const float* __restrict__ xf, const float* __restrict__ xr, int C,
+                                                                       const float* __restrict__ stf, const float* __restrict__ str_,
+                                                                       const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                       const float* __restrict__ mf, const float* __restrict__ wr,
+                                                                       const float* __restrict__ br, const float* __restrict__ mr,
+                                                                       uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                                       int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
+                                                                       const float* __restrict__ w, const float* __restrict__ dpred,
+                                                                       float* __restrict__ G, double* __restrict__ part) {
+  const RowMap rm(C);
+  float4 v[5] = {f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+  if (rm.slot >= 0) {
+    const int c0 = rm.c4 * 4;
+    const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
+    const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+    const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + rm.c4);
+    float4* __restrict__ G4 = reinterpret_cast<float4*>(G);
+    for (int64_t j = (int64_t)blockIdx.x * rm.slots + rm.slot; j < 2 * L; j += (int64_t)gridDim.x * rm.slots) {
+      const int64_t ra = idx[j * sidx], rb = idx[(j ^ 1) * sidx];
+      const float g = dpred[j >> 1];
+      const int64_t ea = ra * rm.cv + rm.c4, eb = rb * rm.cv + rm.c4;
+      const float4 af = ldg_cached(xf4 + ea), ar = ldg_cached(xr4 + ea);
+      const float4 hb = gn2_row(ldg_cached(xf4 + eb), ldg_cached(xr4 + eb), cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)eb);
+      const float4 d = make_float4(g * ww.x * hb.x, g * ww.y * hb.y, g * ww.z * hb.z, g * ww.w * hb.w);
+      G4[j * rm.cv + rm.c4] = d;
+      float gy[4], n[4];
+      gn_gy(af, d, cf.sc, cf.of, cf.nm, cf.ni, thresh, inv_keep, seed_f, (uint64_t)ea, relu, gy, n);
+      v[0].x += gy[0], v[0].y += gy[1], v[0].z += gy[2], v[0].w += gy[3];
+      v[1].x = fmaf(gy[0], n[0], v[1].x), v[1].y = fmaf(gy[1], n[1], v[1].y);
+      v[1].z = fmaf(gy[2], n[2], v[1].z), v[1].w = fmaf(gy[3], n[3], v[1].w);
+      gn_gy(ar, d, cr.sc, cr.of, cr.nm, cr.ni, thresh, inv_keep, seed_r, (uint64_t)ea, relu, gy, n);
+      v[2].x += gy[0], v[2].y += gy[1], v[2].z += gy[2], v[2].w += gy[3];
+      v[3].x = fmaf(gy[0], n[0], v[3].x), v[3].y = fmaf(gy[1], n[1], v[3].y);
+      v[3].z = fmaf(gy[2], n[2], v[3].z), v[3].w = fmaf(gy[3], n[3], v[3].w);
+      if ((j & 1) == 0) {
+        const float4 ha = gn2_row(af, ar, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)ea);
+        v[4].x = fmaf(g, ha.x * hb.x, v[4].x), v[4].y = fmaf(g, ha.y * hb.y, v[4].y);
+        v[4].z = fmaf(g, ha.z * hb.z, v[4].z), v[4].w = fmaf(g, ha.w * hb.w, v[4].w);
+      }
+    }
+  }
+  cta_col_reduce<5>(rm, v, part, C);
+}
+
+// per-row chains of the positions that select it: head[row] -> position -> next[position] -> ... -> -1.
+// The chain ORDER is a race outcome and never reaches a result: consumers add a row's positions in ascending order.
+__global__ void __launch_bounds__(kNormThreads) k_row_chains(const int64_t* __restrict__ idx, int64_t sidx, int64_t n, int64_t M,
+                                                             int32_t* __restrict__ head, int32_t* __restrict__ next) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx[j * sidx];
+    next[j] = (r >= 0 && r < M) ? atomicExch(&head[r], (int32_t)j) : -1;
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx_rows(const float* __restrict__ xf, const float* __restrict__ xr,
+                                                                  const float* __restrict__ G, const int32_t* __restrict__ head,
+                                                                  const int32_t* __restrict__ next, int64_t M, int C,
+                                                                  const float* __restrict__ stf, const float* __restrict__ str_,
+                                                                  const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                  const float* __restrict__ mf, const float* __restrict__ wr,
+                                                                  const float* __restrict__ br, const float* __restrict__ mr,
+                                                                  uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                                  int relu, const float* __restrict__ sums_f,
+                                                                  const float* __restrict__ sums_r, float* __restrict__ dxf,
+                                                                  float* __restrict__ dxr) {
+  const RowMap rm(C);
+  if (rm.slot < 0) return;
+  const int c0 = rm.c4 * 4;
+  const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
+  float bmf[4], cof[4], bmr[4], cor[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bmf[i] = sums_f[C + c0 + i], cof[i] = sums_f[2 * C + c0 + i];
+    bmr[i] = sums_r[C + c0 + i], cor[i] = sums_r[2 * C + c0 + i];
+  }
+  const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+  const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+  const float4* __restrict__ G4 = reinterpret_cast<const float4*>(G);
+  float4* __restrict__ of4 = reinterpret_cast<float4*>(dxf);
+  float4* __restrict__ or4 = reinterpret_cast<float4*>(dxr);
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
+    const int64_t e = r * rm.cv + rm.c4;
+    const float4 a = ldg_stream(xf4 + e), b = ldg_stream(xr4 + e);
+    float4 d = f4_zero();
+    const int h = __ldg(head + r);
+    if (h >= 0) {
+      if (__ldg(next + h) < 0) {
+        d = ldg_cached(G4 + (int64_t)h * rm.cv + rm.c4);
+      } else {  // the row is selected more than once: add its positions in ascending order
+        int last = -1;
+        for (;;) {
+          int best = 0x7fffffff;
+          for (int q = h; q >= 0; q = __ldg(next + q))
+            if (q > last && q < best) best = q;
+          if (best == 0x7fffffff) break;
+          f4_add(d, ldg_cached(G4 + (int64_t)best * rm.cv + rm.c4));
+          last = best;
+        }
+      }
+    }
+    float gy[4], n[4], o[4];
+    gn_gy(a, d, cf.sc, cf.of, cf.nm, cf.ni, thresh, inv_keep, seed_f, (uint64_t)e, relu, gy, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = cf.sc[i] * (gy[i] - n[i] * bmf[i]) - cof[i];
+    of4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    gn_gy(b, d, cr.sc, cr.of, cr.nm, cr.ni, thresh, inv_keep, seed_r, (uint64_t)e, relu, gy, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = cr.sc[i] * (gy[i] - n[i] * bmr[i]) - cor[i];
+    or4[e] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void k_part_colsum_final(const double* __restrict__ part, int nparts, int nv, int voff, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0;
+  for (int b = 0; b < nparts; ++b) s += part[((size_t)b * nv + voff) * C + c];
+  out[c] = (float)s;
+}
+__global__ void k_sum_vec_f(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+  // single CTA, fixed order: per-thread strided double partials, then a tree over 256 threads
+  __shared__ double s[256];
+  double a = 0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) a += (double)v[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)s[0];
+}
+
 // ---------------------------------------------------------------- column sum ---------------------
 __global__ void __launch_bounds__(kNormThreads) k_colsum_partial(const float* __restrict__ x, int64_t M, int C,
                                                                  double* __restrict__ part) {
@@ -529,6 +724,66 @@ extern "C" int twowl_graphnorm_bwd2(const float* xf, const float* xr, const floa
   k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 4, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
   k_gn_bwd2_dx<<<grid, kNormThreads, 0, s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep, seed_f,
                                              seed_r, relu, sums_f, sums_r, dxf, dxr);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                     const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                     const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                     int32_t relu, const int64_t* idx, int64_t sidx, int64_t L, const float* w, const float* b,
+                                     float* pred, void* stream) {
+  if (int rc = check_mc("gn2_readout_fwd", M, C)) return rc;
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(w), "gn2_readout_fwd: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_fwd: dropout p=%f outside [0,1)", p_drop);
+  if (L <= 0) return 0;
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  k_gn2_readout_fwd<<<grid_for(L, kNormThreads / 32, 8), kNormThreads, 0, (cudaStream_t)stream>>>(
+      xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx, sidx, L, w, b, pred);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_gn2_readout_bwd_workspace_bytes(int64_t M, int64_t L, int32_t C) {
+  const size_t l = (size_t)(L > 0 ? L : 1);
+  return align_up(2 * l * (size_t)C * sizeof(float)) + align_up((size_t)(M > 0 ? M : 1) * sizeof(int32_t)) + align_up(2 * l * sizeof(int32_t)) +
+         align_up((size_t)kNormMaxCtas * 5 * (size_t)C * sizeof(double)) + 2 * align_up(3 * (size_t)C * sizeof(float));
+}
+
+extern "C" int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                     const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                     const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                     int32_t relu, const int64_t* idx, int64_t sidx, int64_t L, const float* w, const float* dpred,
+                                     float* dxf, float* dxr, float* dparams_f, float* dparams_r, float* dw, float* db, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("gn2_readout_bwd", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && M < 0x7fffffffLL && L >= 0 && 2 * L < 0x7fffffffLL, "gn2_readout_bwd: sizes out of range");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(dxf) && aligned16(dxr) && aligned16(w),
+               "gn2_readout_bwd: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_bwd: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_gn2_readout_bwd_workspace_bytes(M, L, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t l = (size_t)(L > 0 ? L : 1);
+  Carver c(ws);
+  float* G = c.take<float>(2 * l * C);
+  int32_t* head = c.take<int32_t>((size_t)M);
+  int32_t* next = c.take<int32_t>(2 * l);
+  double* part = c.take<double>((size_t)kNormMaxCtas * 5 * C);
+  float* sums_f = c.take<float>(3 * (size_t)C);
+  float* sums_r = c.take<float>(3 * (size_t)C);
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  TW_CUDA(cudaMemsetAsync(head, 0xFF, (size_t)M * sizeof(int32_t), s));
+  const int grid_l = norm_grid(2 * (int64_t)l, C);
+  k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 5), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
+                                                                      seed_f, seed_r, relu, idx, sidx, L, w, dpred, G, part);
+  if (L > 0) k_row_chains<<<grid_for(2 * L, kNormThreads), kNormThreads, 0, s>>>(idx, sidx, 2 * L, M, head, next);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_part_colsum_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 4, C, dw);
+  k_sum_vec_f<<<1, 256, 0, s>>>(dpred, L, db);
+  k_gn_bwd2_dx_rows<<<norm_grid(M, C), kNormThreads, 0, s>>>(xf, xr, G, head, next, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
+                                                             inv_keep, seed_f, seed_r, relu, sums_f, sums_r, dxf, dxr);
   TW_LAUNCH_CHECK();
   return 0;
 }

@@ -296,14 +296,10 @@ def _pl_setup(ctx, inputs, output):
     ctx.mark_non_differentiable(Of, Or, sf, sr, SHf, SHr)
 
 
-def _pl_bwd(ctx, g, *_unused):
-    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr, SHf,
-     SHr) = ctx.saved_tensors
-    n_node, p_drop, seed_f, seed_r = ctx.meta
-    g = g.contiguous()
+def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars):
+    """Backward of the structured pair-level GCNConv pair from the gradients dO_f, dO_r of its two outputs:
+    -> dh and, per direction, (dW, dbias, d gn.weight, d gn.bias, d gn.mean_scale)."""
     C = wf.shape[0]
-    dOf, dOr, dpf, dpr = ops.graphnorm_bwd2(Of, Or, g, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r, True)
-    dOs, dpars = [dOf, dOr], [dpf, dpr]
     dSs = [ops.seg_reduce(out_ptr, out_ids, n_node, dOs[d], plan=out_plan, flip=d, src_scale=dinv[d]) for d in range(2)]
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
     if ops.pair_dw_supported(C) and h.shape[1] == C:
@@ -318,10 +314,78 @@ def _pl_bwd(ctx, g, *_unused):
         res.append((dW, dpar[3 * C:], dpar[:C], dpar[C:2 * C], dpar[2 * C:3 * C]))
     dh = ops.pair_conv(dOs, [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
                        gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])])
+    return dh, res
+
+
+def _pl_bwd(ctx, g, *_unused):
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr, SHf,
+     SHr) = ctx.saved_tensors
+    n_node, p_drop, seed_f, seed_r = ctx.meta
+    g = g.contiguous()
+    dOf, dOr, dpf, dpr = ops.graphnorm_bwd2(Of, Or, g, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r, True)
+    dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr])
     return (dh,) + res[0] + res[1] + (None,) * 16
 
 
 pair_layer.register_autograd(_pl_bwd, setup_context=_pl_setup)
+
+
+# ------------------------------------------------------------------------------ last pair layer + readout
+#
+# The LAST conv2s / conv2s_r layer only feeds x[idx] (model.py:77-83): the GraphNorm(+Dropout+ReLU) branches are evaluated
+# at the 2L selected rows, h_next [R,C] is never materialised, and the backward starts from a row-sparse gradient.
+
+
+@torch.library.custom_op("twowl::pair_layer_readout", mutates_args=())
+def pair_layer_readout(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf: Tensor, wr: Tensor, br: Tensor, gwr: Tensor,
+                       gbr: Tensor, gmr: Tensor, idx: Tensor, pw: Tensor, pb: Tensor, in_ptr: Tensor, in_ids: Tensor,
+                       in_plan: Tensor, out_ptr: Tensor, out_ids: Tensor, out_plan: Tensor, centre: Tensor, dinv: Tensor,
+                       selfw: Tensor, bnode: Tensor, blocked: Optional[Tensor], n_node: int, eps: float, p_drop: float,
+                       seed_f: int, seed_r: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (pred [L,1], O_f, O_r, stats_f, stats_r, SH_f, SH_r); only pred is differentiable, the rest is saved state."""
+    h = h.contiguous()
+    outs = []
+    for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
+        SH = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, flip=1 - d, src_scale=dinv[d], skip_mask=blocked)
+        S = ops.linear_fwd(SH, w)
+        O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
+                              stats_mean_scale=gm, eps=eps)
+        outs.append((O, st, SH))
+    pred = ops.gn2_readout_fwd(outs[0][0], outs[1][0], outs[0][1], outs[1][1], (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f,
+                               seed_r, True, idx, pw.contiguous(), pb)
+    return pred, outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2]
+
+
+@pair_layer_readout.register_fake
+def _(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre,
+      dinv, selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r):
+    C = wf.shape[0]
+    o = h.new_empty((h.shape[0], C))
+    return (h.new_empty((idx.numel() // 2, 1)), o, torch.empty_like(o), h.new_empty((2 * C,)), h.new_empty((2 * C,)),
+            h.new_empty((n_node, h.shape[1])), h.new_empty((n_node, h.shape[1])))
+
+
+def _plr_setup(ctx, inputs, output):
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, out_ptr, out_ids, out_plan, centre,
+     dinv, selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r) = inputs
+    pred, Of, Or, sf, sr, SHf, SHr = output
+    ctx.save_for_backward(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids, out_plan, dinv, selfw,
+                          bnode, Of, Or, sf, sr, SHf, SHr)
+    ctx.meta = (n_node, p_drop, seed_f, seed_r)
+    ctx.mark_non_differentiable(Of, Or, sf, sr, SHf, SHr)
+
+
+def _plr_bwd(ctx, g, *_unused):
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr,
+     SHf, SHr) = ctx.saved_tensors
+    n_node, p_drop, seed_f, seed_r = ctx.meta
+    dOf, dOr, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r,
+                                                       True, idx, pw.contiguous(), g.reshape(-1))
+    dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr])
+    return (dh,) + res[0] + res[1] + (None, dpw.reshape(pw.shape), dpb) + (None,) * 16
+
+
+pair_layer_readout.register_autograd(_plr_bwd, setup_context=_plr_setup)
 
 
 def pair_layer_supported(wedges, C: int, seq_f, seq_r) -> bool:
@@ -346,4 +410,18 @@ def pair_layer_apply(x, wedges, seq_f, seq_r, training: bool):
     out = pair_layer(x, cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight, gr.bias,
                      gr.mean_scale, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr, wedges.out_ids,
                      wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked, wedges.n_node, gf.eps, p, seeds[0], seeds[1])
+    return out[0]
+
+
+def pair_layer_readout_apply(x, wedges, seq_f, seq_r, training: bool, idx, pred):
+    """Last pair layer fused with the readout: pred(x'[idx] even*odd) of model.py:77-83 without materialising x'."""
+    cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
+    cr, gr = seq_r.modlist[0], seq_r.modlist[1]
+    p = dpf.p if (training and dpf.p > 0.0) else 0.0
+    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(2)] if p > 0.0 else [0, 0]
+    _, centre, dinv, selfw, bnode = wedges.prepared()
+    out = pair_layer_readout(x, cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight,
+                             gr.bias, gr.mean_scale, idx, pred.weight, pred.bias, wedges.in_ptr, wedges.in_ids, wedges.in_plan,
+                             wedges.out_ptr, wedges.out_ids, wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked,
+                             wedges.n_node, gf.eps, p, seeds[0], seeds[1])
     return out[0]

@@ -359,6 +359,49 @@ def readout_bwd(H, idx, w, dpred):
     return dH, dw, db
 
 
+def gn2_readout_fwd(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool, idx, w, b) -> torch.Tensor:
+    """pred[l] of model.py:78-83 straight from the two pre-GraphNorm branch outputs (last pair layer): only the rows
+    idx selects are normalised / activated. pf / pr = (weight, bias, mean_scale) of the two GraphNorms."""
+    _need_cuda(xf, xr, idx, w, b)
+    M, C = xf.shape
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    pred = torch.empty((L, 1), dtype=torch.float32, device=xf.device)
+    p, s = _row(idx)
+    with _P("gn2_readout_fwd", L * (16 * C + 20)):
+        check(lib.twowl_gn2_readout_fwd(xf.data_ptr(), xr.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                        pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(),
+                                        float(p_drop), int(seed_f), int(seed_r), int(relu), p, s, L, w.data_ptr(), b.data_ptr(),
+                                        pred.data_ptr(), _stream()), "gn2_readout_fwd")
+    _count()
+    return pred
+
+
+def gn2_readout_bwd(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool, idx, w, dpred):
+    """-> (dxf, dxr [M,C], dparams_f, dparams_r [4C], dw [1,C], db [1]) from dpred [L]."""
+    M, C = xf.shape
+    dev = xf.device
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    dxf, dxr = torch.empty_like(xf), torch.empty_like(xr)
+    dpf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dpr = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dw = torch.empty((1, C), dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    nb = lib.twowl_gn2_readout_bwd_workspace_bytes(M, L, C)
+    ws = _ws(nb, dev)
+    p, s = _row(idx)
+    dpred = dpred.contiguous()
+    with _P("gn2_readout_bwd", M * (16 * C + 4) + L * (48 * C + 40)):
+        check(lib.twowl_gn2_readout_bwd(xf.data_ptr(), xr.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                        pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(),
+                                        float(p_drop), int(seed_f), int(seed_r), int(relu), p, s, L, w.data_ptr(), dpred.data_ptr(),
+                                        dxf.data_ptr(), dxr.data_ptr(), dpf.data_ptr(), dpr.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                        ws.data_ptr(), nb, _stream()), "gn2_readout_bwd")
+    _count(8)
+    return dxf, dxr, dpf, dpr, dw, db
+
+
 # ------------------------------------------------------------------------------ GraphNorm
 
 def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
