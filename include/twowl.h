@@ -123,6 +123,7 @@ int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, int32_t fl
 /* The one segmented gather-reduce all aggregations run through. For each output row m, with its entries
  * taken from CSR row r = m ^ row_flip (empty if row_skip_mask[r]):
  *   acc      = sum_{k in row r, kept} src_scale[s] * X[s] (* X2[mul_idx[col[k]]] if X2)   with s = col[k] ^ flip
+ *              (pair_sum: X[s] + X[s ^ 1] in place of X[s])
  *   kept     = !(skip_self && s == m) && !(skip_mask && skip_mask[col[k]])
  *   out[m]   = (dst_scale ? dst_scale[m] : 1) * acc
  *            + (self_mode == 1 ? dst_scale[m]^2 * X[m] : 0)          (the GCN self-loop)
@@ -159,6 +160,7 @@ typedef struct twowl_seg_args {
   float* partial;                /* fp32 [chunk_cap, C] scratch */
   int64_t chunk_cap;
   int64_t long_cap;
+  int32_t pair_sum;              /* 1: gather X[s] + X[s ^ 1] (the two directions 2k / 2k+1 of one pair, utils.py:81-90) */
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
 
@@ -166,8 +168,8 @@ int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
  * and cut into chunks of TWOWL_ROW_CHUNK entries; twowl_seg_reduce then reduces the chunks with separate lane
  * groups and adds each row's partial sums in chunk order (deterministic). Built once per CSR.
  * Capacities depend on nnz only, so no device->host read is needed. */
-#define TWOWL_LONG_ROW 512
-#define TWOWL_ROW_CHUNK 256
+#define TWOWL_LONG_ROW 64
+#define TWOWL_ROW_CHUNK 64
 int64_t twowl_seg_plan_long_cap(int64_t nnz);
 int64_t twowl_seg_plan_chunk_cap(int64_t nnz);
 int twowl_seg_plan(const int64_t* ptr, int64_t M, int64_t nnz, int32_t* counts /*[2]*/, int32_t* long_row,

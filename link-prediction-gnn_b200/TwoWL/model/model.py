@@ -215,7 +215,7 @@ class LocalWLNet(nn.Module):
             x = conv1(x, edge1)
 
         pt = G.pair_table(pos, x.shape[0])
-        x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d)
+        x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
         if len(self.conv2s):
             wedges = self._wedges(ei2, pt.R)
             last = len(self.conv2s) - 1

@@ -39,6 +39,7 @@ struct SegParams {
   const int32_t* mul_idx;
   float* out;
   int accumulate;
+  int pair_sum;
   // long-row plan (all NULL/0 when the CSR has no plan)
   const int32_t* plan_counts;  // [0] = number of long rows, [1] = number of chunks
   const int32_t* long_row;     // CSR row of each long row
@@ -60,30 +61,46 @@ struct GroupCtx {
   }
 };
 
-// acc += sum over entries [kb, ke) of the CSR feeding output row m
-template <int G, int VEC>
+// acc += sum over entries [kb, ke) of the CSR feeding output row m.
+// Software-pipelined two blocks deep so that no load is consumed in the iteration that issues it: while block b is
+// gathered and accumulated, the col entries of block b+2 and the (col-dependent) scale / second-factor indices of
+// block b+1 are in flight.
+// MODE: 0 = plain gather, 1 = times X2[mul_idx], 3 = (X[s] + X[s^1]) times X2[mul_idx]  (compile-time, so that the plain
+// path keeps its registers for gathers in flight)
+template <int G, int VEC, int MODE>
 __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCtx<G>& g, int64_t m, int64_t kb, int64_t ke,
                                                float4 (&acc)[VEC]) {
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
-  for (int64_t k0 = kb; k0 < ke; k0 += G) {
-    // stage G entries: source row (or -1 = dropped), its scale, optional second-factor row
-    int s_mine = -1, m2_mine = 0;
-    float w_mine = 0.f;
-    if (k0 + g.gl < ke) {
-      const int c = __ldg(p.col + k0 + g.gl);
+  if (kb >= ke) return;
+  auto load_col = [&](int64_t k0) -> int { return (k0 + g.gl < ke) ? __ldg(p.col + k0 + g.gl) : -1; };
+  // (col entry) -> source row (or -1 = dropped), its scale, optional second-factor row
+  auto stage = [&](int c, int& s_, float& w_, int& m2_) {
+    s_ = -1, w_ = 0.f, m2_ = 0;
+    if (c >= 0) {
       const int s = c ^ p.flip;
       const bool keep = !(p.skip_self && (int64_t)s == m) && !(p.skip_mask && p.skip_mask[c]);
       if (keep) {
-        s_mine = s;
-        w_mine = p.src_scale ? __ldg(p.src_scale + s) : 1.f;
-        if (p.X2) m2_mine = __ldg(p.mul_idx + c);
+        s_ = s;
+        w_ = p.src_scale ? __ldg(p.src_scale + s) : 1.f;
+        if (MODE & 1) m2_ = __ldg(p.mul_idx + c);
       }
     }
+  };
+  int c_b1 = load_col(kb + G);           // col of block b+1
+  int s_mine, m2_mine;
+  float w_mine;
+  stage(load_col(kb), s_mine, w_mine, m2_mine);
+  for (int64_t k0 = kb; k0 < ke; k0 += G) {
+    const int c_b2 = load_col(k0 + 2 * G);
+    int s_next, m2_next;
+    float w_next;
+    stage(c_b1, s_next, w_next, m2_next);
     const int cnt = (ke - k0 < G) ? (int)(ke - k0) : G;
     // UNR gathered rows are requested back to back (predicated 128-bit loads, no branches in between) before
     // any of them is consumed: the kernel lives on memory-level parallelism, not on occupancy
-    constexpr int UNR = (VEC >= 8) ? 1 : (8 / VEC > G ? G : 8 / VEC);
+    constexpr int kLoads = 4;                     // rows in flight per lane and factor: occupancy beats deeper unrolling here
+    constexpr int UNR = (VEC >= kLoads) ? 1 : (kLoads / VEC > G ? G : kLoads / VEC);
     for (int j0 = 0; j0 < cnt; j0 += UNR) {
       int sj[UNR], m2j[UNR];
       float wj[UNR];
@@ -95,7 +112,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
         m2j[u] = __shfl_sync(g.gmask, m2_mine, src_lane);
         if (j0 + u >= cnt) sj[u] = -1;
       }
-      float4 x[UNR][VEC];
+      float4 x[UNR][VEC], xm[(MODE & 2) ? UNR : 1][VEC], y[(MODE & 1) ? UNR : 1][VEC];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
 #pragma unroll
@@ -103,20 +120,25 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
           const int c4 = g.gl + v * G;
           const bool on = sj[u] >= 0 && c4 < g.cv;
           x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
-          if (p.X2) {
-            const float4 y = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
-            x[u][v] = f4_mul(x[u][v], y);
-          }
+          if (MODE & 2) xm[u][v] = on ? ldg_cached(X4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
+          if (MODE & 1) y[u][v] = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
         }
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         if (sj[u] >= 0) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) f4_fma(acc[v], wj[u], x[u][v]);
+          for (int v = 0; v < VEC; ++v) {
+            float4 t = x[u][v];
+            if (MODE & 2) f4_add(t, xm[u][v]);
+            if (MODE & 1) t = f4_mul(t, y[u][v]);
+            f4_fma(acc[v], wj[u], t);
+          }
         }
       }
     }
+    s_mine = s_next, w_mine = w_next, m2_mine = m2_next;
+    c_b1 = c_b2;
   }
 }
 
@@ -140,31 +162,41 @@ __device__ __forceinline__ void seg_finalize(const SegParams& p, const GroupCtx<
 }
 
 // pass 1: one group per row, rows dealt round-robin to groups; long rows (if planned) are left to pass 2/3
-template <int G, int VEC>
+template <int G, int VEC, int MODE>
 __global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
   const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
   const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
+  auto row_range = [&](int64_t m_, int64_t& kb_, int64_t& ke_, bool& masked_) {
+    kb_ = 0, ke_ = 0, masked_ = false;
+    const int64_t r = m_ ^ (int64_t)p.row_flip;
+    if (m_ < p.M && r < p.M) {
+      kb_ = __ldg(p.ptr + r);
+      ke_ = __ldg(p.ptr + r + 1);
+      masked_ = p.row_skip_mask && p.row_skip_mask[r];
+    }
+  };
+  int64_t kb_n, ke_n;
+  bool masked_n;
+  row_range(group0, kb_n, ke_n, masked_n);
   for (int64_t m = group0; m < p.M; m += ngroups) {
+    const int64_t kb = kb_n;
+    int64_t ke = ke_n;
+    const bool masked = masked_n;
+    row_range(m + ngroups, kb_n, ke_n, masked_n);  // next row's range is in flight while this row is reduced
+    if (p.plan_counts && ke - kb > TWOWL_LONG_ROW) continue;  // handled by k_seg_chunks + k_seg_long
+    if (masked) ke = kb;
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-    const int64_t r = m ^ (int64_t)p.row_flip;
-    int64_t kb = 0, ke = 0;
-    if (r < p.M) {
-      kb = p.ptr[r];
-      ke = p.ptr[r + 1];
-      if (p.plan_counts && ke - kb > TWOWL_LONG_ROW) continue;  // handled by k_seg_chunks + k_seg_long
-      if (p.row_skip_mask && p.row_skip_mask[r]) ke = kb;
-    }
-    seg_accumulate<G, VEC>(p, g, m, kb, ke, acc);
+    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc);
     seg_finalize<G, VEC>(p, g, m, acc);
   }
 }
 
 // pass 2: one group per chunk of a long row -> raw partial sums
-template <int G, int VEC>
+template <int G, int VEC, int MODE>
 __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
@@ -182,7 +214,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
     float4 acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-    seg_accumulate<G, VEC>(p, g, m, kb, ke, acc);
+    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const int c4 = g.gl + v * G;
@@ -219,14 +251,20 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   }
 }
 
-template <int G, int VEC>
-static void launch_seg(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
+template <int G, int VEC, int MODE>
+static void launch_seg_mode(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
   constexpr int kGroupsPerCta = kAggThreads / G;
-  k_seg_rows<G, VEC><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+  k_seg_rows<G, VEC, MODE><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   if (p.plan_counts && chunk_cap > 0) {
-    k_seg_chunks<G, VEC><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+    k_seg_chunks<G, VEC, MODE><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
     k_seg_long<G, VEC><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   }
+}
+template <int G, int VEC>
+static void launch_seg(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
+  if (!p.X2) launch_seg_mode<G, VEC, 0>(p, chunk_cap, long_cap, s);
+  else if (!p.pair_sum) launch_seg_mode<G, VEC, 1>(p, chunk_cap, long_cap, s);
+  else launch_seg_mode<G, VEC, 3>(p, chunk_cap, long_cap, s);
 }
 
 // ---------------------------------------------------------------- long-row plan ------------------
@@ -313,6 +351,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
                "seg_reduce: feature pointers must be 16-byte aligned");
   TW_CHECK_ARG(!(a->row_flip && (a->M & 1)), "seg_reduce: row_flip needs an even row count");
   TW_CHECK_ARG((a->X2 == nullptr) == (a->mul_idx == nullptr), "seg_reduce: X2 and mul_idx go together");
+  TW_CHECK_ARG(!a->pair_sum || a->X2 != nullptr, "seg_reduce: pair_sum is only built together with X2");
   const bool planned = a->plan_counts != nullptr;
   TW_CHECK_ARG(!planned || (a->long_row && a->long_base && a->chunk_owner && (a->partial || a->chunk_cap == 0)),
                "seg_reduce: incomplete long-row plan");
@@ -321,7 +360,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   p.ptr = a->ptr, p.col = a->col, p.M = a->M, p.X = a->X, p.C = a->C, p.flip = a->flip, p.row_flip = a->row_flip;
   p.src_scale = a->src_scale, p.skip_mask = a->skip_mask, p.row_skip_mask = a->row_skip_mask;
   p.skip_self = a->skip_self, p.self_mode = a->self_mode, p.dst_scale = a->dst_scale, p.bias = a->bias;
-  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate;
+  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum;
   p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
   p.partial = a->partial;
   cudaStream_t s = (cudaStream_t)stream;

@@ -194,19 +194,20 @@ embedding.register_autograd(_emb_bwd, setup_context=_emb_setup)
 
 @torch.library.custom_op("twowl::pair_init", mutates_args=())
 def pair_init(x: Tensor, src: Tensor, dst: Tensor, ptr_s: Tensor, ids_s: Tensor, plan_s: Optional[Tensor], ptr_d: Tensor,
-              ids_d: Tensor, plan_d: Optional[Tensor]) -> Tensor:
+              ids_d: Tensor, plan_d: Optional[Tensor], mated: bool = False) -> Tensor:
     """H[p] = x[src[p]] * x[dst[p]] (model.py:75); (ptr_s, ids_s) / (ptr_d, ids_d) = pair rows grouped by
-    src / dst node, used by the backward."""
+    src / dst node, used by the backward. mated: rows 2k / 2k+1 are (u,v) / (v,u) (utils.py:81-90)."""
     return ops.pair_init_fwd(x.contiguous(), src, dst)
 
 
 @pair_init.register_fake
-def _(x, src, dst, ptr_s, ids_s, plan_s, ptr_d, ids_d, plan_d):
+def _(x, src, dst, ptr_s, ids_s, plan_s, ptr_d, ids_d, plan_d, mated=False):
     return x.new_empty((src.numel(), x.shape[1]))
 
 
 def _pi_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    ctx.save_for_backward(*inputs[:9])
+    ctx.mated = bool(inputs[9])
 
 
 def _pi_bwd(ctx, g):
@@ -214,9 +215,14 @@ def _pi_bwd(ctx, g):
     g = g.contiguous()
     N = x.shape[0]
     # dx[n] = sum_{p: src[p]=n} g[p]*x[dst[p]] + sum_{p: dst[p]=n} g[p]*x[src[p]]
-    dx = ops.seg_reduce(ptr_s, ids_s, N, g, plan=plan_s, X2=x, mul_idx=dst)
-    ops.seg_reduce(ptr_d, ids_d, N, g, plan=plan_d, X2=x, mul_idx=src, out=dx, accumulate=True)
-    return (dx,) + (None,) * 8
+    if ctx.mated:
+        # the pairs with dst = n are the mates p^1 of the pairs with src = n, and src[p^1] = dst[p]:
+        # dx[n] = sum_{p: src[p]=n} (g[p] + g[p^1]) * x[dst[p]] - one pass, g read once as 2-row blocks
+        dx = ops.seg_reduce(ptr_s, ids_s, N, g, plan=plan_s, X2=x, mul_idx=dst, pair_sum=True)
+    else:
+        dx = ops.seg_reduce(ptr_s, ids_s, N, g, plan=plan_s, X2=x, mul_idx=dst)
+        ops.seg_reduce(ptr_d, ids_d, N, g, plan=plan_d, X2=x, mul_idx=src, out=dx, accumulate=True)
+    return (dx,) + (None,) * 9
 
 
 pair_init.register_autograd(_pi_bwd, setup_context=_pi_setup)

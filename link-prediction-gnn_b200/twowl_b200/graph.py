@@ -96,6 +96,7 @@ class PairTable:
     ids_d: torch.Tensor
     plan_s: torch.Tensor
     plan_d: torch.Tensor
+    mated: bool = False  # rows 2k / 2k+1 are (u,v) / (v,u): the doubled layout of utils.py:81-90
 
 
 def pair_table(pos: torch.Tensor, n: int) -> PairTable:
@@ -104,8 +105,12 @@ def pair_table(pos: torch.Tensor, n: int) -> PairTable:
         ptr_s, ids_s = ops.csr_build(p[:, 0], n)
         ptr_d, ids_d = ops.csr_build(p[:, 1], n)
         R = p.shape[0]
+        mated = False
+        if R % 2 == 0 and R > 0:   # one host read per pair table (cached): does the doubled layout hold?
+            q = p.reshape(R // 2, 2, 2)
+            mated = bool(((q[:, 0, 0] == q[:, 1, 1]) & (q[:, 0, 1] == q[:, 1, 0])).all().item())
         return PairTable(n, R, ops.narrow_i32(p[:, 0]), ops.narrow_i32(p[:, 1]), ptr_s, ids_s, ptr_d, ids_d,
-                         ops.seg_plan(ptr_s, n, R), ops.seg_plan(ptr_d, n, R))
+                         ops.seg_plan(ptr_s, n, R), ops.seg_plan(ptr_d, n, R), mated)
     return _cache.get(pos, ("pos", n), build)
 
 

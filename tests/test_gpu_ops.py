@@ -275,13 +275,16 @@ def test_linear_fwd_bwd(U, M, Ci, Co, impl, monkeypatch):
     assert_close(gw.grad, w.grad, atol=k(w.grad), what="linear dW")
 
 
-def test_pair_init_readout_embedding(U):
+@pytest.mark.parametrize("mated", [False, True])
+def test_pair_init_readout_embedding(U, mated):
     from twowl_b200 import functional as F2
     from twowl_b200 import graph as G
     torch.manual_seed(3)
     N, R, C, V, L = 500, 4000, 24, 37, 300
     X = torch.randn(N, C, dtype=torch.float64).requires_grad_(True)
     pos = torch.randint(0, N, (R, 2))
+    if mated:   # the doubled layout of utils.py:81-90: rows 2k / 2k+1 = (u,v) / (v,u) -> one-pass backward
+        pos[1::2] = pos[0::2].flip(1)
     idx = torch.randint(0, R, (2 * L,))
     idx[5] = idx[4]
     idx[10] = idx[2]                                   # duplicates: gradients must add up
@@ -300,7 +303,8 @@ def test_pair_init_readout_embedding(U):
     gX, gw, gb, gemb = c(X), c(w), c(b), c(emb)
     pt = G.pair_table(pos.cuda(), N)
     g0 = F2.embedding(gemb, deg.cuda()) + gX
-    gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d)
+    assert pt.mated == mated
+    gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
     out = F2.readout(gH, idx.cuda(), gw, gb)
     out.backward(gout.float().cuda())
     assert_close(out, ref.detach(), atol=1e-4, what="readout fwd")
