@@ -205,16 +205,24 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
 
 // sums[0:C] = A = sum g_y, sums[C:2C] = B = sum g_y*n, sums[2C:3C] = (alpha/M) * sum g_o   (fp32, for pass 2)
 // dparams[0:C] = dweight = B, [C:2C] = dbias = A, [2C:3C] = dmean_scale = -mean * sum g_o, [3C:4C] = colsum(dx)
+// one WARP per column: lane l adds the CTA partials l, l+32, ... then a fixed-order xor tree (deterministic)
+__device__ __forceinline__ double warp_part_sum(const double* __restrict__ part, int nparts, int nv, int v, int C, int c) {
+  const int lane = threadIdx.x & 31;
+  double a = 0;
+  for (int b = lane; b < nparts; b += 32) a += part[((size_t)b * nv + v) * C + c];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  return a;
+}
+
 __global__ void k_gn_bwd_final(const double* __restrict__ part, int nparts, int nv, int voff, int64_t M, int C,
                                const float* __restrict__ stats, const float* __restrict__ weight,
                                const float* __restrict__ mean_scale, float* __restrict__ sums, float* __restrict__ dparams) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double A = 0, B = 0;
-  for (int b = 0; b < nparts; ++b) {
-    A += part[((size_t)b * nv + voff + 0) * C + c];
-    B += part[((size_t)b * nv + voff + 1) * C + c];
-  }
+  const double A = warp_part_sum(part, nparts, nv, voff + 0, C, c);
+  const double B = warp_part_sum(part, nparts, nv, voff + 1, C, c);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = stats[c], inv = stats[C + c], w = weight[c], a = mean_scale[c];
   // sum_rows n = inv * M * mean * (1 - a);  sum g_o = inv*w*(A - (B/M) * sum n)
   const double sum_go = inv * w * (A - B * inv * mean * (1.0 - a));
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* _
 
 // per selected position j (row a = idx[j], partner row b = idx[j^1], link l = j/2):
 //   G[j] = dpred[l] * w * hn[b]   (gradient w.r.t. hn[a]),  and the column partial sums of both GraphNorm backwards
-//   (sum g_y, sum g_y*n per branch) plus dw = sum_l dpred[l] * hn[a]*hn[b] (even positions only).
+//   (sum g_y, sum g_y*n per branch) plus dw = sum_l dpred[l] * hn[a]*hn[b] and db = sum_l dpred[l] (even positions only).
 __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const float* __restrict__ xf, const float* __restrict__ xr, int C,
                                                                        const float* __restrict__ stf, const float* __restrict__ str_,
                                                                        const float* __restrict__ wf, const float* __restrict__ bf,
@@ -434,7 +442,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
                                                                        const float* __restrict__ w, const float* __restrict__ dpred,
                                                                        float* __restrict__ G, double* __restrict__ part) {
   const RowMap rm(C);
-  float4 v[5] = {f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+  float4 v[6] = {f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero()};
   if (rm.slot >= 0) {
     const int c0 = rm.c4 * 4;
     const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
@@ -463,10 +471,11 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
         const float4 ha = gn2_row(af, ar, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)ea);
         v[4].x = fmaf(g, ha.x * hb.x, v[4].x), v[4].y = fmaf(g, ha.y * hb.y, v[4].y);
         v[4].z = fmaf(g, ha.z * hb.z, v[4].z), v[4].w = fmaf(g, ha.w * hb.w, v[4].w);
+        if (rm.c4 == 0) v[5].x += g;   // db = sum_l dpred[l], carried in column 0 of a sixth partial
       }
     }
   }
-  cta_col_reduce<5>(rm, v, part, C);
+  cta_col_reduce<6>(rm, v, part, C);
 }
 
 // per-row chains of the positions that select it: head[row] -> position -> next[position] -> ... -> -1.
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kNormThreads) k_row_chains(const int64_t* __re
   }
 }
 
-__global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx_rows(const float* __restrict__ xf, const float* __restrict__ xr,
+__global__ void __launch_bounds__(kNormThreads, 3) k_gn_bwd2_dx_rows(const float* __restrict__ xf, const float* __restrict__ xr,
                                                                   const float* __restrict__ G, const int32_t* __restrict__ head,
                                                                   const int32_t* __restrict__ next, int64_t M, int C,
                                                                   const float* __restrict__ stf, const float* __restrict__ str_,
@@ -505,9 +514,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx_rows(const float* _
   const float4* __restrict__ G4 = reinterpret_cast<const float4*>(G);
   float4* __restrict__ of4 = reinterpret_cast<float4*>(dxf);
   float4* __restrict__ or4 = reinterpret_cast<float4*>(dxr);
-  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
-    const int64_t e = r * rm.cv + rm.c4;
-    const float4 a = ldg_stream(xf4 + e), b = ldg_stream(xr4 + e);
+  auto chain_grad = [&](int64_t r) -> float4 {
     float4 d = f4_zero();
     const int h = __ldg(head + r);
     if (h >= 0) {
@@ -525,39 +532,42 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx_rows(const float* _
         }
       }
     }
+    return d;
+  };
+  auto emit = [&](int64_t e, const float4& a, const float4& b, const float4& d) {
     float gy[4], n[4], o[4];
     gn_gy(a, d, cf.sc, cf.of, cf.nm, cf.ni, thresh, inv_keep, seed_f, (uint64_t)e, relu, gy, n);
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = cf.sc[i] * (gy[i] - n[i] * bmf[i]) - cof[i];
-    of4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    stg_stream(of4 + e, make_float4(o[0], o[1], o[2], o[3]));
     gn_gy(b, d, cr.sc, cr.of, cr.nm, cr.ni, thresh, inv_keep, seed_r, (uint64_t)e, relu, gy, n);
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = cr.sc[i] * (gy[i] - n[i] * bmr[i]) - cor[i];
-    or4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    stg_stream(or4 + e, make_float4(o[0], o[1], o[2], o[3]));
+  };
+  // two rows per thread and iteration: four streaming loads (+ two chain heads) in flight before any is consumed
+  const int64_t stride = (int64_t)gridDim.x * rm.slots;
+  for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += 2 * stride) {
+    const int64_t r1 = r + stride;
+    const bool two = r1 < M;
+    const int64_t e0 = r * rm.cv + rm.c4, e1 = r1 * rm.cv + rm.c4;
+    const float4 a0 = ldg_stream(xf4 + e0), b0 = ldg_stream(xr4 + e0);
+    const float4 a1 = two ? ldg_stream(xf4 + e1) : f4_zero(), b1 = two ? ldg_stream(xr4 + e1) : f4_zero();
+    const float4 d0 = chain_grad(r);
+    const float4 d1 = two ? chain_grad(r1) : f4_zero();
+    emit(e0, a0, b0, d0);
+    if (two) emit(e1, a1, b1, d1);
   }
 }
 
-__global__ void k_part_colsum_final(const double* __restrict__ part, int nparts, int nv, int voff, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0;
-  for (int b = 0; b < nparts; ++b) s += part[((size_t)b * nv + voff) * C + c];
-  out[c] = (float)s;
+// out[c] = sum over CTAs of part[.][voff][c] for c < ncols (a warp per column)
+__global__ void k_part_colsum_final(const double* __restrict__ part, int nparts, int nv, int voff, int C, int ncols,
+                                    float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= ncols) return;
+  const double s = warp_part_sum(part, nparts, nv, voff, C, c);
+  if ((threadIdx.x & 31) == 0) out[c] = (float)s;
 }
-__global__ void k_sum_vec_f(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
-  // single CTA, fixed order: per-thread strided double partials, then a tree over 256 threads
-  __shared__ double s[256];
-  double a = 0;
-  for (int64_t i = threadIdx.x; i < n; i += 256) a += (double)v[i];
-  s[threadIdx.x] = a;
-  __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if ((int)threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = (float)s[0];
-}
-
 // ---------------------------------------------------------------- column sum ---------------------
 __global__ void __launch_bounds__(kNormThreads) k_colsum_partial(const float* __restrict__ x, int64_t M, int C,
                                                                  double* __restrict__ part) {
@@ -651,7 +661,7 @@ extern "C" int twowl_graphnorm_bwd(const float* x, const float* dout, int64_t M,
   const int grid = norm_grid(M, C);
   k_gn_bwd_partial<<<grid, kNormThreads, red_smem(C, 2), s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep,
                                                               seed, relu, part);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 2, 0, M, C, stats, weight, mean_scale, sums, dparams);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid, 2, 0, M, C, stats, weight, mean_scale, sums, dparams);
   k_gn_bwd_dx<<<grid, kNormThreads, 0, s>>>(x, dout, M, C, stats, weight, bias, mean_scale, thresh, inv_keep, seed, relu, sums,
                                             dx);
   TW_LAUNCH_CHECK();
@@ -720,8 +730,8 @@ extern "C" int twowl_graphnorm_bwd2(const float* xf, const float* xr, const floa
   const int grid = norm_grid(M, C);
   k_gn_bwd2_partial<<<grid, kNormThreads, red_smem(C, 4), s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
                                                                inv_keep, seed_f, seed_r, relu, part);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 4, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid, 4, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid, 4, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid, 4, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
   k_gn_bwd2_dx<<<grid, kNormThreads, 0, s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep, seed_f,
                                              seed_r, relu, sums_f, sums_r, dxf, dxr);
   TW_LAUNCH_CHECK();
@@ -747,7 +757,7 @@ extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M
 extern "C" size_t twowl_gn2_readout_bwd_workspace_bytes(int64_t M, int64_t L, int32_t C) {
   const size_t l = (size_t)(L > 0 ? L : 1);
   return align_up(2 * l * (size_t)C * sizeof(float)) + align_up((size_t)(M > 0 ? M : 1) * sizeof(int32_t)) + align_up(2 * l * sizeof(int32_t)) +
-         align_up((size_t)kNormMaxCtas * 5 * (size_t)C * sizeof(double)) + 2 * align_up(3 * (size_t)C * sizeof(float));
+         align_up((size_t)kNormMaxCtas * 6 * (size_t)C * sizeof(double)) + 2 * align_up(3 * (size_t)C * sizeof(float));
 }
 
 extern "C" int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
@@ -768,20 +778,20 @@ extern "C" int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M
   float* G = c.take<float>(2 * l * C);
   int32_t* head = c.take<int32_t>((size_t)M);
   int32_t* next = c.take<int32_t>(2 * l);
-  double* part = c.take<double>((size_t)kNormMaxCtas * 5 * C);
+  double* part = c.take<double>((size_t)kNormMaxCtas * 6 * C);
   float* sums_f = c.take<float>(3 * (size_t)C);
   float* sums_r = c.take<float>(3 * (size_t)C);
   const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
   const float inv_keep = 1.f / (1.f - p_drop);
   TW_CUDA(cudaMemsetAsync(head, 0xFF, (size_t)M * sizeof(int32_t), s));
   const int grid_l = norm_grid(2 * (int64_t)l, C);
-  k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 5), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
+  k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 6), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
                                                                       seed_f, seed_r, relu, idx, sidx, L, w, dpred, G, part);
   if (L > 0) k_row_chains<<<grid_for(2 * L, kNormThreads), kNormThreads, 0, s>>>(idx, sidx, 2 * L, M, head, next);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
-  k_gn_bwd_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
-  k_part_colsum_final<<<(int)cdiv(C, 128), 128, 0, s>>>(part, grid_l, 5, 4, C, dw);
-  k_sum_vec_f<<<1, 256, 0, s>>>(dpred, L, db);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_part_colsum_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 4, C, C, dw);
+  k_part_colsum_final<<<1, 32, 0, s>>>(part, grid_l, 6, 5, C, 1, db);
   k_gn_bwd2_dx_rows<<<norm_grid(M, C), kNormThreads, 0, s>>>(xf, xr, G, head, next, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
                                                              inv_keep, seed_f, seed_r, relu, sums_f, sums_r, dxf, dxr);
   TW_LAUNCH_CHECK();

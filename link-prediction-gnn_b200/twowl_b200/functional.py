@@ -149,6 +149,7 @@ def _gn_setup(ctx, inputs, output):
     ctx.meta = (p_drop, seed, relu)
     ctx.has_addend = addend is not None
     ctx.mark_non_differentiable(output[1])
+    ctx.set_materialize_grads(False)
 
 
 def _gn_bwd(ctx, g, _g_stats):
@@ -300,6 +301,7 @@ def _pl_setup(ctx, inputs, output):
                           Of, Or, sf, sr, SHf, SHr)
     ctx.meta = (n_node, p_drop, seed_f, seed_r)
     ctx.mark_non_differentiable(Of, Or, sf, sr, SHf, SHr)
+    ctx.set_materialize_grads(False)   # no zero-filled [R,C] gradients for the saved-state outputs
 
 
 def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars):
@@ -379,6 +381,7 @@ def _plr_setup(ctx, inputs, output):
                           bnode, Of, Or, sf, sr, SHf, SHr)
     ctx.meta = (n_node, p_drop, seed_f, seed_r)
     ctx.mark_non_differentiable(Of, Or, sf, sr, SHf, SHr)
+    ctx.set_materialize_grads(False)   # no zero-filled [R,C] gradients for the saved-state outputs
 
 
 def _plr_bwd(ctx, g, *_unused):
