@@ -1,5 +1,6 @@
 // common.cuh - shared host/device helpers for libtwowl_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -129,6 +130,11 @@ int scan_exclusive_i64(const int64_t* in, int64_t* out, int64_t n, void* ws, cud
 size_t radix_workspace_bytes(int64_t n);
 int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int64_t n,
                      int bits, void* ws, cudaStream_t s);
+
+// ---- TMA tensor map of a row-major fp32 [rows, cols] matrix (prims.cu): boxes of box_cols x box_rows elements.
+// cuTensorMapEncodeTiled is reached through the runtime's driver entry point, so libcuda is not linked.
+int make_tmap_2d_f32(CUtensorMap* tm, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
+                     CUtensorMapSwizzle swizzle);
 
 // ---- tensor-core linear layer implemented in linear_tc.cu ----------------------------------------
 // C[M,Nd] = A[M,Kd] * B^T with B[n][k] = W[n*Kd+k] (w_kn = 0) or W[k*Nd+n] (w_kn = 1); tcgen05 kind::tf32, 3xTF32.

@@ -4,30 +4,33 @@
 //
 // (reference: autograd of GCNConv.lin at TwoWL/model/model.py:37 for conv2s[i] and conv2s_r[i], which share
 // their input H - model.py:77). The reduction runs over M = rows of the pair table, so both operands are used
-// in their natural row-major form as MN-MAJOR UMMA operands (SWIZZLE_128B_BASE32B, the one layout a transposed tf32
-// operand may use; a 16-byte chunk of a row is stored as loaded): a 64-row tile of dO_f/dO_r is the A operand [128 x 64k],
-// the same rows of H are the B operand [C x 64k]; tcgen05.mma kind::tf32, 3xTF32 split.
-// H is read once for both directions: 3 reads of [M,C] in total.
+// in their natural row-major form as MN-MAJOR UMMA operands: a 64-row tile of dO_f/dO_r is the A operand [128 x 64k],
+// the same rows of H are the B operand [C x 64k]; tcgen05.mma kind::tf32, 3xTF32 split. H is read once for both
+// directions: 3 reads of [M,C] in total.
 //
-// One persistent warp-specialised CTA per SM (same roles as pair_conv.cu). Accuracy of the long reduction: the
-// TMEM accumulator is drained into fp32 registers every kFlush tiles (1024 rows), CTA partials are written to
-// global memory and added in double in CTA order by a second kernel: deterministic.
+// One persistent CTA per SM, 10 warps, warp-specialised:
+//   warp  0    TMA producer: raw fp32 tiles of dO_f, dO_r, H with cp.async.bulk.tensor (SWIZZLE_128B_ATOM_32B tensor maps
+//                            = the one MN-major layout the tensor core accepts for tf32, see below), L2 evict-first
+//   warps 2-5  split       : A: v = selfw[row] * raw written back in place (the tensor core truncates it to tf32 = the `hi`
+//                            operand) and lo = v - trunc(v) into a second buffer; B: lo only (raw H is its own hi)
+//   warp  1    MMA issuer  : 3 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
+//   warps 6-9  drain       : TMEM -> fp32 registers (1024-row partial sums), per-CTA partials to global memory; a second
+//                            kernel adds them in double in CTA order: deterministic.
 #include "common.cuh"
 
 namespace twowl {
 
-constexpr int kDwProducerWarps = 8;
-constexpr int kDwThreads = (kDwProducerWarps + 4 + 1) * 32;  // 416
-constexpr int kDwTileK = 64;                                 // rows of the pair table per stage
+constexpr int kDwSplitWarps = 4;
+constexpr int kDwFirstSplit = 2;
+constexpr int kDwFirstDrain = kDwFirstSplit + kDwSplitWarps;   // 6
+constexpr int kDwThreads = (kDwFirstDrain + 4) * 32;           // 320
+constexpr int kDwTileK = 64;                                   // rows of the pair table per stage
 constexpr int kDwStages = 2;
-constexpr int kDwFlush = 16;                                 // tiles accumulated in TMEM between drains
+constexpr int kDwFlush = 16;                                   // tiles accumulated in TMEM between drains
 
 struct DwParams {
-  const float* dOf;
-  const float* dOr;
   const float* rsf;
   const float* rsr;
-  const float* H;
   int64_t M;
   float* part;  // [gridDim.x][128][C]
 };
@@ -38,19 +41,14 @@ __device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_
 // as the hardware reads it (same probe): element (mn, k) of an operand lives at byte
 //   (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + ((((mn % 32) / 8) ^ (k % 4)) * 32) + (mn % 8) * 4
 // i.e. 512-byte atoms of 4 k-rows x 32 mn-elements whose 32-byte units are XOR-swizzled by the k-row (Swizzle<2,5,2>).
-// A 16-byte chunk of a row-major global row is stored as loaded; 8 consecutive chunks of one row fill one 128-byte line,
-// so the staging stores of a quarter-warp are bank-conflict free.
+// With SBO = 512 a group of 32 mn-elements is [64 k-rows][128 B] - exactly what a TMA box of 32 columns x 64 rows with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes, so row-major global tiles land in operand layout without a register pass.
 constexpr uint32_t kDwSbo = 512u;                                   // next group of 4 k-rows
 constexpr uint32_t kDwLbo = (kDwTileK / 4) * kDwSbo;                // next group of 32 mn-elements (8 KB)
 constexpr uint32_t kDwKStep = 2u * kDwSbo;                          // one tf32 MMA consumes 8 k-rows
 __device__ __forceinline__ uint64_t dw_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((kDwLbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((kDwSbo >> 4) & 0x3FFFu) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
-}
-// byte offset of the 16-byte chunk cc (mn elements 4cc..4cc+3) of k-row rr inside one operand buffer
-__device__ __forceinline__ uint32_t dw_off(int rr, int cc) {
-  return (uint32_t)(cc >> 3) * kDwLbo + (uint32_t)(rr >> 2) * kDwSbo + (uint32_t)(rr & 3) * 128u +
-         (uint32_t)((((cc & 7) >> 1) ^ (rr & 3)) << 5) + (uint32_t)((cc & 1) << 4);
 }
 __device__ __forceinline__ void dw_mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dw_smem_u32(bar)), "r"(count));
@@ -68,6 +66,16 @@ __device__ __forceinline__ void dw_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void dw_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dw_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dw_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dw_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dw_tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          dw_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(dw_smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 __device__ __forceinline__ void dw_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dw_smem_u32(bar)) : "memory");
@@ -92,44 +100,40 @@ __device__ __forceinline__ void dw_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
-}
+__device__ __forceinline__ float dw_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// C = width of dO_f, dO_r and H (32 or 64).
-//   A stage: 4 groups of 32 M-elements, hi then lo  (M = 128 = [f cols | r cols | zero padding when C = 32])
-//   B stage: C/32 groups hi + C/32 lo
+// C = width of dO_f, dO_r and H (32 or 64). One stage:
+//   A_hi: 4 groups of 32 M-elements (M = 128 = [f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
 template <int C>
-__global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
-  constexpr int C4 = C / 4;                        // 16-byte chunks per row
-  constexpr uint32_t kAHalf = 4u * kDwLbo;         // hi (or lo) part of the A stage: 128 M elements = 4 groups
-  constexpr uint32_t kBHalf = (uint32_t)(C / 32) * kDwLbo;
+__global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
+                                                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmH) {
+  constexpr int GS = C / 32;                          // 32-column groups per source
+  constexpr uint32_t kAHalf = 4u * kDwLbo;            // hi (or lo) part of the A stage: 128 M elements = 4 groups
+  constexpr uint32_t kBHalf = (uint32_t)GS * kDwLbo;
   constexpr uint32_t kStage = 2u * kAHalf + 2u * kBHalf;
-  constexpr int kChunksSrc = kDwTileK * C4 / (kDwProducerWarps * 32);  // chunks per producer thread per source
+  constexpr uint32_t kTxBytes = 3u * GS * kDwLbo;     // raw bytes landing per tile
   extern __shared__ uint8_t dw_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kStage);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 2;
-  uint64_t* tfull = bars + 4;
-  uint64_t* tempty = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* raw_full = bars;        // [stages] TMA -> split
+  uint64_t* split_done = bars + 2;  // [stages] split -> MMA
+  uint64_t* empty = bars + 4;       // [stages] MMA -> TMA
+  uint64_t* tfull = bars + 6;       // [2] MMA -> drain
+  uint64_t* tempty = bars + 8;      // [2] drain -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (p.M + kDwTileK - 1) / kDwTileK;
   const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == 12) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dw_smem_u32(tmem_slot)), "r"(2 * 64) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     for (int s = 0; s < kDwStages; ++s) {
-      dw_mbar_init(&full[s], kDwProducerWarps * 32);
+      dw_mbar_init(&raw_full[s], 1);
+      dw_mbar_init(&split_done[s], kDwSplitWarps * 32);
       dw_mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -137,13 +141,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
       dw_mbar_init(&tempty[a], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmF)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
   }
-  // zero the padding slabs of A (C = 32 only): written once, never touched by the producers
-  if (2 * C < 128) {
+  // zero the padding groups of A (C = 32 only): written once, never touched again
+  if (2 * GS < 4) {
     for (int st = 0; st < kDwStages; ++st)
       for (int half = 0; half < 2; ++half) {
-        float4* z = reinterpret_cast<float4*>(smem + st * kStage + half * kAHalf + (2 * C / 32) * kDwLbo);
-        for (int i = tid; i < (int)((4 - 2 * C / 32) * kDwLbo / 16); i += kDwThreads) z[i] = f4_zero();
+        float4* z = reinterpret_cast<float4*>(smem + st * kStage + half * kAHalf + 2 * GS * kDwLbo);
+        for (int i = tid; i < (int)((4 - 2 * GS) * kDwLbo / 16); i += kDwThreads) z[i] = f4_zero();
       }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -152,66 +159,29 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kDwProducerWarps) {
-    // ===================================================== producers
-    float4 regs[2][3][kChunksSrc];
-    auto issue = [&](int64_t it, float4 (&r)[3][kChunksSrc]) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int64_t rows_left = p.M - tile * kDwTileK;
-      const float4* __restrict__ s0 = reinterpret_cast<const float4*>(p.dOf) + tile * kDwTileK * C4;
-      const float4* __restrict__ s1 = reinterpret_cast<const float4*>(p.dOr) + tile * kDwTileK * C4;
-      const float4* __restrict__ s2 = reinterpret_cast<const float4*>(p.H) + tile * kDwTileK * C4;
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int st = (int)(it % kDwStages);
+        const int row = (int)(tile * kDwTileK);
+        dw_mbar_wait(&empty[st], (uint32_t)(((it / kDwStages) & 1) ^ 1));
+        dw_mbar_expect_tx(&raw_full[st], kTxBytes);
+        uint8_t* Ahi = smem + st * kStage;
+        uint8_t* Bhi = Ahi + 2 * kAHalf;
 #pragma unroll
-      for (int j = 0; j < kChunksSrc; ++j) {
-        const int idx = j * (kDwProducerWarps * 32) + tid;
-        const bool ok = idx / C4 < rows_left;
-        r[0][j] = ok ? ldg_stream(s0 + idx) : f4_zero();
-        r[1][j] = ok ? ldg_stream(s1 + idx) : f4_zero();
-        r[2][j] = ok ? ldg_stream(s2 + idx) : f4_zero();
+        for (int g = 0; g < GS; ++g) {
+          dw_tma_load_2d(Ahi + (size_t)g * kDwLbo, &tmF, g * 32, row, &raw_full[st], policy);
+          dw_tma_load_2d(Ahi + (size_t)(GS + g) * kDwLbo, &tmR, g * 32, row, &raw_full[st], policy);
+          dw_tma_load_2d(Bhi + (size_t)g * kDwLbo, &tmH, g * 32, row, &raw_full[st], policy);
+        }
       }
-    };
-    auto stage = [&](int64_t it, float4 (&r)[3][kChunksSrc]) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
-      const int st = (int)(it % kDwStages);
-      dw_mbar_wait(&empty[st], (uint32_t)(((it / kDwStages) & 1) ^ 1));
-      uint8_t* Ahi = smem + st * kStage;
-      uint8_t* Alo = Ahi + kAHalf;
-      uint8_t* Bhi = Alo + kAHalf;
-      uint8_t* Blo = Bhi + kBHalf;
-      const int64_t row0 = tile * kDwTileK;
-#pragma unroll
-      for (int j = 0; j < kChunksSrc; ++j) {
-        const int idx = j * (kDwProducerWarps * 32) + tid;
-        const int rr = idx / C4, c4 = idx % C4;
-        const bool ok = row0 + rr < p.M;
-        const float scf = ok ? __ldg(p.rsf + row0 + rr) : 0.f;
-        const float scr = ok ? __ldg(p.rsr + row0 + rr) : 0.f;
-        const uint32_t off = dw_off(rr, c4), off_r = dw_off(rr, c4 + C4);
-        float4 v = r[0][j], hi, lo;
-        v.x *= scf, v.y *= scf, v.z *= scf, v.w *= scf;
-        dw_split(v, hi, lo);
-        *reinterpret_cast<float4*>(Ahi + off) = hi;
-        *reinterpret_cast<float4*>(Alo + off) = lo;
-        v = r[1][j];
-        v.x *= scr, v.y *= scr, v.z *= scr, v.w *= scr;
-        dw_split(v, hi, lo);
-        *reinterpret_cast<float4*>(Ahi + off_r) = hi;
-        *reinterpret_cast<float4*>(Alo + off_r) = lo;
-        dw_split(r[2][j], hi, lo);
-        *reinterpret_cast<float4*>(Bhi + off) = hi;
-        *reinterpret_cast<float4*>(Blo + off) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      dw_mbar_arrive(&full[st]);
-    };
-    if (my_tiles > 0) issue(0, regs[0]);
-    for (int64_t it = 0; it < my_tiles; it += 2) {
-      if (it + 1 < my_tiles) issue(it + 1, regs[1]);
-      stage(it, regs[0]);
-      if (it + 2 < my_tiles) issue(it + 2, regs[0]);
-      if (it + 1 < my_tiles) stage(it + 1, regs[1]);
     }
-  } else if (warp == 12) {
+    __syncwarp();
+  } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       // D[128, C] (+)= A[128 x 8] * B[C x 8]^T per K-step; A and B both MN-major
@@ -224,7 +194,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int st = (int)(it % kDwStages);
-        dw_mbar_wait(&full[st], (uint32_t)((it / kDwStages) & 1));
+        dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
+        dw_mbar_wait(&split_done[st], (uint32_t)((it / kDwStages) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* Ahi = smem + st * kStage;
         const uint8_t* Alo = Ahi + kAHalf;
@@ -246,9 +217,52 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
       }
     }
     __syncwarp();
+  } else if (warp < kDwFirstDrain) {
+    // ===================================================== split (scale + hi/lo), linear over the swizzled buffers
+    const int t = tid - kDwFirstSplit * 32;                  // 0..127
+    constexpr int kSplitThreads = kDwSplitWarps * 32;
+    constexpr int kAChunks = 2 * GS * (int)(kDwLbo / 16);    // 16-byte chunks of the live A groups (f then r)
+    constexpr int kBChunks = GS * (int)(kDwLbo / 16);
+    constexpr int kAIter = kAChunks / kSplitThreads, kBIter = kBChunks / kSplitThreads;
+    // chunk i of a group region sits in k-row (i % 512) / 8; with i = j*128 + t that is (j % 4) * 16 + t / 8
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int st = (int)(it % kDwStages);
+      const int64_t row0 = tile * kDwTileK;
+      float sf[4], sr[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // row scales first: they do not depend on the TMA data
+        const int64_t row = row0 + q * 16 + (t >> 3);
+        sf[q] = row < p.M ? __ldg(p.rsf + row) : 0.f;
+        sr[q] = row < p.M ? __ldg(p.rsr + row) : 0.f;
+      }
+      dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
+      float4* Ahi = reinterpret_cast<float4*>(smem + st * kStage);
+      float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
+      const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
+      float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
+#pragma unroll 4
+      for (int j = 0; j < kAIter; ++j) {
+        const int i = j * kSplitThreads + t;
+        const bool is_r = i >= GS * (int)(kDwLbo / 16);
+        const float sc = is_r ? sr[j & 3] : sf[j & 3];
+        float4 v = Ahi[i];
+        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
+        Ahi[i] = v;
+        Alo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
+      }
+#pragma unroll 4
+      for (int j = 0; j < kBIter; ++j) {
+        const int i = j * kSplitThreads + t;
+        const float4 v = Bhi[i];
+        Blo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      dw_mbar_arrive(&split_done[st]);
+    }
   } else {
-    // ===================================================== drain: warp ew <-> TMEM lanes (= rows of [dW_f; dW_r]) 32ew..32ew+31
-    const int ew = warp - kDwProducerWarps;
+    // ===================================================== drain: a warp may only touch TMEM lanes 32*(warp%4)..+31
+    const int ew = warp & 3;   // TMEM lane quarter = rows 32ew..32ew+31 of [dW_f; dW_r]
     float acc[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) acc[i] = 0.f;
@@ -270,11 +284,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p) {
     }
     float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * 128 + ew * 32 + lane) * C);
 #pragma unroll
-    for (int q = 0; q < C4; ++q) dst[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+    for (int q = 0; q < C / 4; ++q) dst[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * 64) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * 64) : "memory");
 }
 
 // dW_f[co][ci] = sum_cta part[cta][co][ci], dW_r = rows C..2C-1, added in CTA order in double
@@ -299,10 +313,14 @@ static size_t dw_smem() {
 }
 
 template <int C>
-static int dw_launch(const DwParams& p, cudaStream_t s) {
+static int dw_launch(const DwParams& p, const float* dOf, const float* dOr, const float* H, cudaStream_t s) {
+  CUtensorMap tf, tr, th;
+  if (int rc = make_tmap_2d_f32(&tf, dOf, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tr, dOr, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const size_t smem = dw_smem<C>();
   TW_CUDA(cudaFuncSetAttribute(k_dw_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dw_tc<C><<<dw_grid(p.M), kDwThreads, smem, s>>>(p);
+  k_dw_tc<C><<<dw_grid(p.M), kDwThreads, smem, s>>>(p, tf, tr, th);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -324,9 +342,9 @@ extern "C" int twowl_pair_dw(const float* dOf, const float* dOr, const float* rs
   TW_CHECK_ARG(M > 0, "pair_dw: needs M > 0");
   TW_CHECK_ARG(aligned16(dOf) && aligned16(dOr) && aligned16(H) && rsf && rsr, "pair_dw: bad pointers");
   TW_CHECK_WS(ws_bytes, twowl_pair_dw_workspace_bytes(M, C));
-  DwParams p{dOf, dOr, rsf, rsr, H, M, (float*)ws};
+  DwParams p{rsf, rsr, M, (float*)ws};
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = (C == 32) ? dw_launch<32>(p, s) : dw_launch<64>(p, s);
+  int rc = (C == 32) ? dw_launch<32>(p, dOf, dOr, H, s) : dw_launch<64>(p, dOf, dOr, H, s);
   if (rc) return rc;
   k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>((const float*)ws, dw_grid(M), C, dWf, dWr);
   TW_LAUNCH_CHECK();

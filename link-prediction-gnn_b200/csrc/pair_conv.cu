@@ -23,8 +23,6 @@
 //                            128-byte row segments: gather terms, bias, store, column sums (fp32 per tile -> double per
 //                            CTA, fixed order)
 // HBM-bound by design: 4*M*(nsrc*Kd + Nd) bytes + gathers for 6*M*Kd*Nd*nsrc tensor flop.
-#include <cuda.h>
-
 #include "common.cuh"
 
 namespace twowl {
@@ -460,32 +458,9 @@ static int pc_grid(int64_t M) {
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not linked
-typedef CUresult (*pc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static pc_encode_fn pc_encoder() {
-  static pc_encode_fn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<pc_encode_fn>(sym);
-  }
-  return fn;
-}
 // row-major fp32 [M, Kd] -> boxes of 32 columns x 128 rows, SWIZZLE_128B (the UMMA K-major canonical layout)
 static int pc_make_tmap(CUtensorMap* tm, const float* A, int64_t M, int Kd) {
-  pc_encode_fn enc = pc_encoder();
-  TW_CHECK_ARG(enc != nullptr, "pair_conv: cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t gdim[2] = {(cuuint64_t)Kd, (cuuint64_t)M};
-  const cuuint64_t gstr[1] = {(cuuint64_t)Kd * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)kPcTileM};
-  const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  TW_CHECK_ARG(r == CUDA_SUCCESS, "pair_conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return 0;
+  return make_tmap_2d_f32(tm, A, M, Kd, 32, kPcTileM, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int KD, int NG>

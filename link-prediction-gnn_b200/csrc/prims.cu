@@ -242,6 +242,34 @@ int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, u
   return 0;
 }
 
+// ---------------------------------------------------------------- TMA tensor maps ----------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tmap_encode_fn>(sym);
+  }
+  return fn;
+}
+int make_tmap_2d_f32(CUtensorMap* tm, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
+                     CUtensorMapSwizzle swizzle) {
+  tmap_encode_fn enc = tmap_encoder();
+  TW_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TW_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 }  // namespace twowl
 
 extern "C" int twowl_version(void) { return 100; }
