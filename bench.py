@@ -89,11 +89,12 @@ def make_graph(workload, seed, device, scale_override=None, samples_override=Non
     return dict(n=n, pos=pos, pred=pred, pos1=pos1, und=m)
 
 
-def draw_batch(und, n_pred_und, nb, seed):
-    """Host-side batch draw, as train.py:18-23: nb positive + nb negative undirected ids (pinned)."""
-    rng = np.random.default_rng(seed)
-    i1 = torch.from_numpy(rng.choice(und, size=nb, replace=False).astype(np.int64)).pin_memory()
-    i2 = torch.from_numpy(rng.choice(n_pred_und, size=nb, replace=False).astype(np.int64)).pin_memory()
+def draw_batch(und, n_pred_und, nb, step):
+    """Host-side batch draw, as train.py:18-23: nb positive + nb negative undirected ids (pinned). Under torchrun every
+    rank takes its own disjoint slice of ONE seeded global permutation per step (twowl_b200.dist.shard_batch)."""
+    from twowl_b200 import dist as D
+    i1 = D.shard_batch(und, nb, step, seed=1).pin_memory()
+    i2 = D.shard_batch(n_pred_und, nb, step, seed=2).pin_memory()
     y = torch.cat((torch.ones(nb), torch.zeros(nb))).unsqueeze(-1).pin_memory()
     return i1, i2, y
 
@@ -271,6 +272,8 @@ def main():
     explicit = args.pair_path == "explicit"
     ei2 = U.get_ei2(n, pos, pred) if explicit else U.get_ei2_implicit(n, pos, pred)
     nb = max(2, g["und"] // 10)
+    if world > 1:                      # the slices of the ranks are disjoint: cap the global batch at the id range
+        nb = min(nb, g["und"] // world, (P // 2) // world)
     L = 2 * nb
 
     torch.manual_seed(0)
@@ -279,10 +282,12 @@ def main():
 
     # every rank runs the same model on its own batches (replicated graph, data-parallel over target-link
     # batches, gradients all-reduced): see DESIGN.md "Multi-GPU"
+    from twowl_b200 import dist as D
+    params = list(mod.parameters())
+
     def sync_grads():
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in mod.parameters() if p.grad is not None])
-            dist.all_reduce(flat)
+            D.allreduce_grads(params)   # one NCCL all-reduce of the flat gradient buffer, written back into .grad
 
     def prepare(batch):
         i1, i2, y = (t.to(dev, non_blocking=True) for t in batch)
@@ -301,7 +306,7 @@ def main():
         sync_grads()
         return loss
 
-    batches = [draw_batch(g["und"], P // 2, nb, 1000 + rank * 100 + i) for i in range(args.steps + args.warmup)]
+    batches = [draw_batch(g["und"], P // 2, nb, i) for i in range(args.steps + args.warmup)]
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -387,8 +392,14 @@ def main():
     tname, (tcnt, tbytes, tms) = top[0], top[1]
     achieved = (tbytes / tcnt) / (tms / tcnt * 1e-3) / 1e9 if tms > 0 else 0.0
     agg_bytes = sum(d[1] for d in by_op.values())
+    traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj.get(tname, {}).get(f"{args.workload}/hidden{hidden}", {}).get("bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": tname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches": tcnt, "avg_ms": round(tms / tcnt, 4), "share_of_kernel_time": round(tms / tot_kernel_ms, 4),
                 "algorithmic_bytes_per_launch": int(tbytes / tcnt),
                 "all_kernels_algorithmic_GBps": round(agg_bytes / (tot_kernel_ms * 1e-3) / 1e9, 1),
@@ -408,7 +419,8 @@ def main():
         "config": {"workload": args.workload, "nodes": n, "undirected_edges": g["und"], "E": E, "R": E + P,
                    "hidden": hidden, "depth1": 1, "depth2": 1, "target_links_per_step": L, "pair_path": args.pair_path,
                    "wedges_T": ei2.shape[1] if explicit else None, "l2": "256 MiB flush write between timed steps; "
-                   "activations exceed L2", "parallelism": f"dp{world}: replicated graph, one batch per rank, grad all-reduce"},
+                   "activations exceed L2", "parallelism": f"dp{world}: target links sharded over ranks (disjoint slices of one global batch per step), "
+                   "graph replicated, one all-reduce of the parameter gradients"},
         "clocks": clocks.summary(),
         "e2e": {"value": links / (e2e_ms * 1e-3), "unit": "target-links/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "includes": "H2D batch ids+labels, double, "

@@ -1,0 +1,114 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in twowl_b200/dist.py: disjoint target-link slices, the
+flat gradient all-reduce, max-over-ranks timing, even/balanced row blocks, Chan merge of GraphNorm column statistics."""
+import importlib.util
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_dist():
+    # twowl_b200/__init__ pulls the CUDA library in; dist.py itself is pure host logic, so load it by path
+    spec = importlib.util.spec_from_file_location("twowl_dist", os.path.join(ROOT, "link-prediction-gnn_b200", "twowl_b200", "dist.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = _load_dist()
+    try:
+        assert D.world() == (rank, world)
+        # 1. disjoint slices of one global batch
+        mine = D.shard_batch(1000, 37, step=5, seed=3)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        allids = torch.cat(gathered)
+        assert allids.unique().numel() == world * 37
+        assert torch.equal(mine, D.shard_batch(1000, 37, step=5, seed=3))           # reproducible
+        assert not torch.equal(mine, D.shard_batch(1000, 37, step=6, seed=3))       # a new draw per step
+        # 2. gradient all-reduce: same model, rank-dependent gradients; one parameter without a gradient on rank 1
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        extra = torch.nn.Parameter(torch.zeros(4))
+        lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+        lin.bias.grad = torch.arange(3.0) * (rank + 1)
+        if rank == 0:
+            extra.grad = torch.ones(4)
+        nred = D.allreduce_grads(list(lin.parameters()) + [extra])
+        assert nred == 15 + 3 + 4
+        tot = sum(range(1, world + 1))
+        assert torch.equal(lin.weight.grad, torch.full_like(lin.weight, float(tot)))
+        assert torch.equal(lin.bias.grad, torch.arange(3.0) * tot)
+        assert torch.equal(extra.grad, torch.ones(4))
+        # 3. slowest rank's time
+        assert D.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+        # 4. per-rank column statistics merged with Chan's formula == statistics of the concatenation
+        torch.manual_seed(7)
+        full = torch.randn(101, 6, dtype=torch.float64) * 3 + 5
+        blocks = D.row_blocks([1] * 100, world)
+        lo, hi = blocks[rank]
+        part = full[lo:hi] if rank < world - 1 else full[lo:]
+        stat = torch.cat((torch.tensor([float(part.shape[0])], dtype=torch.float64), part.mean(0), ((part - part.mean(0)) ** 2).sum(0)))
+        stats = [torch.empty_like(stat) for _ in range(world)]
+        dist.all_gather(stats, stat)
+        S = torch.stack(stats)
+        N, mu, M2 = D.merge_column_stats(S[:, 0], S[:, 1:7], S[:, 7:])
+        assert N == 101
+        assert torch.allclose(mu, full.mean(0), rtol=1e-12, atol=1e-12)
+        assert torch.allclose(M2 / N, full.var(0, unbiased=False), rtol=1e-12, atol=1e-12)
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_row_blocks_even_and_balanced():
+    D = _load_dist()
+    w = [1] * 10 + [50, 50] + [1] * 28                      # a hub pair in the middle
+    blocks = D.row_blocks(w, 4)
+    assert blocks[0][0] == 0 and blocks[-1][1] == len(w)
+    assert all(lo % 2 == 0 and hi % 2 == 0 and lo <= hi for lo, hi in blocks)
+    assert all(blocks[i][1] == blocks[i + 1][0] for i in range(3))
+    sums = [sum(w[lo:hi]) for lo, hi in blocks]
+    assert max(sums) <= 100 + 2                              # no block holds more than the hub + its share
+    with pytest.raises(ValueError):
+        D.row_blocks([1, 2, 3], 2)
+    assert D.row_blocks([], 3) == [(0, 0)] * 3
+
+
+def test_single_process_defaults():
+    D = _load_dist()
+    assert D.world() == (0, 1)
+    assert D.max_over_ranks(3.5) == 3.5
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    assert D.allreduce_grads([p]) == 3 and torch.equal(p.grad, torch.full((3,), 2.0))
