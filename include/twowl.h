@@ -311,6 +311,15 @@ size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C);
 int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
                   int32_t C, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ metrics -------------------- */
+
+/* ROC-AUC on the device (replaces pred.sigmoid().cpu().numpy() + sklearn.metrics.roc_auc_score, TwoWL/model/train.py:41-43,
+ * :61-66): out[0] = AUC with tied scores sharing their average rank (= the trapezoidal area sklearn integrates),
+ * out[1] = number of positives (label > 0.5), out[2] = number of negatives; AUC is NaN when one class is empty.
+ * score, label: fp32[n]; out: double[3] on the device. Deterministic (radix sort + fixed-order double sums). */
+size_t twowl_auc_workspace_bytes(int64_t n);
+int twowl_auc(const float* score, const float* label, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ structured wedge path ------- */
 
 /* When ei2 is the full wedge join of (pos_edge, pred_edge) minus the wedges whose source edge is blocked

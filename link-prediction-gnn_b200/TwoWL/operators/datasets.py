@@ -138,7 +138,7 @@ def load(args, device="cuda"):
     """datasets.py:154-168 - CSV edge list -> split dict."""
     import pandas as pd
     df = pd.read_csv(args.get("csv", PATH_CSV_EDGES), header=None)
-    edge_index = torch.tensor([df[0].to_numpy(), df[1].to_numpy()], dtype=torch.long, device=device)
+    edge_index = torch.from_numpy(df[[0, 1]].to_numpy(dtype="int64").T.copy()).to(device)
     return do_edge_split(_Data(edge_index), args["val_ratio"], args["test_ratio"], False)
 
 

@@ -618,3 +618,21 @@ def graphnorm_bwd2(xf, xr, dout, sf, sr, pf, pr, p_drop: float, seed_f: int, see
               "graphnorm_bwd2")
     _count(4)
     return dxf, dxr, dpf, dpr
+
+
+# ------------------------------------------------------------------------------ metrics
+
+def auc(score: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """ROC-AUC of fp32 scores against {0,1} labels on the device -> float64[3] = (auc, n_pos, n_neg), no host sync.
+    Ties share their average rank, as sklearn.metrics.roc_auc_score (train.py:41-43, :61-66)."""
+    _need_cuda(score, label)
+    score = score.detach().reshape(-1).float().contiguous()
+    label = label.detach().reshape(-1).float().contiguous()
+    n = score.numel()
+    assert label.numel() == n, "auc: score / label size mismatch"
+    out = torch.empty(3, dtype=torch.float64, device=score.device)
+    nb = lib.twowl_auc_workspace_bytes(n)
+    ws = _ws(nb, score.device)
+    check(lib.twowl_auc(score.data_ptr(), label.data_ptr(), n, out.data_ptr(), ws.data_ptr(), nb, _stream()), "auc")
+    _count(4 + 3 * 4)
+    return out

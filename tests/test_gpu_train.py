@@ -1,0 +1,80 @@
+"""GPU tests of the caller-side rows of SURVEY 8(f): device ROC-AUC (vs sklearn), the drop-in train / test / train_routine
+loop (reference TwoWL/model/train.py) and the headless driver (reference TwoWL/TwoWL_work.py) with its record files."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.mark.parametrize("n,ties", [(2, False), (1000, False), (5000, True), (200001, True)])
+def test_auc_matches_sklearn(cuda, n, ties):
+    from sklearn.metrics import roc_auc_score
+    from twowl_b200 import ops
+    rng = np.random.default_rng(n)
+    y = (rng.random(n) < 0.3).astype(np.float32)
+    y[0], y[1] = 1.0, 0.0
+    s = (rng.normal(size=n) + 0.7 * y).astype(np.float32)
+    if ties:
+        s = np.round(s, 1)                 # heavy ties, negative zero included
+        s[s == 0] = -0.0
+    out = ops.auc(torch.from_numpy(s).cuda(), torch.from_numpy(y).cuda()).cpu().numpy()
+    assert out[1] == y.sum() and out[2] == n - y.sum()
+    assert abs(out[0] - roc_auc_score(y, s)) < 1e-12
+    one = ops.auc(torch.from_numpy(s).cuda(), torch.ones(n, device="cuda")).cpu().numpy()
+    assert np.isnan(one[0])                # a single class has no AUC (sklearn raises)
+
+
+def _planted_partition_csv(path, n=360, groups=6, p_in=0.12, p_out=0.004, seed=0):
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, groups, size=n)
+    iu, ju = np.triu_indices(n, 1)
+    p = np.where(g[iu] == g[ju], p_in, p_out)
+    keep = rng.random(iu.size) < p
+    edges = np.stack([iu[keep], ju[keep]], 1)
+    np.savetxt(path, edges, fmt="%d", delimiter=",")
+    return int(keep.sum())
+
+
+def test_headless_driver_trains_and_writes_the_reference_record_files(cuda, tmp_path, monkeypatch):
+    import TwoWL.TwoWL_work as W
+    import TwoWL.model.train as T
+    csv = tmp_path / "edges.csv"
+    m = _planted_partition_csv(csv)
+    assert m > 500
+    monkeypatch.chdir(tmp_path)           # fpr.json / tpr.json / logs.json land in the working directory, as in the reference
+    monkeypatch.setitem(W.SEARCH_SPACE, "lr", [0.05])
+    monkeypatch.setitem(W.SEARCH_SPACE, "depth1", [2])
+    monkeypatch.setitem(W.SEARCH_SPACE, "depth2", [1, 2])
+    for k in ("dp_lin0", "dp_lin1", "dp_emb", "dp_1wl0", "dp_1wl1", "dp_2wl"):
+        monkeypatch.setitem(W.SEARCH_SPACE, k, [0.0, 0.1])
+    args = argparse.Namespace(pattern="2wl_l", epoch=300, trials=2, seed=0, csv=str(csv), dataset="planted",
+                              record_dir=str(tmp_path / "records_auc") + os.sep, time_dir=str(tmp_path / "assets"))
+    res = W.work(args, "cuda")
+    assert set(res["best_params"]) == set(W.SEARCH_SPACE)
+    assert res["best_val"] > 0.6, res      # the planted communities are learnable (0.70-0.73 after 400 epochs; the validation
+                                           # split has ~65 pairs, so the bar leaves room for its noise)
+    aucs, infer, walls = W.read_results_twowl("planted", args.record_dir, args.time_dir)
+    assert len(aucs) == 2 and len(infer) == 2 and len(walls) == 2
+    assert all(0.4 < a <= 1.0 for a in aucs) and all(t >= 0 for t in infer)
+    line = open(os.path.join(args.record_dir, "planted_auc_record_twowl.txt")).readline()
+    assert line.startswith("AUC:") and "   Time:" in line           # train.py:110-112 format
+    assert os.path.isfile("logs.json") and os.path.isfile("fpr.json") and os.path.isfile("tpr.json")
+
+    # test() returns the reference's triple; the device AUC equals sklearn's on the same scores
+    from sklearn.metrics import auc as sk_auc
+    bg, trn, val, tst = W._datasets(args, torch.device("cuda"))
+    mod = W.LocalWLNet(int(bg.x[2].max()), False, None, channels_1wl=32, channels_2wl=16).cuda()
+    tst.pos1 = tst.pos1.to(torch.long)
+    a, fpr, tpr = T.test(mod, tst)
+    assert abs(a - sk_auc(fpr, tpr)) < 1e-9
+    assert T.test(mod, tst, curve=False)[1] is None
