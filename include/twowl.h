@@ -119,6 +119,12 @@ int twowl_narrow_i32(const int64_t* in, int64_t stride, int64_t n, int32_t* out,
  * i.e. self-loops removed, one self-loop added. A CSR row r with row_skip_mask[r] set counts as empty. */
 int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, int32_t flip, int32_t row_flip,
                    const uint8_t* skip_mask, const uint8_t* row_skip_mask, float* dinv, void* stream);
+/* same with entries removed by a per-ENTRY mask (entry_mask[k] != 0: entry k of the CSR does not exist) - the node graph
+ * of one training step is the cached CSR of the whole graph minus the sampled edges (sample_block, utils.py:61-64). */
+int twowl_gcn_dinv_entries(const int64_t* ptr, const int32_t* col, int64_t M, const uint8_t* entry_mask, float* dinv,
+                           void* stream);
+/* out[k] = mask[ids[k]] (uint8) - a per-edge mask carried to the entry order of a CSR built by twowl_csr_build. */
+int twowl_gather_u8(const uint8_t* mask, const int32_t* ids, int64_t n, uint8_t* out, void* stream);
 
 /* The one segmented gather-reduce all aggregations run through. For each output row m, with its entries
  * taken from CSR row r = m ^ row_flip (empty if row_skip_mask[r]):
@@ -161,6 +167,7 @@ typedef struct twowl_seg_args {
   int64_t chunk_cap;
   int64_t long_cap;
   int32_t pair_sum;              /* 1: gather X[s] + X[s ^ 1] (the two directions 2k / 2k+1 of one pair, utils.py:81-90) */
+  const uint8_t* entry_mask;     /* indexed by CSR ENTRY k (not by col[k]) or NULL: entries removed from a cached CSR */
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
 

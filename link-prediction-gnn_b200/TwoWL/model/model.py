@@ -49,7 +49,7 @@ class GCNConv(nn.Module):
     def forward(self, x, edge_index):
         g = G.node_graph(edge_index, x.shape[0])
         z = self.lin(x)
-        return F2.gcn_aggregate(z, self.bias, g.dinv, g.ptr, g.col, g.plan, g.tptr, g.tcol, g.tplan, None, 0, 0)
+        return F2.gcn_aggregate(z, self.bias, g.dinv, g.ptr, g.col, g.plan, g.tptr, g.tcol, g.tplan, None, 0, 0, g.emask, g.temask)
 
     def forward_pairs(self, x, wedges, direction: int):
         """The pair-level call of model.py:77: direction 0 = conv(x, edge2), 1 = conv_r(x, edge2_r)."""

@@ -94,6 +94,7 @@ def sample_block(sample_idx, size, ei, ei2=None):
     row-sum of utils.py:66-67), filter ei2 with blockei2. Returns (ei_new, x_new, ei2_new)."""
     mask = ops.mask_from_idx(sample_idx, ei.shape[1])
     ei_new = ops.select_columns(ei, mask, 0)
+    ei_new._twowl_edges = (ei, mask, ei_new._version)   # lets GCNConv reuse the cached CSRs of `ei` (graph.node_graph)
     x_new = ops.degree(ei_new[0], int(size))
     ei2_new = blockei2(ei2, sample_idx) if ei2 is not None else None
     return ei_new, x_new, ei2_new

@@ -40,6 +40,7 @@ struct SegParams {
   float* out;
   int accumulate;
   int pair_sum;
+  const uint8_t* entry_mask;
   // long-row plan (all NULL/0 when the CSR has no plan)
   const int32_t* plan_counts;  // [0] = number of long rows, [1] = number of chunks
   const int32_t* long_row;     // CSR row of each long row
@@ -73,7 +74,10 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
   if (kb >= ke) return;
-  auto load_col = [&](int64_t k0) -> int { return (k0 + g.gl < ke) ? __ldg(p.col + k0 + g.gl) : -1; };
+  auto load_col = [&](int64_t k0) -> int {
+    const int64_t k = k0 + g.gl;
+    return (k < ke && !(p.entry_mask && p.entry_mask[k])) ? __ldg(p.col + k) : -1;
+  };
   // (col entry) -> source row (or -1 = dropped), its scale, optional second-factor row
   auto stage = [&](int c, int& s_, float& w_, int& m2_) {
     s_ = -1, w_ = 0.f, m2_ = 0;
@@ -289,7 +293,8 @@ __global__ void __launch_bounds__(kAggThreads) k_plan_long(const int64_t* __rest
 __global__ void __launch_bounds__(kAggThreads) k_gcn_dinv(const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
                                                           int64_t M, int flip, int row_flip,
                                                           const uint8_t* __restrict__ skip_mask,
-                                                          const uint8_t* __restrict__ row_skip_mask, float* __restrict__ dinv) {
+                                                          const uint8_t* __restrict__ row_skip_mask,
+                                                          const uint8_t* __restrict__ entry_mask, float* __restrict__ dinv) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * kAggThreads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kAggThreads) >> 5;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kAggThreads) k_gcn_dinv(const int64_t* __restr
       bool keep = false;
       if (k < ke) {
         const int cc = __ldg(col + k);
-        keep = ((int64_t)(cc ^ flip) != m) && !(skip_mask && skip_mask[cc]);
+        keep = ((int64_t)(cc ^ flip) != m) && !(skip_mask && skip_mask[cc]) && !(entry_mask && entry_mask[k]);
       }
       c += __popc(__ballot_sync(0xffffffffu, keep));
     }
@@ -323,7 +328,29 @@ extern "C" int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M,
   TW_CHECK_ARG(!(row_flip && (M & 1)), "gcn_dinv: row_flip needs an even row count");
   if (M == 0) return 0;
   k_gcn_dinv<<<grid_for(M, kAggThreads / 32, 8), kAggThreads, 0, (cudaStream_t)stream>>>(ptr, col, M, flip, row_flip, skip_mask,
-                                                                                      row_skip_mask, dinv);
+                                                                                      row_skip_mask, nullptr, dinv);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_gcn_dinv_entries(const int64_t* ptr, const int32_t* col, int64_t M, const uint8_t* entry_mask, float* dinv,
+                                      void* stream) {
+  TW_CHECK_ARG(M >= 0, "gcn_dinv_entries: negative M");
+  if (M == 0) return 0;
+  k_gcn_dinv<<<grid_for(M, kAggThreads / 32, 8), kAggThreads, 0, (cudaStream_t)stream>>>(ptr, col, M, 0, 0, nullptr, nullptr,
+                                                                                      entry_mask, dinv);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(kAggThreads) k_gather_u8(const uint8_t* __restrict__ mask, const int32_t* __restrict__ ids, int64_t n,
+                                                           uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = mask[ids[i]];
+}
+extern "C" int twowl_gather_u8(const uint8_t* mask, const int32_t* ids, int64_t n, uint8_t* out, void* stream) {
+  TW_CHECK_ARG(n >= 0, "gather_u8: negative n");
+  if (n == 0) return 0;
+  k_gather_u8<<<grid_for(n, kAggThreads, 8), kAggThreads, 0, (cudaStream_t)stream>>>(mask, ids, n, out);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -360,7 +387,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   p.ptr = a->ptr, p.col = a->col, p.M = a->M, p.X = a->X, p.C = a->C, p.flip = a->flip, p.row_flip = a->row_flip;
   p.src_scale = a->src_scale, p.skip_mask = a->skip_mask, p.row_skip_mask = a->row_skip_mask;
   p.skip_self = a->skip_self, p.self_mode = a->self_mode, p.dst_scale = a->dst_scale, p.bias = a->bias;
-  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum;
+  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum, p.entry_mask = a->entry_mask;
   p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
   p.partial = a->partial;
   cudaStream_t s = (cudaStream_t)stream;

@@ -32,7 +32,7 @@ class SegArgs(ctypes.Structure):
         ("mul_idx", ctypes.c_void_p), ("out", ctypes.c_void_p), ("accumulate", ctypes.c_int32),
         ("plan_counts", ctypes.c_void_p), ("long_row", ctypes.c_void_p), ("long_base", ctypes.c_void_p),
         ("chunk_owner", ctypes.c_void_p), ("partial", ctypes.c_void_p), ("chunk_cap", ctypes.c_int64),
-        ("long_cap", ctypes.c_int64), ("pair_sum", ctypes.c_int32),
+        ("long_cap", ctypes.c_int64), ("pair_sum", ctypes.c_int32), ("entry_mask", ctypes.c_void_p),
     ]
 
 

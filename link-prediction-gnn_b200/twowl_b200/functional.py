@@ -48,35 +48,36 @@ linear.register_autograd(_linear_bwd, setup_context=_linear_setup)
 
 @torch.library.custom_op("twowl::gcn_aggregate", mutates_args=())
 def gcn_aggregate(z: Tensor, bias: Tensor, dinv: Tensor, ptr: Tensor, col: Tensor, plan: Optional[Tensor], tptr: Tensor,
-                  tcol: Tensor, tplan: Optional[Tensor], mask: Optional[Tensor], flip: int, row_flip: int) -> Tensor:
+                  tcol: Tensor, tplan: Optional[Tensor], mask: Optional[Tensor], flip: int, row_flip: int,
+                  emask: Optional[Tensor] = None, temask: Optional[Tensor] = None) -> Tensor:
     """out[m] = dinv[m] * sum_{k in row m^row_flip, s=col[k]^flip != m, !mask[col[k]]} dinv[s] z[s]
                + dinv[m]^2 z[m] + bias   (PyG GCNConv.propagate with gcn_norm)."""
     return ops.seg_reduce(ptr, col, z.shape[0], z.contiguous(), plan=plan, flip=flip, row_flip=row_flip, src_scale=dinv,
-                          dst_scale=dinv, skip_self=True, self_mode=1, bias=bias, skip_mask=mask)
+                          dst_scale=dinv, skip_self=True, self_mode=1, bias=bias, skip_mask=mask, entry_mask=emask)
 
 
 @gcn_aggregate.register_fake
-def _(z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip):
+def _(z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip, emask=None, temask=None):
     return torch.empty_like(z)
 
 
 def _gcn_setup(ctx, inputs, output):
-    z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip = inputs
-    ctx.save_for_backward(dinv, tptr, tcol, tplan, mask)
+    z, bias, dinv, ptr, col, plan, tptr, tcol, tplan, mask, flip, row_flip, emask, temask = inputs
+    ctx.save_for_backward(dinv, tptr, tcol, tplan, mask, temask)
     ctx.flip, ctx.row_flip = flip, row_flip
 
 
 def _gcn_bwd(ctx, g):
-    dinv, tptr, tcol, tplan, mask = ctx.saved_tensors
+    dinv, tptr, tcol, tplan, mask, temask = ctx.saved_tensors
     g = g.contiguous()
     dz = dbias = None
     if ctx.needs_input_grad[0]:
         # transpose: rows by SOURCE; the roles of flip / row_flip swap; the column mask becomes a row mask
         dz = ops.seg_reduce(tptr, tcol, g.shape[0], g, plan=tplan, flip=ctx.row_flip, row_flip=ctx.flip, src_scale=dinv,
-                            dst_scale=dinv, skip_self=True, self_mode=1, row_skip_mask=mask)
+                            dst_scale=dinv, skip_self=True, self_mode=1, row_skip_mask=mask, entry_mask=temask)
     if ctx.needs_input_grad[1]:
         dbias = ops.colsum(g)
-    return (dz, dbias) + (None,) * 10
+    return (dz, dbias) + (None,) * 12
 
 
 gcn_aggregate.register_autograd(_gcn_bwd, setup_context=_gcn_setup)

@@ -67,9 +67,23 @@ class NodeGraph:
     dinv: torch.Tensor   # (1 + in-degree without self-loops)^-1/2
     plan: torch.Tensor   # long-row plans (ops.seg_plan) of the two CSRs
     tplan: torch.Tensor
+    ids: Optional[torch.Tensor] = None     # edge position of every CSR entry (by target / by source)
+    tids: Optional[torch.Tensor] = None
+    emask: Optional[torch.Tensor] = None   # uint8 per ENTRY: removed from the cached CSRs (sample_block)
+    temask: Optional[torch.Tensor] = None
 
 
 def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
+    """CSR by target / by source + gcn_norm degrees of an int64 [2,E] edge tensor, cached per tensor. An edge tensor that
+    sample_block produced (utils.py:61-64: the whole graph minus the sampled edge ids) reuses the cached CSRs of the
+    whole graph with a per-entry mask instead of sorting its E' edges again every step."""
+    tag = getattr(edge1, "_twowl_edges", None)
+    if tag is not None and tag[2] == edge1._version and tag[0].shape[1] >= edge1.shape[1]:
+        base = node_graph(tag[0], n)
+        emask, temask = ops.gather_u8(tag[1], base.ids), ops.gather_u8(tag[1], base.tids)
+        return NodeGraph(n, base.ptr, base.col, base.tptr, base.tcol, ops.gcn_dinv_entries(base.ptr, base.col, n, emask),
+                         base.plan, base.tplan, base.ids, base.tids, emask, temask)
+
     def build():
         ei = _i64(edge1)
         ptr, ids = ops.csr_build(ei[1], n)
@@ -78,7 +92,7 @@ def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
         tcol = ops.gather_cols(tids, ei[1])
         m = ei.shape[1]
         return NodeGraph(n, ptr, col, tptr, tcol, ops.gcn_dinv(ptr, col, n), ops.seg_plan(ptr, n, m),
-                         ops.seg_plan(tptr, n, m))
+                         ops.seg_plan(tptr, n, m), ids, tids)
     return _cache.get(edge1, ("node", n), build)
 
 

@@ -263,6 +263,25 @@ def gcn_dinv(ptr, col, M: int, flip: int = 0, row_flip: int = 0, skip_mask=None,
     return dinv
 
 
+def gcn_dinv_entries(ptr, col, M: int, entry_mask) -> torch.Tensor:
+    """gcn_norm degree of a cached CSR minus the entries a per-entry mask removes."""
+    _need_cuda(ptr, col, entry_mask)
+    dinv = torch.empty(M, dtype=torch.float32, device=ptr.device)
+    check(lib.twowl_gcn_dinv_entries(ptr.data_ptr(), col.data_ptr(), M, entry_mask.data_ptr(), dinv.data_ptr(), _stream()),
+          "gcn_dinv_entries")
+    _count()
+    return dinv
+
+
+def gather_u8(mask: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """out[k] = mask[ids[k]] (uint8): a per-edge mask in the entry order of a CSR."""
+    _need_cuda(mask, ids)
+    out = torch.empty(ids.numel(), dtype=torch.uint8, device=mask.device)
+    check(lib.twowl_gather_u8(mask.data_ptr(), ids.data_ptr(), ids.numel(), out.data_ptr(), _stream()), "gather_u8")
+    _count()
+    return out
+
+
 def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
     """Long-row plan of a CSR as ONE int32 tensor: [counts(2) | long_row(lc) | long_base(lc) | chunk_owner(cc)],
     lc / cc being the capacities twowl_seg_plan_{long,chunk}_cap give for nnz (no host read needed)."""
@@ -278,7 +297,7 @@ def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
 
 def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
                row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
-               out=None, accumulate=False, pair_sum=False) -> torch.Tensor:
+               out=None, accumulate=False, pair_sum=False, entry_mask=None) -> torch.Tensor:
     _need_cuda(ptr, col, X)
     assert X.dtype == torch.float32 and X.is_contiguous()
     C = X.shape[1]
@@ -287,7 +306,7 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
     a = SegArgs(ptr=ptr.data_ptr(), col=col.data_ptr(), M=M, X=X.data_ptr(), C=C, flip=int(flip), row_flip=int(row_flip),
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
-                mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate), pair_sum=int(pair_sum))
+                mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate), pair_sum=int(pair_sum), entry_mask=_p(entry_mask))
     partial = None
     if plan is not None:
         nnz = col.numel()
