@@ -260,6 +260,19 @@ int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M, int32_t C
                           const float* w, const float* dpred, float* dxf, float* dxr, float* dparams_f, float* dparams_r, float* dw,
                           float* db, void* ws, size_t ws_bytes, void* stream);
 
+/* The same backward without its dense pass, for a consumer that makes dxf / dxr on the fly (twowl_pair_dw_gn): everything
+ * row-sparse is done here - G[2L,C] = gradient w.r.t. hn at every selected position, head[M] / next[2L] = the chains of positions
+ * that select the same row, the parameter gradients, and per branch consts[4][C] = (P, Q, sc, of) such that
+ *   dx[r] = P*x[r] + Q + sc * mask(sc*x[r] + of) * sum_{positions j selecting r, ascending} G[j]
+ * (consts = [f: P,Q,sc,of | r: P,Q,sc,of], 8*C floats). */
+size_t twowl_gn2_readout_bwd_prepare_workspace_bytes(int64_t M, int64_t L, int32_t C);
+int twowl_gn2_readout_bwd_prepare(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                  const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                  const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                  int32_t relu, const int64_t* idx, int64_t sidx, int64_t L, const float* w,
+                                  const float* dpred, float* G, int32_t* head, int32_t* next, float* consts, float* dparams_f,
+                                  float* dparams_r, float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+
 /* out[c] = sum_m x[m,c] (bias gradients). Deterministic two-level sum. */
 size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C);
 int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream);
@@ -317,6 +330,15 @@ int twowl_pair_dw_supported(int32_t C);
 size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C);
 int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
                   int32_t C, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream);
+
+/* The same with the gradients made on the fly from the layer's OUTPUTS Of, Or (last pair layer, after
+ * twowl_gn2_readout_bwd_prepare): the shared-memory pass that scales and splits the tiles first turns them into
+ * dO = P*O + Q (+ the selected rows' term), writes dOf / dOr [M,C] for the later consumers, and the dense GraphNorm-backward
+ * pass (2 reads + 2 writes of [M,C]) disappears. ws as twowl_pair_dw. */
+int twowl_pair_dw_gn(const float* Of, const float* Or, const float* consts, const float* G, const int32_t* head,
+                     const int32_t* next, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const float* rsf,
+                     const float* rsr, const float* H, int64_t M, int32_t C, float* dOf, float* dOr, float* dWf, float* dWr,
+                     void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ metrics -------------------- */
 

@@ -53,6 +53,13 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+// dropout threshold on the 32-bit hash for probability p
+inline uint32_t drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -112,6 +119,18 @@ __device__ __forceinline__ void f4_add(float4& a, const float4& x) {
 __device__ __forceinline__ float4 f4_mul(const float4& a, const float4& b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the dropout mask
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// 1/(1-p) if element kept else 0
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
+  return hash_u32(seed, idx) >= thresh ? inv_keep : 0.f;
+}
 __device__ __forceinline__ float4 f4_shfl_xor(const float4& v, int m) {
   return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
                      __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
@@ -136,7 +155,7 @@ int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, u
 int make_tmap_2d_f32(CUtensorMap* tm, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
                      CUtensorMapSwizzle swizzle);
 
-// ---- tensor-core linear layer implemented in linear_tc.cu ----------------------------------------
+// ---- tensor-core linear layer: the pair_conv kernel with one source and no epilogue terms (pair_conv.cu) ----------------------------------------
 // C[M,Nd] = A[M,Kd] * B^T with B[n][k] = W[n*Kd+k] (w_kn = 0) or W[k*Nd+n] (w_kn = 1); tcgen05 kind::tf32, 3xTF32.
 bool linear_tc_supported(int Kd, int Nd);
 int linear_tc(const float* A, const float* W, float* C, int64_t M, int Kd, int Nd, int w_kn, cudaStream_t s);

@@ -33,6 +33,18 @@ struct DwParams {
   const float* rsr;
   int64_t M;
   float* part;  // [gridDim.x][128][C]
+  // GN = true: the A tiles are the OUTPUTS O_f, O_r of the last pair layer and the gradients are made on the fly
+  // (twowl_pair_dw_gn): dO = P * O + Q (+ sc * g_y on the rows the readout selected), written to dOf / dOr as well
+  const float* consts;   // [2 branches][4][C] = (P, Q, sc, of), twowl_gn2_readout_bwd_prepare
+  const float* G;        // [2L, C] gradient of the selected rows, by position
+  const int32_t* head;   // [M] first position that selects a row, -1 = none
+  const int32_t* next;   // [2L] next position selecting the same row
+  float* dOf;
+  float* dOr;
+  uint32_t thresh;
+  float inv_keep;
+  uint64_t seed_f, seed_r;
+  int relu;
 };
 
 __device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,11 +112,22 @@ __device__ __forceinline__ void dw_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one lane of a converged warp: the loops around the single-thread instructions run on the whole warp with warp-uniform
+// values, so descriptors live in uniform registers and the UTCHMMA / UTMALDG issue back to back (see pair_conv.cu)
+__device__ __forceinline__ bool dw_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float dw_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // C = width of dO_f, dO_r and H (32 or 64). One stage:
 //   A_hi: 4 groups of 32 M-elements (M = 128 = [f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
-template <int C>
+template <int C, bool GN>
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
                                                          const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmH) {
   constexpr int GS = C / 32;                          // 32-column groups per source
@@ -157,18 +180,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      uint64_t policy;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t tile = blockIdx.x + it * gridDim.x;
-        const int st = (int)(it % kDwStages);
-        const int row = (int)(tile * kDwTileK);
-        dw_mbar_wait(&empty[st], (uint32_t)(((it / kDwStages) & 1) ^ 1));
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int st = (int)(it % kDwStages);
+      const int row = (int)(tile * kDwTileK);
+      dw_mbar_wait(&empty[st], (uint32_t)(((it / kDwStages) & 1) ^ 1));
+      if (dw_elect_one()) {
         dw_mbar_expect_tx(&raw_full[st], kTxBytes);
         uint8_t* Ahi = smem + st * kStage;
         uint8_t* Bhi = Ahi + 2 * kAHalf;
@@ -179,44 +202,43 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
           dw_tma_load_2d(Bhi + (size_t)g * kDwLbo, &tmH, g * 32, row, &raw_full[st], policy);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      // D[128, C] (+)= A[128 x 8] * B[C x 8]^T per K-step; A and B both MN-major
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t grp = it / kDwFlush;
-        const int a = (int)(grp & 1);
-        if (it % kDwFlush == 0) {
-          dw_mbar_wait(&tempty[a], (uint32_t)(((grp >> 1) & 1) ^ 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const int st = (int)(it % kDwStages);
-        dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
-        dw_mbar_wait(&split_done[st], (uint32_t)((it / kDwStages) & 1));
+    // D[128, C] (+)= A[128 x 8] * B[C x 8]^T per K-step; A and B both MN-major
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t grp = it / kDwFlush;
+      const int a = (int)(grp & 1);
+      if (it % kDwFlush == 0) {
+        dw_mbar_wait(&tempty[a], (uint32_t)(((grp >> 1) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint8_t* Ahi = smem + st * kStage;
-        const uint8_t* Alo = Ahi + kAHalf;
-        const uint8_t* Bhi = Alo + kAHalf;
-        const uint8_t* Blo = Bhi + kBHalf;
-        uint32_t acc = (it % kDwFlush == 0) ? 0u : 1u;
+      }
+      const int st = (int)(it % kDwStages);
+      dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
+      dw_mbar_wait(&split_done[st], (uint32_t)((it / kDwStages) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // descriptors advance by byte offset >> 4 in their low word
+      const uint64_t Ahi = dw_desc(dw_smem_u32(smem) + (uint32_t)st * kStage);
+      const uint64_t Alo = Ahi + (kAHalf >> 4), Bhi = Alo + (kAHalf >> 4), Blo = Bhi + (kBHalf >> 4);
+      const uint32_t acc0 = (it % kDwFlush == 0) ? 0u : 1u;
+      const bool last = (it + 1) % kDwFlush == 0 || it + 1 == my_tiles;
+      if (dw_elect_one()) {
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint8_t* Ap = (pass == 0) ? Alo : Ahi;
-          const uint8_t* Bp = (pass == 1) ? Blo : Bhi;
+          const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+          const uint64_t Bp = (pass == 1) ? Blo : Bhi;
 #pragma unroll
-          for (int k = 0; k < kDwTileK / 8; ++k) {  // one group of 8 k-rows per K-step
-            dw_mma(tmem_base + (uint32_t)(a * 64), dw_desc(dw_smem_u32(Ap) + k * kDwKStep), dw_desc(dw_smem_u32(Bp) + k * kDwKStep), idesc, acc);
-            acc = 1;
-          }
+          for (int k = 0; k < kDwTileK / 8; ++k)   // one group of 8 k-rows per K-step
+            dw_mma(tmem_base + (uint32_t)(a * 64), Ap + (uint64_t)(k * (kDwKStep >> 4)), Bp + (uint64_t)(k * (kDwKStep >> 4)), idesc,
+                   (pass | k) ? 1u : acc0);
         }
         dw_commit(&empty[st]);
-        if ((it + 1) % kDwFlush == 0 || it + 1 == my_tiles) dw_commit(&tfull[a]);
+        if (last) dw_commit(&tfull[a]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp < kDwFirstDrain) {
     // ===================================================== split (scale + hi/lo), linear over the swizzled buffers
     const int t = tid - kDwFirstSplit * 32;                  // 0..127
@@ -225,28 +247,98 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
     constexpr int kBChunks = GS * (int)(kDwLbo / 16);
     constexpr int kAIter = kAChunks / kSplitThreads, kBIter = kBChunks / kSplitThreads;
     // chunk i of a group region sits in k-row (i % 512) / 8; with i = j*128 + t that is (j % 4) * 16 + t / 8
+    // GN: this thread's 4 columns inside a 32-column group are fixed (unit ((t & 7) >> 1) ^ (k & 3), k & 3 = (t >> 3) & 3), so
+    // the per-column constants of its (branch, group) chunks live in registers
+    const int tcol = (((((t & 7) >> 1) ^ ((t >> 3) & 3))) << 3) + ((t & 1) << 2);
+    float4 P4[GN ? 2 * GS : 1], Q4[GN ? 2 * GS : 1];
+    if (GN) {
+#pragma unroll
+      for (int gb = 0; gb < 2 * GS; ++gb) {
+        const float* __restrict__ cb = p.consts + (gb >= GS ? 4 * C : 0) + (gb % GS) * 32 + tcol;
+        P4[gb] = __ldg(reinterpret_cast<const float4*>(cb)), Q4[gb] = __ldg(reinterpret_cast<const float4*>(cb + C));
+      }
+    }
+    int hdn[4] = {-1, -1, -1, -1};   // chain heads of the NEXT tile's rows: one tile ahead, off the latency chain
+    if (GN && my_tiles > 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t row = (int64_t)blockIdx.x * kDwTileK + q * 16 + (t >> 3);
+        hdn[q] = row < p.M ? __ldg(p.head + row) : -1;
+      }
+    }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int st = (int)(it % kDwStages);
       const int64_t row0 = tile * kDwTileK;
       float sf[4], sr[4];
+      int hd[4], nx[4];
+      float4 Gd[4][GN ? GS : 1];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {   // row scales first: they do not depend on the TMA data
+      for (int q = 0; q < 4; ++q) {   // row scales and the selected rows' gradients first: they do not depend on the TMA data
         const int64_t row = row0 + q * 16 + (t >> 3);
         sf[q] = row < p.M ? __ldg(p.rsf + row) : 0.f;
         sr[q] = row < p.M ? __ldg(p.rsr + row) : 0.f;
+        hd[q] = hdn[q], nx[q] = -1;
+        if (GN) {
+          if (hd[q] >= 0) nx[q] = __ldg(p.next + hd[q]);
+#pragma unroll
+          for (int g = 0; g < GS; ++g)
+            Gd[q][g] = hd[q] >= 0 ? ldg_cached(reinterpret_cast<const float4*>(p.G + (int64_t)hd[q] * C + g * 32 + tcol)) : f4_zero();
+          const int64_t rown = row + (int64_t)gridDim.x * kDwTileK;
+          hdn[q] = (it + 1 < my_tiles && rown < p.M) ? __ldg(p.head + rown) : -1;
+        }
       }
       dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
       float4* Ahi = reinterpret_cast<float4*>(smem + st * kStage);
       float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
       const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
       float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
-#pragma unroll 4
+#pragma unroll
       for (int j = 0; j < kAIter; ++j) {
         const int i = j * kSplitThreads + t;
-        const bool is_r = i >= GS * (int)(kDwLbo / 16);
-        const float sc = is_r ? sr[j & 3] : sf[j & 3];
+        const int q = j & 3, gb = j >> 2;          // row slot, (branch, 32-column group): f groups then r groups
+        const bool is_r = gb >= GS;
+        const float sc = is_r ? sr[q] : sf[q];
         float4 v = Ahi[i];
+        if (GN) {
+          const int col = (gb % GS) * 32 + tcol;
+          const int64_t row = row0 + q * 16 + (t >> 3);
+          float4 o = make_float4(fmaf(P4[gb].x, v.x, Q4[gb].x), fmaf(P4[gb].y, v.y, Q4[gb].y), fmaf(P4[gb].z, v.z, Q4[gb].z),
+                                 fmaf(P4[gb].w, v.w, Q4[gb].w));
+          if (hd[q] >= 0) {   // a row the readout selected: + sc * (dropout / ReLU mask) * sum of its positions' gradients
+            float4 d = Gd[q][gb % GS];
+            if (nx[q] >= 0) {   // selected more than once: positions in ascending order (deterministic)
+              const float4* __restrict__ G4 = reinterpret_cast<const float4*>(p.G + col);
+              d = f4_zero();
+              int last = -1;
+              for (;;) {
+                int best = 0x7fffffff;
+                for (int c = hd[q]; c >= 0; c = __ldg(p.next + c))
+                  if (c > last && c < best) best = c;
+                if (best == 0x7fffffff) break;
+                f4_add(d, ldg_cached(G4 + (int64_t)best * (C / 4)));
+                last = best;
+              }
+            }
+            const float* __restrict__ cb = p.consts + (is_r ? 4 * C : 0) + col;
+            const float4 S4 = __ldg(reinterpret_cast<const float4*>(cb + 2 * C)), O4 = __ldg(reinterpret_cast<const float4*>(cb + 3 * C));
+            const float xa[4] = {v.x, v.y, v.z, v.w}, da[4] = {d.x, d.y, d.z, d.w}, sa[4] = {S4.x, S4.y, S4.z, S4.w},
+                        oa[4] = {O4.x, O4.y, O4.z, O4.w};
+            float add[4];
+            const uint64_t e0 = (uint64_t)row * C + col;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float g = da[c], keep = 1.f;
+              if (p.thresh) keep = drop_scale(is_r ? p.seed_r : p.seed_f, e0 + c, p.thresh, p.inv_keep);
+              g *= keep;
+              if (p.relu && !(fmaf(sa[c], xa[c], oa[c]) * keep > 0.f)) g = 0.f;
+              add[c] = sa[c] * g;
+            }
+            o.x += add[0], o.y += add[1], o.z += add[2], o.w += add[3];
+          }
+          if (row < p.M) stg_stream(reinterpret_cast<float4*>((is_r ? p.dOr : p.dOf) + row * C + col), o);
+          v = o;
+        }
         v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
         Ahi[i] = v;
         Alo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
@@ -312,15 +404,15 @@ static size_t dw_smem() {
   return (size_t)kDwStages * stage + 128 + 1024;
 }
 
-template <int C>
-static int dw_launch(const DwParams& p, const float* dOf, const float* dOr, const float* H, cudaStream_t s) {
+template <int C, bool GN>
+static int dw_launch(const DwParams& p, const float* Af, const float* Ar, const float* H, cudaStream_t s) {
   CUtensorMap tf, tr, th;
-  if (int rc = make_tmap_2d_f32(&tf, dOf, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = make_tmap_2d_f32(&tr, dOr, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tf, Af, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tr, Ar, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const size_t smem = dw_smem<C>();
-  TW_CUDA(cudaFuncSetAttribute(k_dw_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dw_tc<C><<<dw_grid(p.M), kDwThreads, smem, s>>>(p, tf, tr, th);
+  TW_CUDA(cudaFuncSetAttribute(k_dw_tc<C, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_dw_tc<C, GN><<<dw_grid(p.M), kDwThreads, smem, s>>>(p, tf, tr, th);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -342,9 +434,36 @@ extern "C" int twowl_pair_dw(const float* dOf, const float* dOr, const float* rs
   TW_CHECK_ARG(M > 0, "pair_dw: needs M > 0");
   TW_CHECK_ARG(aligned16(dOf) && aligned16(dOr) && aligned16(H) && rsf && rsr, "pair_dw: bad pointers");
   TW_CHECK_WS(ws_bytes, twowl_pair_dw_workspace_bytes(M, C));
-  DwParams p{rsf, rsr, M, (float*)ws};
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.rsf = rsf, p.rsr = rsr, p.M = M, p.part = (float*)ws;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = (C == 32) ? dw_launch<32>(p, dOf, dOr, H, s) : dw_launch<64>(p, dOf, dOr, H, s);
+  int rc = (C == 32) ? dw_launch<32, false>(p, dOf, dOr, H, s) : dw_launch<64, false>(p, dOf, dOr, H, s);
+  if (rc) return rc;
+  k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>((const float*)ws, dw_grid(M), C, dWf, dWr);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_pair_dw_gn(const float* Of, const float* Or, const float* consts, const float* G, const int32_t* head,
+                                const int32_t* next, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const float* rsf,
+                                const float* rsr, const float* H, int64_t M, int32_t C, float* dOf, float* dOr, float* dWf, float* dWr,
+                                void* ws, size_t ws_bytes, void* stream) {
+  TW_CHECK_ARG(C == 32 || C == 64, "pair_dw_gn: C=%d unsupported (32 or 64)", C);
+  TW_CHECK_ARG(M > 0 && M < 0x7fffffffLL, "pair_dw_gn: needs 0 < M < 2^31");
+  TW_CHECK_ARG(aligned16(Of) && aligned16(Or) && aligned16(H) && aligned16(dOf) && aligned16(dOr) && aligned16(consts) && aligned16(G) &&
+                   rsf && rsr && head && next,
+               "pair_dw_gn: bad pointers");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "pair_dw_gn: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_pair_dw_workspace_bytes(M, C));
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.rsf = rsf, p.rsr = rsr, p.M = M, p.part = (float*)ws;
+  p.consts = consts, p.G = G, p.head = head, p.next = next, p.dOf = dOf, p.dOr = dOr;
+  p.thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u, p.inv_keep = 1.f / (1.f - p_drop);
+  p.seed_f = seed_f, p.seed_r = seed_r, p.relu = relu;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = (C == 32) ? dw_launch<32, true>(p, Of, Or, H, s) : dw_launch<64, true>(p, Of, Or, H, s);
   if (rc) return rc;
   k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>((const float*)ws, dw_grid(M), C, dWf, dWr);
   TW_LAUNCH_CHECK();

@@ -3,7 +3,7 @@
 //
 // impl 0 (this file): SIMT FFMA register-tiled GEMM, exact fp32 accumulation - the parity baseline.
 // The shapes are tall-skinny (M = rows of the pair table, up to 6e7; Ci, Co <= 256) so the op is HBM-bound
-// up to C ~ 64 on FFMA and needs tensor cores (3xTF32 on tcgen05, see linear_tc.cu) beyond that.
+// up to C ~ 64 on FFMA and needs tensor cores (3xTF32 on tcgen05, the kernel of pair_conv.cu) beyond that.
 #include "common.cuh"
 
 namespace twowl {

@@ -28,25 +28,6 @@ struct RowMap {
   }
 };
 
-__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
-  // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the mask
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
-}
-// 1/(1-p) if element kept else 0
-__device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {
-  return hash_u32(seed, idx) >= thresh ? inv_keep : 0.f;
-}
-static inline uint32_t drop_thresh(float p) {
-  double t = (double)p * 4294967296.0;
-  if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
-  return (uint32_t)t;
-}
-
 // Reduce NV float4 values per thread over the CTA's row slots, in slot order, into doubles:
 // part[blockIdx.x][v][C].  smem: slots*cv float4 per value.
 template <int NV>
@@ -568,6 +549,21 @@ __global__ void k_part_colsum_final(const double* __restrict__ part, int nparts,
   const double s = warp_part_sum(part, nparts, nv, voff, C, c);
   if ((threadIdx.x & 31) == 0) out[c] = (float)s;
 }
+// consts[4][C] = (P, Q, sc, of) of one GraphNorm branch for a consumer that applies its backward on the fly (twowl_pair_dw_gn):
+//   dx = P*x + Q + sc*g_y,   P = -sc*ni*bm, Q = -(P*nm) - co   (the dense pass above, regrouped; g_y = 0 outside the selected rows)
+//   and y = sc*x + of is the forward value the ReLU mask needs on the selected rows
+__global__ void k_gn_bwd_consts(const float* __restrict__ stats, const float* __restrict__ weight, const float* __restrict__ bias,
+                                const float* __restrict__ mean_scale, const float* __restrict__ sums, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float ni = stats[C + c], nm = mean_scale[c] * stats[c], sc = weight[c] * ni;
+  const float P = -(sc * ni * sums[C + c]);
+  out[c] = P;
+  out[C + c] = -(P * nm) - sums[2 * C + c];
+  out[2 * C + c] = sc;
+  out[3 * C + c] = bias[c] - sc * nm;
+}
+
 // ---------------------------------------------------------------- column sum ---------------------
 __global__ void __launch_bounds__(kNormThreads) k_colsum_partial(const float* __restrict__ x, int64_t M, int C,
                                                                  double* __restrict__ part) {
@@ -754,6 +750,26 @@ extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M
   return 0;
 }
 
+// everything of the fused GraphNorm-pair + readout backward except the dense dx pass
+static int gn2_prepare(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                       const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
+                       uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx,
+                       int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next, double* part, float* sums_f,
+                       float* sums_r, float* dparams_f, float* dparams_r, float* dw, float* db, cudaStream_t s) {
+  const size_t l = (size_t)(L > 0 ? L : 1);
+  TW_CUDA(cudaMemsetAsync(head, 0xFF, (size_t)M * sizeof(int32_t), s));
+  const int grid_l = norm_grid(2 * (int64_t)l, C);
+  k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 6), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
+                                                                      seed_f, seed_r, relu, idx, sidx, L, w, dpred, G, part);
+  if (L > 0) k_row_chains<<<grid_for(2 * L, kNormThreads), kNormThreads, 0, s>>>(idx, sidx, 2 * L, M, head, next);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_part_colsum_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 4, C, C, dw);
+  k_part_colsum_final<<<1, 32, 0, s>>>(part, grid_l, 6, 5, C, 1, db);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" size_t twowl_gn2_readout_bwd_workspace_bytes(int64_t M, int64_t L, int32_t C) {
   const size_t l = (size_t)(L > 0 ? L : 1);
   return align_up(2 * l * (size_t)C * sizeof(float)) + align_up((size_t)(M > 0 ? M : 1) * sizeof(int32_t)) + align_up(2 * l * sizeof(int32_t)) +
@@ -783,17 +799,43 @@ extern "C" int twowl_gn2_readout_bwd(const float* xf, const float* xr, int64_t M
   float* sums_r = c.take<float>(3 * (size_t)C);
   const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
   const float inv_keep = 1.f / (1.f - p_drop);
-  TW_CUDA(cudaMemsetAsync(head, 0xFF, (size_t)M * sizeof(int32_t), s));
-  const int grid_l = norm_grid(2 * (int64_t)l, C);
-  k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 6), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
-                                                                      seed_f, seed_r, relu, idx, sidx, L, w, dpred, G, part);
-  if (L > 0) k_row_chains<<<grid_for(2 * L, kNormThreads), kNormThreads, 0, s>>>(idx, sidx, 2 * L, M, head, next);
-  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
-  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
-  k_part_colsum_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 4, C, C, dw);
-  k_part_colsum_final<<<1, 32, 0, s>>>(part, grid_l, 6, 5, C, 1, db);
+  if (int rc = gn2_prepare(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep, seed_f, seed_r, relu, idx, sidx, L, w,
+                           dpred, G, head, next, part, sums_f, sums_r, dparams_f, dparams_r, dw, db, s))
+    return rc;
   k_gn_bwd2_dx_rows<<<norm_grid(M, C), kNormThreads, 0, s>>>(xf, xr, G, head, next, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
                                                              inv_keep, seed_f, seed_r, relu, sums_f, sums_r, dxf, dxr);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_gn2_readout_bwd_prepare_workspace_bytes(int64_t M, int64_t L, int32_t C) {
+  (void)M, (void)L;
+  return align_up((size_t)kNormMaxCtas * 6 * (size_t)C * sizeof(double)) + 2 * align_up(3 * (size_t)C * sizeof(float));
+}
+
+extern "C" int twowl_gn2_readout_bwd_prepare(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                             const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                             const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                             int32_t relu, const int64_t* idx, int64_t sidx, int64_t L, const float* w,
+                                             const float* dpred, float* G, int32_t* head, int32_t* next, float* consts, float* dparams_f,
+                                             float* dparams_r, float* dw, float* db, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("gn2_readout_bwd_prepare", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && M < 0x7fffffffLL && L >= 0 && 2 * L < 0x7fffffffLL, "gn2_readout_bwd_prepare: sizes out of range");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(G) && aligned16(w) && aligned16(consts) && head && next,
+               "gn2_readout_bwd_prepare: bad pointers");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_bwd_prepare: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_gn2_readout_bwd_prepare_workspace_bytes(M, L, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver c(ws);
+  double* part = c.take<double>((size_t)kNormMaxCtas * 6 * C);
+  float* sums_f = c.take<float>(3 * (size_t)C);
+  float* sums_r = c.take<float>(3 * (size_t)C);
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  if (int rc = gn2_prepare(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx,
+                           sidx, L, w, dpred, G, head, next, part, sums_f, sums_r, dparams_f, dparams_r, dw, db, s))
+    return rc;
+  k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_f, wf, bf, mf, sums_f, C, consts);
+  k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_r, wr, br, mr, sums_r, C, consts + 4 * (size_t)C);
   TW_LAUNCH_CHECK();
   return 0;
 }

@@ -33,7 +33,11 @@ constexpr int kPcFirstSplit = 2;
 constexpr int kPcFirstEpi = kPcFirstSplit + kPcSplitWarps;                    // 4
 constexpr int kPcThreads = (kPcFirstEpi + kPcEpilogueWarps) * 32;            // 384: 12 warps -> up to 168 registers per thread
 constexpr int kPcTileM = 128;
-constexpr int kPcMaxStages = 4;
+constexpr uint32_t kPcSlab = kPcTileM * 128u;  // 128 rows x 32 fp32 columns = one SWIZZLE_128B K-slab (16 KB)
+constexpr int kPcGroup = 2;                    // pipeline unit: up to 2 K-slabs (one barrier round trip per 32 KB)
+constexpr uint32_t kPcStage = kPcGroup * kPcSlab;
+constexpr int kPcMaxStages = 4;                // raw-stage ring
+constexpr int kPcMaxLo = 2;                    // lo-stage ring
 
 struct ConvParams {
   const float* rs[2];
@@ -41,16 +45,18 @@ struct ConvParams {
   int w_kn[2];
   int nsrc;
   int64_t M;
-  int Nd;
+  int Kd, Nd;          // full widths of A and out
+  int Nsub, nsplit;    // output columns per CTA (multiple of 16) and the number of column windows
   const float* T[2];
   const int32_t* tidx[2];
   const float* tcoef[2];
   int ngather;
   const float* bias;
   float* out;
-  double* stats_part;  // [gridDim.x][2][Nd] column (sum, sum of squares) of `out`, or NULL
+  double* stats_part;  // [gridDim.x][2][Nsub] column (sum, sum of squares) of this CTA's window of `out`, or NULL
   int tmem_cols;
-  int stages;          // raw-tile ring depth (2..kPcMaxStages)
+  int stages;          // raw-stage ring depth (2..kPcMaxStages)
+  int lo_stages;       // lo-stage ring depth (1..kPcMaxLo)
 };
 
 __device__ __forceinline__ uint32_t pc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,36 +121,62 @@ __device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo
   hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
   lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
 }
+// One lane of a converged warp. The single-thread instructions (TMA, tcgen05.mma / commit) are issued under this predicate
+// with the WHOLE warp running the surrounding loop on warp-uniform values: the compiler then keeps descriptors and
+// addresses in uniform registers and emits the UTCHMMA / UTMALDG back to back. Under a divergent `if (lane == 0)` every
+// one of them is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~16-30 instructions of serial latency per MMA),
+// which made the issuing thread the bottleneck of the kernel.
+__device__ __forceinline__ bool pc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// ring position: slot and the parity of the round it is in
+struct PcRing {
+  int slot = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void next(int depth) {
+    if (++slot == depth) slot = 0, phase ^= 1u;
+  }
+};
 
-template <int KD, int NG>
+// CTA b works on column window b % nsplit of the tiles (b / nsplit) + j * (gridDim.x / nsplit): the CTAs that share a
+// tile run side by side, so the re-reads of its A slabs are L2 hits.
+template <int NG>
 __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1) {
-  constexpr int KB = KD / 32;
-  constexpr int K4 = KD / 4;
-  constexpr uint32_t kTile = (uint32_t)kPcTileM * KD * 4u;  // one raw (or lo) tile
   extern __shared__ uint8_t pc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int Nd = p.Nd;
-  const int S = p.stages;
-  const uint32_t kBMat = (uint32_t)KD * Nd * 4u;  // one of hi / lo of one source
-  uint8_t* Bs = smem;                                   // [nsrc][hi, lo]
-  uint8_t* As = Bs + (size_t)p.nsrc * 2 * kBMat;        // [S] raw tiles
-  uint8_t* Ls = As + (size_t)S * kTile;                 // lo tile
-  uint8_t* Es = Ls + kTile;                             // [epilogue warp] 32 rows x 32 cols fp32 transpose buffer
+  const int Nd = p.Nd, Nsub = p.Nsub, Kd = p.Kd;
+  const int KB = (Kd + 31) >> 5;                 // K-slabs per tile
+  const int Nsp = (Nsub + 31) & ~31;             // TMEM columns per source accumulator (the epilogue reads 32-column blocks)
+  const int S = p.stages, LS = p.lo_stages;
+  const uint32_t kStage = KB > 1 ? kPcStage : kPcSlab;  // bytes per pipeline stage
+  const uint32_t kBSlab = (uint32_t)Nsub * 128u;         // one K-slab of one of hi / lo of one source
+  const uint32_t kBMat = (uint32_t)KB * kBSlab;
+  uint8_t* Bs = smem;                                   // [nsrc][hi, lo][KB][Nsub rows x 128 B]
+  uint8_t* As = Bs + (size_t)p.nsrc * 2 * kBMat;        // [S] raw stages of kPcGroup slabs
+  uint8_t* Ls = As + (size_t)S * kStage;              // [LS] lo stages
+  uint8_t* Es = Ls + (size_t)LS * kStage;             // [epilogue warp] 32 rows x 32 cols fp32 transpose buffer
   uint64_t* bars = reinterpret_cast<uint64_t*>(Es + kPcEpilogueWarps * 4096);
-  uint64_t* raw_full = bars;                       // [S]  TMA -> split, MMA
-  uint64_t* raw_empty = bars + kPcMaxStages;       // [S]  MMA -> TMA
-  uint64_t* lo_full = bars + 2 * kPcMaxStages;     //      split -> MMA
-  uint64_t* lo_empty = lo_full + 1;                //      MMA -> split
-  uint64_t* tfull = lo_full + 2;                   // [2]  MMA -> epilogue
-  uint64_t* tempty = lo_full + 4;                  // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 6);
-  double* red = reinterpret_cast<double*>(lo_full + 8);   // [epilogue warps][2][Nd] end-of-kernel reduction
+  uint64_t* raw_full = bars;                            // [S]  TMA -> split, MMA
+  uint64_t* raw_empty = raw_full + kPcMaxStages;        // [S]  MMA -> TMA
+  uint64_t* lo_full = raw_empty + kPcMaxStages;         // [LS] split -> MMA
+  uint64_t* lo_empty = lo_full + kPcMaxLo;              // [LS] MMA -> split
+  uint64_t* tfull = lo_empty + kPcMaxLo;                // [2]  MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                         // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  double* red = reinterpret_cast<double*>(tempty + 4);  // [epilogue warps][2][Nsub] end-of-kernel reduction
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = (int)(blockIdx.x % p.nsplit), grp = (int)(blockIdx.x / p.nsplit), ngrp = (int)(gridDim.x / p.nsplit);
+  const int n0 = split * Nsub;
   const int64_t ntiles = (p.M + kPcTileM - 1) / kPcTileM;
-  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t nuse = my_tiles * p.nsrc;  // stage uses, in order (tile, src)
+  const int64_t my_tiles = (ntiles > grp) ? (ntiles - grp + ngrp - 1) / ngrp : 0;
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pc_smem_u32(tmem_slot)), "r"(p.tmem_cols)
@@ -156,8 +188,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
       pc_mbar_init(&raw_full[s], 1);
       pc_mbar_init(&raw_empty[s], 1);
     }
-    pc_mbar_init(lo_full, kPcSplitWarps * 32);
-    pc_mbar_init(lo_empty, 1);
+    for (int s = 0; s < kPcMaxLo; ++s) {
+      pc_mbar_init(&lo_full[s], kPcSplitWarps * 32);
+      pc_mbar_init(&lo_empty[s], 1);
+    }
     for (int a = 0; a < 2; ++a) {
       pc_mbar_init(&tfull[a], 1);
       pc_mbar_init(&tempty[a], kPcEpilogueWarps * 32);
@@ -166,124 +200,158 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
     if (p.nsrc > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA1)) : "memory");
   }
-  // resident weights: hi/lo split in the canonical layout (slab = 32 k-values, Nd rows of 128 bytes)
+  // resident weights of this CTA's column window: hi/lo split in the canonical layout (K-slab = 32 k-values, Nsub rows of
+  // 128 bytes); rows beyond Nd and k beyond Kd are zero
   for (int s = 0; s < p.nsrc; ++s) {
     const float* __restrict__ W = (s == 0) ? p.W[0] : p.W[1];
     const int w_kn = (s == 0) ? p.w_kn[0] : p.w_kn[1];
     uint8_t* Bhi = Bs + (size_t)s * 2 * kBMat;
     uint8_t* Blo = Bhi + kBMat;
-    for (int i = tid; i < Nd * K4; i += kPcThreads) {
-      const int n = i / K4, k4 = i % K4;
-      float4 v;
-      if (!w_kn) {
-        v = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * KD + k4 * 4));
-      } else {
-        v.x = __ldg(W + (size_t)(k4 * 4 + 0) * Nd + n);
-        v.y = __ldg(W + (size_t)(k4 * 4 + 1) * Nd + n);
-        v.z = __ldg(W + (size_t)(k4 * 4 + 2) * Nd + n);
-        v.w = __ldg(W + (size_t)(k4 * 4 + 3) * Nd + n);
+    const int K4p = KB * 8;
+    for (int i = tid; i < Nsub * K4p; i += kPcThreads) {
+      const int n = i / K4p, k4 = i % K4p;
+      const int gn = n0 + n, k = k4 * 4;
+      float4 v = f4_zero();
+      if (gn < Nd && k < Kd) {
+        if (!w_kn) {
+          v = __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * Kd + k));
+        } else {
+          v.x = __ldg(W + (size_t)(k + 0) * Nd + gn);
+          v.y = __ldg(W + (size_t)(k + 1) * Nd + gn);
+          v.z = __ldg(W + (size_t)(k + 2) * Nd + gn);
+          v.w = __ldg(W + (size_t)(k + 3) * Nd + gn);
+        }
       }
       float4 hi, lo;
       pc_split(v, hi, lo);
-      const uint32_t off = (uint32_t)(k4 >> 3) * (uint32_t)Nd * 128u + pc_sw128(n, k4 & 7);
+      const uint32_t off = (uint32_t)(k4 >> 3) * kBSlab + pc_sw128(n, k4 & 7);
       *reinterpret_cast<float4*>(Bhi + off) = hi;
       *reinterpret_cast<float4*>(Blo + off) = lo;
     }
   }
   if (p.stats_part)
-    for (int i = tid; i < kPcEpilogueWarps * 2 * Nd; i += kPcThreads) red[i] = 0.0;
+    for (int i = tid; i < kPcEpilogueWarps * 2 * Nsub; i += kPcThreads) red[i] = 0.0;
   pc_proxy_fence();
   pc_fence_before();
   __syncthreads();
   pc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      uint64_t policy;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      for (int64_t u = 0; u < nuse; ++u) {
-        const int64_t tile = blockIdx.x + (u / p.nsrc) * gridDim.x;
-        const int s = (int)(u % p.nsrc);
-        const int st = (int)(u % S);
-        pc_mbar_wait(&raw_empty[st], (uint32_t)(((u / S) & 1) ^ 1));
-        pc_mbar_expect_tx(&raw_full[st], kTile);
+    // ===================================================== TMA producer: stages in (tile, source, k-group) order
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    PcRing r;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int row0 = (int)((grp + ti * ngrp) * kPcTileM);
+      for (int s = 0; s < p.nsrc; ++s) {
         const CUtensorMap* tm = s ? &tmA1 : &tmA0;
-        uint8_t* dst = As + (size_t)st * kTile;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) pc_tma_load_2d(dst + (size_t)kb * kPcTileM * 128, tm, kb * 32, (int)(tile * kPcTileM), &raw_full[st], policy);
+        for (int kb = 0; kb < KB; kb += kPcGroup) {
+          const int ns = KB - kb < kPcGroup ? KB - kb : kPcGroup;
+          pc_mbar_wait(&raw_empty[r.slot], r.phase ^ 1u);
+          if (pc_elect_one()) {
+            pc_mbar_expect_tx(&raw_full[r.slot], (uint32_t)ns * kPcSlab);
+            for (int j = 0; j < ns; ++j)
+              pc_tma_load_2d(As + (size_t)r.slot * kStage + (size_t)j * kPcSlab, tm, (kb + j) * 32, row0, &raw_full[r.slot], policy);
+          }
+          __syncwarp();
+          r.next(S);
+        }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nd >> 3) << 17) | ((uint32_t)(kPcTileM >> 4) << 24);
-      int64_t u = 0;
-      for (int64_t ti = 0; ti < my_tiles; ++ti) {
-        const int a = (int)(ti & 1);
-        pc_mbar_wait(&tempty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));
-        pc_fence_after();
-        for (int s = 0; s < p.nsrc; ++s, ++u) {
-          const int st = (int)(u % S);
-          const uint32_t tacc = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1) + s * Nd);
-          pc_mbar_wait(&raw_full[st], (uint32_t)((u / S) & 1));
-          pc_mbar_wait(lo_full, (uint32_t)(u & 1));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nsub >> 3) << 17) | ((uint32_t)(kPcTileM >> 4) << 24);
+    PcRing r, l;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int a = (int)(ti & 1);
+      pc_mbar_wait(&tempty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));
+      pc_fence_after();
+      for (int s = 0; s < p.nsrc; ++s) {
+        const uint32_t tacc = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1) + s * Nsp);
+        const uint32_t Bhi = pc_smem_u32(Bs + (size_t)s * 2 * kBMat), Blo = Bhi + kBMat;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; kb += kPcGroup) {
+          const int ns = KB - kb < kPcGroup ? KB - kb : kPcGroup;
+          pc_mbar_wait(&raw_full[r.slot], r.phase);
+          pc_mbar_wait(&lo_full[l.slot], l.phase);
           pc_fence_after();
-          const uint8_t* Ahi = As + (size_t)st * kTile;
-          const uint8_t* Alo = Ls;
-          const uint8_t* Bhi = Bs + (size_t)s * 2 * kBMat;
-          const uint8_t* Blo = Bhi + kBMat;
-          uint32_t acc = 0;
+          // descriptors advance by byte offset >> 4 in their low word (no carry out of the 14-bit address field: smem < 256 KB)
+          const uint64_t Ahi = pc_desc(pc_smem_u32(As) + (uint32_t)r.slot * kStage), Alo = pc_desc(pc_smem_u32(Ls) + (uint32_t)l.slot * kStage);
+          const uint64_t bhi = pc_desc(Bhi + (uint32_t)kb * kBSlab), blo = pc_desc(Blo + (uint32_t)kb * kBSlab);
+          const uint32_t bstep = kBSlab >> 4;
+          if (pc_elect_one()) {
+            if (ns == kPcGroup && Kd - kb * 32 >= kPcGroup * 32) {
+              // full stage: 3 passes (lo*hi, hi*lo, hi*hi: small terms first) x 2 slabs x 4 k-steps, back to back
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // lo*hi, hi*lo, hi*hi: small terms first
-            const uint8_t* Ap = (pass == 0) ? Alo : Ahi;
-            const uint8_t* Bp = (pass == 1) ? Blo : Bhi;
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
+                for (int j = 0; j < kPcGroup; ++j) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                pc_mma(tacc, pc_desc(pc_smem_u32(Ap + (size_t)kb * kPcTileM * 128) + k * 32),
-                       pc_desc(pc_smem_u32(Bp + (size_t)kb * Nd * 128) + k * 32), idesc, acc);
-                acc = 1;
+                  for (int k = 0; k < 4; ++k) {
+                    pc_mma(tacc, Ap + (uint64_t)(j * (kPcSlab >> 4) + k * 2), Bp + (uint64_t)(j * bstep + k * 2), idesc, acc);
+                    acc = 1;
+                  }
+                }
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);  // the lo stage is free once the first pass has read it
+              }
+            } else {
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
+                for (int j = 0; j < ns; ++j) {
+                  const int rem = Kd - (kb + j) * 32;
+                  const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;   // 8 k-values per tf32 MMA; the padding is zero on both sides
+                  for (int k = 0; k < ksteps; ++k) {
+                    pc_mma(tacc, Ap + (uint64_t)(j * (kPcSlab >> 4) + k * 2), Bp + (uint64_t)(j * bstep + k * 2), idesc, acc);
+                    acc = 1;
+                  }
+                }
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);
               }
             }
-            if (pass == 0) pc_commit(lo_empty);  // the lo tile is free once the first pass has read it
+            pc_commit(&raw_empty[r.slot]);  // stage reusable once these MMAs have read it
           }
-          pc_commit(&raw_empty[st]);  // stage reusable once these MMAs have read it
+          __syncwarp();
+          acc = 1;
+          r.next(S), l.next(LS);
         }
-        pc_commit(&tfull[a]);         // accumulators complete
       }
+      if (pc_elect_one()) pc_commit(&tfull[a]);         // accumulators complete
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp < kPcFirstEpi) {
     // ===================================================== split: lo = x - trunc_tf32(x), same (swizzled) offsets
     const int t = tid - kPcFirstSplit * 32;  // 0..63
     constexpr int kSplitThreads = kPcSplitWarps * 32;
-    constexpr int kBatch = 16;                                       // float4 per thread per batch
-    constexpr int kBatches = (int)(kTile / 16u) / (kSplitThreads * kBatch);
-    for (int64_t u = 0; u < nuse; ++u) {
-      const int st = (int)(u % S);
-      pc_mbar_wait(&raw_full[st], (uint32_t)((u / S) & 1));
-      const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)st * kTile);
-      float4* __restrict__ dst = reinterpret_cast<float4*>(Ls);
-      float4 x[kBatch];
+    constexpr int kBatch = (int)(kPcSlab / 16u) / kSplitThreads;     // 16 float4 per thread per slab
+    const int ngroups = (KB + kPcGroup - 1) / kPcGroup;
+    PcRing r, l;
+    for (int64_t u = 0; u < my_tiles * p.nsrc; ++u) {
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int ns = KB - gi * kPcGroup < kPcGroup ? KB - gi * kPcGroup : kPcGroup;
+        pc_mbar_wait(&raw_full[r.slot], r.phase);
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)r.slot * kStage);
+        float4* __restrict__ dst = reinterpret_cast<float4*>(Ls + (size_t)l.slot * kStage);
+        float4 x[kBatch];
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) x[j] = src[j * kSplitThreads + t];
-      pc_mbar_wait(lo_empty, (uint32_t)((u & 1) ^ 1));
+        for (int j = 0; j < kBatch; ++j) x[j] = src[j * kSplitThreads + t];
+        pc_mbar_wait(&lo_empty[l.slot], l.phase ^ 1u);
+        for (int b = 0; b < ns; ++b) {
 #pragma unroll
-      for (int b = 0; b < kBatches; ++b) {
+          for (int j = 0; j < kBatch; ++j)
+            dst[(b * kBatch + j) * kSplitThreads + t] = make_float4(pc_lo(x[j].x), pc_lo(x[j].y), pc_lo(x[j].z), pc_lo(x[j].w));
+          if (b + 1 < ns) {
 #pragma unroll
-        for (int j = 0; j < kBatch; ++j)
-          dst[(b * kBatch + j) * kSplitThreads + t] = make_float4(pc_lo(x[j].x), pc_lo(x[j].y), pc_lo(x[j].z), pc_lo(x[j].w));
-        if (b + 1 < kBatches) {
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) x[j] = src[((b + 1) * kBatch + j) * kSplitThreads + t];
+            for (int j = 0; j < kBatch; ++j) x[j] = src[((b + 1) * kBatch + j) * kSplitThreads + t];
+          }
         }
+        pc_proxy_fence();
+        pc_mbar_arrive(&lo_full[l.slot]);
+        r.next(S), l.next(LS);
       }
-      pc_proxy_fence();
-      pc_mbar_arrive(lo_full);
     }
   } else {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves
@@ -313,27 +381,29 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         rss[s] = (s < p.nsrc && rsv && myrow < p.M) ? __ldg(rsv + myrow) : 1.f;
       }
     };
-    if (blockIdx.x < ntiles) load_idx(blockIdx.x, ix, cf, rsc);
+    if (grp < ntiles) load_idx(grp, ix, cf, rsc);
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      const int64_t tile = blockIdx.x + ti * gridDim.x;
+      const int64_t tile = grp + ti * ngrp;
       const int a = (int)(ti & 1);
       const uint32_t taddr = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
       const int64_t wrow0 = tile * kPcTileM + quarter * 32;
       bool waited = false;
-      for (int c0 = half * 32; c0 < Nd; c0 += 64) {
-        const int col = c0 + lchunk * 4;
+      for (int c0 = half * 32; c0 < Nsub; c0 += 64) {
+        const int lcol = c0 + lchunk * 4;        // column inside this CTA's window
+        const int col = n0 + lcol;               // column of `out`
+        const bool cok = lcol < Nsub && col < Nd;
         // gathered rows first: they do not depend on the accumulator, so their latency hides behind the wait for it
         float4 gv[NGA][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
           for (int g = 0; g < NGA; ++g)
-            gv[g][i] = (NG > g && ix[g][i] >= 0 && col < Nd)
+            gv[g][i] = (NG > g && ix[g][i] >= 0 && cok)
                            ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
         }
         if (!waited) {
           // next tile's indices / coefficients / row scales - one more load latency off the chain (NG <= 1: registers)
-          if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + gridDim.x, ixn, cfn, rscn);
+          if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + ngrp, ixn, cfn, rscn);
           pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
           pc_fence_after();
           waited = true;
@@ -344,7 +414,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         for (int q2 = 0; q2 < 4; ++q2) {
           uint32_t v0[8], v1[8];
           pc_tmem_ld8(taddr + c0 + q2 * 8, v0);
-          if (p.nsrc > 1) pc_tmem_ld8(taddr + Nd + c0 + q2 * 8, v1);
+          if (p.nsrc > 1) pc_tmem_ld8(taddr + Nsp + c0 + q2 * 8, v1);
           pc_tmem_wait_ld();
           float o[8];
 #pragma unroll
@@ -358,13 +428,13 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         }
         __syncwarp();
         float4 bsum = f4_zero(), bsq = f4_zero();
-        const float4 bias4 = (p.bias && col < Nd) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
+        const float4 bias4 = (p.bias && cok) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : f4_zero();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + lrow;
           const int64_t row = wrow0 + rl;
           float4 o = *reinterpret_cast<const float4*>(Et + rl * 128 + ((lchunk ^ (rl & 7)) << 4));
-          if (row < p.M && col < Nd) {
+          if (row < p.M && cok) {
 #pragma unroll
             for (int g = 0; g < NGA; ++g)
               if (NG > g) f4_fma(o, cf[g][i], gv[g][i]);
@@ -383,18 +453,18 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
             ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);
             ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16);
           }
-          if (lrow == 0 && col < Nd) {
+          if (lrow == 0 && lcol < Nsub) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              red[(ew * 2 + 0) * Nd + col + e] += (double)ps[e];
-              red[(ew * 2 + 1) * Nd + col + e] += (double)ps[4 + e];
+              red[(ew * 2 + 0) * Nsub + lcol + e] += (double)ps[e];
+              red[(ew * 2 + 1) * Nsub + lcol + e] += (double)ps[4 + e];
             }
           }
         }
         __syncwarp();
       }
-      if (!waited) {  // this warp has no column block (Nd <= 32 and half == 1): still take part in the handshake
-        if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + gridDim.x, ixn, cfn, rscn);
+      if (!waited) {  // this warp has no column block (Nsub <= 32 and half == 1): still take part in the handshake
+        if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + ngrp, ixn, cfn, rscn);
         pc_mbar_wait(&tfull[a], (uint32_t)((ti >> 1) & 1));
         pc_fence_after();
       }
@@ -405,32 +475,34 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         for (int i = 0; i < 8; ++i) ix[0][i] = ixn[0][i], cf[0][i] = cfn[0][i];
         rsc[0] = rscn[0], rsc[1] = rscn[1];
       } else if (ti + 1 < my_tiles) {
-        load_idx(tile + gridDim.x, ix, cf, rsc);
+        load_idx(tile + ngrp, ix, cf, rsc);
       }
     }
   }
   pc_fence_before();
   __syncthreads();
   if (p.stats_part) {
-    for (int i = tid; i < 2 * Nd; i += kPcThreads) {
-      const int v = i / Nd, c = i % Nd;
+    for (int i = tid; i < 2 * Nsub; i += kPcThreads) {
+      const int v = i / Nsub, c = i % Nsub;
       double s = 0;
-      for (int w = 0; w < kPcEpilogueWarps; ++w) s += red[(w * 2 + v) * Nd + c];
-      p.stats_part[((size_t)blockIdx.x * 2 + v) * Nd + c] = s;
+      for (int w = 0; w < kPcEpilogueWarps; ++w) s += red[(w * 2 + v) * Nsub + c];
+      p.stats_part[((size_t)blockIdx.x * 2 + v) * Nsub + c] = s;
     }
   }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
-// mean / inv_std of GraphNorm from per-CTA (sum, sum of squares) double partials (norm.cu semantics)
-__global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, int64_t M, int C, const float* __restrict__ mean_scale,
-                                 float eps, float* __restrict__ stats) {
+// mean / inv_std of GraphNorm from per-CTA (sum, sum of squares) double partials (norm.cu semantics); CTA b holds the
+// columns of window b % nsplit
+__global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, int nsplit, int Nsub, int64_t M, int C,
+                                 const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const int split = c / Nsub, cl = c % Nsub;
   double s = 0, q = 0;
-  for (int b = 0; b < nparts; ++b) {
-    s += part[((size_t)b * 2 + 0) * C + c];
-    q += part[((size_t)b * 2 + 1) * C + c];
+  for (int b = split; b < nparts; b += nsplit) {
+    s += part[((size_t)b * 2 + 0) * Nsub + cl];
+    q += part[((size_t)b * 2 + 1) * Nsub + cl];
   }
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
@@ -440,58 +512,106 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
   stats[C + c] = (float)(1.0 / sqrt(var + (1.0 - a) * (1.0 - a) * mean * mean + (double)eps));
 }
 
-static size_t pc_smem_bytes(int Kd, int Nd, int nsrc, bool with_stats, int stages) {
-  return (size_t)nsrc * 2 * Kd * Nd * 4 + (size_t)(stages + 1) * kPcTileM * Kd * 4 + kPcEpilogueWarps * 4096 + (2 * kPcMaxStages + 8) * 8 +
-         (with_stats ? (size_t)kPcEpilogueWarps * 2 * Nd * 8 : 0) + 1024;
+// How one launch is cut: column windows of Nsub (multiple of 16) output columns per CTA, raw / lo ring depths.
+struct PcConfig {
+  int nsplit = 0, Nsub = 0, stages = 0, lo_stages = 0, tmem_cols = 0;
+  size_t smem = 0;
+};
+static size_t pc_smem_bytes(int Kd, int Nsub, int nsrc, bool with_stats, int stages, int lo_stages) {
+  const int KB = (Kd + 31) / 32;
+  return (size_t)nsrc * 2 * KB * Nsub * 128 + (size_t)(stages + lo_stages) * ((Kd + 31) / 32 > 1 ? kPcStage : kPcSlab) + kPcEpilogueWarps * 4096 +
+         (2 * kPcMaxStages + 2 * kPcMaxLo + 8) * 8 + (with_stats ? (size_t)kPcEpilogueWarps * 2 * Nsub * 8 : 0) + 1024;
 }
-// deepest raw-tile ring (<= kPcMaxStages) that fits the 227 KB of shared memory, 0 if not even 2 stages fit
-static int pc_stages(int Kd, int Nd, int nsrc, bool with_stats) {
-  for (int st = kPcMaxStages; st >= 2; --st)
-    if (pc_smem_bytes(Kd, Nd, nsrc, with_stats, st) <= 227 * 1024) return st;
-  return 0;
+static int pc_tmem_cols(int Nsub, int nsrc) {
+  const int need = 2 * nsrc * ((Nsub + 31) / 32 * 32);   // the epilogue reads 32-column blocks
+  int cols = 32;
+  while (cols < need) cols <<= 1;
+  return cols;
 }
-static bool pc_supported(int Kd, int Nd, int nsrc) {
-  return (Kd == 32 || Kd == 64) && Nd >= 16 && Nd <= 256 && (Nd % 16) == 0 && 2 * nsrc * Nd <= 512 && pc_stages(Kd, Nd, nsrc, nsrc == 1) >= 2;
+// Fewest column windows whose resident weights leave room for a ring of >= 3 raw stages + 1 lo stage; failing that, the
+// first split that fits at all (2 + 1). force_nsplit > 0 pins the split (tuning / tests).
+static PcConfig pc_config(int Kd, int Nd, int nsrc, bool with_stats, int force_nsplit = 0) {
+  PcConfig best;
+  if (Kd < 4 || Kd > 1024 || (Kd % 4) || Nd < 4 || Nd > 1024 || (Nd % 4) || nsrc < 1 || nsrc > 2) return best;
+  const size_t cap = 227 * 1024;
+  for (int want = 3; want >= 2 && !best.nsplit; --want) {
+    for (int ns = 1; ns <= 32; ns *= 2) {
+      if (force_nsplit > 0 && ns != force_nsplit) continue;
+      const int Nsub = (int)(cdiv(cdiv(Nd, ns), 16) * 16);
+      if (Nsub > 256 || (ns > 1 && (int64_t)(ns - 1) * Nsub >= Nd)) continue;
+      if (pc_tmem_cols(Nsub, nsrc) > 512) continue;
+      int lo = 1;
+      if (pc_smem_bytes(Kd, Nsub, nsrc, with_stats, want, lo) > cap) continue;
+      int st = want;
+      while (st < kPcMaxStages && pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st + 1, lo) <= cap) ++st;
+      if (const char* e = getenv("TWOWL_PC_STAGES")) st = atoi(e) < st ? (atoi(e) < 2 ? 2 : atoi(e)) : st;   // tuning knob
+      if (const char* e = getenv("TWOWL_PC_LO")) lo = atoi(e) >= 2 ? lo : 1;
+      best.nsplit = ns, best.Nsub = Nsub, best.stages = st, best.lo_stages = lo;
+      best.tmem_cols = pc_tmem_cols(Nsub, nsrc);
+      best.smem = pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo);
+      break;
+    }
+  }
+  return best;
 }
-static int pc_grid(int64_t M) {
+static int pc_force_nsplit() {
+  const char* e = getenv("TWOWL_PC_NSPLIT");
+  return e ? atoi(e) : 0;
+}
+static bool pc_supported(int Kd, int Nd, int nsrc) { return pc_config(Kd, Nd, nsrc, nsrc == 1).nsplit > 0; }
+static int pc_grid(int64_t M, int nsplit) {
   const int64_t ntiles = cdiv(M, kPcTileM);
-  return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+  const int64_t groups = kNumSMs / nsplit;
+  return (int)((ntiles < groups ? ntiles : groups) * nsplit);
 }
 
-// row-major fp32 [M, Kd] -> boxes of 32 columns x 128 rows, SWIZZLE_128B (the UMMA K-major canonical layout)
+// row-major fp32 [M, Kd] -> boxes of 32 columns x 128 rows, SWIZZLE_128B (the UMMA K-major canonical layout); columns
+// beyond Kd are zero-filled by the TMA unit
 static int pc_make_tmap(CUtensorMap* tm, const float* A, int64_t M, int Kd) {
   return make_tmap_2d_f32(tm, A, M, Kd, 32, kPcTileM, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int KD, int NG>
-static int pc_launch(const ConvParams& p, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
-  const size_t smem = pc_smem_bytes(KD, p.Nd, p.nsrc, p.stats_part != nullptr, p.stages);
-  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<KD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_conv<KD, NG><<<pc_grid(p.M), kPcThreads, smem, s>>>(p, t0, t1);
+template <int NG>
+static int pc_launch(const ConvParams& p, size_t smem, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
+  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pair_conv<NG><<<pc_grid(p.M, p.nsplit), kPcThreads, smem, s>>>(p, t0, t1);
   TW_LAUNCH_CHECK();
   return 0;
-}
-template <int KD>
-static int pc_launch_ng(const ConvParams& p, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
-  return p.ngather == 0 ? pc_launch<KD, 0>(p, t0, t1, s) : p.ngather == 1 ? pc_launch<KD, 1>(p, t0, t1, s) : pc_launch<KD, 2>(p, t0, t1, s);
 }
 
 }  // namespace twowl
 
 using namespace twowl;
 
+extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_bytes, void* stream);
+
+// The plain linear layer (linear.cu: twowl_linear_fwd / twowl_linear_bwd_input, impl 1 / 2) is this kernel with one
+// source and no epilogue terms: C[M,Nd] = A[M,Kd] * B^T, B = W[Nd,Kd] (w_kn = 0) or W[Kd,Nd] (w_kn = 1).
+namespace twowl {
+bool linear_tc_supported(int Kd, int Nd) { return pc_config(Kd, Nd, 1, false).nsplit > 0; }
+int linear_tc(const float* A, const float* W, float* C, int64_t M, int Kd, int Nd, int w_kn, cudaStream_t s) {
+  twowl_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.nsrc = 1, a.Kd = Kd, a.Nd = Nd, a.M = M;
+  a.A[0] = A, a.W[0] = W, a.w_kn[0] = w_kn, a.out = C;
+  return twowl_pair_conv(&a, nullptr, 0, (void*)s);
+}
+}  // namespace twowl
+
 extern "C" int twowl_pair_conv_supported(int32_t Kd, int32_t Nd, int32_t nsrc) { return pc_supported(Kd, Nd, nsrc) ? 1 : 0; }
 
 extern "C" size_t twowl_pair_conv_workspace_bytes(int64_t M, int32_t Nd) {
   (void)M;
-  return align_up((size_t)kNumSMs * 2 * (size_t)Nd * sizeof(double));
+  return align_up((size_t)kNumSMs * 2 * (size_t)(Nd < 256 ? 256 : Nd) * sizeof(double));
 }
 
 extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_bytes, void* stream) {
   TW_CHECK_ARG(a != nullptr && a->nsrc >= 1 && a->nsrc <= 2 && a->ngather >= 0 && a->ngather <= 2, "pair_conv: bad nsrc/ngather");
-  TW_CHECK_ARG(pc_supported(a->Kd, a->Nd, a->nsrc), "pair_conv: Kd=%d Nd=%d nsrc=%d unsupported (Kd in {32,64}, Nd %% 16, smem)",
-               a->Kd, a->Nd, a->nsrc);
   TW_CHECK_ARG(a->M >= 0, "pair_conv: negative M");
+  const bool want_stats = a->stats != nullptr;
+  const PcConfig cfg = pc_config(a->Kd, a->Nd, a->nsrc, want_stats, pc_force_nsplit());
+  TW_CHECK_ARG(cfg.nsplit > 0, "pair_conv: Kd=%d Nd=%d nsrc=%d%s unsupported (widths %% 4, <= 1024, shared memory)", a->Kd, a->Nd,
+               a->nsrc, want_stats ? " with statistics" : "");
   ConvParams p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < a->nsrc; ++s) {
@@ -503,31 +623,28 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     p.T[g] = a->T[g], p.tidx[g] = a->tidx[g], p.tcoef[g] = a->tcoef[g];
   }
   TW_CHECK_ARG(aligned16(a->out) && aligned16(a->bias), "pair_conv: out/bias must be 16-byte aligned");
-  p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
-  int cols = 32;
-  while (cols < 2 * a->nsrc * a->Nd) cols <<= 1;
-  p.tmem_cols = cols;
+  p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Kd = a->Kd, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
+  p.Nsub = cfg.Nsub, p.nsplit = cfg.nsplit, p.stages = cfg.stages, p.lo_stages = cfg.lo_stages, p.tmem_cols = cfg.tmem_cols;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool want_stats = a->stats != nullptr;
   if (want_stats) {
     TW_CHECK_ARG(a->mean_scale != nullptr && a->M > 0, "pair_conv: stats need mean_scale and M > 0");
     TW_CHECK_WS(ws_bytes, twowl_pair_conv_workspace_bytes(a->M, a->Nd));
     p.stats_part = (double*)ws;
   }
   if (a->M == 0) return 0;
-  p.stages = pc_stages(a->Kd, a->Nd, a->nsrc, want_stats);
-  TW_CHECK_ARG(p.stages >= 2, "pair_conv: shared memory does not hold Kd=%d Nd=%d nsrc=%d%s", a->Kd, a->Nd, a->nsrc,
-               want_stats ? " with statistics" : "");
   CUtensorMap tm[2];
   memset(tm, 0, sizeof(tm));
   for (int i = 0; i < a->nsrc; ++i) {
     const int rc_t = pc_make_tmap(&tm[i], a->A[i], a->M, a->Kd);
     if (rc_t) return rc_t;
   }
-  int rc = (a->Kd == 32) ? pc_launch_ng<32>(p, tm[0], tm[1], s) : pc_launch_ng<64>(p, tm[0], tm[1], s);
+  const int rc = a->ngather == 0   ? pc_launch<0>(p, cfg.smem, tm[0], tm[1], s)
+                 : a->ngather == 1 ? pc_launch<1>(p, cfg.smem, tm[0], tm[1], s)
+                                   : pc_launch<2>(p, cfg.smem, tm[0], tm[1], s);
   if (rc) return rc;
   if (want_stats) {
-    k_pc_stats_final<<<(int)cdiv(a->Nd, 128), 128, 0, s>>>(p.stats_part, pc_grid(a->M), a->M, a->Nd, a->mean_scale, a->eps, a->stats);
+    k_pc_stats_final<<<(int)cdiv(a->Nd, 128), 128, 0, s>>>(p.stats_part, pc_grid(a->M, cfg.nsplit), cfg.nsplit, cfg.Nsub, a->M, a->Nd,
+                                                           a->mean_scale, a->eps, a->stats);
     TW_LAUNCH_CHECK();
   }
   return 0;

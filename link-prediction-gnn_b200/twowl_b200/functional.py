@@ -305,13 +305,16 @@ def _pl_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)   # no zero-filled [R,C] gradients for the saved-state outputs
 
 
-def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars):
+def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars, dWs=None):
     """Backward of the structured pair-level GCNConv pair from the gradients dO_f, dO_r of its two outputs:
-    -> dh and, per direction, (dW, dbias, d gn.weight, d gn.bias, d gn.mean_scale)."""
+    -> dh and, per direction, (dW, dbias, d gn.weight, d gn.bias, d gn.mean_scale).
+    dWs: the (selfw_d * dO_d)^T H parts when the caller already has them (pair_dw_gn)."""
     C = wf.shape[0]
     dSs = [ops.seg_reduce(out_ptr, out_ids, n_node, dOs[d], plan=out_plan, flip=d, src_scale=dinv[d]) for d in range(2)]
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
-    if ops.pair_dw_supported(C) and h.shape[1] == C:
+    if dWs is not None:
+        pass
+    elif ops.pair_dw_supported(C) and h.shape[1] == C:
         dWs = list(ops.pair_dw(dOs[0], dOs[1], selfw[0], selfw[1], h))
     else:
         dWs = [ops.linear_bwd_weight(dOs[d], h, row_scale=selfw[d]) for d in range(2)]
@@ -389,9 +392,20 @@ def _plr_bwd(ctx, g, *_unused):
     (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr,
      SHf, SHr) = ctx.saved_tensors
     n_node, p_drop, seed_f, seed_r = ctx.meta
-    dOf, dOr, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r,
-                                                       True, idx, pw.contiguous(), g.reshape(-1))
-    dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr])
+    C = wf.shape[0]
+    if ops.pair_dw_supported(C) and h.shape[1] == C:
+        # the dense GraphNorm-backward pass rides on the weight-gradient kernel's shared-memory pass (twowl_pair_dw_gn)
+        G, head, nxt, consts, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd_prepare(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr),
+                                                                               p_drop, seed_f, seed_r, True, idx, pw.contiguous(),
+                                                                               g.reshape(-1))
+        dOf, dOr, dWf, dWr = ops.pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop, seed_f, seed_r, True, selfw[0], selfw[1], h)
+        dWs = [dWf, dWr]
+    else:
+        dOf, dOr, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r,
+                                                           True, idx, pw.contiguous(), g.reshape(-1))
+        dWs = None
+    dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr],
+                           dWs=dWs)
     return (dh,) + res[0] + res[1] + (None, dpw.reshape(pw.shape), dpb) + (None,) * 16
 
 

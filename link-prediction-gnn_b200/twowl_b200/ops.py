@@ -421,6 +421,36 @@ def gn2_readout_bwd(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: 
     return dxf, dxr, dpf, dpr, dw, db
 
 
+def gn2_readout_bwd_prepare(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool, idx, w, dpred):
+    """The row-sparse part of gn2_readout_bwd for a consumer that makes dxf / dxr on the fly (pair_dw_gn):
+    -> (G [2L,C], head int32[M], next int32[2L], consts [8C], dparams_f, dparams_r [4C], dw [1,C], db [1])."""
+    M, C = xf.shape
+    dev = xf.device
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    G = torch.empty((max(2 * L, 1), C), dtype=torch.float32, device=dev)
+    head = torch.empty(M, dtype=torch.int32, device=dev)
+    nxt = torch.empty(max(2 * L, 1), dtype=torch.int32, device=dev)
+    consts = torch.empty(8 * C, dtype=torch.float32, device=dev)
+    dpf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dpr = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dw = torch.empty((1, C), dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    nb = lib.twowl_gn2_readout_bwd_prepare_workspace_bytes(M, L, C)
+    ws = _ws(nb, dev)
+    p, s = _row(idx)
+    dpred = dpred.contiguous()
+    with _P("gn2_readout_bwd_prepare", M * 4 + L * (48 * C + 40)):
+        check(lib.twowl_gn2_readout_bwd_prepare(xf.data_ptr(), xr.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                                pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(),
+                                                pr[2].data_ptr(), float(p_drop), int(seed_f), int(seed_r), int(relu), p, s, L,
+                                                w.data_ptr(), dpred.data_ptr(), G.data_ptr(), head.data_ptr(), nxt.data_ptr(),
+                                                consts.data_ptr(), dpf.data_ptr(), dpr.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                                ws.data_ptr(), nb, _stream()), "gn2_readout_bwd_prepare")
+    _count(9)
+    return G, head, nxt, consts, dpf, dpr, dw, db
+
+
 # ------------------------------------------------------------------------------ GraphNorm
 
 def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
@@ -607,6 +637,25 @@ def pair_dw(dOf, dOr, rsf, rsr, H):
                                 dWf.data_ptr(), dWr.data_ptr(), ws.data_ptr(), nb, _stream()), "pair_dw")
     _count(2)
     return dWf, dWr
+
+
+def pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop: float, seed_f: int, seed_r: int, relu: bool, rsf, rsr, H):
+    """pair_dw with the gradients made on the fly from the last pair layer's outputs (after gn2_readout_bwd_prepare):
+    -> (dOf, dOr [M,C], dWf, dWr [C,C]). One pass: reads Of, Or, H, writes dOf, dOr."""
+    _need_cuda(Of, Or, H)
+    M, C = H.shape
+    dOf, dOr = torch.empty_like(Of), torch.empty_like(Or)
+    dWf = torch.empty((C, C), dtype=torch.float32, device=H.device)
+    dWr = torch.empty((C, C), dtype=torch.float32, device=H.device)
+    nb = lib.twowl_pair_dw_workspace_bytes(M, C)
+    ws = _ws(nb, H.device)
+    with _P("pair_dw_gn", 20 * M * C + 12 * M):
+        check(lib.twowl_pair_dw_gn(Of.data_ptr(), Or.data_ptr(), consts.data_ptr(), G.data_ptr(), head.data_ptr(), nxt.data_ptr(),
+                                   float(p_drop), int(seed_f), int(seed_r), int(relu), rsf.data_ptr(), rsr.data_ptr(), H.data_ptr(),
+                                   M, C, dOf.data_ptr(), dOr.data_ptr(), dWf.data_ptr(), dWr.data_ptr(), ws.data_ptr(), nb,
+                                   _stream()), "pair_dw_gn")
+    _count(2)
+    return dOf, dOr, dWf, dWr
 
 
 def graphnorm_apply2(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool):

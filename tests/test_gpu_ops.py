@@ -316,6 +316,10 @@ def test_pair_init_readout_embedding(U, mated):
     (1, 64, 64, 1, 0, False), (127, 32, 32, 1, 1, True), (128, 64, 64, 2, 2, False), (129, 64, 32, 1, 1, True),
     (1000, 32, 64, 2, 1, False), (40001, 64, 64, 1, 1, True), (40001, 64, 64, 2, 2, False), (5000, 64, 128, 1, 2, True),
     (300000, 64, 64, 1, 1, True),
+    # widths beyond one K-slab / one column window, and widths that are not multiples of 16 / 32 (fb: channels_2wl = 24)
+    (3001, 24, 24, 1, 1, True), (3001, 24, 24, 2, 2, False), (777, 20, 36, 1, 0, True), (20001, 128, 128, 1, 1, True),
+    (20001, 128, 128, 2, 2, False), (9001, 256, 256, 1, 1, True), (9001, 256, 256, 2, 2, False), (5000, 96, 48, 2, 1, False),
+    (5000, 128, 64, 1, 0, False), (5000, 64, 256, 1, 2, True),
 ])
 def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
     """The fused tensor-core kernel (3xTF32 GEMM + row scale + gathered-row epilogue + GraphNorm statistics)."""
@@ -370,3 +374,37 @@ def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     assert_close(gr, ref_r, rtol=1e-5, atol=tol, what="pair_dw r")
     gf2, gr2 = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
     assert torch.equal(gf, gf2) and torch.equal(gr, gr2)      # deterministic
+
+
+@pytest.mark.parametrize("M,C,L,p", [(64, 64, 10, 0.0), (5000, 32, 700, 0.3), (70001, 64, 9000, 0.0), (70001, 64, 9000, 0.5)])
+def test_pair_dw_gn_matches_two_pass(U, M, C, L, p):
+    """twowl_gn2_readout_bwd_prepare + twowl_pair_dw_gn (GraphNorm backward made inside the weight-gradient kernel) against
+    the two-pass path twowl_gn2_readout_bwd + twowl_pair_dw: same dO_f, dO_r, dW_f, dW_r and parameter gradients."""
+    from twowl_b200 import ops
+    torch.manual_seed(M + C + L)
+    dev = "cuda"
+    Of, Or, H = (torch.randn(M, C, device=dev) for _ in range(3))
+    rsf = torch.rand(M, device=dev) * (torch.rand(M, device=dev) > 0.3)
+    rsr = torch.rand(M, device=dev)
+    pf = tuple(torch.rand(C, device=dev) + 0.5 for _ in range(3))
+    pr = tuple(torch.rand(C, device=dev) + 0.5 for _ in range(3))
+    sf, sr = ops.graphnorm_stats(Of, pf[2], 1e-5), ops.graphnorm_stats(Or, pr[2], 1e-5)
+    idx = torch.randint(0, M, (2 * L,), device=dev)
+    idx[3] = idx[1]
+    idx[7] = idx[1]                       # a row selected three times: positions add in ascending order
+    w = torch.randn(1, C, device=dev)
+    dpred = torch.randn(L, device=dev)
+    seeds = (1234567, 7654321)
+    dxf, dxr, dpf, dpr, dw, db = ops.gn2_readout_bwd(Of, Or, sf, sr, pf, pr, p, seeds[0], seeds[1], True, idx, w, dpred)
+    dWf, dWr = ops.pair_dw(dxf, dxr, rsf, rsr, H)
+    G, head, nxt, consts, dpf2, dpr2, dw2, db2 = ops.gn2_readout_bwd_prepare(Of, Or, sf, sr, pf, pr, p, seeds[0], seeds[1], True, idx, w,
+                                                                           dpred)
+    dOf, dOr, dWf2, dWr2 = ops.pair_dw_gn(Of, Or, consts, G, head, nxt, p, seeds[0], seeds[1], True, rsf, rsr, H)
+    for a, b in ((dpf, dpf2), (dpr, dpr2), (dw, dw2), (db, db2)):
+        assert torch.equal(a, b)
+    tol = 1e-5 * max(float(dxf.abs().max()), float(dxr.abs().max()))
+    assert_close(dOf, dxf.double().cpu(), rtol=1e-5, atol=tol, what="dO_f on the fly")
+    assert_close(dOr, dxr.double().cpu(), rtol=1e-5, atol=tol, what="dO_r on the fly")
+    wt = 1e-5 * max(float(dWf.abs().max()), float(dWr.abs().max()), 1.0)
+    assert_close(dWf2, dWf.double().cpu(), rtol=1e-5, atol=wt, what="dW_f")
+    assert_close(dWr2, dWr.double().cpu(), rtol=1e-5, atol=wt, what="dW_r")
