@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   constexpr uint32_t kStage = 2u * kAHalf + 2u * kBHalf;
   constexpr uint32_t kTxBytes = 3u * GS * kDwLbo;     // raw bytes landing per tile
   extern __shared__ uint8_t dw_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the shared array: a pointer rebuilt from an integer would be generic (LD.E / ST.E)
+  uint8_t* smem = dw_smem_raw + ((1024u - (dw_smem_u32(dw_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kStage);
   uint64_t* raw_full = bars;        // [stages] TMA -> split
   uint64_t* split_done = bars + 2;  // [stages] split -> MMA
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
             }
             o.x += add[0], o.y += add[1], o.z += add[2], o.w += add[3];
           }
-          if (row < p.M) stg_stream(reinterpret_cast<float4*>((is_r ? p.dOr : p.dOf) + row * C + col), o);
+          if (row < p.M) __stcs(reinterpret_cast<float4*>((is_r ? p.dOr : p.dOf) + row * C + col), o);   // no asm: free to schedule
           v = o;
         }
         v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;

@@ -150,7 +150,8 @@ template <int NG>
 __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1) {
   extern __shared__ uint8_t pc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the shared array: a pointer rebuilt from an integer would be generic (LD.E / ST.E)
+  uint8_t* smem = pc_smem_raw + ((1024u - (pc_smem_u32(pc_smem_raw) & 1023u)) & 1023u);
   const int Nd = p.Nd, Nsub = p.Nsub, Kd = p.Kd;
   const int KB = (Kd + 31) >> 5;                 // K-slabs per tile
   const int Nsp = (Nsub + 31) & ~31;             // TMEM columns per source accumulator (the epilogue reads 32-column blocks)
