@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   uint64_t* tfull = bars + 6;       // [2] MMA -> drain
   uint64_t* tempty = bars + 8;      // [2] drain -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* cs = reinterpret_cast<float*>(bars + 16);   // GN: [2 branches][P, Q][C] column constants
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (p.M + kDwTileK - 1) / kDwTileK;
@@ -169,6 +170,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
   }
+  if (GN)
+    for (int i = tid; i < 4 * C; i += kDwThreads) cs[i] = __ldg(p.consts + (i / (2 * C)) * 4 * C + (i % (2 * C)));
   // zero the padding groups of A (C = 32 only): written once, never touched again
   if (2 * GS < 4) {
     for (int st = 0; st < kDwStages; ++st)
@@ -246,103 +249,146 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
     constexpr int kSplitThreads = kDwSplitWarps * 32;
     constexpr int kAChunks = 2 * GS * (int)(kDwLbo / 16);    // 16-byte chunks of the live A groups (f then r)
     constexpr int kBChunks = GS * (int)(kDwLbo / 16);
-    constexpr int kAIter = kAChunks / kSplitThreads, kBIter = kBChunks / kSplitThreads;
+    constexpr int kBIter = kBChunks / kSplitThreads;
+    static_assert(kAChunks == 2 * GS * 4 * kSplitThreads, "4 rows x 2*GS chunks per split thread");
     // chunk i of a group region sits in k-row (i % 512) / 8; with i = j*128 + t that is (j % 4) * 16 + t / 8
     // GN: this thread's 4 columns inside a 32-column group are fixed (unit ((t & 7) >> 1) ^ (k & 3), k & 3 = (t >> 3) & 3), so
-    // the per-column constants of its (branch, group) chunks live in registers
+    // the per-column constants of its (branch, group) chunks are 2 LDS.128 per chunk
     const int tcol = (((((t & 7) >> 1) ^ ((t >> 3) & 3))) << 3) + ((t & 1) << 2);
-    float4 P4[GN ? 2 * GS : 1], Q4[GN ? 2 * GS : 1];
-    if (GN) {
-#pragma unroll
-      for (int gb = 0; gb < 2 * GS; ++gb) {
-        const float* __restrict__ cb = p.consts + (gb >= GS ? 4 * C : 0) + (gb % GS) * 32 + tcol;
-        P4[gb] = __ldg(reinterpret_cast<const float4*>(cb)), Q4[gb] = __ldg(reinterpret_cast<const float4*>(cb + C));
-      }
-    }
-    int hdn[4] = {-1, -1, -1, -1};   // chain heads of the NEXT tile's rows: one tile ahead, off the latency chain
-    if (GN && my_tiles > 0) {
+    // Everything a tile needs from global memory besides the TMA data is loaded ONE tile ahead (row scales, chain links, the
+    // selected rows' gradients) and the chain heads TWO tiles ahead (the gradients' addresses depend on them), so no global
+    // load latency sits between the arrival of a tile and its transform.
+    float sf[4], sr[4], sfn[4], srn[4];
+    int hd[4], nx[4], hdn[4], nxn[4], hdnn[4];
+    float4 Gd[4][GN ? GS : 1], Gdn[4][GN ? GS : 1];
+    const int64_t tstride = (int64_t)gridDim.x * kDwTileK;
+    auto load_heads = [&](int64_t row0_, bool live, int (&h)[4]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int64_t row = (int64_t)blockIdx.x * kDwTileK + q * 16 + (t >> 3);
-        hdn[q] = row < p.M ? __ldg(p.head + row) : -1;
+        const int64_t row = row0_ + q * 16 + (t >> 3);
+        h[q] = (GN && live && row < p.M) ? __ldg(p.head + row) : -1;
       }
+    };
+    auto load_rows = [&](int64_t row0_, bool live, const int (&h)[4], float (&a)[4], float (&b)[4], int (&n)[4], float4 (&g)[4][GN ? GS : 1]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t row = row0_ + q * 16 + (t >> 3);
+        const bool ok = live && row < p.M;
+        a[q] = ok ? __ldg(p.rsf + row) : 0.f;
+        b[q] = ok ? __ldg(p.rsr + row) : 0.f;
+        n[q] = -1;
+        if (GN) {
+          if (h[q] >= 0) n[q] = __ldg(p.next + h[q]);
+#pragma unroll
+          for (int gi = 0; gi < GS; ++gi)
+            g[q][gi] = h[q] >= 0 ? ldg_cached(reinterpret_cast<const float4*>(p.G + (int64_t)h[q] * C + gi * 32 + tcol)) : f4_zero();
+        }
+      }
+    };
+    {
+      const int64_t r0 = (int64_t)blockIdx.x * kDwTileK;
+      load_heads(r0, my_tiles > 0, hdn);
+      load_heads(r0 + tstride, my_tiles > 1, hdnn);
+      load_rows(r0, my_tiles > 0, hdn, sfn, srn, nxn, Gdn);
     }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int st = (int)(it % kDwStages);
       const int64_t row0 = tile * kDwTileK;
-      float sf[4], sr[4];
-      int hd[4], nx[4];
-      float4 Gd[4][GN ? GS : 1];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {   // row scales and the selected rows' gradients first: they do not depend on the TMA data
-        const int64_t row = row0 + q * 16 + (t >> 3);
-        sf[q] = row < p.M ? __ldg(p.rsf + row) : 0.f;
-        sr[q] = row < p.M ? __ldg(p.rsr + row) : 0.f;
-        hd[q] = hdn[q], nx[q] = -1;
-        if (GN) {
-          if (hd[q] >= 0) nx[q] = __ldg(p.next + hd[q]);
+      for (int q = 0; q < 4; ++q) {
+        sf[q] = sfn[q], sr[q] = srn[q], hd[q] = hdn[q], nx[q] = nxn[q], hdn[q] = hdnn[q];
 #pragma unroll
-          for (int g = 0; g < GS; ++g)
-            Gd[q][g] = hd[q] >= 0 ? ldg_cached(reinterpret_cast<const float4*>(p.G + (int64_t)hd[q] * C + g * 32 + tcol)) : f4_zero();
-          const int64_t rown = row + (int64_t)gridDim.x * kDwTileK;
-          hdn[q] = (it + 1 < my_tiles && rown < p.M) ? __ldg(p.head + rown) : -1;
-        }
+        for (int gi = 0; gi < (GN ? GS : 1); ++gi) Gd[q][gi] = Gdn[q][gi];
       }
       dw_mbar_wait(&raw_full[st], (uint32_t)((it / kDwStages) & 1));
+      // next tile's row data and the heads of the tile after it: in flight while this tile is transformed
+      load_rows(row0 + tstride, it + 1 < my_tiles, hdn, sfn, srn, nxn, Gdn);
+      load_heads(row0 + 2 * tstride, it + 2 < my_tiles, hdnn);
       float4* Ahi = reinterpret_cast<float4*>(smem + st * kStage);
       float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
       const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
       float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
+      // one branch (f, then r) at a time: 4 rows x GS column groups per thread
 #pragma unroll
-      for (int j = 0; j < kAIter; ++j) {
-        const int i = j * kSplitThreads + t;
-        const int q = j & 3, gb = j >> 2;          // row slot, (branch, 32-column group): f groups then r groups
-        const bool is_r = gb >= GS;
-        const float sc = is_r ? sr[q] : sf[q];
-        float4 v = Ahi[i];
+      for (int br = 0; br < 2; ++br) {
+        float4 v[GS][4];
+        // phase 1, branch-free: load, dense part of the GraphNorm backward
+#pragma unroll
+        for (int gi = 0; gi < GS; ++gi) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = (br * GS + gi) * 4 + q;
+            float4 x = Ahi[j * kSplitThreads + t];
+            if (GN) {
+              const float4 P4 = *reinterpret_cast<const float4*>(cs + br * 2 * C + gi * 32 + tcol);
+              const float4 Q4 = *reinterpret_cast<const float4*>(cs + br * 2 * C + C + gi * 32 + tcol);
+              x = make_float4(fmaf(P4.x, x.x, Q4.x), fmaf(P4.y, x.y, Q4.y), fmaf(P4.z, x.z, Q4.z), fmaf(P4.w, x.w, Q4.w));
+            }
+            v[gi][q] = x;
+          }
+        }
+        // phase 2: rows the readout selected: + sc * (dropout / ReLU mask) * sum of their positions' gradients
         if (GN) {
-          const int col = (gb % GS) * 32 + tcol;
-          const int64_t row = row0 + q * 16 + (t >> 3);
-          float4 o = make_float4(fmaf(P4[gb].x, v.x, Q4[gb].x), fmaf(P4[gb].y, v.y, Q4[gb].y), fmaf(P4[gb].z, v.z, Q4[gb].z),
-                                 fmaf(P4[gb].w, v.w, Q4[gb].w));
-          if (hd[q] >= 0) {   // a row the readout selected: + sc * (dropout / ReLU mask) * sum of its positions' gradients
-            float4 d = Gd[q][gb % GS];
-            if (nx[q] >= 0) {   // selected more than once: positions in ascending order (deterministic)
-              const float4* __restrict__ G4 = reinterpret_cast<const float4*>(p.G + col);
-              d = f4_zero();
-              int last = -1;
-              for (;;) {
-                int best = 0x7fffffff;
-                for (int c = hd[q]; c >= 0; c = __ldg(p.next + c))
-                  if (c > last && c < best) best = c;
-                if (best == 0x7fffffff) break;
-                f4_add(d, ldg_cached(G4 + (int64_t)best * (C / 4)));
-                last = best;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (hd[q] >= 0) {
+              const int64_t row = row0 + q * 16 + (t >> 3);
+#pragma unroll
+              for (int gi = 0; gi < GS; ++gi) {
+                const int col = gi * 32 + tcol;
+                float4 d = Gd[q][gi];
+                if (nx[q] >= 0) {   // selected more than once: positions in ascending order (deterministic)
+                  const float4* __restrict__ G4 = reinterpret_cast<const float4*>(p.G + col);
+                  d = f4_zero();
+                  int last = -1;
+                  for (;;) {
+                    int best = 0x7fffffff;
+                    for (int c = hd[q]; c >= 0; c = __ldg(p.next + c))
+                      if (c > last && c < best) best = c;
+                    if (best == 0x7fffffff) break;
+                    f4_add(d, ldg_cached(G4 + (int64_t)best * (C / 4)));
+                    last = best;
+                  }
+                }
+                const float* __restrict__ cb = p.consts + (br ? 4 * C : 0) + col;
+                const float4 S4 = __ldg(reinterpret_cast<const float4*>(cb + 2 * C)), O4 = __ldg(reinterpret_cast<const float4*>(cb + 3 * C));
+                // the forward value y = sc*x + of from dO = P*x + Q would lose x when P is tiny: keep it exact from the raw tile
+                const float4 xr = Ahi[((br * GS + gi) * 4 + q) * kSplitThreads + t];
+                const float xa[4] = {xr.x, xr.y, xr.z, xr.w}, da[4] = {d.x, d.y, d.z, d.w}, sa[4] = {S4.x, S4.y, S4.z, S4.w},
+                            oa[4] = {O4.x, O4.y, O4.z, O4.w};
+                float add[4];
+                const uint64_t e0 = (uint64_t)row * C + col;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  float g = da[c], keep = 1.f;
+                  if (p.thresh) keep = drop_scale(br ? p.seed_r : p.seed_f, e0 + c, p.thresh, p.inv_keep);
+                  g *= keep;
+                  if (p.relu && !(fmaf(sa[c], xa[c], oa[c]) * keep > 0.f)) g = 0.f;
+                  add[c] = sa[c] * g;
+                }
+                v[gi][q].x += add[0], v[gi][q].y += add[1], v[gi][q].z += add[2], v[gi][q].w += add[3];
               }
             }
-            const float* __restrict__ cb = p.consts + (is_r ? 4 * C : 0) + col;
-            const float4 S4 = __ldg(reinterpret_cast<const float4*>(cb + 2 * C)), O4 = __ldg(reinterpret_cast<const float4*>(cb + 3 * C));
-            const float xa[4] = {v.x, v.y, v.z, v.w}, da[4] = {d.x, d.y, d.z, d.w}, sa[4] = {S4.x, S4.y, S4.z, S4.w},
-                        oa[4] = {O4.x, O4.y, O4.z, O4.w};
-            float add[4];
-            const uint64_t e0 = (uint64_t)row * C + col;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float g = da[c], keep = 1.f;
-              if (p.thresh) keep = drop_scale(is_r ? p.seed_r : p.seed_f, e0 + c, p.thresh, p.inv_keep);
-              g *= keep;
-              if (p.relu && !(fmaf(sa[c], xa[c], oa[c]) * keep > 0.f)) g = 0.f;
-              add[c] = sa[c] * g;
-            }
-            o.x += add[0], o.y += add[1], o.z += add[2], o.w += add[3];
           }
-          if (row < p.M) __stcs(reinterpret_cast<float4*>((is_r ? p.dOr : p.dOf) + row * C + col), o);   // no asm: free to schedule
-          v = o;
         }
-        v.x *= sc, v.y *= sc, v.z *= sc, v.w *= sc;
-        Ahi[i] = v;
-        Alo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
+        // phase 3, branch-free: gradient out, row scale, hi (in place) / lo
+#pragma unroll
+        for (int gi = 0; gi < GS; ++gi) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = (br * GS + gi) * 4 + q;
+            float4 x = v[gi][q];
+            if (GN) {
+              const int64_t row = row0 + q * 16 + (t >> 3);
+              if (row < p.M) __stcs(reinterpret_cast<float4*>((br ? p.dOr : p.dOf) + row * C + gi * 32 + tcol), x);
+            }
+            const float sc = br ? sr[q] : sf[q];
+            x.x *= sc, x.y *= sc, x.z *= sc, x.w *= sc;
+            Ahi[j * kSplitThreads + t] = x;
+            Alo[j * kSplitThreads + t] = make_float4(dw_lo(x.x), dw_lo(x.y), dw_lo(x.z), dw_lo(x.w));
+          }
+        }
       }
 #pragma unroll 4
       for (int j = 0; j < kBIter; ++j) {
@@ -402,7 +448,7 @@ static int dw_grid(int64_t M) {
 template <int C>
 static size_t dw_smem() {
   const size_t stage = 2 * 4 * (size_t)kDwLbo + 2 * (C / 32) * (size_t)kDwLbo;
-  return (size_t)kDwStages * stage + 128 + 1024;
+  return (size_t)kDwStages * stage + 128 + 4 * C * sizeof(float) + 1024;
 }
 
 template <int C, bool GN>
