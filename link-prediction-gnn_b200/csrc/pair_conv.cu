@@ -111,6 +111,14 @@ __device__ __forceinline__ void pc_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
+// gathered table rows are the only data of this kernel with reuse: ask L2 to keep them (the streamed tiles are evict-first)
+__device__ __forceinline__ float4 pc_ldg_keep(const float4* p, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
 __device__ __forceinline__ void pc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pc_sw128(int r, int c) { return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4)); }
 __device__ __forceinline__ float pc_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -359,21 +367,27 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
     const int ew = warp - kPcFirstEpi;
     const int quarter = warp & 3, half = ew >> 2;   // a warp may only touch TMEM lanes 32*(warp%4)..+31
     uint8_t* Et = Es + ew * 4096;
+    uint64_t keep_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     const int lrow = lane >> 3, lchunk = lane & 7;   // coalesced phase: 4 rows x 8 chunks of 16 bytes per pass
     constexpr int NGA = NG > 0 ? NG : 1;
     int ix[NGA][8], ixn[NGA][8];
     float cf[NGA][8], cfn[NGA][8];
     float rsc[2], rscn[2];
-    auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8], float (&rss)[2]) {
+    auto load_ix = [&](int64_t tile_, int (&ixx)[NGA][8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t row = tile_ * kPcTileM + quarter * 32 + i * 4 + lrow;
 #pragma unroll
-        for (int g = 0; g < NGA; ++g) {
-          const bool ok = g < NG && row < p.M;
-          ixx[g][i] = ok ? __ldg(p.tidx[g] + row) : -1;
-          cff[g][i] = ok ? __ldg(p.tcoef[g] + row) : 0.f;
-        }
+        for (int g = 0; g < NGA; ++g) ixx[g][i] = (g < NG && row < p.M) ? __ldg(p.tidx[g] + row) : -1;
+      }
+    };
+    auto load_cf = [&](int64_t tile_, float (&cff)[NGA][8], float (&rss)[2]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = tile_ * kPcTileM + quarter * 32 + i * 4 + lrow;
+#pragma unroll
+        for (int g = 0; g < NGA; ++g) cff[g][i] = (g < NG && row < p.M) ? __ldg(p.tcoef[g] + row) : 0.f;
       }
       const int64_t myrow = tile_ * kPcTileM + quarter * 32 + lane;   // TMEM phase: lane = row
 #pragma unroll
@@ -382,6 +396,22 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         rss[s] = (s < p.nsrc && rsv && myrow < p.M) ? __ldg(rsv + myrow) : 1.f;
       }
     };
+    auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8], float (&rss)[2]) {
+      load_ix(tile_, ixx);
+      load_cf(tile_, cff, rss);
+    };
+    auto gather = [&](const int (&ixx)[NGA][8], int c0_, float4 (&g4)[NGA][8]) {
+      const int lcol_ = c0_ + lchunk * 4, col_ = n0 + lcol_;
+      const bool ok = lcol_ < Nsub && col_ < Nd;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int g = 0; g < NGA; ++g)
+          g4[g][i] = (NG > g && ixx[g][i] >= 0 && ok)
+                         ? pc_ldg_keep(reinterpret_cast<const float4*>(p.T[g] + (size_t)ixx[g][i] * Nd + col_), keep_policy) : f4_zero();
+      }
+    };
+    float4 gv[NGA][8];
     if (grp < ntiles) load_idx(grp, ix, cf, rsc);
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const int64_t tile = grp + ti * ngrp;
@@ -394,14 +424,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         const int col = n0 + lcol;               // column of `out`
         const bool cok = lcol < Nsub && col < Nd;
         // gathered rows first: they do not depend on the accumulator, so their latency hides behind the wait for it
-        float4 gv[NGA][8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-#pragma unroll
-          for (int g = 0; g < NGA; ++g)
-            gv[g][i] = (NG > g && ix[g][i] >= 0 && cok)
-                           ? ldg_cached(reinterpret_cast<const float4*>(p.T[g] + (size_t)ix[g][i] * Nd + col)) : f4_zero();
-        }
+        gather(ix, c0, gv);
         if (!waited) {
           // next tile's indices / coefficients / row scales - one more load latency off the chain (NG <= 1: registers)
           if (NG <= 1 && ti + 1 < my_tiles) load_idx(tile + ngrp, ixn, cfn, rscn);
@@ -440,7 +463,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
             for (int g = 0; g < NGA; ++g)
               if (NG > g) f4_fma(o, cf[g][i], gv[g][i]);
             f4_add(o, bias4);
-            *reinterpret_cast<float4*>(p.out + row * Nd + col) = o;
+            __stcs(reinterpret_cast<float4*>(p.out + row * Nd + col), o);   // written once, read by a later kernel: evict first
             f4_add(bsum, o);
             bsq.x = fmaf(o.x, o.x, bsq.x), bsq.y = fmaf(o.y, o.y, bsq.y), bsq.z = fmaf(o.z, o.z, bsq.z), bsq.w = fmaf(o.w, o.w, bsq.w);
           }
