@@ -168,6 +168,13 @@ typedef struct twowl_seg_args {
   int64_t long_cap;
   int32_t pair_sum;              /* 1: gather X[s] + X[s ^ 1] (the two directions 2k / 2k+1 of one pair, utils.py:81-90) */
   const uint8_t* entry_mask;     /* indexed by CSR ENTRY k (not by col[k]) or NULL: entries removed from a cached CSR */
+  /* dual output (out2 != NULL; plain gather, flip = row_flip = 0): one pass over the 2-row blocks (s, s^1) gives
+   *   out[m]  = sum src_scale[s]    * X[s]        (edge2_r's in-list sum of the pair layer, model.py:77)
+   *   out2[m] = sum src_scale2[s^1] * X[s^1]      (edge2's: the same entries, the mates' rows)
+   * so the two directions read H once, as 512-byte blocks. partial2 = second [chunk_cap, C] scratch when planned. */
+  const float* src_scale2;
+  float* out2;
+  float* partial2;
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
 

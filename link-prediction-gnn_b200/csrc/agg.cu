@@ -41,6 +41,11 @@ struct SegParams {
   int accumulate;
   int pair_sum;
   const uint8_t* entry_mask;
+  // dual mode (MODE & 4): one pass over the 2-row blocks (s, s^1) feeds TWO outputs: out += src_scale[s] * X[s],
+  // out2 += src_scale2[s^1] * X[s^1] - both directions of the pair layer's in-list sum, H read as 512-byte blocks
+  const float* src_scale2;
+  float* out2;
+  float* partial2;
   // long-row plan (all NULL/0 when the CSR has no plan)
   const int32_t* plan_counts;  // [0] = number of long rows, [1] = number of chunks
   const int32_t* long_row;     // CSR row of each long row
@@ -66,11 +71,11 @@ struct GroupCtx {
 // Software-pipelined two blocks deep so that no load is consumed in the iteration that issues it: while block b is
 // gathered and accumulated, the col entries of block b+2 and the (col-dependent) scale / second-factor indices of
 // block b+1 are in flight.
-// MODE: 0 = plain gather, 1 = times X2[mul_idx], 3 = (X[s] + X[s^1]) times X2[mul_idx]  (compile-time, so that the plain
-// path keeps its registers for gathers in flight)
+// MODE: 0 = plain gather, 1 = times X2[mul_idx], 3 = (X[s] + X[s^1]) times X2[mul_idx], 4 = dual (X[s] -> acc, X[s^1] -> acc2)
+// (compile-time, so that the plain path keeps its registers for gathers in flight)
 template <int G, int VEC, int MODE>
 __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCtx<G>& g, int64_t m, int64_t kb, int64_t ke,
-                                               float4 (&acc)[VEC]) {
+                                               float4 (&acc)[VEC], float4 (&acc2)[(MODE & 4) ? VEC : 1]) {
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
   if (kb >= ke) return;
@@ -79,6 +84,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
     return (k < ke && !(p.entry_mask && p.entry_mask[k])) ? __ldg(p.col + k) : -1;
   };
   // (col entry) -> source row (or -1 = dropped), its scale, optional second-factor row
+  // m2_ carries the second-factor row (MODE & 1) or, bit-cast, the second scale (MODE & 4)
   auto stage = [&](int c, int& s_, float& w_, int& m2_) {
     s_ = -1, w_ = 0.f, m2_ = 0;
     if (c >= 0) {
@@ -88,6 +94,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
         s_ = s;
         w_ = p.src_scale ? __ldg(p.src_scale + s) : 1.f;
         if (MODE & 1) m2_ = __ldg(p.mul_idx + c);
+        if (MODE & 4) m2_ = __float_as_int(p.src_scale2 ? __ldg(p.src_scale2 + (s ^ 1)) : 1.f);
       }
     }
   };
@@ -116,7 +123,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
         m2j[u] = __shfl_sync(g.gmask, m2_mine, src_lane);
         if (j0 + u >= cnt) sj[u] = -1;
       }
-      float4 x[UNR][VEC], xm[(MODE & 2) ? UNR : 1][VEC], y[(MODE & 1) ? UNR : 1][VEC];
+      float4 x[UNR][VEC], xm[(MODE & 6) ? UNR : 1][VEC], y[(MODE & 1) ? UNR : 1][VEC];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
 #pragma unroll
@@ -124,7 +131,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
           const int c4 = g.gl + v * G;
           const bool on = sj[u] >= 0 && c4 < g.cv;
           x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
-          if (MODE & 2) xm[u][v] = on ? ldg_cached(X4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
+          if (MODE & 6) xm[u][v] = on ? ldg_cached(X4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
           if (MODE & 1) y[u][v] = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
         }
       }
@@ -137,6 +144,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
             if (MODE & 2) f4_add(t, xm[u][v]);
             if (MODE & 1) t = f4_mul(t, y[u][v]);
             f4_fma(acc[v], wj[u], t);
+            if (MODE & 4) f4_fma(acc2[v], __int_as_float(m2j[u]), xm[u][v]);
           }
         }
       }
@@ -162,6 +170,16 @@ __device__ __forceinline__ void seg_finalize(const SegParams& p, const GroupCtx<
       if (p.accumulate) f4_add(o, *dst);
       *dst = o;
     }
+  }
+}
+
+// dual mode: the second output takes no epilogue terms
+template <int G, int VEC>
+__device__ __forceinline__ void seg_store2(const SegParams& p, const GroupCtx<G>& g, int64_t m, const float4 (&acc2)[VEC]) {
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c4 = g.gl + v * G;
+    if (c4 < g.cv) reinterpret_cast<float4*>(p.out2)[m * g.cv + c4] = acc2[v];
   }
 }
 
@@ -191,11 +209,14 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
     row_range(m + ngroups, kb_n, ke_n, masked_n);  // next row's range is in flight while this row is reduced
     if (p.plan_counts && ke - kb > TWOWL_LONG_ROW) continue;  // handled by k_seg_chunks + k_seg_long
     if (masked) ke = kb;
-    float4 acc[VEC];
+    float4 acc[VEC], acc2[(MODE & 4) ? VEC : 1];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc);
+#pragma unroll
+    for (int v = 0; v < ((MODE & 4) ? VEC : 1); ++v) acc2[v] = f4_zero();
+    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc, acc2);
     seg_finalize<G, VEC>(p, g, m, acc);
+    if constexpr ((MODE & 4) != 0) seg_store2<G, VEC>(p, g, m, acc2);
   }
 }
 
@@ -215,20 +236,25 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
     int64_t kb = p.ptr[r] + c * TWOWL_ROW_CHUNK;
     int64_t ke = kb + TWOWL_ROW_CHUNK < p.ptr[r + 1] ? kb + TWOWL_ROW_CHUNK : p.ptr[r + 1];
     if (p.row_skip_mask && p.row_skip_mask[r]) ke = kb;
-    float4 acc[VEC];
+    float4 acc[VEC], acc2[(MODE & 4) ? VEC : 1];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc);
+#pragma unroll
+    for (int v = 0; v < ((MODE & 4) ? VEC : 1); ++v) acc2[v] = f4_zero();
+    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc, acc2);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const int c4 = g.gl + v * G;
-      if (c4 < g.cv) reinterpret_cast<float4*>(p.partial)[ch * g.cv + c4] = acc[v];
+      if (c4 < g.cv) {
+        reinterpret_cast<float4*>(p.partial)[ch * g.cv + c4] = acc[v];
+        if constexpr ((MODE & 4) != 0) reinterpret_cast<float4*>(p.partial2)[ch * g.cv + c4] = acc2[v];
+      }
     }
   }
 }
 
 // pass 3: one group per long row: partials added in chunk order, then the usual epilogue
-template <int G, int VEC>
+template <int G, int VEC, bool DUAL>
 __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
@@ -241,17 +267,23 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
     const int64_t len = p.ptr[r + 1] - p.ptr[r];
     const int64_t nch = (len + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK;
     const int64_t base = p.long_base[slot];
-    float4 acc[VEC];
+    float4 acc[VEC], acc2[DUAL ? VEC : 1];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+#pragma unroll
+    for (int v = 0; v < (DUAL ? VEC : 1); ++v) acc2[v] = f4_zero();
     for (int64_t c = 0; c < nch; ++c) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int c4 = g.gl + v * G;
-        if (c4 < g.cv) f4_add(acc[v], reinterpret_cast<const float4*>(p.partial)[(base + c) * g.cv + c4]);
+        if (c4 < g.cv) {
+          f4_add(acc[v], reinterpret_cast<const float4*>(p.partial)[(base + c) * g.cv + c4]);
+          if constexpr (DUAL) f4_add(acc2[v], reinterpret_cast<const float4*>(p.partial2)[(base + c) * g.cv + c4]);
+        }
       }
     }
     seg_finalize<G, VEC>(p, g, m, acc);
+    if constexpr (DUAL) seg_store2<G, VEC>(p, g, m, acc2);
   }
 }
 
@@ -261,12 +293,13 @@ static void launch_seg_mode(const SegParams& p, int64_t chunk_cap, int64_t long_
   k_seg_rows<G, VEC, MODE><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   if (p.plan_counts && chunk_cap > 0) {
     k_seg_chunks<G, VEC, MODE><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
-    k_seg_long<G, VEC><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+    k_seg_long<G, VEC, (MODE & 4) != 0><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   }
 }
 template <int G, int VEC>
 static void launch_seg(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
-  if (!p.X2) launch_seg_mode<G, VEC, 0>(p, chunk_cap, long_cap, s);
+  if (p.out2) launch_seg_mode<G, VEC, 4>(p, chunk_cap, long_cap, s);
+  else if (!p.X2) launch_seg_mode<G, VEC, 0>(p, chunk_cap, long_cap, s);
   else if (!p.pair_sum) launch_seg_mode<G, VEC, 1>(p, chunk_cap, long_cap, s);
   else launch_seg_mode<G, VEC, 3>(p, chunk_cap, long_cap, s);
 }
@@ -379,8 +412,11 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   TW_CHECK_ARG(!(a->row_flip && (a->M & 1)), "seg_reduce: row_flip needs an even row count");
   TW_CHECK_ARG((a->X2 == nullptr) == (a->mul_idx == nullptr), "seg_reduce: X2 and mul_idx go together");
   TW_CHECK_ARG(!a->pair_sum || a->X2 != nullptr, "seg_reduce: pair_sum is only built together with X2");
+  TW_CHECK_ARG(!a->out2 || (!a->X2 && !a->flip && !a->row_flip && !a->accumulate && aligned16(a->out2) && aligned16(a->partial2)),
+               "seg_reduce: dual output goes with a plain, unflipped, non-accumulating gather");
   const bool planned = a->plan_counts != nullptr;
-  TW_CHECK_ARG(!planned || (a->long_row && a->long_base && a->chunk_owner && (a->partial || a->chunk_cap == 0)),
+  TW_CHECK_ARG(!planned || (a->long_row && a->long_base && a->chunk_owner && (a->partial || a->chunk_cap == 0) &&
+                            (!a->out2 || a->partial2 || a->chunk_cap == 0)),
                "seg_reduce: incomplete long-row plan");
   if (a->M == 0) return 0;
   SegParams p;
@@ -390,6 +426,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum, p.entry_mask = a->entry_mask;
   p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
   p.partial = a->partial;
+  p.src_scale2 = a->src_scale2, p.out2 = a->out2, p.partial2 = a->partial2;
   cudaStream_t s = (cudaStream_t)stream;
   const int cv = a->C >> 2;
   const int64_t cc = a->chunk_cap, lc = a->long_cap;

@@ -33,6 +33,7 @@ class SegArgs(ctypes.Structure):
         ("plan_counts", ctypes.c_void_p), ("long_row", ctypes.c_void_p), ("long_base", ctypes.c_void_p),
         ("chunk_owner", ctypes.c_void_p), ("partial", ctypes.c_void_p), ("chunk_cap", ctypes.c_int64),
         ("long_cap", ctypes.c_int64), ("pair_sum", ctypes.c_int32), ("entry_mask", ctypes.c_void_p),
+        ("src_scale2", ctypes.c_void_p), ("out2", ctypes.c_void_p), ("partial2", ctypes.c_void_p),
     ]
 
 

@@ -274,8 +274,11 @@ def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf:
     """-> (h_next, O_f, O_r, stats_f, stats_r, SH_f, SH_r); only h_next is differentiable, the rest is saved state."""
     h = h.contiguous()
     outs = []
+    # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
+    SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
+                              src_scale2=dinv[0])
     for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
-        SH = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, flip=1 - d, src_scale=dinv[d], skip_mask=blocked)
+        SH = SHf if d == 0 else SHr
         S = ops.linear_fwd(SH, w)
         O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
                               stats_mean_scale=gm, eps=eps)
@@ -357,8 +360,11 @@ def pair_layer_readout(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tens
     """-> (pred [L,1], O_f, O_r, stats_f, stats_r, SH_f, SH_r); only pred is differentiable, the rest is saved state."""
     h = h.contiguous()
     outs = []
+    # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
+    SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
+                              src_scale2=dinv[0])
     for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
-        SH = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, flip=1 - d, src_scale=dinv[d], skip_mask=blocked)
+        SH = SHf if d == 0 else SHr
         S = ops.linear_fwd(SH, w)
         O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
                               stats_mean_scale=gm, eps=eps)

@@ -297,12 +297,14 @@ def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
 
 def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
                row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
-               out=None, accumulate=False, pair_sum=False, entry_mask=None) -> torch.Tensor:
+               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None):
+    """dual=True -> (out, out2): out2[m] = sum src_scale2[s^1] * X[s^1] over the same entries (see twowl_seg_args)."""
     _need_cuda(ptr, col, X)
     assert X.dtype == torch.float32 and X.is_contiguous()
     C = X.shape[1]
     if out is None:
         out = torch.empty((M, C), dtype=torch.float32, device=X.device)
+    out2 = torch.empty((M, C), dtype=torch.float32, device=X.device) if dual else None
     a = SegArgs(ptr=ptr.data_ptr(), col=col.data_ptr(), M=M, X=X.data_ptr(), C=C, flip=int(flip), row_flip=int(row_flip),
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
@@ -316,10 +318,17 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
         base = plan.data_ptr()
         a.plan_counts, a.long_row, a.long_base, a.chunk_owner = base, base + 8, base + 8 + 4 * lc, base + 8 + 8 * lc
         a.partial, a.chunk_cap, a.long_cap = partial.data_ptr(), cc, lc
-    with _P("seg_reduce", col.numel() * (4 * C * (1 + int(pair_sum) + int(X2 is not None)) + 8) + M * (4 * C + 8)):
+        if dual:
+            partial2 = torch.empty((cc, C), dtype=torch.float32, device=X.device)
+            a.partial2 = partial2.data_ptr()
+    if dual:
+        a.src_scale2, a.out2 = _p(src_scale2), out2.data_ptr()
+    nbytes = col.numel() * (4 * C * (1 + int(pair_sum) + int(X2 is not None) + int(dual)) + 8 + 4 * int(dual)) + \
+        M * (4 * C + 8) * (1 + int(dual))
+    with _P("seg_reduce", nbytes):
         check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
     _count(1 if plan is None else 3)
-    return out
+    return (out, out2) if dual else out
 
 
 def gather_rows(W: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

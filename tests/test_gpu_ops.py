@@ -214,6 +214,25 @@ def test_seg_reduce_vs_fp64(U, C):
         assert_close(d, deg.pow(-0.5), rtol=2e-7, atol=0, what="gcn_dinv")
 
 
+@pytest.mark.parametrize("C", [24, 64, 128, 260])
+def test_seg_reduce_dual_output(U, C):
+    """One pass over the mated 2-row blocks gives both directions' sums: bit-identical to the two separate passes."""
+    from twowl_b200 import ops
+    rng = np.random.default_rng(C + 1)
+    N, R, nnz = 1500, 4000, 30000
+    rows = np.minimum((rng.pareto(1.0, size=nnz) * 30).astype(np.int64), N - 1)
+    cols = rng.integers(0, R, size=nnz)
+    ptr, col = _csr_from(rows, cols, N)
+    X = torch.randn(R, C).cuda()
+    s_r, s_f = torch.rand(R).cuda() + 0.1, torch.rand(R).cuda() + 0.1
+    mask = dev((rng.random(R) < 0.2).astype(np.uint8))
+    for plan in (None, ops.seg_plan(ptr, N, nnz)):
+        a = ops.seg_reduce(ptr, col, N, X, plan=plan, flip=0, src_scale=s_r, skip_mask=mask)
+        b = ops.seg_reduce(ptr, col, N, X, plan=plan, flip=1, src_scale=s_f, skip_mask=mask)
+        a2, b2 = ops.seg_reduce(ptr, col, N, X, plan=plan, src_scale=s_r, skip_mask=mask, dual=True, src_scale2=s_f)
+        assert torch.equal(a, a2) and torch.equal(b, b2)
+
+
 @pytest.mark.parametrize("M,C,p,relu", [(1, 4, 0.0, True), (620, 64, 0.0, False), (6576, 24, 0.0, True),
                                         (100003, 128, 0.0, True), (5000, 32, 0.5, True), (777, 1024, 0.0, True)])
 def test_graphnorm_fwd_bwd(U, M, C, p, relu):
