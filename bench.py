@@ -413,7 +413,7 @@ def main():
                            for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][2])}}
 
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU leg runs at N = 1 only
         cb = cpu_baseline_sample(args.workload, hidden)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

@@ -8,22 +8,22 @@
 // the same rows of H are the B operand [C x 64k]; tcgen05.mma kind::tf32, 3xTF32 split. H is read once for both
 // directions: 3 reads of [M,C] in total.
 //
-// One persistent CTA per SM, 10 warps, warp-specialised:
+// One persistent CTA per SM, 14 warps, warp-specialised:
 //   warp  0    TMA producer: raw fp32 tiles of dO_f, dO_r, H with cp.async.bulk.tensor (SWIZZLE_128B_ATOM_32B tensor maps
 //                            = the one MN-major layout the tensor core accepts for tf32, see below), L2 evict-first
-//   warps 2-5  split       : A: v = selfw[row] * raw written back in place (the tensor core truncates it to tf32 = the `hi`
+//   warps 2-9  split       : A: v = selfw[row] * raw written back in place (the tensor core truncates it to tf32 = the `hi`
 //                            operand) and lo = v - trunc(v) into a second buffer; B: lo only (raw H is its own hi)
 //   warp  1    MMA issuer  : 3 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
-//   warps 6-9  drain       : TMEM -> fp32 registers (1024-row partial sums), per-CTA partials to global memory; a second
+//   warps 10-13 drain      : TMEM -> fp32 registers (1024-row partial sums), per-CTA partials to global memory; a second
 //                            kernel adds them in double in CTA order: deterministic.
 #include "common.cuh"
 
 namespace twowl {
 
-constexpr int kDwSplitWarps = 4;
+constexpr int kDwSplitWarps = 8;    // the split pass is latency-bound per warp: 8 warps halve each thread's rows
 constexpr int kDwFirstSplit = 2;
-constexpr int kDwFirstDrain = kDwFirstSplit + kDwSplitWarps;   // 6
-constexpr int kDwThreads = (kDwFirstDrain + 4) * 32;           // 320
+constexpr int kDwFirstDrain = kDwFirstSplit + kDwSplitWarps;   // 10
+constexpr int kDwThreads = (kDwFirstDrain + 4) * 32;           // 448
 constexpr int kDwTileK = 64;                                   // rows of the pair table per stage
 constexpr int kDwStages = 2;
 constexpr int kDwFlush = 16;                                   // tiles accumulated in TMEM between drains
@@ -247,32 +247,34 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
     // ===================================================== split (scale + hi/lo), linear over the swizzled buffers
     const int t = tid - kDwFirstSplit * 32;                  // 0..127
     constexpr int kSplitThreads = kDwSplitWarps * 32;
+    constexpr int RPT = kDwTileK * 8 / kSplitThreads;        // pair-table rows per split thread (8 threads cover a row's 128 B)
+    constexpr int RSTEP = kSplitThreads / 8;                 // rows between a thread's consecutive rows
     constexpr int kAChunks = 2 * GS * (int)(kDwLbo / 16);    // 16-byte chunks of the live A groups (f then r)
     constexpr int kBChunks = GS * (int)(kDwLbo / 16);
     constexpr int kBIter = kBChunks / kSplitThreads;
-    static_assert(kAChunks == 2 * GS * 4 * kSplitThreads, "4 rows x 2*GS chunks per split thread");
-    // chunk i of a group region sits in k-row (i % 512) / 8; with i = j*128 + t that is (j % 4) * 16 + t / 8
+    static_assert(kAChunks == 2 * GS * RPT * kSplitThreads, "RPT rows x 2*GS chunks per split thread");
+    // chunk i of a group region sits in k-row (i % 512) / 8; with i = j*kSplitThreads + t that is (j % RPT) * RSTEP + t / 8
     // GN: this thread's 4 columns inside a 32-column group are fixed (unit ((t & 7) >> 1) ^ (k & 3), k & 3 = (t >> 3) & 3), so
     // the per-column constants of its (branch, group) chunks are 2 LDS.128 per chunk
     const int tcol = (((((t & 7) >> 1) ^ ((t >> 3) & 3))) << 3) + ((t & 1) << 2);
     // Everything a tile needs from global memory besides the TMA data is loaded ONE tile ahead (row scales, chain links, the
     // selected rows' gradients) and the chain heads TWO tiles ahead (the gradients' addresses depend on them), so no global
     // load latency sits between the arrival of a tile and its transform.
-    float sf[4], sr[4], sfn[4], srn[4];
-    int hd[4], nx[4], hdn[4], nxn[4], hdnn[4];
-    float4 Gd[4][GN ? GS : 1], Gdn[4][GN ? GS : 1];
+    float sf[RPT], sr[RPT], sfn[RPT], srn[RPT];
+    int hd[RPT], nx[RPT], hdn[RPT], nxn[RPT], hdnn[RPT];
+    float4 Gd[RPT][GN ? GS : 1], Gdn[RPT][GN ? GS : 1];
     const int64_t tstride = (int64_t)gridDim.x * kDwTileK;
-    auto load_heads = [&](int64_t row0_, bool live, int (&h)[4]) {
+    auto load_heads = [&](int64_t row0_, bool live, int (&h)[RPT]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t row = row0_ + q * 16 + (t >> 3);
+      for (int q = 0; q < RPT; ++q) {
+        const int64_t row = row0_ + q * RSTEP + (t >> 3);
         h[q] = (GN && live && row < p.M) ? __ldg(p.head + row) : -1;
       }
     };
-    auto load_rows = [&](int64_t row0_, bool live, const int (&h)[4], float (&a)[4], float (&b)[4], int (&n)[4], float4 (&g)[4][GN ? GS : 1]) {
+    auto load_rows = [&](int64_t row0_, bool live, const int (&h)[RPT], float (&a)[RPT], float (&b)[RPT], int (&n)[RPT], float4 (&g)[RPT][GN ? GS : 1]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t row = row0_ + q * 16 + (t >> 3);
+      for (int q = 0; q < RPT; ++q) {
+        const int64_t row = row0_ + q * RSTEP + (t >> 3);
         const bool ok = live && row < p.M;
         a[q] = ok ? __ldg(p.rsf + row) : 0.f;
         b[q] = ok ? __ldg(p.rsr + row) : 0.f;
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
       const int st = (int)(it % kDwStages);
       const int64_t row0 = tile * kDwTileK;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < RPT; ++q) {
         sf[q] = sfn[q], sr[q] = srn[q], hd[q] = hdn[q], nx[q] = nxn[q], hdn[q] = hdnn[q];
 #pragma unroll
         for (int gi = 0; gi < (GN ? GS : 1); ++gi) Gd[q][gi] = Gdn[q][gi];
@@ -309,16 +311,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
       float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
       const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
       float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
-      // one branch (f, then r) at a time: 4 rows x GS column groups per thread
+      // one branch (f, then r) at a time: RPT rows x GS column groups per thread
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        float4 v[GS][4];
+        float4 v[GS][RPT];
         // phase 1, branch-free: load, dense part of the GraphNorm backward
 #pragma unroll
         for (int gi = 0; gi < GS; ++gi) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = (br * GS + gi) * 4 + q;
+          for (int q = 0; q < RPT; ++q) {
+            const int j = (br * GS + gi) * RPT + q;
             float4 x = Ahi[j * kSplitThreads + t];
             if (GN) {
               const float4 P4 = *reinterpret_cast<const float4*>(cs + br * 2 * C + gi * 32 + tcol);
@@ -331,9 +333,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
         // phase 2: rows the readout selected: + sc * (dropout / ReLU mask) * sum of their positions' gradients
         if (GN) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < RPT; ++q) {
             if (hd[q] >= 0) {
-              const int64_t row = row0 + q * 16 + (t >> 3);
+              const int64_t row = row0 + q * RSTEP + (t >> 3);
 #pragma unroll
               for (int gi = 0; gi < GS; ++gi) {
                 const int col = gi * 32 + tcol;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
                 const float* __restrict__ cb = p.consts + (br ? 4 * C : 0) + col;
                 const float4 S4 = __ldg(reinterpret_cast<const float4*>(cb + 2 * C)), O4 = __ldg(reinterpret_cast<const float4*>(cb + 3 * C));
                 // the forward value y = sc*x + of from dO = P*x + Q would lose x when P is tiny: keep it exact from the raw tile
-                const float4 xr = Ahi[((br * GS + gi) * 4 + q) * kSplitThreads + t];
+                const float4 xr = Ahi[((br * GS + gi) * RPT + q) * kSplitThreads + t];
                 const float xa[4] = {xr.x, xr.y, xr.z, xr.w}, da[4] = {d.x, d.y, d.z, d.w}, sa[4] = {S4.x, S4.y, S4.z, S4.w},
                             oa[4] = {O4.x, O4.y, O4.z, O4.w};
                 float add[4];
@@ -376,11 +378,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
 #pragma unroll
         for (int gi = 0; gi < GS; ++gi) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int j = (br * GS + gi) * 4 + q;
+          for (int q = 0; q < RPT; ++q) {
+            const int j = (br * GS + gi) * RPT + q;
             float4 x = v[gi][q];
             if (GN) {
-              const int64_t row = row0 + q * 16 + (t >> 3);
+              const int64_t row = row0 + q * RSTEP + (t >> 3);
               if (row < p.M) __stcs(reinterpret_cast<float4*>((br ? p.dOr : p.dOf) + row * C + gi * 32 + tcol), x);
             }
             const float sc = br ? sr[q] : sf[q];
