@@ -253,26 +253,23 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
   }
 }
 
-// pass 3: one group per long row: partials added in chunk order, then the usual epilogue
+// pass 3: partials of a long row added in a FIXED order, then the usual epilogue. Rows of up to kLongWide chunks: one lane
+// group per row, chunk order. Longer rows (hubs: 980 chunks at degree 62 745; the embedding backward's "degree 1" row has
+// thousands) would serialise thousands of dependent adds in one group, so a whole CTA takes the row: group j adds chunks
+// j, j + n, j + 2n, ... in order, and the groups' sums are combined through shared memory in group order - a function of the
+// chunk count only, hence still deterministic.
+constexpr int kLongWide = 32;
 template <int G, int VEC, bool DUAL>
 __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
   const int nlong = p.plan_counts[0];
-  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
+  const int gid = threadIdx.x / G;
+  const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + gid;
   const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
-  for (int64_t slot = group0; slot < nlong; slot += ngroups) {
-    const int64_t r = p.long_row[slot];
-    const int64_t m = r ^ (int64_t)p.row_flip;
-    const int64_t len = p.ptr[r + 1] - p.ptr[r];
-    const int64_t nch = (len + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK;
-    const int64_t base = p.long_base[slot];
-    float4 acc[VEC], acc2[DUAL ? VEC : 1];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
-#pragma unroll
-    for (int v = 0; v < (DUAL ? VEC : 1); ++v) acc2[v] = f4_zero();
-    for (int64_t c = 0; c < nch; ++c) {
+  auto chunks_of = [&](int64_t r) { return (p.ptr[r + 1] - p.ptr[r] + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK; };
+  auto add_chunks = [&](int64_t base, int64_t c0, int64_t cstep, int64_t nch, float4 (&acc)[VEC], float4 (&acc2)[DUAL ? VEC : 1]) {
+    for (int64_t c = c0; c < nch; c += cstep) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int c4 = g.gl + v * G;
@@ -282,8 +279,64 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
         }
       }
     }
+  };
+  // (a) short lists: one group per row
+  for (int64_t slot = group0; slot < nlong; slot += ngroups) {
+    const int64_t r = p.long_row[slot];
+    const int64_t nch = chunks_of(r);
+    if (nch > kLongWide) continue;
+    float4 acc[VEC], acc2[DUAL ? VEC : 1];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+#pragma unroll
+    for (int v = 0; v < (DUAL ? VEC : 1); ++v) acc2[v] = f4_zero();
+    add_chunks(p.long_base[slot], 0, 1, nch, acc, acc2);
+    const int64_t m = r ^ (int64_t)p.row_flip;
     seg_finalize<G, VEC>(p, g, m, acc);
     if constexpr (DUAL) seg_store2<G, VEC>(p, g, m, acc2);
+  }
+  // (b) long lists: one CTA per row
+  extern __shared__ float4 seg_long_smem[];   // [kGroupsPerCta][DUAL ? 2 : 1][C / 4]
+  for (int64_t slot = blockIdx.x; slot < nlong; slot += gridDim.x) {
+    const int64_t r = p.long_row[slot];
+    const int64_t nch = chunks_of(r);
+    if (nch <= kLongWide) continue;
+    float4 acc[VEC], acc2[DUAL ? VEC : 1];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+#pragma unroll
+    for (int v = 0; v < (DUAL ? VEC : 1); ++v) acc2[v] = f4_zero();
+    add_chunks(p.long_base[slot], gid, kGroupsPerCta, nch, acc, acc2);
+    constexpr int NV = DUAL ? 2 : 1;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c4 = g.gl + v * G;
+      if (c4 < g.cv) {
+        seg_long_smem[((size_t)gid * NV + 0) * g.cv + c4] = acc[v];
+        if constexpr (DUAL) seg_long_smem[((size_t)gid * NV + 1) * g.cv + c4] = acc2[v];
+      }
+    }
+    __syncthreads();
+    if (gid == 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
+#pragma unroll
+      for (int v = 0; v < (DUAL ? VEC : 1); ++v) acc2[v] = f4_zero();
+      for (int j = 0; j < kGroupsPerCta; ++j) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int c4 = g.gl + v * G;
+          if (c4 < g.cv) {
+            f4_add(acc[v], seg_long_smem[((size_t)j * NV + 0) * g.cv + c4]);
+            if constexpr (DUAL) f4_add(acc2[v], seg_long_smem[((size_t)j * NV + 1) * g.cv + c4]);
+          }
+        }
+      }
+      const int64_t m = r ^ (int64_t)p.row_flip;
+      seg_finalize<G, VEC>(p, g, m, acc);
+      if constexpr (DUAL) seg_store2<G, VEC>(p, g, m, acc2);
+    }
+    __syncthreads();
   }
 }
 
@@ -293,7 +346,9 @@ static void launch_seg_mode(const SegParams& p, int64_t chunk_cap, int64_t long_
   k_seg_rows<G, VEC, MODE><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   if (p.plan_counts && chunk_cap > 0) {
     k_seg_chunks<G, VEC, MODE><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
-    k_seg_long<G, VEC, (MODE & 4) != 0><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+    const size_t lsm = (size_t)kGroupsPerCta * ((MODE & 4) ? 2 : 1) * (size_t)(p.C / 4) * sizeof(float4);
+    if (lsm > 48 * 1024) cudaFuncSetAttribute(k_seg_long<G, VEC, (MODE & 4) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+    k_seg_long<G, VEC, (MODE & 4) != 0><<<grid_for(long_cap, kGroupsPerCta, 8), kAggThreads, lsm, s>>>(p);
   }
 }
 template <int G, int VEC>
