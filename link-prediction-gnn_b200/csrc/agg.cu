@@ -393,15 +393,25 @@ __global__ void __launch_bounds__(kAggThreads) k_gcn_dinv(const int64_t* __restr
       kb = ptr[r];
       ke = ptr[r + 1];
     }
-    int64_t c = 0;
-    for (int64_t k = kb + lane; k - lane < ke; k += 32) {
-      bool keep = false;
-      if (k < ke) {
-        const int cc = __ldg(col + k);
-        keep = ((int64_t)(cc ^ flip) != m) && !(skip_mask && skip_mask[cc]) && !(entry_mask && entry_mask[k]);
+    // 8 x 32 entries per iteration, all loads issued before any is used: a hub row (62 745 entries) is one warp's serial
+    // loop, and its latency chain was the whole kernel's tail (1.5 ms at R-MAT 1M/16M)
+    int c = 0;
+    constexpr int U = 8;
+    for (int64_t k0 = kb; k0 < ke; k0 += 32 * U) {
+      int cc[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t k = k0 + u * 32 + lane;
+        on[u] = k < ke && !(entry_mask && entry_mask[k]);
+        cc[u] = on[u] ? __ldg(col + k) : 0;
       }
-      c += __popc(__ballot_sync(0xffffffffu, keep));
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        c += (on[u] && ((int64_t)(cc[u] ^ flip) != m) && !(skip_mask && skip_mask[cc[u]])) ? 1 : 0;
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     if (lane == 0) dinv[m] = rsqrtf_exact((float)(c + 1));
   }
 }

@@ -24,15 +24,22 @@ constexpr int kDwSplitWarps = 8;    // the split pass is latency-bound per warp:
 constexpr int kDwFirstSplit = 2;
 constexpr int kDwFirstDrain = kDwFirstSplit + kDwSplitWarps;   // 10
 constexpr int kDwThreads = (kDwFirstDrain + 4) * 32;           // 448
-constexpr int kDwTileK = 64;                                   // rows of the pair table per stage
 constexpr int kDwStages = 2;
-constexpr int kDwFlush = 16;                                   // tiles accumulated in TMEM between drains
+// per width C: rows of the pair table per stage (the stage holds hi + lo of dO_f, dO_r and H: 96 KB at C = 64 / TK = 64 and at
+// C = 128 / TK = 32), accumulators (C <= 64: ONE 128-row D = [f cols | r cols]; C = 128: D_f and D_r), tiles accumulated in
+// TMEM between drains (1024 rows)
+__host__ __device__ constexpr int dw_tile_k(int C) { return C <= 64 ? 64 : 32; }
+__host__ __device__ constexpr int dw_nacc(int C) { return C <= 64 ? 1 : 2; }
+// (the tensor core's fp32 accumulate TRUNCATES: the error of a TMEM-resident sum grows linearly with the number of
+// accumulate steps - 2048 rows at C = 128 measured 1.6e-5 relative - so both widths drain after 384 MMA steps)
+__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? 16 : 32; }
+__host__ __device__ constexpr int dw_part_rows(int C) { return C <= 64 ? 128 : 2 * C; }
 
 struct DwParams {
   const float* rsf;
   const float* rsr;
   int64_t M;
-  float* part;  // [gridDim.x][128][C]
+  float* part;  // [gridDim.x][dw_part_rows(C)][C]
   // GN = true: the A tiles are the OUTPUTS O_f, O_r of the last pair layer and the gradients are made on the fly
   // (twowl_pair_dw_gn): dO = P * O + Q (+ sc * g_y on the rows the readout selected), written to dOf / dOr as well
   const float* consts;   // [2 branches][4][C] = (P, Q, sc, of), twowl_gn2_readout_bwd_prepare
@@ -56,10 +63,9 @@ __device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_
 // With SBO = 512 a group of 32 mn-elements is [64 k-rows][128 B] - exactly what a TMA box of 32 columns x 64 rows with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes, so row-major global tiles land in operand layout without a register pass.
 constexpr uint32_t kDwSbo = 512u;                                   // next group of 4 k-rows
-constexpr uint32_t kDwLbo = (kDwTileK / 4) * kDwSbo;                // next group of 32 mn-elements (8 KB)
 constexpr uint32_t kDwKStep = 2u * kDwSbo;                          // one tf32 MMA consumes 8 k-rows
-__device__ __forceinline__ uint64_t dw_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((kDwLbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((kDwSbo >> 4) & 0x3FFFu) << 32) |
+__device__ __forceinline__ uint64_t dw_desc(uint32_t saddr, uint32_t lbo) {   // lbo: next group of 32 mn-elements
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((kDwSbo >> 4) & 0x3FFFu) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 __device__ __forceinline__ void dw_mbar_init(uint64_t* bar, int count) {
@@ -125,13 +131,17 @@ __device__ __forceinline__ bool dw_elect_one() {
 }
 __device__ __forceinline__ float dw_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// C = width of dO_f, dO_r and H (32 or 64). One stage:
-//   A_hi: 4 groups of 32 M-elements (M = 128 = [f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
+// C = width of dO_f, dO_r and H (32, 64 or 128). One stage:
+//   A_hi: AG groups of 32 M-elements ([f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
 template <int C, bool GN>
 __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
                                                          const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmH) {
   constexpr int GS = C / 32;                          // 32-column groups per source
-  constexpr uint32_t kAHalf = 4u * kDwLbo;            // hi (or lo) part of the A stage: 128 M elements = 4 groups
+  constexpr int kDwTileK = dw_tile_k(C), NACC = dw_nacc(C), kDwFlush = dw_flush(C);
+  constexpr int AG = NACC == 1 ? 4 : 2 * GS;          // A groups: one 128-row D (C <= 64) or D_f | D_r of 128 rows each
+  constexpr int TB = NACC == 1 ? 64 : 2 * C;          // TMEM columns per accumulator buffer
+  constexpr uint32_t kDwLbo = (kDwTileK / 4) * kDwSbo;   // next group of 32 mn-elements
+  constexpr uint32_t kAHalf = (uint32_t)AG * kDwLbo;  // hi (or lo) part of the A stage
   constexpr uint32_t kBHalf = (uint32_t)GS * kDwLbo;
   constexpr uint32_t kStage = 2u * kAHalf + 2u * kBHalf;
   constexpr uint32_t kTxBytes = 3u * GS * kDwLbo;     // raw bytes landing per tile
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dw_smem_u32(tmem_slot)), "r"(2 * 64) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dw_smem_u32(tmem_slot)), "r"(2 * TB) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -173,11 +183,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   if (GN)
     for (int i = tid; i < 4 * C; i += kDwThreads) cs[i] = __ldg(p.consts + (i / (2 * C)) * 4 * C + (i % (2 * C)));
   // zero the padding groups of A (C = 32 only): written once, never touched again
-  if (2 * GS < 4) {
+  if (2 * GS < AG) {
     for (int st = 0; st < kDwStages; ++st)
       for (int half = 0; half < 2; ++half) {
         float4* z = reinterpret_cast<float4*>(smem + st * kStage + half * kAHalf + 2 * GS * kDwLbo);
-        for (int i = tid; i < (int)((4 - 2 * GS) * kDwLbo / 16); i += kDwThreads) z[i] = f4_zero();
+        for (int i = tid; i < (int)((AG - 2 * GS) * kDwLbo / 16); i += kDwThreads) z[i] = f4_zero();
       }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -224,19 +234,22 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
       dw_mbar_wait(&split_done[st], (uint32_t)((it / kDwStages) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // descriptors advance by byte offset >> 4 in their low word
-      const uint64_t Ahi = dw_desc(dw_smem_u32(smem) + (uint32_t)st * kStage);
+      const uint64_t Ahi = dw_desc(dw_smem_u32(smem) + (uint32_t)st * kStage, kDwLbo);
       const uint64_t Alo = Ahi + (kAHalf >> 4), Bhi = Alo + (kAHalf >> 4), Blo = Bhi + (kBHalf >> 4);
       const uint32_t acc0 = (it % kDwFlush == 0) ? 0u : 1u;
       const bool last = (it + 1) % kDwFlush == 0 || it + 1 == my_tiles;
       if (dw_elect_one()) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t Ap = (pass == 0) ? Alo : Ahi;
-          const uint64_t Bp = (pass == 1) ? Blo : Bhi;
+        for (int ac = 0; ac < NACC; ++ac) {   // C = 128: D_f from the f groups of A, D_r from the r groups
 #pragma unroll
-          for (int k = 0; k < kDwTileK / 8; ++k)   // one group of 8 k-rows per K-step
-            dw_mma(tmem_base + (uint32_t)(a * 64), Ap + (uint64_t)(k * (kDwKStep >> 4)), Bp + (uint64_t)(k * (kDwKStep >> 4)), idesc,
-                   (pass | k) ? 1u : acc0);
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint64_t Ap = ((pass == 0) ? Alo : Ahi) + (uint64_t)(ac * GS * (kDwLbo >> 4));
+            const uint64_t Bp = (pass == 1) ? Blo : Bhi;
+#pragma unroll
+            for (int k = 0; k < kDwTileK / 8; ++k)   // one group of 8 k-rows per K-step
+              dw_mma(tmem_base + (uint32_t)(a * TB + ac * C), Ap + (uint64_t)(k * (kDwKStep >> 4)), Bp + (uint64_t)(k * (kDwKStep >> 4)),
+                     idesc, (pass | k) ? 1u : acc0);
+          }
         }
         dw_commit(&empty[st]);
         if (last) dw_commit(&tfull[a]);
@@ -403,65 +416,103 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
     }
   } else {
     // ===================================================== drain: a warp may only touch TMEM lanes 32*(warp%4)..+31
-    const int ew = warp & 3;   // TMEM lane quarter = rows 32ew..32ew+31 of [dW_f; dW_r]
-    float acc[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) acc[i] = 0.f;
+    const int ew = warp & 3;   // TMEM lane quarter = rows 32ew..32ew+31 of [dW_f; dW_r] (or of dW_f and of dW_r)
     const int64_t ngroups = (my_tiles + kDwFlush - 1) / kDwFlush;
-    for (int64_t grp = 0; grp < ngroups; ++grp) {
-      const int a = (int)(grp & 1);
-      dw_mbar_wait(&tfull[a], (uint32_t)((grp >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + (uint32_t)(a * 64) + ((uint32_t)(ew * 32) << 16);
+    if constexpr (NACC == 1) {
+      float acc[C];
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t v[32];
-        dw_tmem_ld32(taddr + c0, v);
+      for (int i = 0; i < C; ++i) acc[i] = 0.f;
+      for (int64_t grp = 0; grp < ngroups; ++grp) {
+        const int a = (int)(grp & 1);
+        dw_mbar_wait(&tfull[a], (uint32_t)((grp >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + (uint32_t)(a * TB) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint32_t v[32];
+          dw_tmem_ld32(taddr + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        dw_mbar_arrive(&tempty[a]);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      dw_mbar_arrive(&tempty[a]);
-    }
-    float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * 128 + ew * 32 + lane) * C);
+      float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * 128 + ew * 32 + lane) * C);
 #pragma unroll
-    for (int q = 0; q < C / 4; ++q) dst[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+      for (int q = 0; q < C / 4; ++q) dst[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+    } else {
+      // two 128 x C accumulators do not fit a thread's registers: the running sums live in this CTA's slice of `part`
+      // (L2-resident: read-add-write by the owning thread every kDwFlush tiles)
+      for (int64_t grp = 0; grp < ngroups; ++grp) {
+        const int a = (int)(grp & 1);
+        dw_mbar_wait(&tfull[a], (uint32_t)((grp >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int ac = 0; ac < NACC; ++ac) {
+          const uint32_t taddr = tmem_base + (uint32_t)(a * TB + ac * C) + ((uint32_t)(ew * 32) << 16);
+          float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * dw_part_rows(C) + ac * C + ew * 32 + lane) * C);
+#pragma unroll
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t v[32];
+            dw_tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                     __uint_as_float(v[q * 4 + 3]));
+              if (grp > 0) f4_add(o, dst[c0 / 4 + q]);
+              dst[c0 / 4 + q] = o;
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        dw_mbar_arrive(&tempty[a]);
+      }
+      if (ngroups == 0) {   // a CTA without tiles still owns a slice of `part`
+#pragma unroll
+        for (int ac = 0; ac < NACC; ++ac) {
+          float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * dw_part_rows(C) + ac * C + ew * 32 + lane) * C);
+          for (int q = 0; q < C / 4; ++q) dst[q] = f4_zero();
+        }
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * 64) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TB) : "memory");
 }
 
 // dW_f[co][ci] = sum_cta part[cta][co][ci], dW_r = rows C..2C-1, added in CTA order in double
-__global__ void k_dw_tc_final(const float* __restrict__ part, int nparts, int C, float* __restrict__ dWf, float* __restrict__ dWr) {
+__global__ void k_dw_tc_final(const float* __restrict__ part, int nparts, int C, int prows, float* __restrict__ dWf,
+                              float* __restrict__ dWr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * C * C) return;
   const int row = i / C, col = i % C;
   double s = 0;
-  for (int b = 0; b < nparts; ++b) s += (double)part[((size_t)b * 128 + row) * C + col];
+  for (int b = 0; b < nparts; ++b) s += (double)part[((size_t)b * prows + row) * C + col];
   if (row < C) dWf[row * C + col] = (float)s;
   else dWr[(row - C) * C + col] = (float)s;
 }
 
-static int dw_grid(int64_t M) {
-  const int64_t ntiles = cdiv(M, kDwTileK);
+static int dw_grid(int64_t M, int C) {
+  const int64_t ntiles = cdiv(M, dw_tile_k(C));
   return (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
 }
 template <int C>
 static size_t dw_smem() {
-  const size_t stage = 2 * 4 * (size_t)kDwLbo + 2 * (C / 32) * (size_t)kDwLbo;
+  const size_t lbo = (size_t)(dw_tile_k(C) / 4) * kDwSbo;
+  const size_t stage = 2 * (dw_nacc(C) == 1 ? 4 : 2 * (C / 32)) * lbo + 2 * (C / 32) * lbo;
   return (size_t)kDwStages * stage + 128 + 4 * C * sizeof(float) + 1024;
 }
 
 template <int C, bool GN>
 static int dw_launch(const DwParams& p, const float* Af, const float* Ar, const float* H, cudaStream_t s) {
   CUtensorMap tf, tr, th;
-  if (int rc = make_tmap_2d_f32(&tf, Af, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = make_tmap_2d_f32(&tr, Ar, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, kDwTileK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tf, Af, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tr, Ar, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const size_t smem = dw_smem<C>();
   TW_CUDA(cudaFuncSetAttribute(k_dw_tc<C, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_dw_tc<C, GN><<<dw_grid(p.M), kDwThreads, smem, s>>>(p, tf, tr, th);
+  k_dw_tc<C, GN><<<dw_grid(p.M, C), kDwThreads, smem, s>>>(p, tf, tr, th);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -470,35 +521,39 @@ static int dw_launch(const DwParams& p, const float* Af, const float* Ar, const 
 
 using namespace twowl;
 
-extern "C" int twowl_pair_dw_supported(int32_t C) { return (C == 32 || C == 64) ? 1 : 0; }
+extern "C" int twowl_pair_dw_supported(int32_t C) { return (C == 32 || C == 64 || C == 128) ? 1 : 0; }
+
+template <bool GN>
+static int dw_dispatch(const DwParams& p, int C, const float* Af, const float* Ar, const float* H, float* dWf, float* dWr, cudaStream_t s) {
+  const int rc = C == 32 ? dw_launch<32, GN>(p, Af, Ar, H, s) : C == 64 ? dw_launch<64, GN>(p, Af, Ar, H, s) : dw_launch<128, GN>(p, Af, Ar, H, s);
+  if (rc) return rc;
+  k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>(p.part, dw_grid(p.M, C), C, dw_part_rows(C), dWf, dWr);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C) {
   (void)M;
-  return align_up((size_t)kNumSMs * 128 * (size_t)C * sizeof(float));
+  return align_up((size_t)kNumSMs * (size_t)dw_part_rows(C) * (size_t)C * sizeof(float));
 }
 
 extern "C" int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
                              int32_t C, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream) {
-  TW_CHECK_ARG(C == 32 || C == 64, "pair_dw: C=%d unsupported (32 or 64)", C);
+  TW_CHECK_ARG(twowl_pair_dw_supported(C), "pair_dw: C=%d unsupported (32, 64 or 128)", C);
   TW_CHECK_ARG(M > 0, "pair_dw: needs M > 0");
   TW_CHECK_ARG(aligned16(dOf) && aligned16(dOr) && aligned16(H) && rsf && rsr, "pair_dw: bad pointers");
   TW_CHECK_WS(ws_bytes, twowl_pair_dw_workspace_bytes(M, C));
   DwParams p;
   memset(&p, 0, sizeof(p));
   p.rsf = rsf, p.rsr = rsr, p.M = M, p.part = (float*)ws;
-  cudaStream_t s = (cudaStream_t)stream;
-  int rc = (C == 32) ? dw_launch<32, false>(p, dOf, dOr, H, s) : dw_launch<64, false>(p, dOf, dOr, H, s);
-  if (rc) return rc;
-  k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>((const float*)ws, dw_grid(M), C, dWf, dWr);
-  TW_LAUNCH_CHECK();
-  return 0;
+  return dw_dispatch<false>(p, C, dOf, dOr, H, dWf, dWr, (cudaStream_t)stream);
 }
 
 extern "C" int twowl_pair_dw_gn(const float* Of, const float* Or, const float* consts, const float* G, const int32_t* head,
                                 const int32_t* next, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const float* rsf,
                                 const float* rsr, const float* H, int64_t M, int32_t C, float* dOf, float* dOr, float* dWf, float* dWr,
                                 void* ws, size_t ws_bytes, void* stream) {
-  TW_CHECK_ARG(C == 32 || C == 64, "pair_dw_gn: C=%d unsupported (32 or 64)", C);
+  TW_CHECK_ARG(twowl_pair_dw_supported(C), "pair_dw_gn: C=%d unsupported (32, 64 or 128)", C);
   TW_CHECK_ARG(M > 0 && M < 0x7fffffffLL, "pair_dw_gn: needs 0 < M < 2^31");
   TW_CHECK_ARG(aligned16(Of) && aligned16(Or) && aligned16(H) && aligned16(dOf) && aligned16(dOr) && aligned16(consts) && aligned16(G) &&
                    rsf && rsr && head && next,
@@ -511,10 +566,5 @@ extern "C" int twowl_pair_dw_gn(const float* Of, const float* Or, const float* c
   p.consts = consts, p.G = G, p.head = head, p.next = next, p.dOf = dOf, p.dOr = dOr;
   p.thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u, p.inv_keep = 1.f / (1.f - p_drop);
   p.seed_f = seed_f, p.seed_r = seed_r, p.relu = relu;
-  cudaStream_t s = (cudaStream_t)stream;
-  int rc = (C == 32) ? dw_launch<32, true>(p, Of, Or, H, s) : dw_launch<64, true>(p, Of, Or, H, s);
-  if (rc) return rc;
-  k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>((const float*)ws, dw_grid(M), C, dWf, dWr);
-  TW_LAUNCH_CHECK();
-  return 0;
+  return dw_dispatch<true>(p, C, Of, Or, H, dWf, dWr, (cudaStream_t)stream);
 }

@@ -376,7 +376,8 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
             assert_close(res[1][Nd:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what="pair_conv inv_std")
 
 
-@pytest.mark.parametrize("M,C", [(1, 64), (63, 32), (64, 64), (65, 64), (5000, 32), (70001, 64), (400000, 64)])
+@pytest.mark.parametrize("M,C", [(1, 64), (63, 32), (64, 64), (65, 64), (5000, 32), (70001, 64), (400000, 64), (1, 128), (33, 128),
+                                 (70001, 128), (300000, 128)])
 def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     """[dW_f; dW_r] = [selfw_f*dO_f | selfw_r*dO_r]^T H with MN-major tcgen05 operands."""
     from twowl_b200 import ops
@@ -395,7 +396,8 @@ def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     assert torch.equal(gf, gf2) and torch.equal(gr, gr2)      # deterministic
 
 
-@pytest.mark.parametrize("M,C,L,p", [(64, 64, 10, 0.0), (5000, 32, 700, 0.3), (70001, 64, 9000, 0.0), (70001, 64, 9000, 0.5)])
+@pytest.mark.parametrize("M,C,L,p", [(64, 64, 10, 0.0), (5000, 32, 700, 0.3), (70001, 64, 9000, 0.0), (70001, 64, 9000, 0.5),
+                                     (40001, 128, 5000, 0.0), (40001, 128, 5000, 0.4)])
 def test_pair_dw_gn_matches_two_pass(U, M, C, L, p):
     """twowl_gn2_readout_bwd_prepare + twowl_pair_dw_gn (GraphNorm backward made inside the weight-gradient kernel) against
     the two-pass path twowl_gn2_readout_bwd + twowl_pair_dw: same dO_f, dO_r, dW_f, dW_r and parameter gradients."""
