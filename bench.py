@@ -89,12 +89,12 @@ def make_graph(workload, seed, device, scale_override=None, samples_override=Non
     return dict(n=n, pos=pos, pred=pred, pos1=pos1, und=m)
 
 
-def draw_batch(und, n_pred_und, nb, step):
+def draw_batch(und, n_pred_und, nb, step, replicate=False):
     """Host-side batch draw, as train.py:18-23: nb positive + nb negative undirected ids (pinned). Under torchrun every
     rank takes its own disjoint slice of ONE seeded global permutation per step (twowl_b200.dist.shard_batch)."""
     from twowl_b200 import dist as D
-    i1 = D.shard_batch(und, nb, step, seed=1).pin_memory()
-    i2 = D.shard_batch(n_pred_und, nb, step, seed=2).pin_memory()
+    i1 = D.shard_batch(und, nb, step, seed=1, replicate=replicate).pin_memory()
+    i2 = D.shard_batch(n_pred_und, nb, step, seed=2, replicate=replicate).pin_memory()
     y = torch.cat((torch.ones(nb), torch.zeros(nb))).unsqueeze(-1).pin_memory()
     return i1, i2, y
 
@@ -244,6 +244,10 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override the R-MAT edge samples (debug)")
     ap.add_argument("--pair-path", default="auto", choices=["auto", "structured", "explicit"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="links", choices=["links", "rows"],
+                    help="multi-GPU: 'links' = every rank steps its own disjoint slice of the target links (weak scaling, the "
+                         "default); 'rows' = ONE step whose pair rows are cut into row blocks over the ranks (strong scaling, "
+                         "twowl_b200.rowshard)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -272,13 +276,17 @@ def main():
     explicit = args.pair_path == "explicit"
     ei2 = U.get_ei2(n, pos, pred) if explicit else U.get_ei2_implicit(n, pos, pred)
     nb = max(2, g["und"] // 10)
-    if world > 1:                      # the slices of the ranks are disjoint: cap the global batch at the id range
+    rows = args.shard == "rows" and world > 1
+    if world > 1 and not rows:         # the slices of the ranks are disjoint: cap the global batch at the id range
         nb = min(nb, g["und"] // world, (P // 2) // world)
     L = 2 * nb
 
     torch.manual_seed(0)
     mod = model.LocalWLNet(max_x, False, None, hidden, hidden, 1, 1, 0., 0., 0., 0., 0., 0.).to(dev).train()
     mod.pair_path = args.pair_path
+    if rows:
+        from twowl_b200.rowshard import RowShard
+        mod.row_shard = RowShard()
 
     # every rank runs the same model on its own batches (replicated graph, data-parallel over target-link
     # batches, gradients all-reduced): see DESIGN.md "Multi-GPU"
@@ -306,7 +314,7 @@ def main():
         sync_grads()
         return loss
 
-    batches = [draw_batch(g["und"], P // 2, nb, i) for i in range(args.steps + args.warmup)]
+    batches = [draw_batch(g["und"], P // 2, nb, i, replicate=rows) for i in range(args.steps + args.warmup)]
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -417,16 +425,20 @@ def main():
         cb = cpu_baseline_sample(args.workload, hidden)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    links = L * world * args.steps
+    links = L * (1 if rows else world) * args.steps
+    par = (f"rows{world}: ONE batch per step, its pair rows cut into {world} row blocks (twowl_b200.rowshard); node-level part "
+           "replicated; all-reduces of the per-node sums [2,N,C] forward and backward, GraphNorm column sums, logits, parameter "
+           "gradients") if rows else (
+        f"dp{world}: target links sharded over ranks (disjoint slices of one global batch per step), graph replicated, one "
+        "all-reduce of the parameter gradients")
     line = {
         "metric": "twowl_fwd_bwd_target_links_per_s", "value": links / (total_ms * 1e-3), "unit": "target-links/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if rows else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "nodes": n, "undirected_edges": g["und"], "E": E, "R": E + P,
                    "hidden": hidden, "depth1": 1, "depth2": 1, "target_links_per_step": L, "pair_path": args.pair_path,
                    "wedges_T": ei2.shape[1] if explicit else None, "l2": "256 MiB flush write between timed steps; "
-                   "activations exceed L2", "parallelism": f"dp{world}: target links sharded over ranks (disjoint slices of one global batch per step), "
-                   "graph replicated, one all-reduce of the parameter gradients"},
+                   "activations exceed L2", "parallelism": par},
         "clocks": clocks.summary(),
         "e2e": {"value": links / (e2e_ms * 1e-3), "unit": "target-links/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "includes": "H2D batch ids+labels, double, "

@@ -177,6 +177,7 @@ typedef struct twowl_seg_args {
   float* partial2;
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
+size_t twowl_sizeof_seg_args(void);   /* binding guard: a foreign-language mirror of the struct must have this size */
 
 /* Load balance for power-law degree: rows of a CSR longer than TWOWL_LONG_ROW entries are listed (order free)
  * and cut into chunks of TWOWL_ROW_CHUNK entries; twowl_seg_reduce then reduces the chunks with separate lane
@@ -280,6 +281,28 @@ int twowl_gn2_readout_bwd_prepare(const float* xf, const float* xr, int64_t M, i
                                   const float* dpred, float* G, int32_t* head, int32_t* next, float* consts, float* dparams_f,
                                   float* dparams_r, float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
 
+/* Row-sharded pair table (the pair rows cut into contiguous blocks over several GPUs): every column reduction
+ * of the path stops at raw double sums that the caller adds over the ranks (torch.distributed all_reduce of a few KB), then the
+ * second half runs on the global sums. One GPU never needs these: twowl_pair_conv / twowl_gn2_readout_bwd_prepare do both halves.
+ *   twowl_graphnorm_stats_from_moments: GraphNorm (mean, inv_std) from moments[2C] = column (sum, sum of squares) over M rows
+ *     (twowl_conv_args.moments, summed over ranks; M = global row count) - replaces the per-rank finalize of model.py:38.
+ *   twowl_gn2_readout_bwd_rows: the row part of twowl_gn2_readout_bwd_prepare over this rank's positions -> G, head, next and
+ *     colsums[6][C] (per branch sum g_y, sum g_y*n; dpred.weight; dpred.bias in column 0 of the sixth).
+ *   twowl_gn2_readout_bwd_finish: from the rank-summed colsums and M_total -> consts[8C], dparams_f/r[4C], dw[C], db[1]. */
+int twowl_graphnorm_stats_from_moments(const double* moments, int64_t M, int32_t C, const float* mean_scale, float eps,
+                                       float* stats, void* stream);
+size_t twowl_gn2_readout_bwd_rows_workspace_bytes(int64_t M, int64_t L, int32_t C);
+int twowl_gn2_readout_bwd_rows(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                               const float* wf, const float* bf, const float* mf, const float* wr, const float* br,
+                               const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx,
+                               int64_t sidx, int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next,
+                               double* colsums, void* ws, size_t ws_bytes, void* stream);
+size_t twowl_gn2_readout_bwd_finish_workspace_bytes(int32_t C);
+int twowl_gn2_readout_bwd_finish(const double* colsums, int64_t M_total, int32_t C, const float* stats_f, const float* stats_r,
+                                 const float* wf, const float* bf, const float* mf, const float* wr, const float* br,
+                                 const float* mr, float* consts, float* dparams_f, float* dparams_r, float* dw, float* db,
+                                 void* ws, size_t ws_bytes, void* stream);
+
 /* out[c] = sum_m x[m,c] (bias gradients). Deterministic two-level sum. */
 size_t twowl_colsum_workspace_bytes(int64_t M, int32_t C);
 int twowl_colsum(const float* x, int64_t M, int32_t C, float* out, void* ws, size_t ws_bytes, void* stream);
@@ -326,10 +349,13 @@ typedef struct twowl_conv_args {
   float* stats;               /* [2*Nd] or NULL */
   const float* mean_scale;    /* [Nd], needed with stats */
   float eps;
+  double* moments;            /* [2*Nd] or NULL (needs stats): the raw column (sum, sum of squares) of `out` over this call's
+                                 M rows - what a row-sharded caller sums over ranks before twowl_graphnorm_stats_from_moments */
 } twowl_conv_args;
 int twowl_pair_conv_supported(int32_t Kd, int32_t Nd, int32_t nsrc);
 size_t twowl_pair_conv_workspace_bytes(int64_t M, int32_t Nd);
 int twowl_pair_conv(const twowl_conv_args* h_args, void* ws, size_t ws_bytes, void* stream);
+size_t twowl_sizeof_conv_args(void);  /* binding guard, as twowl_sizeof_seg_args */
 
 /* Weight gradients of both pair-level linear layers in one pass over the rows (tcgen05 kind::tf32, 3xTF32, MN-major
  * operands): dWf[C,C] = (rsf * dOf)^T H, dWr[C,C] = (rsr * dOr)^T H. H is read once. C in {32, 64}. */

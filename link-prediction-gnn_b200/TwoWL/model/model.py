@@ -163,6 +163,9 @@ class LocalWLNet(nn.Module):
         # the LAST pair layer only feeds x[idx] (model.py:77-83): fuse it with the readout so its GraphNorm / ReLU run
         # on the selected rows only (needs fused_pair_layer and an idx)
         self.fused_readout = True
+        # a twowl_b200.rowshard.RowShard: forward / backward run on this rank's block of pair rows (multi-GPU, one step cut
+        # over the ranks; node-level part replicated). None = the whole pair table on this GPU.
+        self.row_shard = None
 
         if use_node_feat:
             self.lin1 = nn.Sequential(
@@ -214,6 +217,9 @@ class LocalWLNet(nn.Module):
         for conv1 in self.conv1s:
             x = conv1(x, edge1)
 
+        if self.row_shard is not None and self.row_shard.world > 1:
+            from twowl_b200 import rowshard
+            return rowshard.forward_pairs(self, x, pos, idx, ei2)
         pt = G.pair_table(pos, x.shape[0])
         x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
         if len(self.conv2s):

@@ -468,6 +468,8 @@ extern "C" int twowl_seg_plan(const int64_t* ptr, int64_t M, int64_t nnz, int32_
   return 0;
 }
 
+extern "C" size_t twowl_sizeof_seg_args(void) { return sizeof(twowl_seg_args); }
+
 extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   TW_CHECK_ARG(a != nullptr, "seg_reduce: null args");
   TW_CHECK_ARG(a->M >= 0 && a->C > 0 && (a->C & 3) == 0 && a->C <= 1024, "seg_reduce: C=%d must be a multiple of 4 in [4,1024]",

@@ -751,23 +751,44 @@ extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M
 }
 
 // everything of the fused GraphNorm-pair + readout backward except the dense dx pass
-static int gn2_prepare(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
-                       const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
-                       uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx,
-                       int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next, double* part, float* sums_f,
-                       float* sums_r, float* dparams_f, float* dparams_r, float* dw, float* db, cudaStream_t s) {
+// rows: everything that touches the selected positions (per-position gradients G, chains, per-CTA column partials);
+// finish: the column sums -> parameter gradients and the `sums` vectors the dense pass needs. M_stat = number of rows the
+// GraphNorm statistics were taken over (= M on one GPU, the global row count when the pair table is row-sharded).
+static int gn2_prepare_rows(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                            const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
+                            uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx,
+                            int64_t sidx, int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next,
+                            double* part, int* nparts, cudaStream_t s) {
   const size_t l = (size_t)(L > 0 ? L : 1);
   TW_CUDA(cudaMemsetAsync(head, 0xFF, (size_t)M * sizeof(int32_t), s));
   const int grid_l = norm_grid(2 * (int64_t)l, C);
   k_gn2_readout_bwd_rows<<<grid_l, kNormThreads, red_smem(C, 6), s>>>(xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep,
                                                                       seed_f, seed_r, relu, idx, sidx, L, w, dpred, G, part);
   if (L > 0) k_row_chains<<<grid_for(2 * L, kNormThreads), kNormThreads, 0, s>>>(idx, sidx, 2 * L, M, head, next);
-  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 0, M, C, stats_f, wf, mf, sums_f, dparams_f);
-  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 2, M, C, stats_r, wr, mr, sums_r, dparams_r);
-  k_part_colsum_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, grid_l, 6, 4, C, C, dw);
-  k_part_colsum_final<<<1, 32, 0, s>>>(part, grid_l, 6, 5, C, 1, db);
+  TW_LAUNCH_CHECK();
+  *nparts = grid_l;
+  return 0;
+}
+static int gn2_prepare_finish(const double* part, int nparts, int64_t M_stat, int32_t C, const float* stats_f, const float* stats_r,
+                              const float* wf, const float* mf, const float* wr, const float* mr, float* sums_f, float* sums_r,
+                              float* dparams_f, float* dparams_r, float* dw, float* db, cudaStream_t s) {
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, nparts, 6, 0, M_stat, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, nparts, 6, 2, M_stat, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_part_colsum_final<<<(int)cdiv(C, 4), 128, 0, s>>>(part, nparts, 6, 4, C, C, dw);
+  k_part_colsum_final<<<1, 32, 0, s>>>(part, nparts, 6, 5, C, 1, db);
   TW_LAUNCH_CHECK();
   return 0;
+}
+static int gn2_prepare(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
+                       const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
+                       uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx,
+                       int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next, double* part, float* sums_f,
+                       float* sums_r, float* dparams_f, float* dparams_r, float* dw, float* db, cudaStream_t s) {
+  int nparts = 0;
+  if (int rc = gn2_prepare_rows(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, inv_keep, seed_f, seed_r, relu, idx, sidx,
+                                L, w, dpred, G, head, next, part, &nparts, s))
+    return rc;
+  return gn2_prepare_finish(part, nparts, M, C, stats_f, stats_r, wf, mf, wr, mr, sums_f, sums_r, dparams_f, dparams_r, dw, db, s);
 }
 
 extern "C" size_t twowl_gn2_readout_bwd_workspace_bytes(int64_t M, int64_t L, int32_t C) {
@@ -833,6 +854,89 @@ extern "C" int twowl_gn2_readout_bwd_prepare(const float* xf, const float* xr, i
   const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
   if (int rc = gn2_prepare(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx,
                            sidx, L, w, dpred, G, head, next, part, sums_f, sums_r, dparams_f, dparams_r, dw, db, s))
+    return rc;
+  k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_f, wf, bf, mf, sums_f, C, consts);
+  k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_r, wr, br, mr, sums_r, C, consts + 4 * (size_t)C);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- row-sharded pair table ----------
+// The pair table cut into row blocks over several GPUs: column reductions stop at raw double sums, the caller adds them over
+// the ranks (one all-reduce of a few KB), and the second half runs on the global sums.
+
+// colsums[v][c] = sum over CTAs of part[.][v][c] (a warp per (v, c), fixed order)
+__global__ void k_part_reduce_raw(const double* __restrict__ part, int nparts, int nv, int C, double* __restrict__ out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= nv * C) return;
+  const double s = warp_part_sum(part, nparts, nv, i / C, C, i % C);
+  if ((threadIdx.x & 31) == 0) out[i] = s;
+}
+
+__global__ void k_gn_stats_from_moments(const double* __restrict__ mom, int64_t M, int C, const float* __restrict__ mean_scale,
+                                        float eps, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = mom[c] / (double)M;
+  double var = mom[C + c] / (double)M - mean * mean;
+  if (var < 0) var = 0;
+  const double a = (double)mean_scale[c];
+  stats[c] = (float)mean;
+  stats[C + c] = (float)(1.0 / sqrt(var + (1.0 - a) * (1.0 - a) * mean * mean + (double)eps));
+}
+
+extern "C" int twowl_graphnorm_stats_from_moments(const double* moments, int64_t M, int32_t C, const float* mean_scale, float eps,
+                                                  float* stats, void* stream) {
+  if (int rc = check_mc("graphnorm_stats_from_moments", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && moments && mean_scale && stats, "graphnorm_stats_from_moments: M > 0 and non-null pointers required");
+  k_gn_stats_from_moments<<<(int)cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(moments, M, C, mean_scale, eps, stats);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_gn2_readout_bwd_rows_workspace_bytes(int64_t M, int64_t L, int32_t C) {
+  (void)M, (void)L;
+  return align_up((size_t)kNormMaxCtas * 6 * (size_t)C * sizeof(double));
+}
+
+extern "C" int twowl_gn2_readout_bwd_rows(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f,
+                                          const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                          const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r,
+                                          int32_t relu, const int64_t* idx, int64_t sidx, int64_t L, const float* w,
+                                          const float* dpred, float* G, int32_t* head, int32_t* next, double* colsums, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("gn2_readout_bwd_rows", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && M < 0x7fffffffLL && L >= 0 && 2 * L < 0x7fffffffLL, "gn2_readout_bwd_rows: sizes out of range");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(G) && aligned16(w) && head && next && colsums,
+               "gn2_readout_bwd_rows: bad pointers");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_bwd_rows: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_gn2_readout_bwd_rows_workspace_bytes(M, L, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  double* part = (double*)ws;
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  int nparts = 0;
+  if (int rc = gn2_prepare_rows(xf, xr, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu,
+                                idx, sidx, L, w, dpred, G, head, next, part, &nparts, s))
+    return rc;
+  k_part_reduce_raw<<<(int)cdiv(6 * C, 4), 128, 0, s>>>(part, nparts, 6, C, colsums);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_gn2_readout_bwd_finish_workspace_bytes(int32_t C) { return 2 * align_up(3 * (size_t)C * sizeof(float)); }
+
+extern "C" int twowl_gn2_readout_bwd_finish(const double* colsums, int64_t M_total, int32_t C, const float* stats_f,
+                                            const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                                            const float* br, const float* mr, float* consts, float* dparams_f, float* dparams_r,
+                                            float* dw, float* db, void* ws, size_t ws_bytes, void* stream) {
+  if (int rc = check_mc("gn2_readout_bwd_finish", M_total, C)) return rc;
+  TW_CHECK_ARG(M_total > 0 && colsums && consts && dparams_f && dparams_r && dw && db, "gn2_readout_bwd_finish: bad arguments");
+  TW_CHECK_WS(ws_bytes, twowl_gn2_readout_bwd_finish_workspace_bytes(C));
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver c(ws);
+  float* sums_f = c.take<float>(3 * (size_t)C);
+  float* sums_r = c.take<float>(3 * (size_t)C);
+  if (int rc = gn2_prepare_finish(colsums, 1, M_total, C, stats_f, stats_r, wf, mf, wr, mr, sums_f, sums_r, dparams_f, dparams_r, dw, db, s))
     return rc;
   k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_f, wf, bf, mf, sums_f, C, consts);
   k_gn_bwd_consts<<<(int)cdiv(C, 128), 128, 0, s>>>(stats_r, wr, br, mr, sums_r, C, consts + 4 * (size_t)C);

@@ -519,7 +519,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
 // mean / inv_std of GraphNorm from per-CTA (sum, sum of squares) double partials (norm.cu semantics); CTA b holds the
 // columns of window b % nsplit
 __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, int nsplit, int Nsub, int64_t M, int C,
-                                 const float* __restrict__ mean_scale, float eps, float* __restrict__ stats) {
+                                 const float* __restrict__ mean_scale, float eps, float* __restrict__ stats,
+                                 double* __restrict__ moments) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int split = c / Nsub, cl = c % Nsub;
@@ -528,6 +529,8 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
     s += part[((size_t)b * 2 + 0) * Nsub + cl];
     q += part[((size_t)b * 2 + 1) * Nsub + cl];
   }
+  if (moments) moments[c] = s, moments[C + c] = q;  // raw column sums for a row-sharded caller (summed over ranks, then
+                                                    // twowl_graphnorm_stats_from_moments)
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
   if (var < 0) var = 0;
@@ -607,6 +610,8 @@ static int pc_launch(const ConvParams& p, size_t smem, const CUtensorMap& t0, co
 
 using namespace twowl;
 
+extern "C" size_t twowl_sizeof_conv_args(void) { return sizeof(twowl_conv_args); }
+
 extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_bytes, void* stream);
 
 // The plain linear layer (linear.cu: twowl_linear_fwd / twowl_linear_bwd_input, impl 1 / 2) is this kernel with one
@@ -668,7 +673,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
   if (rc) return rc;
   if (want_stats) {
     k_pc_stats_final<<<(int)cdiv(a->Nd, 128), 128, 0, s>>>(p.stats_part, pc_grid(a->M, cfg.nsplit), cfg.nsplit, cfg.Nsub, a->M, a->Nd,
-                                                           a->mean_scale, a->eps, a->stats);
+                                                           a->mean_scale, a->eps, a->stats, a->moments);
     TW_LAUNCH_CHECK();
   }
   return 0;

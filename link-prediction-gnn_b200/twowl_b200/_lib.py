@@ -45,6 +45,7 @@ class ConvArgs(ctypes.Structure):
         ("W", ctypes.c_void_p * 2), ("w_kn", ctypes.c_int32 * 2), ("T", ctypes.c_void_p * 2),
         ("tidx", ctypes.c_void_p * 2), ("tcoef", ctypes.c_void_p * 2), ("bias", ctypes.c_void_p),
         ("out", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("mean_scale", ctypes.c_void_p), ("eps", ctypes.c_float),
+        ("moments", ctypes.c_void_p),
     ]
 
 
@@ -81,6 +82,10 @@ if not os.path.isfile(LIB_PATH):
 lib = ctypes.CDLL(LIB_PATH)
 PROTOS = parse_header()
 _bind(lib, PROTOS)
+for _name, _cls in (("twowl_sizeof_seg_args", SegArgs), ("twowl_sizeof_conv_args", ConvArgs)):
+    if getattr(lib, _name)() != ctypes.sizeof(_cls):
+        raise ImportError(f"{_cls.__name__} (ctypes) is {ctypes.sizeof(_cls)} bytes but the library's struct is "
+                          f"{getattr(lib, _name)()}: twowl_b200/_lib.py and include/twowl.h disagree")
 
 
 def check(rc: int, op: str = "") -> None:

@@ -21,11 +21,12 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
-def shard_batch(n_items: int, batch: int, step: int, seed: int = 0) -> torch.Tensor:
+def shard_batch(n_items: int, batch: int, step: int, seed: int = 0, replicate: bool = False) -> torch.Tensor:
     """This rank's slice of step `step`'s global batch: `batch` ids per rank, drawn without replacement from ONE
     seeded global permutation of range(n_items), so the slices of different ranks are disjoint and their union is
-    a uniform sample of world*batch ids (train.py:18-23 draws one such permutation per epoch). CPU int64 tensor."""
-    rank, ws = world()
+    a uniform sample of world*batch ids (train.py:18-23 draws one such permutation per epoch). CPU int64 tensor.
+    replicate=True: every rank gets the SAME `batch` ids (row-sharded steps: the ranks cut one batch's pair rows)."""
+    rank, ws = (0, 1) if replicate else world()
     if batch * ws > n_items:
         raise ValueError(f"global batch {batch}*{ws} exceeds the {n_items} available ids")
     g = torch.Generator().manual_seed(seed * 1_000_003 + step)

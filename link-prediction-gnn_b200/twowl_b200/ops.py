@@ -462,6 +462,61 @@ def gn2_readout_bwd_prepare(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, 
 
 # ------------------------------------------------------------------------------ GraphNorm
 
+def graphnorm_stats_from_moments(moments, M_total: int, mean_scale, eps: float) -> torch.Tensor:
+    """GraphNorm (mean, inv_std)[2C] from the rank-summed column (sum, sum of squares) float64[2C] over M_total rows."""
+    _need_cuda(moments, mean_scale)
+    C = mean_scale.numel()
+    stats = torch.empty(2 * C, dtype=torch.float32, device=moments.device)
+    check(lib.twowl_graphnorm_stats_from_moments(moments.data_ptr(), int(M_total), C, mean_scale.data_ptr(), float(eps),
+                                                 stats.data_ptr(), _stream()), "graphnorm_stats_from_moments")
+    _count()
+    return stats
+
+
+def gn2_readout_bwd_rows(xf, xr, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool, idx, w, dpred):
+    """Row part of gn2_readout_bwd_prepare over this rank's rows / positions:
+    -> (G [2L,C], head int32[M], next int32[2L], colsums float64[6,C]) - colsums are summed over the ranks by the caller."""
+    M, C = xf.shape
+    dev = xf.device
+    idx = idx.reshape(-1)
+    L = idx.numel() // 2
+    G = torch.empty((max(2 * L, 1), C), dtype=torch.float32, device=dev)
+    head = torch.empty(M, dtype=torch.int32, device=dev)
+    nxt = torch.empty(max(2 * L, 1), dtype=torch.int32, device=dev)
+    colsums = torch.empty((6, C), dtype=torch.float64, device=dev)
+    nb = lib.twowl_gn2_readout_bwd_rows_workspace_bytes(M, L, C)
+    ws = _ws(nb, dev)
+    p, s = _row(idx) if L > 0 else (0, 1)
+    dpred = dpred.contiguous()
+    with _P("gn2_readout_bwd_prepare", M * 4 + L * (48 * C + 40)):
+        check(lib.twowl_gn2_readout_bwd_rows(xf.data_ptr(), xr.data_ptr(), M, C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                             pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(),
+                                             pr[2].data_ptr(), float(p_drop), int(seed_f), int(seed_r), int(relu), p, s, L,
+                                             w.data_ptr(), dpred.data_ptr(), G.data_ptr(), head.data_ptr(), nxt.data_ptr(),
+                                             colsums.data_ptr(), ws.data_ptr(), nb, _stream()), "gn2_readout_bwd_rows")
+    _count(4)
+    return G, head, nxt, colsums
+
+
+def gn2_readout_bwd_finish(colsums, M_total: int, sf, sr, pf, pr):
+    """-> (consts [8C], dparams_f, dparams_r [4C], dw [1,C], db [1]) from the rank-summed colsums of gn2_readout_bwd_rows."""
+    C = colsums.shape[1]
+    dev = colsums.device
+    consts = torch.empty(8 * C, dtype=torch.float32, device=dev)
+    dpf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dpr = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dw = torch.empty((1, C), dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    nb = lib.twowl_gn2_readout_bwd_finish_workspace_bytes(C)
+    ws = _ws(nb, dev)
+    check(lib.twowl_gn2_readout_bwd_finish(colsums.data_ptr(), int(M_total), C, sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(),
+                                           pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(),
+                                           consts.data_ptr(), dpf.data_ptr(), dpr.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                           ws.data_ptr(), nb, _stream()), "gn2_readout_bwd_finish")
+    _count(6)
+    return consts, dpf, dpr, dw, db
+
+
 def graphnorm_stats(x, mean_scale, eps: float) -> torch.Tensor:
     _need_cuda(x)
     M, C = x.shape
@@ -597,10 +652,12 @@ def pair_conv_supported(Kd: int, Nd: int, nsrc: int) -> bool:
     return bool(lib.twowl_pair_conv_supported(Kd, Nd, nsrc))
 
 
-def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_scale=None, eps: float = 1e-5):
+def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_scale=None, eps: float = 1e-5,
+              want_moments: bool = False):
     """out = sum_s (row_scale_s * A_s) B_s^T + sum_g coef_g * T_g[idx_g] + bias on tcgen05 (3xTF32).
     A, W, w_kn, row_scale: sequences of length nsrc; gathers: sequence of (T, idx int32, coef).
-    Returns out, or (out, stats[2*Nd]) when stats_mean_scale is given (GraphNorm mean / inv_std of out)."""
+    Returns out, or (out, stats[2*Nd]) when stats_mean_scale is given (GraphNorm mean / inv_std of out), or
+    (out, moments float64[2*Nd]) with want_moments (raw column sum / sum of squares, for a row-sharded caller)."""
     nsrc = len(A)
     M, Kd = A[0].shape
     Nd = W[0].shape[1] if w_kn[0] else W[0].shape[0]
@@ -622,10 +679,17 @@ def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_s
         nb = lib.twowl_pair_conv_workspace_bytes(M, Nd)
         ws = _ws(nb, dev)
         a.stats, a.mean_scale = stats.data_ptr(), stats_mean_scale.data_ptr()
+    moments = None
+    if want_moments:
+        assert stats is not None, "pair_conv: moments need stats_mean_scale"
+        moments = torch.zeros(2 * Nd, dtype=torch.float64, device=dev)   # zeros: an empty row block contributes nothing
+        a.moments = moments.data_ptr()
     nbytes = M * (4 * Kd * nsrc + 4 * Nd + 8 * len(gathers) + (4 * Nd + 8) * len(gathers))
     with _P("pair_conv", nbytes):
         check(lib.twowl_pair_conv(ctypes.byref(a), _p(ws), nb, _stream()), "pair_conv")
     _count(1 if stats is None else 2)
+    if moments is not None:
+        return out, moments
     return out if stats is None else (out, stats)
 
 

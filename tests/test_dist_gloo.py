@@ -112,3 +112,23 @@ def test_single_process_defaults():
     p = torch.nn.Parameter(torch.ones(3))
     p.grad = torch.full((3,), 2.0)
     assert D.allreduce_grads([p]) == 3 and torch.equal(p.grad, torch.full((3,), 2.0))
+
+
+def test_row_shard_blocks_cover_the_pair_table_with_even_boundaries():
+    """twowl_b200.rowshard.block_of: contiguous, disjoint, even boundaries (mates 2k / 2k+1 stay together), sizes differ by
+    at most one pair; replicate=True hands every rank the same batch (row-sharded steps cut ONE batch)."""
+    from twowl_b200 import dist as D
+    from twowl_b200.rowshard import block_of
+    for R in (2, 6, 6576, 60007608):
+        for world in (1, 2, 3, 8):
+            blocks = [block_of(R, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == R
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            assert all(lo % 2 == 0 and hi % 2 == 0 and hi >= lo for lo, hi in blocks)
+            sizes = [(hi - lo) // 2 for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        block_of(7, 0, 2)
+    a = D.shard_batch(1000, 100, step=3, seed=1, replicate=True)
+    b = D.shard_batch(1000, 100, step=3, seed=1)            # world size 1: the same draw
+    assert torch.equal(a, b) and a.unique().numel() == 100
