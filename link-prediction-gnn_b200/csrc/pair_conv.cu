@@ -53,6 +53,7 @@ struct ConvParams {
   int ngather;
   const float* bias;
   float* out;
+  int group;           // K-slabs per pipeline stage (1 or 2)
   double* stats_part;  // [gridDim.x][2][Nsub] column (sum, sum of squares) of this CTA's window of `out`, or NULL
   int tmem_cols;
   int stages;          // raw-stage ring depth (2..kPcMaxStages)
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
   const int KB = (Kd + 31) >> 5;                 // K-slabs per tile
   const int Nsp = (Nsub + 31) & ~31;             // TMEM columns per source accumulator (the epilogue reads 32-column blocks)
   const int S = p.stages, LS = p.lo_stages;
-  const uint32_t kStage = KB > 1 ? kPcStage : kPcSlab;  // bytes per pipeline stage
+  const int G = KB > 1 ? p.group : 1;            // K-slabs per pipeline stage
+  const uint32_t kStage = (uint32_t)G * kPcSlab;  // bytes per pipeline stage
   const uint32_t kBSlab = (uint32_t)Nsub * 128u;         // one K-slab of one of hi / lo of one source
   const uint32_t kBMat = (uint32_t)KB * kBSlab;
   uint8_t* Bs = smem;                                   // [nsrc][hi, lo][KB][Nsub rows x 128 B]
@@ -248,15 +250,21 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
 
   if (warp == 0) {
     // ===================================================== TMA producer: stages in (tile, source, k-group) order
+    // a tile streamed once is evict-first; with column windows the nsplit CTAs of a tile fetch it one after the other, so the
+    // first fetch must stay in L2 for the others (evict-first made every window re-read its tile from DRAM: 27.5 GB read for
+    // 15.4 GB of input at C = 128)
     uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (p.nsplit > 1)
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+    else
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     PcRing r;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const int row0 = (int)((grp + ti * ngrp) * kPcTileM);
       for (int s = 0; s < p.nsrc; ++s) {
         const CUtensorMap* tm = s ? &tmA1 : &tmA0;
-        for (int kb = 0; kb < KB; kb += kPcGroup) {
-          const int ns = KB - kb < kPcGroup ? KB - kb : kPcGroup;
+        for (int kb = 0; kb < KB; kb += G) {
+          const int ns = KB - kb < G ? KB - kb : G;
           pc_mbar_wait(&raw_empty[r.slot], r.phase ^ 1u);
           if (pc_elect_one()) {
             pc_mbar_expect_tx(&raw_full[r.slot], (uint32_t)ns * kPcSlab);
@@ -280,8 +288,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         const uint32_t tacc = tmem_base + (uint32_t)(a * (p.tmem_cols >> 1) + s * Nsp);
         const uint32_t Bhi = pc_smem_u32(Bs + (size_t)s * 2 * kBMat), Blo = Bhi + kBMat;
         uint32_t acc = 0;
-        for (int kb = 0; kb < KB; kb += kPcGroup) {
-          const int ns = KB - kb < kPcGroup ? KB - kb : kPcGroup;
+        for (int kb = 0; kb < KB; kb += G) {
+          const int ns = KB - kb < G ? KB - kb : G;
           pc_mbar_wait(&raw_full[r.slot], r.phase);
           pc_mbar_wait(&lo_full[l.slot], l.phase);
           pc_fence_after();
@@ -290,7 +298,20 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
           const uint64_t bhi = pc_desc(Bhi + (uint32_t)kb * kBSlab), blo = pc_desc(Blo + (uint32_t)kb * kBSlab);
           const uint32_t bstep = kBSlab >> 4;
           if (pc_elect_one()) {
-            if (ns == kPcGroup && Kd - kb * 32 >= kPcGroup * 32) {
+            if (ns == 1 && Kd - kb * 32 >= 32) {
+              // one full slab per stage (the 16 KB ring of the wide two-source launches)
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  pc_mma(tacc, Ap + (uint64_t)(k * 2), Bp + (uint64_t)(k * 2), idesc, acc);
+                  acc = 1;
+                }
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);
+              }
+            } else if (ns == kPcGroup && Kd - kb * 32 >= kPcGroup * 32) {
               // full stage: 3 passes (lo*hi, hi*lo, hi*hi: small terms first) x 2 slabs x 4 k-steps, back to back
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass) {
@@ -336,11 +357,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
     const int t = tid - kPcFirstSplit * 32;  // 0..63
     constexpr int kSplitThreads = kPcSplitWarps * 32;
     constexpr int kBatch = (int)(kPcSlab / 16u) / kSplitThreads;     // 16 float4 per thread per slab
-    const int ngroups = (KB + kPcGroup - 1) / kPcGroup;
+    const int ngroups = (KB + G - 1) / G;
     PcRing r, l;
     for (int64_t u = 0; u < my_tiles * p.nsrc; ++u) {
       for (int gi = 0; gi < ngroups; ++gi) {
-        const int ns = KB - gi * kPcGroup < kPcGroup ? KB - gi * kPcGroup : kPcGroup;
+        const int ns = KB - gi * G < G ? KB - gi * G : G;
         pc_mbar_wait(&raw_full[r.slot], r.phase);
         const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)r.slot * kStage);
         float4* __restrict__ dst = reinterpret_cast<float4*>(Ls + (size_t)l.slot * kStage);
@@ -541,12 +562,12 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
 
 // How one launch is cut: column windows of Nsub (multiple of 16) output columns per CTA, raw / lo ring depths.
 struct PcConfig {
-  int nsplit = 0, Nsub = 0, stages = 0, lo_stages = 0, tmem_cols = 0;
+  int nsplit = 0, Nsub = 0, stages = 0, lo_stages = 0, tmem_cols = 0, group = kPcGroup;
   size_t smem = 0;
 };
-static size_t pc_smem_bytes(int Kd, int Nsub, int nsrc, bool with_stats, int stages, int lo_stages) {
+static size_t pc_smem_bytes(int Kd, int Nsub, int nsrc, bool with_stats, int stages, int lo_stages, int group) {
   const int KB = (Kd + 31) / 32;
-  return (size_t)nsrc * 2 * KB * Nsub * 128 + (size_t)(stages + lo_stages) * ((Kd + 31) / 32 > 1 ? kPcStage : kPcSlab) + kPcEpilogueWarps * 4096 +
+  return (size_t)nsrc * 2 * KB * Nsub * 128 + (size_t)(stages + lo_stages) * ((Kd + 31) / 32 > 1 ? group * kPcSlab : kPcSlab) + kPcEpilogueWarps * 4096 +
          (2 * kPcMaxStages + 2 * kPcMaxLo + 8) * 8 + (with_stats ? (size_t)kPcEpilogueWarps * 2 * Nsub * 8 : 0) + 1024;
 }
 static int pc_tmem_cols(int Nsub, int nsrc) {
@@ -555,29 +576,30 @@ static int pc_tmem_cols(int Nsub, int nsrc) {
   while (cols < need) cols <<= 1;
   return cols;
 }
-// Fewest column windows whose resident weights leave room for a ring of >= 3 raw stages + 1 lo stage; failing that, the
-// first split that fits at all (2 + 1). force_nsplit > 0 pins the split (tuning / tests).
+// Fewest column windows that fit at all: every extra window re-reads (and re-splits) the whole A tile, which costs far more than
+// a shallower ring (measured at C = 128, M = 15 M: 2 windows with 2 raw stages 5.3 ms, 4 windows with 3 stages 8.2 ms, 8 windows
+// 15.2 ms). The ring is then grown to what the remaining shared memory holds. force_nsplit > 0 pins the split (tuning / tests).
 static PcConfig pc_config(int Kd, int Nd, int nsrc, bool with_stats, int force_nsplit = 0) {
   PcConfig best;
   if (Kd < 4 || Kd > 1024 || (Kd % 4) || Nd < 4 || Nd > 1024 || (Nd % 4) || nsrc < 1 || nsrc > 2) return best;
   const size_t cap = 227 * 1024;
-  for (int want = 3; want >= 2 && !best.nsplit; --want) {
-    for (int ns = 1; ns <= 32; ns *= 2) {
-      if (force_nsplit > 0 && ns != force_nsplit) continue;
-      const int Nsub = (int)(cdiv(cdiv(Nd, ns), 16) * 16);
-      if (Nsub > 256 || (ns > 1 && (int64_t)(ns - 1) * Nsub >= Nd)) continue;
-      if (pc_tmem_cols(Nsub, nsrc) > 512) continue;
-      int lo = 1;
-      if (pc_smem_bytes(Kd, Nsub, nsrc, with_stats, want, lo) > cap) continue;
-      int st = want;
-      while (st < kPcMaxStages && pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st + 1, lo) <= cap) ++st;
-      if (const char* e = getenv("TWOWL_PC_STAGES")) st = atoi(e) < st ? (atoi(e) < 2 ? 2 : atoi(e)) : st;   // tuning knob
-      if (const char* e = getenv("TWOWL_PC_LO")) lo = atoi(e) >= 2 ? lo : 1;
-      best.nsplit = ns, best.Nsub = Nsub, best.stages = st, best.lo_stages = lo;
-      best.tmem_cols = pc_tmem_cols(Nsub, nsrc);
-      best.smem = pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo);
-      break;
+  for (int ns = 1; ns <= 32 && !best.nsplit; ns *= 2) {
+    if (force_nsplit > 0 && ns != force_nsplit) continue;
+    const int Nsub = (int)(cdiv(cdiv(Nd, ns), 16) * 16);
+    if (Nsub > 256 || (ns > 1 && (int64_t)(ns - 1) * Nsub >= Nd)) continue;
+    if (pc_tmem_cols(Nsub, nsrc) > 512) continue;
+    int lo = 1, grp = kPcGroup, st = 2;
+    if (pc_smem_bytes(Kd, Nsub, nsrc, with_stats, 2, lo, kPcGroup) > cap) {
+      // two 32 KB stages do not fit: a ring of >= 3 single-slab (16 KB) stages still beats doubling the windows
+      grp = 1, st = 3;
+      if (pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo, grp) > cap) continue;
     }
+    while (st < kPcMaxStages && pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st + 1, lo, grp) <= cap) ++st;
+    if (const char* e = getenv("TWOWL_PC_STAGES")) st = atoi(e) < st ? (atoi(e) < 2 ? 2 : atoi(e)) : st;   // tuning knob
+    if (const char* e = getenv("TWOWL_PC_LO")) lo = atoi(e) >= 2 ? lo : 1;
+    best.nsplit = ns, best.Nsub = Nsub, best.stages = st, best.lo_stages = lo, best.group = grp;
+    best.tmem_cols = pc_tmem_cols(Nsub, nsrc);
+    best.smem = pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo, grp);
   }
   return best;
 }
@@ -653,7 +675,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
   }
   TW_CHECK_ARG(aligned16(a->out) && aligned16(a->bias), "pair_conv: out/bias must be 16-byte aligned");
   p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Kd = a->Kd, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
-  p.Nsub = cfg.Nsub, p.nsplit = cfg.nsplit, p.stages = cfg.stages, p.lo_stages = cfg.lo_stages, p.tmem_cols = cfg.tmem_cols;
+  p.Nsub = cfg.Nsub, p.nsplit = cfg.nsplit, p.stages = cfg.stages, p.lo_stages = cfg.lo_stages, p.tmem_cols = cfg.tmem_cols, p.group = cfg.group;
   cudaStream_t s = (cudaStream_t)stream;
   if (want_stats) {
     TW_CHECK_ARG(a->mean_scale != nullptr && a->M > 0, "pair_conv: stats need mean_scale and M > 0");
