@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override the R-MAT edge samples (debug)")
     ap.add_argument("--pair-path", default="auto", choices=["auto", "structured", "explicit"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step (edge blocking + forward + BCE + backward) as ONE captured CUDA graph "
+                         "(twowl_b200.graphed): for the launch-bound small workloads")
     ap.add_argument("--shard", default="links", choices=["links", "rows"],
                     help="multi-GPU: 'links' = every rank steps its own disjoint slice of the target links (weak scaling, the "
                          "default); 'rows' = ONE step whose pair rows are cut into row blocks over the ranks (strong scaling, "
@@ -297,14 +300,27 @@ def main():
         if world > 1:
             D.allreduce_grads(params)   # one NCCL all-reduce of the flat gradient buffer, written back into .grad
 
-    def prepare(batch):
+    gstep = None
+    if args.graph:
+        if rows or explicit:
+            raise SystemExit("--graph covers the structured single-process step (not --shard rows / --pair-path explicit)")
+        from twowl_b200.graphed import GraphedTrainStep
+        gstep = GraphedTrainStep(mod, n, pos, pos1, ei2, n_block=2 * nb, n_links=L)
+
+    def prepare(batch, eager=False):
         i1, i2, y = (t.to(dev, non_blocking=True) for t in batch)
         idx1 = U.double(i1, for_index=True)
         idx2 = U.double(i2, for_index=True) + E
+        if gstep is not None and not eager:  # edge blocking happens inside the captured step
+            return idx1, torch.cat((idx1, idx2)), y
         ei_new, x_new, ei2_new = U.sample_block(idx1, n, pos, ei2)
         return x_new, ei_new, torch.cat((idx1, idx2)), ei2_new, y
 
     def fwd_bwd(inp):
+        if len(inp) == 3:
+            loss = gstep(*inp)
+            sync_grads()
+            return loss
         x_new, ei_new, idx, ei2_new, y = inp
         for p_ in mod.parameters():
             p_.grad = None
@@ -340,6 +356,8 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     # ---- the same K steps once more with CUDA events around every kernel group (roofline); kept out of the timed
     #      region above because two extra events per op are not free for the launch-bound small workloads ----
+    if gstep is not None:   # a replayed graph has no per-op events: the per-kernel roofline comes from the eager path
+        inputs = [prepare(b, eager=True) for b in batches]
     ops.profile_start()
     for i in range(args.steps):
         l2_flush.fill_(i & 255)
@@ -437,7 +455,7 @@ def main():
         "higher_is_better": True, "scaling": "strong" if rows else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "nodes": n, "undirected_edges": g["und"], "E": E, "R": E + P,
                    "hidden": hidden, "depth1": 1, "depth2": 1, "target_links_per_step": L, "pair_path": args.pair_path,
-                   "wedges_T": ei2.shape[1] if explicit else None, "l2": "256 MiB flush write between timed steps; "
+                   "wedges_T": ei2.shape[1] if explicit else None, "cuda_graph": bool(args.graph), "l2": "256 MiB flush write between timed steps; "
                    "activations exceed L2", "parallelism": par},
         "clocks": clocks.summary(),
         "e2e": {"value": links / (e2e_ms * 1e-3), "unit": "target-links/s", "h2d_bytes_per_step": h2d,

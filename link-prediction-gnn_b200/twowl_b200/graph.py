@@ -73,12 +73,30 @@ class NodeGraph:
     temask: Optional[torch.Tensor] = None
 
 
-def node_graph(edge1: torch.Tensor, n: int) -> NodeGraph:
+class MaskedEdges:
+    """The edge tensor `ei[:, ~mask]` of sample_block (utils.py:62-63) WITHOUT materialising it: the whole graph's edges plus a
+    uint8[E] mask of the removed ones. Accepted by GCNConv.forward in place of the int64 [2,E'] tensor; needed where the
+    data-dependent size E' must not reach the host (CUDA-graph capture of the step, twowl_b200.graphed)."""
+
+    def __init__(self, ei: torch.Tensor, mask: torch.Tensor):
+        self.ei, self.mask = ei, mask
+
+    @property
+    def device(self):
+        return self.ei.device
+
+
+def node_graph(edge1, n: int) -> NodeGraph:
     """CSR by target / by source + gcn_norm degrees of an int64 [2,E] edge tensor, cached per tensor. An edge tensor that
     sample_block produced (utils.py:61-64: the whole graph minus the sampled edge ids) reuses the cached CSRs of the
     whole graph with a per-entry mask instead of sorting its E' edges again every step."""
-    tag = getattr(edge1, "_twowl_edges", None)
-    if tag is not None and tag[2] == edge1._version and tag[0].shape[1] >= edge1.shape[1]:
+    if isinstance(edge1, MaskedEdges):
+        tag = (edge1.ei, edge1.mask)
+    else:
+        tag = getattr(edge1, "_twowl_edges", None)
+        if tag is not None and not (tag[2] == edge1._version and tag[0].shape[1] >= edge1.shape[1]):
+            tag = None
+    if tag is not None:
         base = node_graph(tag[0], n)
         emask, temask = ops.gather_u8(tag[1], base.ids), ops.gather_u8(tag[1], base.tids)
         return NodeGraph(n, base.ptr, base.col, base.tptr, base.tcol, ops.gcn_dinv_entries(base.ptr, base.col, n, emask),

@@ -1,0 +1,90 @@
+"""One training step of TwoWL/model/train.py:16-38 (block the batch's edges -> forward -> BCE-with-logits -> backward) captured
+ONCE as a CUDA graph and replayed for every batch of the same size.
+
+On the small configurations (fb-pages-food, Cora scale) a step is ~90 kernel launches of a few microseconds each and the host
+(Python dispatch, ctypes, allocator) sets the pace; replaying the captured graph removes that cost. Nothing in forward / backward
+reads the device from the host, so the whole step is capturable; the only data-dependent SIZE of the reference's step,
+`ei_new = ei[:, ~mask]` (utils.py:62-63), is never needed as a tensor: the node-level GCNConv reads the cached CSRs of the whole
+graph with a per-entry mask (graph.MaskedEdges), and the degree feature is the full degree minus the blocked edges' sources.
+
+Replay-time inputs are copied into static buffers (blocked edge ids, readout row ids, labels); outputs are the static loss /
+logits tensors and the parameters' `.grad`. Dropout seeds are drawn on the host at capture time, so a captured step repeats its
+masks: capture with dropout 0 / eval mode, or re-capture per epoch.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import graph as G
+from . import ops
+
+
+class GraphedTrainStep:
+    def __init__(self, mod, n_node: int, ei: torch.Tensor, pos1: torch.Tensor, ei2, n_block: int, n_links: int,
+                 loss_fn=torch.nn.functional.binary_cross_entropy_with_logits, warmup: int = 3):
+        """mod: LocalWLNet; ei: int64 [2,E] observed edges; pos1: int64 [R,2]; ei2: what get_ei2 / get_ei2_implicit returned for
+        them; n_block: blocked edge ids per step (= 2 x positive undirected links); n_links: target links per step."""
+        from TwoWL.utils import _struct_of
+        self.mod, self.n, self.ei, self.pos1, self.loss_fn = mod, int(n_node), ei, pos1, loss_fn
+        self.struct = ei2.struct if isinstance(ei2, G.WedgeIndex) else _struct_of(ei2)
+        if self.struct is None:
+            raise RuntimeError("GraphedTrainStep needs an ei2 made by TwoWL.utils.get_ei2 / get_ei2_implicit")
+        dev = ei.device
+        self.E = ei.shape[1]
+        self.deg_src = ops.degree(ei[0], self.n)                      # utils.py:66-67 counts by SOURCE
+        self.s_block = torch.zeros(n_block, dtype=torch.int64, device=dev)
+        self.s_idx = torch.zeros(2 * n_links, dtype=torch.int64, device=dev)
+        self.s_y = torch.zeros((n_links, 1), dtype=torch.float32, device=dev)
+        self.params = [p for p in mod.parameters() if p.requires_grad]
+        self.graph = None
+        self.loss = self.logits = None
+        self._warmup = warmup
+
+    def _body(self):
+        mask = ops.mask_from_idx(self.s_block, self.E)
+        x_new = self.deg_src.clone()
+        x_new.index_add_(0, self.ei[0].index_select(0, self.s_block), torch.full_like(self.s_block, -1))
+        edges = G.MaskedEdges(self.ei, mask)
+        wedges = G.WedgeIndex(self.struct.with_blocked(mask))
+        self.logits = self.mod(x_new, edges, self.pos1, self.s_idx, wedges)
+        self.loss = self.loss_fn(self.logits, self.s_y)
+        self.loss.backward()
+
+    def _load(self, blocked_ids, idx, y):
+        self.s_block.copy_(blocked_ids.reshape(-1), non_blocking=True)
+        self.s_idx.copy_(idx.reshape(-1), non_blocking=True)
+        self.s_y.copy_(y.reshape(self.s_y.shape), non_blocking=True)
+
+    def capture(self, blocked_ids, idx, y):
+        """Warm up on a side stream (builds every cached index structure), then capture one step."""
+        self._load(blocked_ids, idx, y)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):
+                for p in self.params:
+                    p.grad = None
+                self._body()
+                self.loss = self.logits = None      # drop the autograd graph before the next iteration / the capture
+        cur.wait_stream(side)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        launches0 = ops.launches()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = ops.launches() - launches0
+        self.static_grads = [p.grad for p in self.params]     # the buffers every replay writes
+        return self
+
+    def __call__(self, blocked_ids, idx, y):
+        """-> loss (a static tensor, overwritten by the next call). Gradients land in the parameters' .grad."""
+        if self.graph is None:
+            self.capture(blocked_ids, idx, y)
+        self._load(blocked_ids, idx, y)
+        self.graph.replay()
+        ops.add_launches(self.launches_per_step)
+        for p, g in zip(self.params, self.static_grads):       # the caller may have cleared .grad (optimizer.zero_grad)
+            p.grad = g
+        return self.loss

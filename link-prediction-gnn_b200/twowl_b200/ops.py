@@ -63,6 +63,11 @@ def _count(n: int = 1):
     _launches += n
 
 
+def add_launches(n: int):
+    """Kernels launched outside the Python wrappers: a CUDA-graph replay of a captured step (twowl_b200.graphed)."""
+    _count(int(n))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
