@@ -42,51 +42,23 @@ WORKLOADS = {
 
 # ------------------------------------------------------------------------------ synthetic graphs (input generation)
 
-def rmat_undirected(scale, samples, abcd, seed, device):
-    """Seeded R-MAT edge samples with a random vertex relabelling -> canonical (r<c) unique edge keys."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    a, b, c, _ = abcd
-    src = torch.zeros(samples, dtype=torch.int64, device=device)
-    dst = torch.zeros(samples, dtype=torch.int64, device=device)
-    for _ in range(scale):
-        r = torch.rand(samples, generator=g, device=device)
-        src = src * 2 + (r >= a + b).to(torch.int64)
-        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
-    n = 1 << scale
-    perm = torch.randperm(n, generator=g, device=device)
-    return perm[src], perm[dst], n
-
-
 def make_graph(workload, seed, device, scale_override=None, samples_override=None):
-    """-> dict(n, pos [2,E], pred [2,P], pos1 [R,2]) in the reference's doubled layout."""
+    """-> dict(n, pos [2,E], pred [2,P], pos1 [R,2]) in the reference's doubled layout; the generators live in
+    TwoWL/operators/synthetic.py."""
+    from TwoWL.operators.synthetic import rmat_edges, synthetic_link_graph
     from TwoWL.utils import double
     scale, samples, abcd, _ = WORKLOADS[workload]
-    g = torch.Generator(device=device).manual_seed(seed + 1)
     if workload == "cora":
         n = 2708
+        g = torch.Generator(device=device).manual_seed(seed + 1)
         s = torch.randint(0, n, (samples,), generator=g, device=device)
         d = torch.randint(0, n, (samples,), generator=g, device=device)
     else:
-        s, d, n = rmat_undirected(scale_override or scale, samples_override or samples, abcd, seed, device)
-    lo, hi = torch.minimum(s, d), torch.maximum(s, d)
-    keys = torch.unique((lo * n + hi)[lo != hi])
-    m = keys.numel()
-    keys = keys[torch.randperm(m, generator=g, device=device)]
-    skeys = torch.sort(keys).values
-    neg = torch.empty(0, dtype=torch.int64, device=device)
-    while neg.numel() < m:                       # one uniform non-edge per positive
-        k = int(1.2 * (m - neg.numel())) + 64
-        r = torch.randint(0, n, (k,), generator=g, device=device)
-        c = torch.randint(0, n, (k,), generator=g, device=device)
-        lo, hi = torch.minimum(r, c), torch.maximum(r, c)
-        cand = (lo * n + hi)[lo != hi]
-        p = torch.searchsorted(skeys, cand).clamp_(max=m - 1)
-        neg = torch.unique(torch.cat((neg, cand[skeys[p] != cand])))
-    neg = neg[torch.randperm(neg.numel(), generator=g, device=device)[:m]]
-    pos = double(torch.stack((keys // n, keys % n)))
-    pred = double(torch.stack((neg // n, neg % n)))
+        s, d, n = rmat_edges(scale_override or scale, samples_override or samples, abcd, seed, device)
+    sg = synthetic_link_graph(n, s, d, seed)
+    pos, pred = double(sg["pos_und"]), double(sg["neg_und"])
     pos1 = torch.cat((pos.t(), pred.t()), dim=0).contiguous()
-    return dict(n=n, pos=pos, pred=pred, pos1=pos1, und=m)
+    return dict(n=n, pos=pos, pred=pred, pos1=pos1, und=pos.shape[1] // 2)
 
 
 def draw_batch(und, n_pred_und, nb, step, replicate=False):

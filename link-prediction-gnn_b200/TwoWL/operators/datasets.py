@@ -135,10 +135,10 @@ def do_edge_split(data, val_ratio=0.05, test_ratio=0.1, neg_pool_max=False):
 
 
 def load(args, device="cuda"):
-    """datasets.py:154-168 - CSV edge list -> split dict."""
-    import pandas as pd
-    df = pd.read_csv(args.get("csv", PATH_CSV_EDGES), header=None)
-    edge_index = torch.from_numpy(df[[0, 1]].to_numpy(dtype="int64").T.copy()).to(device)
+    """datasets.py:154-168 - edge list (the reference's CSV; also .npy / raw binary, operators/synthetic.load_edge_list)
+    -> split dict."""
+    from TwoWL.operators.synthetic import load_edge_list
+    edge_index = load_edge_list(args.get("csv", PATH_CSV_EDGES), device)
     return do_edge_split(_Data(edge_index), args["val_ratio"], args["test_ratio"], False)
 
 
