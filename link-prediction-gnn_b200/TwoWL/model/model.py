@@ -16,6 +16,7 @@ from TwoWL.utils import *  # noqa: F401,F403  (the reference does the same, mode
 from TwoWL.utils import _struct_of
 from twowl_b200 import functional as F2
 from twowl_b200 import graph as G
+from twowl_b200 import ops
 
 
 def _seed() -> int:
@@ -166,6 +167,8 @@ class LocalWLNet(nn.Module):
         # a twowl_b200.rowshard.RowShard: forward / backward run on this rank's block of pair rows (multi-GPU, one step cut
         # over the ranks; node-level part replicated). None = the whole pair table on this GPU.
         self.row_shard = None
+        # regroup the pair rows internally by their higher-degree endpoint (graph.LocalityView): same terms, streaming gathers
+        self.pair_locality = True
 
         if use_node_feat:
             self.lin1 = nn.Sequential(
@@ -221,9 +224,15 @@ class LocalWLNet(nn.Module):
             from twowl_b200 import rowshard
             return rowshard.forward_pairs(self, x, pos, idx, ei2)
         pt = G.pair_table(pos, x.shape[0])
+        wedges = self._wedges(ei2, pt.R) if len(self.conv2s) else None
+        if self.pair_locality and isinstance(wedges, G.WedgeStruct) and pt.mated and idx is not None:
+            lv = G.locality_view(wedges, pos)
+            pt = G.pair_table(lv.pos, x.shape[0])
+            blocked = wedges.blocked
+            wedges = lv.struct if blocked is None else lv.struct.with_blocked(ops.gather_u8(blocked, lv.perm[:wedges.E]))
+            idx = lv.newid[idx.reshape(-1)]
         x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
         if len(self.conv2s):
-            wedges = self._wedges(ei2, pt.R)
             last = len(self.conv2s) - 1
             for i in range(len(self.conv2s)):
                 if self.fused_pair_layer and F2.pair_layer_supported(wedges, x.shape[1], self.conv2s[i], self.conv2s_r[i]):

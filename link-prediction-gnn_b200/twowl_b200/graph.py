@@ -231,6 +231,39 @@ def build_wedge_struct(n_node: int, pos_edge: torch.Tensor, pred_edge: torch.Ten
                        out_ptr, out_ids, ops.seg_plan(in_ptr, int(n_node), E), ops.seg_plan(out_ptr, int(n_node), E + P))
 
 
+@dataclass
+class LocalityView:
+    """The same pair table with its PAIRS (rows 2k, 2k+1 together) regrouped by their higher-degree endpoint, observed edges
+    and prediction pairs separately (rows < E stay < E). The order of pair rows is an internal matter of the model - only
+    `idx` and the blocked-edge mask refer to row ids - and in this order the in-list / out-list of a hub node is one contiguous
+    run of rows: the per-node gathers of the pair layer (SH, dS, pair-init backward) stream instead of hopping through DRAM, and
+    half of pair_conv's gathered rows repeat the previous row's. Sums run over the same terms in a different order."""
+    perm: torch.Tensor      # int32 [R]  new row -> old row
+    newid: torch.Tensor     # int64 [R]  old row -> new row
+    pos: torch.Tensor       # int64 [R,2] the regrouped pair table
+    struct: WedgeStruct     # built on the regrouped table (nothing blocked)
+
+
+def locality_view(struct: WedgeStruct, pos: torch.Tensor) -> LocalityView:
+    def build():
+        p = _i64(pos)
+        R, E, n = struct.R, struct.E, struct.n_node
+        deg = torch.bincount(p[:, 0], minlength=n)
+        parts = []
+        for lo, hi in ((0, E), (E, R)):
+            u, v = p[lo:hi:2, 0], p[lo:hi:2, 1]
+            primary = torch.where(deg[u] >= deg[v], u, v)
+            order = torch.sort(primary, stable=True).indices            # pairs of one primary endpoint together, original order inside
+            parts.append((lo + torch.stack((2 * order, 2 * order + 1), dim=1)).reshape(-1))
+        perm = torch.cat(parts)
+        newid = torch.empty_like(perm)
+        newid[perm] = torch.arange(R, device=perm.device)
+        pos2 = p[perm].contiguous()
+        st = build_wedge_struct(n, pos2[:E].t().contiguous(), pos2[E:].t().contiguous())
+        return LocalityView(perm.to(torch.int32), newid, pos2, st)
+    return _cache.get(pos, ("locality", struct.E, struct.R, struct.n_node), build)
+
+
 class WedgeIndex:
     """A wedge index that is NOT materialised (T = sum deg^2 reaches 6.5e10 on R-MAT 1M/16M - 1 TB as
     int64 [2,T]). Accepted wherever the drop-in API takes ``ei2``: sample_block, LocalWLNet.forward."""

@@ -68,7 +68,10 @@ def test_headless_driver_trains_and_writes_the_reference_record_files(cuda, tmp_
     assert all(0.4 < a <= 1.0 for a in aucs) and all(t >= 0 for t in infer)
     line = open(os.path.join(args.record_dir, "planted_auc_record_twowl.txt")).readline()
     assert line.startswith("AUC:") and "   Time:" in line           # train.py:110-112 format
-    assert os.path.isfile("logs.json") and os.path.isfile("fpr.json") and os.path.isfile("tpr.json")
+    assert os.path.isfile("logs.json")
+    # train.py:126 of the reference compares the UNROUNDED test score with the records rounded to 4 decimals, so the curve files
+    # appear only when the best trial's score happened to round down - mirrored as is: both files or neither
+    assert os.path.isfile("fpr.json") == os.path.isfile("tpr.json")
 
     # test() returns the reference's triple; the device AUC equals sklearn's on the same scores
     from sklearn.metrics import auc as sk_auc
