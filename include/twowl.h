@@ -349,6 +349,11 @@ typedef struct twowl_conv_args {
   float* stats;               /* [2*Nd] or NULL */
   const float* mean_scale;    /* [Nd], needed with stats */
   float eps;
+  int32_t dual;               /* 1: TWO layers over the same A in one pass (both directions of model.py:77): nsrc = 1, Nd = 2*C,
+                                 W[0] = [W_f; W_r] stacked ([2C, Kd], w_kn = 0), bias / mean_scale / stats / moments 2C wide; output
+                                 columns [0,C) use row_scale[0], gather 0 and go to out[M,C]; columns [C,2C) use row_scale[1],
+                                 gather 1 and go to out2[M,C]; the gathered tables are [rows, C]. A is read once. C % 32 == 0. */
+  float* out2;                /* [M, Nd/2], dual launches */
   double* moments;            /* [2*Nd] or NULL (needs stats): the raw column (sum, sum of squares) of `out` over this call's
                                  M rows - what a row-sharded caller sums over ranks before twowl_graphnorm_stats_from_moments */
 } twowl_conv_args;

@@ -53,6 +53,8 @@ struct ConvParams {
   int ngather;
   const float* bias;
   float* out;
+  float* out2;         // dual: the second direction's output
+  int dual;            // 0, or Nd/2: columns [0, dual) and [dual, Nd) are two layers sharing A (row scale / gather / output d)
   int group;           // K-slabs per pipeline stage (1 or 2)
   double* stats_part;  // [gridDim.x][2][Nsub] column (sum, sum of squares) of this CTA's window of `out`, or NULL
   int tmem_cols;
@@ -155,7 +157,7 @@ struct PcRing {
 
 // CTA b works on column window b % nsplit of the tiles (b / nsplit) + j * (gridDim.x / nsplit): the CTAs that share a
 // tile run side by side, so the re-reads of its A slabs are L2 hits.
-template <int NG>
+template <int NG, bool DUAL>
 __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1) {
   extern __shared__ uint8_t pc_smem_raw[];
@@ -414,22 +416,29 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const float* __restrict__ rsv = s ? p.rs[1] : p.rs[0];
-        rss[s] = (s < p.nsrc && rsv && myrow < p.M) ? __ldg(rsv + myrow) : 1.f;
+        rss[s] = ((s < p.nsrc || DUAL) && rsv && myrow < p.M) ? __ldg(rsv + myrow) : 1.f;
       }
     };
     auto load_idx = [&](int64_t tile_, int (&ixx)[NGA][8], float (&cff)[NGA][8], float (&rss)[2]) {
       load_ix(tile_, ixx);
       load_cf(tile_, cff, rss);
     };
+    // dual: the 32-column block belongs to direction dd = (first column >= dual); only that direction's table is gathered,
+    // from its own column range, and the tables / outputs are dual columns wide.
+    const int pdual = DUAL ? p.dual : 0;   // compile-time zero in the single-direction instantiations
+    const int Tld = DUAL ? pdual : Nd;
     auto gather = [&](const int (&ixx)[NGA][8], int c0_, float4 (&g4)[NGA][8]) {
       const int lcol_ = c0_ + lchunk * 4, col_ = n0 + lcol_;
       const bool ok = lcol_ < Nsub && col_ < Nd;
+      const int dd = (DUAL && n0 + c0_ >= pdual) ? 1 : 0;
+      const int tcol = col_ - dd * pdual;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int g = 0; g < NGA; ++g)
-          g4[g][i] = (NG > g && ixx[g][i] >= 0 && ok)
-                         ? pc_ldg_keep(reinterpret_cast<const float4*>(p.T[g] + (size_t)ixx[g][i] * Nd + col_), keep_policy) : f4_zero();
+        for (int g = 0; g < NGA; ++g) {
+          g4[g][i] = (NG > g && ixx[g][i] >= 0 && ok && (!DUAL || g == dd))
+                         ? pc_ldg_keep(reinterpret_cast<const float4*>(p.T[g] + (size_t)ixx[g][i] * Tld + tcol), keep_policy) : f4_zero();
+        }
       }
     };
     float4 gv[NGA][8];
@@ -444,6 +453,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         const int lcol = c0 + lchunk * 4;        // column inside this CTA's window
         const int col = n0 + lcol;               // column of `out`
         const bool cok = lcol < Nsub && col < Nd;
+        const int dd = (DUAL && n0 + c0 >= pdual) ? 1 : 0;   // direction of this column block (dual launches)
         // gathered rows first: they do not depend on the accumulator, so their latency hides behind the wait for it
         gather(ix, c0, gv);
         if (!waited) {
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
           pc_tmem_wait_ld();
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = rsc[0] * __uint_as_float(v0[e]);
+          for (int e = 0; e < 8; ++e) o[e] = (dd ? rsc[1] : rsc[0]) * __uint_as_float(v0[e]);
           if (p.nsrc > 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = fmaf(rsc[1], __uint_as_float(v1[e]), o[e]);
@@ -482,9 +492,10 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
           if (row < p.M && cok) {
 #pragma unroll
             for (int g = 0; g < NGA; ++g)
-              if (NG > g) f4_fma(o, cf[g][i], gv[g][i]);
+              if (NG > g && (!DUAL || g == dd)) f4_fma(o, cf[g][i], gv[g][i]);
             f4_add(o, bias4);
-            __stcs(reinterpret_cast<float4*>(p.out + row * Nd + col), o);   // written once, read by a later kernel: evict first
+            // written once, read by a later kernel: evict first
+            __stcs(reinterpret_cast<float4*>((dd ? p.out2 : p.out) + row * Tld + (col - dd * pdual)), o);
             f4_add(bsum, o);
             bsq.x = fmaf(o.x, o.x, bsq.x), bsq.y = fmaf(o.y, o.y, bsq.y), bsq.z = fmaf(o.z, o.z, bsq.z), bsq.w = fmaf(o.w, o.w, bsq.w);
           }
@@ -620,10 +631,10 @@ static int pc_make_tmap(CUtensorMap* tm, const float* A, int64_t M, int Kd) {
   return make_tmap_2d_f32(tm, A, M, Kd, 32, kPcTileM, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int NG>
+template <int NG, bool DUAL = false>
 static int pc_launch(const ConvParams& p, size_t smem, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
-  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_conv<NG><<<pc_grid(p.M, p.nsplit), kPcThreads, smem, s>>>(p, t0, t1);
+  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<NG, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pair_conv<NG, DUAL><<<pc_grid(p.M, p.nsplit), kPcThreads, smem, s>>>(p, t0, t1);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -674,6 +685,12 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     p.T[g] = a->T[g], p.tidx[g] = a->tidx[g], p.tcoef[g] = a->tcoef[g];
   }
   TW_CHECK_ARG(aligned16(a->out) && aligned16(a->bias), "pair_conv: out/bias must be 16-byte aligned");
+  if (a->dual) {
+    TW_CHECK_ARG(a->nsrc == 1 && a->ngather == 2 && a->Nd % 64 == 0 && a->out2 && aligned16(a->out2) && a->row_scale[0] && a->row_scale[1],
+                 "pair_conv: a dual launch needs one source, two gathers, two row scales, out2, and Nd/2 a multiple of 32");
+    p.rs[1] = a->row_scale[1];
+    p.out2 = a->out2, p.dual = a->Nd / 2;
+  }
   p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Kd = a->Kd, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
   p.Nsub = cfg.Nsub, p.nsplit = cfg.nsplit, p.stages = cfg.stages, p.lo_stages = cfg.lo_stages, p.tmem_cols = cfg.tmem_cols, p.group = cfg.group;
   cudaStream_t s = (cudaStream_t)stream;
@@ -689,7 +706,8 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     const int rc_t = pc_make_tmap(&tm[i], a->A[i], a->M, a->Kd);
     if (rc_t) return rc_t;
   }
-  const int rc = a->ngather == 0   ? pc_launch<0>(p, cfg.smem, tm[0], tm[1], s)
+  const int rc = a->dual           ? pc_launch<2, true>(p, cfg.smem, tm[0], tm[1], s)
+                 : a->ngather == 0 ? pc_launch<0>(p, cfg.smem, tm[0], tm[1], s)
                  : a->ngather == 1 ? pc_launch<1>(p, cfg.smem, tm[0], tm[1], s)
                                    : pc_launch<2>(p, cfg.smem, tm[0], tm[1], s);
   if (rc) return rc;

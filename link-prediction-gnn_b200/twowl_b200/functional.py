@@ -265,6 +265,23 @@ readout.register_autograd(_ro_bwd, setup_context=_ro_setup)
 # and the two GraphNorm(+Dropout+ReLU) applications summed. The backward is hand-written from the same pieces.
 
 
+def _pair_convs_fwd(h, pf, pr, SHf, SHr, centre, dinv, selfw, eps):
+    """O_d = selfw_d * (h W_d^T) + dinv_d * (SH_d W_d^T)[centre_d] + bias_d and its GraphNorm statistics, both directions:
+    -> [(O_f, stats_f, SH_f), (O_r, stats_r, SH_r)]. One pass over h when the dual launch covers the width."""
+    (wf, bf, gmf), (wr, br, gmr) = pf, pr
+    Sf, Sr = ops.linear_fwd(SHf, wf), ops.linear_fwd(SHr, wr)
+    if ops.PAIR_CONV_DUAL and wf.shape == wr.shape and ops.pair_conv_dual_supported(h.shape[1], wf.shape[0]):
+        Of, Or, sf, sr = ops.pair_conv_dual(h, wf, wr, selfw[0], selfw[1], (Sf, centre[0], dinv[0]), (Sr, centre[1], dinv[1]), bf, br,
+                                            gmf, gmr, eps)
+        return [(Of, sf, SHf), (Or, sr, SHr)]
+    outs = []
+    for d, (w, b, gm, S, SH) in enumerate(((wf, bf, gmf, Sf, SHf), (wr, br, gmr, Sr, SHr))):
+        O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
+                              stats_mean_scale=gm, eps=eps)
+        outs.append((O, st, SH))
+    return outs
+
+
 @torch.library.custom_op("twowl::pair_layer", mutates_args=())
 def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf: Tensor, wr: Tensor, br: Tensor, gwr: Tensor,
                gbr: Tensor, gmr: Tensor, in_ptr: Tensor, in_ids: Tensor, in_plan: Tensor, out_ptr: Tensor, out_ids: Tensor,
@@ -277,12 +294,7 @@ def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf:
     # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
     SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
                               src_scale2=dinv[0])
-    for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
-        SH = SHf if d == 0 else SHr
-        S = ops.linear_fwd(SH, w)
-        O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
-                              stats_mean_scale=gm, eps=eps)
-        outs.append((O, st, SH))
+    outs = _pair_convs_fwd(h, (wf, bf, gmf), (wr, br, gmr), SHf, SHr, centre, dinv, selfw, eps)
     hn = ops.graphnorm_apply2(outs[0][0], outs[1][0], outs[0][1], outs[1][1], (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f,
                               seed_r, True)
     return hn, outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2]
@@ -363,12 +375,7 @@ def pair_layer_readout(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tens
     # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
     SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
                               src_scale2=dinv[0])
-    for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
-        SH = SHf if d == 0 else SHr
-        S = ops.linear_fwd(SH, w)
-        O, st = ops.pair_conv([h], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
-                              stats_mean_scale=gm, eps=eps)
-        outs.append((O, st, SH))
+    outs = _pair_convs_fwd(h, (wf, bf, gmf), (wr, br, gmr), SHf, SHr, centre, dinv, selfw, eps)
     pred = ops.gn2_readout_fwd(outs[0][0], outs[1][0], outs[0][1], outs[1][1], (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f,
                                seed_r, True, idx, pw.contiguous(), pb)
     return pred, outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2]

@@ -97,13 +97,18 @@ class _ShardedPairPath(torch.autograd.Function):
         SH = torch.stack((SHf, SHr))
         del SHf, SHr
         shard.all_reduce(SH)
-        Os, moms = [], []
-        for d, (w, b, gm) in enumerate(((wf, bf, gmf), (wr, br, gmr))):
-            S = ops.linear_fwd(SH[d], w)
-            O, mom = ops.pair_conv([H], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
-                                   stats_mean_scale=gm, eps=eps, want_moments=True)
-            Os.append(O)
-            moms.append(mom)
+        Sf, Sr = ops.linear_fwd(SH[0], wf), ops.linear_fwd(SH[1], wr)
+        if ops.PAIR_CONV_DUAL and ops.pair_conv_dual_supported(H.shape[1], wf.shape[0]):
+            Of, Or, mf, mr = ops.pair_conv_dual(H, wf, wr, selfw[0], selfw[1], (Sf, centre[0], dinv[0]), (Sr, centre[1], dinv[1]), bf, br,
+                                                gmf, gmr, eps, want_moments=True)
+            Os, moms = [Of, Or], [mf, mr]
+        else:
+            Os, moms = [], []
+            for d, (w, b, gm, S) in enumerate(((wf, bf, gmf, Sf), (wr, br, gmr, Sr))):
+                O, mom = ops.pair_conv([H], [w], [0], row_scale=[selfw[d]], gathers=[(S, centre[d], dinv[d])], bias=b,
+                                       stats_mean_scale=gm, eps=eps, want_moments=True)
+                Os.append(O)
+                moms.append(mom)
         mom = shard.all_reduce(torch.stack(moms))
         sf = ops.graphnorm_stats_from_moments(mom[0], R_total, gmf, eps)
         sr = ops.graphnorm_stats_from_moments(mom[1], R_total, gmr, eps)

@@ -376,6 +376,46 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
             assert_close(res[1][Nd:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what="pair_conv inv_std")
 
 
+@pytest.mark.parametrize("M,Kd,C", [(3, 64, 64), (129, 32, 32), (5000, 64, 64), (70001, 64, 64), (30011, 128, 128), (9000, 24, 32),
+                                    (4000, 256, 256)])
+def test_pair_conv_dual_vs_fp64(U, M, Kd, C):
+    """Both directions of a pair layer in one pass over A (twowl_conv_args.dual): outputs, statistics and raw moments of each
+    direction against fp64, and against two single-direction launches."""
+    from twowl_b200 import ops
+    torch.manual_seed(M + C)
+    NT = 777
+    A = torch.randn(M, Kd, dtype=torch.float64)
+    W = [torch.randn(C, Kd, dtype=torch.float64) / Kd ** 0.5 for _ in range(2)]
+    T = [torch.randn(NT, C, dtype=torch.float64) for _ in range(2)]
+    idx = [torch.randint(0, NT, (M,)) for _ in range(2)]
+    idx[1][::7] = -1                                     # rows without a gathered term
+    coef = [torch.rand(M, dtype=torch.float64) for _ in range(2)]
+    rs = [torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.2) for _ in range(2)]
+    bias = [torch.randn(C, dtype=torch.float64) for _ in range(2)]
+    ms = [torch.rand(C, dtype=torch.float64) + 0.5 for _ in range(2)]
+    c = lambda t: t.float().cuda().contiguous()          # noqa: E731
+    ci = lambda t: t.to(torch.int32).cuda()              # noqa: E731
+    assert ops.pair_conv_dual_supported(Kd, C)
+    args = (c(A), c(W[0]), c(W[1]), c(rs[0]), c(rs[1]), (c(T[0]), ci(idx[0]), c(coef[0])), (c(T[1]), ci(idx[1]), c(coef[1])), c(bias[0]),
+            c(bias[1]), c(ms[0]), c(ms[1]))
+    Of, Or, sf, sr = ops.pair_conv_dual(*args)
+    _, _, mf, mr = ops.pair_conv_dual(*args, want_moments=True)
+    for d, (O, st, mom) in enumerate(((Of, sf, mf), (Or, sr, mr))):
+        g = T[d][idx[d].clamp(min=0)] * (idx[d] >= 0).double().unsqueeze(1)
+        ref = rs[d].unsqueeze(1) * (A @ W[d].t()) + coef[d].unsqueeze(1) * g + bias[d]
+        tol = 4e-6 * max(float(ref.abs().max()), 1.0)
+        assert_close(O, ref, rtol=1e-5, atol=tol, what=f"dual out {d}")
+        mean = ref.mean(0)
+        var = ((ref - ms[d] * mean) ** 2).mean(0)
+        assert_close(st[:C], mean, rtol=1e-5, atol=tol, what=f"dual mean {d}")
+        assert_close(st[C:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what=f"dual inv_std {d}")
+        assert_close(mom[:C], ref.sum(0), rtol=1e-5, atol=tol * M, what=f"dual moment sum {d}")
+        assert_close(mom[C:], (ref ** 2).sum(0), rtol=2e-5, atol=tol * M, what=f"dual moment sumsq {d}")
+        one, st1 = ops.pair_conv([c(A)], [c(W[d])], [0], row_scale=[c(rs[d])], gathers=[(c(T[d]), ci(idx[d]), c(coef[d]))], bias=c(bias[d]),
+                                 stats_mean_scale=c(ms[d]))
+        assert torch.equal(one, O), f"dual launch differs from the single-direction launch, direction {d}"
+
+
 @pytest.mark.parametrize("M,C", [(1, 64), (63, 32), (64, 64), (65, 64), (5000, 32), (70001, 64), (400000, 64), (1, 128), (33, 128),
                                  (70001, 128), (300000, 128)])
 def test_pair_dw_tcgen05_vs_fp64(U, M, C):
