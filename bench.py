@@ -406,6 +406,9 @@ def main():
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches": tcnt, "avg_ms": round(tms / tcnt, 4), "share_of_kernel_time": round(tms / tot_kernel_ms, 4),
                 "algorithmic_bytes_per_launch": int(tbytes / tcnt),
+                "note": "achieved = algorithmic bytes (every gathered row counted as read, SURVEY 8(d)) / measured time; gathered rows "
+                        "that repeat the previous row's are served from L1/L2, so achieved can exceed the DRAM copy peak - `traffic` "
+                        "is the DRAM bytes ncu measured for the same launch",
                 "all_kernels_algorithmic_GBps": round(agg_bytes / (tot_kernel_ms * 1e-3) / 1e9, 1),
                 "per_op": {k: {"n": v[0], "ms": round(v[2], 3), "GBps": round(v[1] / (v[2] * 1e-3) / 1e9, 1) if v[2] > 0 else None}
                            for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][2])}}
