@@ -373,7 +373,65 @@ __device__ __forceinline__ float4 gn2_row(const float4& a, const float4& b, cons
   return make_float4(o[0], o[1], o[2], o[3]);
 }
 
-// one warp per target link l: pred[l] = sum_c hn[i0,c]*hn[i1,c]*w[c] + b   (xor-shuffle tree, fixed order)
+// pred[l] = sum_c hn[i0,c]*hn[i1,c]*w[c] + b. A lane GROUP of GW = 8 / 16 / 32 lanes (the smallest power of two >= C/4) owns a
+// link, so a warp works on 32/GW links at once; two links per group are in flight per iteration (the row loads of a link depend
+// on its idx load: one link at a time left this kernel latency-bound at 1.7 TB/s). Per-column constants are loaded once per
+// thread. Fixed xor-shuffle tree inside the group: deterministic. C > 128 takes the strided loop of the general kernel.
+template <int GW>
+__global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float* __restrict__ xf, const float* __restrict__ xr, int C,
+                                                                    const float* __restrict__ stf, const float* __restrict__ str_,
+                                                                    const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                    const float* __restrict__ mf, const float* __restrict__ wr,
+                                                                    const float* __restrict__ br, const float* __restrict__ mr,
+                                                                    uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
+                                                                    int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
+                                                                    const float* __restrict__ w, const float* __restrict__ b,
+                                                                    float* __restrict__ pred) {
+  constexpr int kPer = 32 / GW;
+  const int lane = threadIdx.x & 31, sub = lane / GW, c4 = lane % GW;
+  const int cv = C >> 2;
+  const bool act = c4 < cv;
+  const int cc = act ? c4 : 0;
+  const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
+  const float4* __restrict__ xr4 = reinterpret_cast<const float4*>(xr);
+  const GnCols cf(C, cc * 4, stf, wf, bf, mf), cr(C, cc * 4, str_, wr, br, mr);
+  const float4 ww = act ? __ldg(reinterpret_cast<const float4*>(w) + cc) : f4_zero();
+  const float bias = b[0];
+  // groups of one warp leave the loop at different iterations: shuffles name only the group's own lanes
+  const uint32_t gmask = GW == 32 ? 0xffffffffu : (((1u << (GW & 31)) - 1u) << (sub * GW));
+  const int64_t grp0 = (((int64_t)blockIdx.x * kNormThreads + threadIdx.x) >> 5) * kPer + sub;
+  const int64_t ngrp = (((int64_t)gridDim.x * kNormThreads) >> 5) * kPer;
+  for (int64_t l0 = grp0; l0 < L; l0 += 2 * ngrp) {
+    const int64_t l1 = l0 + ngrp;
+    const bool two = l1 < L;
+    const int64_t a0 = idx[(2 * l0) * sidx], a1 = idx[(2 * l0 + 1) * sidx];
+    const int64_t b0 = two ? idx[(2 * l1) * sidx] : a0, b1 = two ? idx[(2 * l1 + 1) * sidx] : a1;
+    const int64_t ea0 = a0 * cv + cc, ea1 = a1 * cv + cc, eb0 = b0 * cv + cc, eb1 = b1 * cv + cc;
+    const float4 fa0 = ldg_cached(xf4 + ea0), ra0 = ldg_cached(xr4 + ea0), fa1 = ldg_cached(xf4 + ea1), ra1 = ldg_cached(xr4 + ea1);
+    const float4 fb0 = ldg_cached(xf4 + eb0), rb0 = ldg_cached(xr4 + eb0), fb1 = ldg_cached(xf4 + eb1), rb1 = ldg_cached(xr4 + eb1);
+    const float4 ha0 = gn2_row(fa0, ra0, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)ea0);
+    const float4 ha1 = gn2_row(fa1, ra1, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)ea1);
+    const float4 hb0 = gn2_row(fb0, rb0, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)eb0);
+    const float4 hb1 = gn2_row(fb1, rb1, cf, cr, thresh, inv_keep, seed_f, seed_r, relu, (uint64_t)eb1);
+    float acc0 = 0.f, acc1 = 0.f;
+    acc0 = fmaf(ha0.x * ha1.x, ww.x, acc0), acc0 = fmaf(ha0.y * ha1.y, ww.y, acc0);
+    acc0 = fmaf(ha0.z * ha1.z, ww.z, acc0), acc0 = fmaf(ha0.w * ha1.w, ww.w, acc0);
+    acc1 = fmaf(hb0.x * hb1.x, ww.x, acc1), acc1 = fmaf(hb0.y * hb1.y, ww.y, acc1);
+    acc1 = fmaf(hb0.z * hb1.z, ww.z, acc1), acc1 = fmaf(hb0.w * hb1.w, ww.w, acc1);
+    if (!act) acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int d = GW / 2; d > 0; d >>= 1) {
+      acc0 += __shfl_xor_sync(gmask, acc0, d);
+      acc1 += __shfl_xor_sync(gmask, acc1, d);
+    }
+    if (c4 == 0) {
+      pred[l0] = acc0 + bias;
+      if (two) pred[l1] = acc1 + bias;
+    }
+  }
+}
+
+// general widths (C > 128): one warp per target link, columns strided over the lanes
 __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* __restrict__ xf, const float* __restrict__ xr, int C,
                                                                   const float* __restrict__ stf, const float* __restrict__ str_,
                                                                   const float* __restrict__ wf, const float* __restrict__ bf,
@@ -744,8 +802,18 @@ extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M
   TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_fwd: dropout p=%f outside [0,1)", p_drop);
   if (L <= 0) return 0;
   const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
-  k_gn2_readout_fwd<<<grid_for(L, kNormThreads / 32, 8), kNormThreads, 0, (cudaStream_t)stream>>>(
-      xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx, sidx, L, w, b, pred);
+#define TW_RO_ARGS xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx, sidx, L, w, b, pred
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cv = C >> 2;
+  if (cv <= 8)
+    k_gn2_readout_fwd_g<8><<<grid_for(L, (kNormThreads / 32) * 4 * 2, 8), kNormThreads, 0, s>>>(TW_RO_ARGS);
+  else if (cv <= 16)
+    k_gn2_readout_fwd_g<16><<<grid_for(L, (kNormThreads / 32) * 2 * 2, 8), kNormThreads, 0, s>>>(TW_RO_ARGS);
+  else if (cv <= 32)
+    k_gn2_readout_fwd_g<32><<<grid_for(L, (kNormThreads / 32) * 2, 8), kNormThreads, 0, s>>>(TW_RO_ARGS);
+  else
+    k_gn2_readout_fwd<<<grid_for(L, kNormThreads / 32, 8), kNormThreads, 0, s>>>(TW_RO_ARGS);
+#undef TW_RO_ARGS
   TW_LAUNCH_CHECK();
   return 0;
 }
