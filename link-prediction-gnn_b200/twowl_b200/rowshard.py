@@ -194,12 +194,19 @@ def forward_pairs(model, x, pos, idx, ei2):
         why = "row sharding needs the doubled pair layout (rows 2k / 2k+1 = (u,v) / (v,u))"
     if why is not None:
         raise NotImplementedError(why)
+    idx = idx.reshape(-1)
+    if getattr(model, "pair_locality", False):
+        # the blocks are cut from the pair table regrouped by hub (graph.LocalityView): same rows, streaming per-node gathers
+        lv = G.locality_view(wedges, pos)
+        pt = G.pair_table(lv.pos, x.shape[0])
+        blocked = wedges.blocked
+        wedges = lv.struct if blocked is None else lv.struct.with_blocked(ops.gather_u8(blocked, lv.perm[:wedges.E]))
+        idx = lv.newid[idx]
     lo, hi = block_of(pt.R, shard.rank, shard.world)
     loc = _local(wedges, pt, lo, hi)
     _, centre, dinv, selfw, bnode = wedges.prepared()
     rows = tuple(t[:, lo:hi].contiguous() for t in (centre, dinv, selfw, bnode))
     blocked_l = wedges.blocked[lo:lo + loc.E_loc] if wedges.blocked is not None else None
-    idx = idx.reshape(-1)
     L = idx.numel() // 2
     inb = ((idx >= lo) & (idx < hi)).reshape(L, 2)
     links_l = torch.nonzero(inb[:, 0]).reshape(-1)          # one host read: the block's target links
