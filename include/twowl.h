@@ -288,7 +288,9 @@ int twowl_gn2_readout_bwd_prepare(const float* xf, const float* xr, int64_t M, i
  *     (twowl_conv_args.moments, summed over ranks; M = global row count) - replaces the per-rank finalize of model.py:38.
  *   twowl_gn2_readout_bwd_rows: the row part of twowl_gn2_readout_bwd_prepare over this rank's positions -> G, head, next and
  *     colsums[6][C] (per branch sum g_y, sum g_y*n; dpred.weight; dpred.bias in column 0 of the sixth).
- *   twowl_gn2_readout_bwd_finish: from the rank-summed colsums and M_total -> consts[8C], dparams_f/r[4C], dw[C], db[1]. */
+ *   twowl_gn2_readout_bwd_finish: from the rank-summed colsums and M_total -> consts[8C], dparams_f/r[4C], dw[C], db[1].
+ *   twowl_graphnorm_bwd2_sums / _apply: twowl_graphnorm_bwd2 (non-last pair layers) cut the same way: colsums[4][C] = per branch
+ *     (sum g_y, sum g_y*n) over the rank's rows; _apply = finals on the rank-summed sums with M_total + the dense dx pass. */
 int twowl_graphnorm_stats_from_moments(const double* moments, int64_t M, int32_t C, const float* mean_scale, float eps,
                                        float* stats, void* stream);
 size_t twowl_gn2_readout_bwd_rows_workspace_bytes(int64_t M, int64_t L, int32_t C);
@@ -297,6 +299,17 @@ int twowl_gn2_readout_bwd_rows(const float* xf, const float* xr, int64_t M, int3
                                const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx,
                                int64_t sidx, int64_t L, const float* w, const float* dpred, float* G, int32_t* head, int32_t* next,
                                double* colsums, void* ws, size_t ws_bytes, void* stream);
+size_t twowl_graphnorm_bwd2_sums_workspace_bytes(int64_t M, int32_t C);
+int twowl_graphnorm_bwd2_sums(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C, const float* stats_f,
+                              const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                              const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu,
+                              double* colsums, void* ws, size_t ws_bytes, void* stream);
+size_t twowl_graphnorm_bwd2_apply_workspace_bytes(int32_t C);
+int twowl_graphnorm_bwd2_apply(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C, const float* stats_f,
+                               const float* stats_r, const float* wf, const float* bf, const float* mf, const float* wr,
+                               const float* br, const float* mr, float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu,
+                               const double* colsums, int64_t M_total, float* dxf, float* dxr, float* dparams_f, float* dparams_r,
+                               void* ws, size_t ws_bytes, void* stream);
 size_t twowl_gn2_readout_bwd_finish_workspace_bytes(int32_t C);
 int twowl_gn2_readout_bwd_finish(const double* colsums, int64_t M_total, int32_t C, const float* stats_f, const float* stats_r,
                                  const float* wf, const float* bf, const float* mf, const float* wr, const float* br,

@@ -1011,3 +1011,59 @@ extern "C" int twowl_gn2_readout_bwd_finish(const double* colsums, int64_t M_tot
   TW_LAUNCH_CHECK();
   return 0;
 }
+
+// twowl_graphnorm_bwd2 cut at its column reduction (non-last pair layers of a row-sharded pair table): _sums gives the raw
+// fp64 column sums [4][C] = per branch (sum g_y, sum g_y*n) over this rank's rows; _apply runs the finals on the rank-summed
+// sums with the global row count M_total, then the dense dx pass over the local rows.
+extern "C" size_t twowl_graphnorm_bwd2_sums_workspace_bytes(int64_t M, int32_t C) {
+  (void)M;
+  return align_up((size_t)kNormMaxCtas * 4 * (size_t)C * sizeof(double));
+}
+
+extern "C" int twowl_graphnorm_bwd2_sums(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C,
+                                         const float* stats_f, const float* stats_r, const float* wf, const float* bf,
+                                         const float* mf, const float* wr, const float* br, const float* mr, float p_drop,
+                                         uint64_t seed_f, uint64_t seed_r, int32_t relu, double* colsums, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  if (int rc = check_mc("graphnorm_bwd2_sums", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && colsums, "graphnorm_bwd2_sums: needs at least one row and an output");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(dout), "graphnorm_bwd2_sums: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_bwd2_sums: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_graphnorm_bwd2_sums_workspace_bytes(M, C));
+  cudaStream_t s = (cudaStream_t)stream;
+  double* part = (double*)ws;
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  const int grid = norm_grid(M, C);
+  k_gn_bwd2_partial<<<grid, kNormThreads, red_smem(C, 4), s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
+                                                               1.f / (1.f - p_drop), seed_f, seed_r, relu, part);
+  k_part_reduce_raw<<<(int)cdiv(4 * C, 4), 128, 0, s>>>(part, grid, 4, C, colsums);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t twowl_graphnorm_bwd2_apply_workspace_bytes(int32_t C) { return 2 * align_up(3 * (size_t)C * sizeof(float)); }
+
+extern "C" int twowl_graphnorm_bwd2_apply(const float* xf, const float* xr, const float* dout, int64_t M, int32_t C,
+                                          const float* stats_f, const float* stats_r, const float* wf, const float* bf,
+                                          const float* mf, const float* wr, const float* br, const float* mr, float p_drop,
+                                          uint64_t seed_f, uint64_t seed_r, int32_t relu, const double* colsums, int64_t M_total,
+                                          float* dxf, float* dxr, float* dparams_f, float* dparams_r, void* ws, size_t ws_bytes,
+                                          void* stream) {
+  if (int rc = check_mc("graphnorm_bwd2_apply", M, C)) return rc;
+  TW_CHECK_ARG(M > 0 && M_total >= M && colsums, "graphnorm_bwd2_apply: needs rows, M_total >= M and the column sums");
+  TW_CHECK_ARG(aligned16(xf) && aligned16(xr) && aligned16(dout) && aligned16(dxf) && aligned16(dxr),
+               "graphnorm_bwd2_apply: 16-byte alignment required");
+  TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "graphnorm_bwd2_apply: dropout p=%f outside [0,1)", p_drop);
+  TW_CHECK_WS(ws_bytes, twowl_graphnorm_bwd2_apply_workspace_bytes(C));
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver c(ws);
+  float* sums_f = c.take<float>(3 * (size_t)C);
+  float* sums_r = c.take<float>(3 * (size_t)C);
+  const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(colsums, 1, 4, 0, M_total, C, stats_f, wf, mf, sums_f, dparams_f);
+  k_gn_bwd_final<<<(int)cdiv(C, 4), 128, 0, s>>>(colsums, 1, 4, 2, M_total, C, stats_r, wr, mr, sums_r, dparams_r);
+  k_gn_bwd2_dx<<<norm_grid(M, C), kNormThreads, 0, s>>>(xf, xr, dout, M, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh,
+                                                        1.f / (1.f - p_drop), seed_f, seed_r, relu, sums_f, sums_r, dxf, dxr);
+  TW_LAUNCH_CHECK();
+  return 0;
+}

@@ -815,6 +815,34 @@ def graphnorm_bwd2(xf, xr, dout, sf, sr, pf, pr, p_drop: float, seed_f: int, see
     return dxf, dxr, dpf, dpr
 
 
+def graphnorm_bwd2_sharded(xf, xr, dout, sf, sr, pf, pr, p_drop: float, seed_f: int, seed_r: int, relu: bool, M_total: int, all_reduce):
+    """graphnorm_bwd2 over this rank's rows of a row-sharded pair table: the fp64 column sums [4,C] are summed over the ranks by
+    `all_reduce` (a callable applied in place) between the two halves. -> (dxf, dxr, dparams_f, dparams_r) as graphnorm_bwd2."""
+    M, C = xf.shape
+    dev = xf.device
+    colsums = torch.empty((4, C), dtype=torch.float64, device=dev)
+    nb = lib.twowl_graphnorm_bwd2_sums_workspace_bytes(M, C)
+    ws = _ws(nb, dev)
+    ptrs = (sf.data_ptr(), sr.data_ptr(), pf[0].data_ptr(), pf[1].data_ptr(), pf[2].data_ptr(), pr[0].data_ptr(), pr[1].data_ptr(),
+            pr[2].data_ptr(), float(p_drop), int(seed_f), int(seed_r), int(relu))
+    with _P("graphnorm_bwd2", M * C * 4 * 3):
+        check(lib.twowl_graphnorm_bwd2_sums(xf.data_ptr(), xr.data_ptr(), dout.data_ptr(), M, C, *ptrs, colsums.data_ptr(),
+                                            ws.data_ptr(), nb, _stream()), "graphnorm_bwd2_sums")
+    _count(2)
+    all_reduce(colsums)
+    dxf, dxr = torch.empty_like(xf), torch.empty_like(xr)
+    dpf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    dpr = torch.empty(4 * C, dtype=torch.float32, device=dev)
+    nb2 = lib.twowl_graphnorm_bwd2_apply_workspace_bytes(C)
+    ws2 = _ws(nb2, dev)
+    with _P("graphnorm_bwd2", M * C * 4 * 5):
+        check(lib.twowl_graphnorm_bwd2_apply(xf.data_ptr(), xr.data_ptr(), dout.data_ptr(), M, C, *ptrs, colsums.data_ptr(),
+                                             int(M_total), dxf.data_ptr(), dxr.data_ptr(), dpf.data_ptr(), dpr.data_ptr(),
+                                             ws2.data_ptr(), nb2, _stream()), "graphnorm_bwd2_apply")
+    _count(3)
+    return dxf, dxr, dpf, dpr
+
+
 # ------------------------------------------------------------------------------ metrics
 
 def auc(score: torch.Tensor, label: torch.Tensor) -> torch.Tensor:

@@ -1,6 +1,6 @@
 """One rank of the row-sharded TwoWL step (launched by tests/test_gpu_rowshard.py, not collected by pytest).
 
-usage: rowshard_worker.py <rank> <world> <port> <out.npz> <channels_2wl> <seed>
+usage: rowshard_worker.py <rank> <world> <port> <out.npz> <channels_2wl> <seed> <depth2>
 Every rank rebuilds the same fb-pages-food seed-0 train step from tests/golden (train.py:16-38), runs forward + BCE +
 backward on ITS block of pair rows (LocalWLNet.row_shard), sums the parameter gradients over the ranks, and rank 0 writes
 logits / loss / gradients. The ranks share cuda:0 and talk through gloo (NCCL refuses two ranks on one device)."""
@@ -16,11 +16,11 @@ for p in (ROOT, os.path.join(ROOT, "link-prediction-gnn_b200"), os.path.join(ROO
     if p not in sys.path:
         sys.path.insert(0, p)
 
-CFG = dict(channels_1wl=64, depth1=2, depth2=1, dp_lin0=0., dp_lin1=0., dp_emb=0., dp_1wl0=0., dp_2wl=0., dp_1wl1=0.,
+CFG = dict(channels_1wl=64, depth1=2, dp_lin0=0., dp_lin1=0., dp_emb=0., dp_1wl0=0., dp_2wl=0., dp_1wl1=0.,
            act0=True, act1=True)
 
 
-def build_step(c2: int, seed: int):
+def build_step(c2: int, seed: int, depth2: int = 1):
     """(module, args of forward, y) - shared with the single-GPU side of the test."""
     import TwoWL.model.model as model
     import TwoWL.utils as U
@@ -38,7 +38,7 @@ def build_step(c2: int, seed: int):
     bs = idx1.numel() // 2
     y = torch.cat((torch.ones(bs), torch.zeros(bs))).unsqueeze(-1).cuda()
     torch.manual_seed(seed)
-    mod = model.LocalWLNet(int(x_new.max().item()), False, None, channels_2wl=c2, **CFG)
+    mod = model.LocalWLNet(int(x_new.max().item()), False, None, channels_2wl=c2, depth2=depth2, **CFG)
     # GraphNorm / bias parameters away from their (1, 0, 1) initial values so that every gradient path is exercised
     with torch.no_grad():
         for k, p in mod.named_parameters():
@@ -49,12 +49,12 @@ def build_step(c2: int, seed: int):
 
 
 def main():
-    rank, world, port, out, c2, seed = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5]),
-                                        int(sys.argv[6]))
+    rank, world, port, out, c2, seed, depth2 = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5]),
+                                                int(sys.argv[6]), int(sys.argv[7]))
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     from twowl_b200 import dist as D
     from twowl_b200.rowshard import RowShard
-    mod, args, y = build_step(c2, seed)
+    mod, args, y = build_step(c2, seed, depth2)
     mod.row_shard = RowShard()
     logits = mod(*args)
     loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)

@@ -29,10 +29,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_world(world, c2, seed, out):
+def _run_world(world, c2, seed, out, depth2=1):
     port = _free_port()
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "rowshard_worker.py"), str(r), str(world), str(port), out, str(c2),
-                               str(seed)],
+                               str(seed), str(depth2)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     logs = []
     for p in procs:
@@ -46,16 +46,16 @@ def _run_world(world, c2, seed, out):
     return dict(np.load(out))
 
 
-@pytest.mark.parametrize("world,c2,seed", [(2, 32, 7), (3, 64, 5)])
-def test_row_sharded_step_matches_single_gpu_and_oracle(tmp_path, world, c2, seed):
+@pytest.mark.parametrize("world,c2,seed,depth2", [(2, 32, 7, 1), (3, 64, 5, 1), (2, 32, 4, 2)])
+def test_row_sharded_step_matches_single_gpu_and_oracle(tmp_path, world, c2, seed, depth2):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     sys.path.insert(0, HERE)
     from rowshard_worker import CFG, build_step
     from test_gpu_model import close
-    got = _run_world(world, c2, seed, str(tmp_path / "out.npz"))
+    got = _run_world(world, c2, seed, str(tmp_path / "out.npz"), depth2)
 
-    mod, args, y = build_step(c2, seed)
+    mod, args, y = build_step(c2, seed, depth2)
     out = mod(*args)
     loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
     loss.backward()

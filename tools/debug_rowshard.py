@@ -8,8 +8,9 @@ from test_gpu_rowshard import _run_world
 from rowshard_worker import CFG, build_step
 from oracle import twowl_oracle as O
 world, c2, seed = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-got = _run_world(world, c2, seed, "/tmp/rs_out.npz")
-mod, args, y = build_step(c2, seed)
+depth2 = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+got = _run_world(world, c2, seed, "/tmp/rs_out.npz", depth2)
+mod, args, y = build_step(c2, seed, depth2)
 out = mod(*args)
 loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y); loss.backward()
 sd = {k: v.detach().cpu() for k, v in mod.state_dict().items()}
