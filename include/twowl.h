@@ -376,11 +376,16 @@ int twowl_pair_conv(const twowl_conv_args* h_args, void* ws, size_t ws_bytes, vo
 size_t twowl_sizeof_conv_args(void);  /* binding guard, as twowl_sizeof_seg_args */
 
 /* Weight gradients of both pair-level linear layers in one pass over the rows (tcgen05 kind::tf32, 3xTF32, MN-major
- * operands): dWf[C,C] = (rsf * dOf)^T H, dWr[C,C] = (rsr * dOr)^T H. H is read once. C in {32, 64}. */
+ * operands): dWf[C,C] = (rsf * dOf)^T H, dWr[C,C] = (rsr * dOr)^T H. H is read once. C in {32, 64, 128}. */
 int twowl_pair_dw_supported(int32_t C);
 size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C);
 int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
                   int32_t C, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream);
+
+/* The same on C-column blocks of wider matrices (row pitches ld_dO / ld_H in elements): the [C,C] block of the gradients that
+ * belongs to (column block of dO, column block of H). Layers wider than 128 are tiled with it. */
+int twowl_pair_dw_ld(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
+                     int32_t C, int64_t ld_dO, int64_t ld_H, float* dWf, float* dWr, void* ws, size_t ws_bytes, void* stream);
 
 /* The same with the gradients made on the fly from the layer's OUTPUTS Of, Or (last pair layer, after
  * twowl_gn2_readout_bwd_prepare): the shared-memory pass that scales and splits the tiles first turns them into

@@ -152,8 +152,9 @@ int radix_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, u
 
 // ---- TMA tensor map of a row-major fp32 [rows, cols] matrix (prims.cu): boxes of box_cols x box_rows elements.
 // cuTensorMapEncodeTiled is reached through the runtime's driver entry point, so libcuda is not linked.
+// ld = row pitch in elements (0 = cols: a dense matrix); a column block of a wider matrix is base = X + c0, cols = width, ld = X's width.
 int make_tmap_2d_f32(CUtensorMap* tm, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
-                     CUtensorMapSwizzle swizzle);
+                     CUtensorMapSwizzle swizzle, int64_t ld = 0);
 
 // ---- tensor-core linear layer: the pair_conv kernel with one source and no epilogue terms (pair_conv.cu) ----------------------------------------
 // C[M,Nd] = A[M,Kd] * B^T with B[n][k] = W[n*Kd+k] (w_kn = 0) or W[k*Nd+n] (w_kn = 1); tcgen05 kind::tf32, 3xTF32.

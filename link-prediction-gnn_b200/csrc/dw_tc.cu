@@ -505,11 +505,11 @@ static size_t dw_smem() {
 }
 
 template <int C, bool GN>
-static int dw_launch(const DwParams& p, const float* Af, const float* Ar, const float* H, cudaStream_t s) {
+static int dw_launch(const DwParams& p, const float* Af, const float* Ar, const float* H, cudaStream_t s, int64_t ldA = 0, int64_t ldH = 0) {
   CUtensorMap tf, tr, th;
-  if (int rc = make_tmap_2d_f32(&tf, Af, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = make_tmap_2d_f32(&tr, Ar, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-  if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_2d_f32(&tf, Af, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ldA)) return rc;
+  if (int rc = make_tmap_2d_f32(&tr, Ar, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ldA)) return rc;
+  if (int rc = make_tmap_2d_f32(&th, H, p.M, C, 32, dw_tile_k(C), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, ldH)) return rc;
   const size_t smem = dw_smem<C>();
   TW_CUDA(cudaFuncSetAttribute(k_dw_tc<C, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_dw_tc<C, GN><<<dw_grid(p.M, C), kDwThreads, smem, s>>>(p, tf, tr, th);
@@ -524,8 +524,11 @@ using namespace twowl;
 extern "C" int twowl_pair_dw_supported(int32_t C) { return (C == 32 || C == 64 || C == 128) ? 1 : 0; }
 
 template <bool GN>
-static int dw_dispatch(const DwParams& p, int C, const float* Af, const float* Ar, const float* H, float* dWf, float* dWr, cudaStream_t s) {
-  const int rc = C == 32 ? dw_launch<32, GN>(p, Af, Ar, H, s) : C == 64 ? dw_launch<64, GN>(p, Af, Ar, H, s) : dw_launch<128, GN>(p, Af, Ar, H, s);
+static int dw_dispatch(const DwParams& p, int C, const float* Af, const float* Ar, const float* H, float* dWf, float* dWr, cudaStream_t s,
+                       int64_t ldA = 0, int64_t ldH = 0) {
+  const int rc = C == 32   ? dw_launch<32, GN>(p, Af, Ar, H, s, ldA, ldH)
+                 : C == 64 ? dw_launch<64, GN>(p, Af, Ar, H, s, ldA, ldH)
+                           : dw_launch<128, GN>(p, Af, Ar, H, s, ldA, ldH);
   if (rc) return rc;
   k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>(p.part, dw_grid(p.M, C), C, dw_part_rows(C), dWf, dWr);
   TW_LAUNCH_CHECK();
@@ -547,6 +550,22 @@ extern "C" int twowl_pair_dw(const float* dOf, const float* dOr, const float* rs
   memset(&p, 0, sizeof(p));
   p.rsf = rsf, p.rsr = rsr, p.M = M, p.part = (float*)ws;
   return dw_dispatch<false>(p, C, dOf, dOr, H, dWf, dWr, (cudaStream_t)stream);
+}
+
+// Column blocks of wider matrices: dOf / dOr point at a C-column block of [M, ld_dO] matrices, H at a C-column block of an
+// [M, ld_H] matrix (TMA tensor maps with a row pitch) -> the corresponding [C, C] block of the weight gradients. A 256-wide layer
+// is four such launches per direction pair (twowl_b200.ops.pair_dw_wide).
+extern "C" int twowl_pair_dw_ld(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,
+                                int32_t C, int64_t ld_dO, int64_t ld_H, float* dWf, float* dWr, void* ws, size_t ws_bytes,
+                                void* stream) {
+  TW_CHECK_ARG(twowl_pair_dw_supported(C), "pair_dw_ld: C=%d unsupported (32, 64 or 128)", C);
+  TW_CHECK_ARG(M > 0 && ld_dO >= C && ld_H >= C && (ld_dO & 3) == 0 && (ld_H & 3) == 0, "pair_dw_ld: pitches must be >= C and multiples of 4");
+  TW_CHECK_ARG(aligned16(dOf) && aligned16(dOr) && aligned16(H) && rsf && rsr, "pair_dw_ld: bad pointers");
+  TW_CHECK_WS(ws_bytes, twowl_pair_dw_workspace_bytes(M, C));
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.rsf = rsf, p.rsr = rsr, p.M = M, p.part = (float*)ws;
+  return dw_dispatch<false>(p, C, dOf, dOr, H, dWf, dWr, (cudaStream_t)stream, ld_dO, ld_H);
 }
 
 extern "C" int twowl_pair_dw_gn(const float* Of, const float* Or, const float* consts, const float* G, const int32_t* head,

@@ -257,11 +257,11 @@ static tmap_encode_fn tmap_encoder() {
   return fn;
 }
 int make_tmap_2d_f32(CUtensorMap* tm, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
-                     CUtensorMapSwizzle swizzle) {
+                     CUtensorMapSwizzle swizzle, int64_t ld) {
   tmap_encode_fn enc = tmap_encoder();
   TW_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint64_t gstr[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,

@@ -331,6 +331,8 @@ def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf,
         pass
     elif ops.pair_dw_supported(C) and h.shape[1] == C:
         dWs = list(ops.pair_dw(dOs[0], dOs[1], selfw[0], selfw[1], h))
+    elif ops.pair_dw_wide_supported(C, h.shape[1]):
+        dWs = list(ops.pair_dw_wide(dOs[0].contiguous(), dOs[1].contiguous(), selfw[0], selfw[1], h))
     else:
         dWs = [ops.linear_bwd_weight(dOs[d], h, row_scale=selfw[d]) for d in range(2)]
     res, dSWs = [], []

@@ -766,6 +766,36 @@ def pair_dw(dOf, dOr, rsf, rsr, H):
     return dWf, dWr
 
 
+def pair_dw_wide_supported(Co: int, Ci: int) -> bool:
+    """Widths beyond the single-launch kernel, tiled into 128-column blocks."""
+    return Co > 128 and Co % 128 == 0 and Ci % 128 == 0 and Co <= 1024 and Ci <= 1024
+
+
+def pair_dw_wide(dOf, dOr, rsf, rsr, H):
+    """pair_dw for layers wider than 128: one tcgen05 launch per (128-column block of dO, 128-column block of H) through TMA
+    tensor maps with a row pitch (twowl_pair_dw_ld) -> (dWf, dWr) [Co, Ci]."""
+    _need_cuda(dOf, dOr, H)
+    M, Co = dOf.shape
+    Ci = H.shape[1]
+    B = 128
+    dWf = torch.empty((Co, Ci), dtype=torch.float32, device=H.device)
+    dWr = torch.empty((Co, Ci), dtype=torch.float32, device=H.device)
+    nb = lib.twowl_pair_dw_workspace_bytes(M, B)
+    ws = _ws(nb, H.device)
+    tf = torch.empty((B, B), dtype=torch.float32, device=H.device)
+    tr = torch.empty((B, B), dtype=torch.float32, device=H.device)
+    for i in range(Co // B):
+        for j in range(Ci // B):
+            with _P("pair_dw", 12 * M * B + 8 * M):
+                check(lib.twowl_pair_dw_ld(dOf.data_ptr() + 4 * i * B, dOr.data_ptr() + 4 * i * B, rsf.data_ptr(), rsr.data_ptr(),
+                                           H.data_ptr() + 4 * j * B, M, B, Co, Ci, tf.data_ptr(), tr.data_ptr(), ws.data_ptr(), nb,
+                                           _stream()), "pair_dw_ld")
+            _count(2)
+            dWf[i * B:(i + 1) * B, j * B:(j + 1) * B] = tf
+            dWr[i * B:(i + 1) * B, j * B:(j + 1) * B] = tr
+    return dWf, dWr
+
+
 def pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop: float, seed_f: int, seed_r: int, relu: bool, rsf, rsr, H):
     """pair_dw with the gradients made on the fly from the last pair layer's outputs (after gn2_readout_bwd_prepare):
     -> (dOf, dOr [M,C], dWf, dWr [C,C]). One pass: reads Of, Or, H, writes dOf, dOr."""

@@ -436,6 +436,24 @@ def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     assert torch.equal(gf, gf2) and torch.equal(gr, gr2)      # deterministic
 
 
+@pytest.mark.parametrize("M,Co,Ci", [(1, 256, 256), (20001, 256, 256), (5000, 384, 128)])
+def test_pair_dw_wide_tiles_vs_fp64(U, M, Co, Ci):
+    """Layers wider than 128: the weight gradients tiled into 128-column blocks through pitched TMA tensor maps (twowl_pair_dw_ld)."""
+    from twowl_b200 import ops
+    torch.manual_seed(M + Co)
+    dOf, dOr = (torch.randn(M, Co, dtype=torch.float64) for _ in range(2))
+    H = torch.randn(M, Ci, dtype=torch.float64)
+    rsf = torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3)
+    rsr = torch.rand(M, dtype=torch.float64)
+    c = lambda t: t.float().cuda().contiguous()          # noqa: E731
+    assert ops.pair_dw_wide_supported(Co, Ci)
+    gf, gr = ops.pair_dw_wide(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
+    ref_f, ref_r = (rsf.unsqueeze(1) * dOf).t() @ H, (rsr.unsqueeze(1) * dOr).t() @ H
+    tol = 4e-6 * max(float(ref_f.abs().max()), float(ref_r.abs().max()), 1.0)
+    assert_close(gf, ref_f, rtol=1e-5, atol=tol, what="pair_dw_wide f")
+    assert_close(gr, ref_r, rtol=1e-5, atol=tol, what="pair_dw_wide r")
+
+
 @pytest.mark.parametrize("M,C,L,p", [(64, 64, 10, 0.0), (5000, 32, 700, 0.3), (70001, 64, 9000, 0.0), (70001, 64, 9000, 0.5),
                                      (40001, 128, 5000, 0.0), (40001, 128, 5000, 0.4)])
 def test_pair_dw_gn_matches_two_pass(U, M, C, L, p):
