@@ -20,7 +20,7 @@ class _Cache:
     """Tiny LRU keyed by (data_ptr, shape, strides, version). Entries keep the key tensor alive, so a
     data_ptr can never be recycled by the allocator while its entry exists."""
 
-    def __init__(self, cap: int = 8):
+    def __init__(self, cap: int = 24):   # train / val / test splits x (node graph, pair table, regrouped view, its pair table, ...)
         self.cap = cap
         self.d: "OrderedDict[tuple, tuple]" = OrderedDict()
 
