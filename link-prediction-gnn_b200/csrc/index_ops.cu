@@ -85,24 +85,42 @@ __global__ void __launch_bounds__(kThreads) k_ei2_fill(const int64_t* __restrict
   if (cached)
     for (int64_t i = threadIdx.x; i <= n_hi - n_lo + 1; i += blockDim.x) s_off[i] = off[n_lo + i];
   __syncthreads();
+  // a tile inside ONE node's segment (hubs: cin*cout wedges >> tile) needs no search and its divisor is block-uniform
+  const bool one = n_lo == n_hi;
+  int64_t node1 = n_lo, base1 = 0, ob1 = 0, cout1 = 1, ib1 = 0;
+  if (one) {
+    base1 = cached ? s_off[0] : off[n_lo];
+    ob1 = out_ptr[n_lo];
+    cout1 = out_ptr[n_lo + 1] - ob1;
+    ib1 = in_ptr[n_lo];
+  }
   for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    int64_t node, base;
-    if (cached) {
-      const int64_t j = seg_search(s_off, 0, n_hi - n_lo, t);
-      node = n_lo + j;
-      base = s_off[j];
-    } else {
-      node = seg_search(off, n_lo, n_hi, t);
-      base = off[node];
+    int64_t node = node1, base = base1, ob = ob1, cout = cout1, ib0 = ib1;
+    if (!one) {
+      if (cached) {
+        const int64_t j = seg_search(s_off, 0, n_hi - n_lo, t);
+        node = n_lo + j;
+        base = s_off[j];
+      } else {
+        node = seg_search(off, n_lo, n_hi, t);
+        base = off[node];
+      }
+      ob = out_ptr[node];
+      cout = out_ptr[node + 1] - ob;
+      ib0 = in_ptr[node];
     }
-    const int64_t ob = out_ptr[node];
-    const int64_t cout = out_ptr[node + 1] - ob;
     const int64_t local = t - base;
-    const int64_t ia = local / cout, ib = local - ia * cout;
+    int64_t ia, ib;
+    if ((uint64_t)local < 0x100000000ull && (uint64_t)cout < 0x100000000ull) {   // 32-bit divide: ~10x cheaper than the 64-bit one
+      const uint32_t q = (uint32_t)local / (uint32_t)cout;
+      ia = q, ib = (int64_t)((uint32_t)local - q * (uint32_t)cout);
+    } else {
+      ia = local / cout, ib = local - ia * cout;
+    }
     longlong2 v;
-    v.x = (int64_t)in_ids[in_ptr[node] + ia];
-    v.y = (int64_t)out_ids[ob + ib];
-    out_ab[t - t_begin] = v;  // one 128-bit store per wedge
+    v.x = (int64_t)__ldg(in_ids + ib0 + ia);
+    v.y = (int64_t)__ldg(out_ids + ob + ib);
+    __stcs(out_ab + (t - t_begin), v);  // one 128-bit streaming store per wedge
   }
 }
 
@@ -116,30 +134,40 @@ __global__ void __launch_bounds__(kThreads) k_mask_scatter(const int64_t* __rest
   }
 }
 
-__device__ __forceinline__ bool select_keep(const int64_t* row0, int64_t s0, int64_t t, const uint8_t* mask,
-                                            int64_t mask_len, int mode) {
-  const int64_t key = mode == 0 ? t : row0[t * s0];
-  if (key < 0 || key >= mask_len) return true;
-  return mask[key] == 0;
+// tile = 2048 columns = 8 rounds of 256 threads (round r, thread i -> column base + r*256 + i: coalesced). All rounds' keys are
+// requested before any mask byte is looked up, and the order-preserving ranks come from ONE block-wide prefix over the 8 x 8
+// (round, warp) ballot counts - two barriers per tile instead of three per round.
+constexpr int kSelRounds = TWOWL_SELECT_TILE / kThreads;
+constexpr int kSelWarps = kThreads / 32;
+
+__device__ __forceinline__ void select_flags(const int64_t* __restrict__ row0, int64_t s0, int64_t T, const uint8_t* __restrict__ mask,
+                                             int64_t mask_len, int mode, int64_t base, bool (&keep)[kSelRounds]) {
+  int64_t key[kSelRounds];
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r) {
+    const int64_t t = base + r * kThreads + threadIdx.x;
+    key[r] = t < T ? (mode == 0 ? t : __ldg(row0 + t * s0)) : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r)
+    keep[r] = (base + r * kThreads + threadIdx.x < T) && (key[r] < 0 || key[r] >= mask_len || __ldg(mask + key[r]) == 0);
 }
 
-// tile = 2048 columns = 8 rounds of 256 threads; count pass
 __global__ void __launch_bounds__(kThreads) k_select_count(const int64_t* __restrict__ row0, int64_t s0, int64_t T,
                                                            const uint8_t* __restrict__ mask, int64_t mask_len, int mode,
                                                            int64_t* __restrict__ tile_cnt) {
-  __shared__ int s_cnt[kThreads / 32];
+  __shared__ int s_cnt[kSelWarps];
   const int64_t base = (int64_t)blockIdx.x * TWOWL_SELECT_TILE;
+  bool keep[kSelRounds];
+  select_flags(row0, s0, T, mask, mask_len, mode, base, keep);
   int c = 0;
-  for (int r = 0; r < TWOWL_SELECT_TILE / kThreads; ++r) {
-    const int64_t t = base + r * kThreads + threadIdx.x;
-    const bool keep = t < T && select_keep(row0, s0, t, mask, mask_len, mode);
-    c += __popc(__ballot_sync(0xffffffffu, keep));
-  }
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r) c += __popc(__ballot_sync(0xffffffffu, keep[r]));
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
     int tot = 0;
-    for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
+    for (int w = 0; w < kSelWarps; ++w) tot += s_cnt[w];
     tile_cnt[blockIdx.x] = tot;
   }
 }
@@ -149,33 +177,41 @@ __global__ void __launch_bounds__(kThreads) k_select_fill(const int64_t* __restr
                                                           const uint8_t* __restrict__ mask, int64_t mask_len, int mode,
                                                           const int64_t* __restrict__ tile_off, int64_t* __restrict__ out0,
                                                           int64_t* __restrict__ out1) {
-  __shared__ int s_cnt[kThreads / 32];
-  __shared__ int s_run;
+  __shared__ int s_cnt[kSelRounds * kSelWarps];   // [round][warp]: the tile order is round-major, then warp, then lane
+  __shared__ int s_pre[kSelRounds * kSelWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = (int64_t)blockIdx.x * TWOWL_SELECT_TILE;
   const int64_t obase = tile_off[blockIdx.x];
-  if (threadIdx.x == 0) s_run = 0;
-  __syncthreads();
-  for (int r = 0; r < TWOWL_SELECT_TILE / kThreads; ++r) {
+  bool keep[kSelRounds];
+  select_flags(row0, s0, T, mask, mask_len, mode, base, keep);
+  // the payload loads do not depend on the ranks: request them now (row0 again: an L1/L2 hit of the key load above)
+  int64_t v0[kSelRounds], v1[kSelRounds];
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r) {
     const int64_t t = base + r * kThreads + threadIdx.x;
-    const bool keep = t < T && select_keep(row0, s0, t, mask, mask_len, mode);
-    const unsigned b = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_cnt[warp] = __popc(b);
-    __syncthreads();
-    int before = s_run;
-    for (int w = 0; w < warp; ++w) before += s_cnt[w];
-    if (keep) {
-      const int64_t o = obase + before + __popc(b & ((1u << lane) - 1u));
-      out0[o] = row0[t * s0];
-      out1[o] = row1[t * s1];
+    v0[r] = keep[r] ? row0[t * s0] : 0;
+    v1[r] = keep[r] ? row1[t * s1] : 0;
+  }
+  unsigned bal[kSelRounds];
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r) {
+    bal[r] = __ballot_sync(0xffffffffu, keep[r]);
+    if (lane == 0) s_cnt[r * kSelWarps + warp] = __popc(bal[r]);
+  }
+  __syncthreads();
+  if (threadIdx.x < kSelRounds * kSelWarps) {      // exclusive prefix of the 64 counts by one thread each (64 adds at most)
+    int pre = 0;
+    for (int i = 0; i < (int)threadIdx.x; ++i) pre += s_cnt[i];
+    s_pre[threadIdx.x] = pre;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSelRounds; ++r) {
+    if (keep[r]) {
+      const int64_t o = obase + s_pre[r * kSelWarps + warp] + __popc(bal[r] & ((1u << lane) - 1u));
+      __stcs(out0 + o, v0[r]);
+      __stcs(out1 + o, v1[r]);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
-      s_run += tot;
-    }
-    __syncthreads();
   }
 }
 
@@ -206,6 +242,29 @@ __global__ void __launch_bounds__(kThreads) k_reverse(const int64_t* __restrict_
     edge[T + t] = b;
     edge_r[t] = a;
     edge_r[T + t] = b ^ 1;
+  }
+}
+
+// Two wedges per thread with 128-bit accesses. PAIRED: ei2 is the transposed view of a [T,2] buffer (what get_ei2 returns,
+// utils.py:45), one longlong2 = (a, b) of a wedge; otherwise two contiguous rows. Needs T even and 16-byte aligned pointers.
+template <bool PAIRED>
+__global__ void __launch_bounds__(kThreads) k_reverse_v2(const int64_t* __restrict__ row0, const int64_t* __restrict__ row1, int64_t T,
+                                                         int64_t* __restrict__ edge, int64_t* __restrict__ edge_r) {
+  const int64_t half = T >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (int64_t)gridDim.x * blockDim.x) {
+    longlong2 a, b;
+    if (PAIRED) {
+      const longlong2 w0 = __ldcs(reinterpret_cast<const longlong2*>(row0) + 2 * i);
+      const longlong2 w1 = __ldcs(reinterpret_cast<const longlong2*>(row0) + 2 * i + 1);
+      a = make_longlong2(w0.x, w1.x), b = make_longlong2(w0.y, w1.y);
+    } else {
+      a = __ldcs(reinterpret_cast<const longlong2*>(row0) + i);
+      b = __ldcs(reinterpret_cast<const longlong2*>(row1) + i);
+    }
+    __stcs(reinterpret_cast<longlong2*>(edge) + i, make_longlong2(a.x ^ 1, a.y ^ 1));   // utils.py:72-75
+    __stcs(reinterpret_cast<longlong2*>(edge + T) + i, b);
+    __stcs(reinterpret_cast<longlong2*>(edge_r) + i, a);
+    __stcs(reinterpret_cast<longlong2*>(edge_r + T) + i, make_longlong2(b.x ^ 1, b.y ^ 1));
   }
 }
 
@@ -384,7 +443,14 @@ extern "C" int twowl_check_in_set(const int64_t* target, int64_t st, int64_t n, 
 extern "C" int twowl_reverse(const int64_t* row0, int64_t s0, const int64_t* row1, int64_t s1, int64_t T, int64_t* edge,
                              int64_t* edge_r, void* stream) {
   if (T <= 0) return 0;
-  k_reverse<<<grid_for(T, kThreads), kThreads, 0, (cudaStream_t)stream>>>(row0, s0, row1, s1, T, edge, edge_r);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (T & 1) == 0 && aligned16(row0) && aligned16(edge) && aligned16(edge_r);
+  if (vec && s0 == 2 && s1 == 2 && row1 == row0 + 1) {
+    k_reverse_v2<true><<<grid_for(T / 2, kThreads), kThreads, 0, s>>>(row0, row1, T, edge, edge_r);
+  } else if (vec && s0 == 1 && s1 == 1 && aligned16(row1)) {
+    k_reverse_v2<false><<<grid_for(T / 2, kThreads), kThreads, 0, s>>>(row0, row1, T, edge, edge_r);
+  } else
+    k_reverse<<<grid_for(T, kThreads), kThreads, 0, s>>>(row0, s0, row1, s1, T, edge, edge_r);
   TW_LAUNCH_CHECK();
   return 0;
 }
