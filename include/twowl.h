@@ -77,6 +77,12 @@ int twowl_ei2_fill(const int64_t* in_ptr, const int32_t* in_ids, const int64_t* 
                    const int64_t* off, int64_t n_node, int64_t t_begin, int64_t t_end, int64_t* out_ab,
                    void* stream);
 
+/* The same wedges as two contiguous rows: out_rows[0..n) = a, out_rows[n..2n) = b, n = t_end - t_begin - the fresh contiguous
+ * [2,T'] tensor blockei2's boolean indexing returns (utils.py:50). blockei2 of an index that get_ei2 made is this fill over the
+ * in-lists with the blocked edges taken out: 16*T' bytes written instead of 32*T read + 16*T' written by the compaction. */
+int twowl_ei2_fill_rows(const int64_t* in_ptr, const int32_t* in_ids, const int64_t* out_ptr, const int32_t* out_ids,
+                        const int64_t* off, int64_t n_node, int64_t t_begin, int64_t t_end, int64_t* out_rows, void* stream);
+
 /* idx2mask (utils.py:53-57): mask[0..num) = 0 then mask[idx[j]] = 1 (uint8). */
 int twowl_mask_from_idx(const int64_t* idx, int64_t k, uint8_t* mask, int64_t num, void* stream);
 

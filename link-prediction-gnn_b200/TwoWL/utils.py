@@ -56,6 +56,21 @@ def _materialize(struct: WedgeStruct) -> Tensor:
     return full
 
 
+def _materialize_unblocked(struct: WedgeStruct) -> Tensor:
+    """blockei2 of an index get_ei2 made = the join over the in-lists with the blocked edges taken out (same order: centre
+    ascending, a ascending, b ascending), written once as the contiguous [2,T'] tensor utils.py:50 returns - instead of reading
+    the [2,T] tensor twice to compact it."""
+    n = struct.n_node
+    live = ops.gather_u8(struct.blocked, struct.in_ids) == 0           # per in-list ENTRY, in list order
+    in_ids = struct.in_ids[live]
+    cnt = struct.prepared()[0][:n].to(torch.int64)                      # live in-edges per node
+    in_ptr = torch.zeros(n + 1, dtype=torch.int64, device=cnt.device)
+    torch.cumsum(cnt, 0, out=in_ptr[1:])
+    off = ops.ei2_offsets(in_ptr, struct.out_ptr, n)
+    T = int(off[-1].item())
+    return ops.ei2_fill_rows(in_ptr, in_ids, struct.out_ptr, struct.out_ids, off, n, T)
+
+
 def get_ei2(n_node: int, pos_edge, pred_edge):
     """utils.py:36-45 - the wedge join: for centre node i ascending, every observed edge id a with
     pos_edge[1][a]==i (ascending) x every pair id b with cat(pos_edge,pred_edge)[0][b]==i (ascending).
@@ -78,6 +93,8 @@ def blockei2(ei2, blocked_idx):
         new_struct = struct.with_blocked(mask)
         if isinstance(ei2, WedgeIndex):
             return WedgeIndex(new_struct)
+        if struct.E % 2 == 0 and struct.R % 2 == 0:
+            return _tag(_materialize_unblocked(new_struct), new_struct)
         return _tag(ops.select_columns(ei2, mask, 1), new_struct)
     num = int(blocked_idx.max().item()) + 1 if blocked_idx.numel() else 1
     mask = ops.mask_from_idx(blocked_idx, max(num, 1))

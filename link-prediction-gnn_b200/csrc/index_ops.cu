@@ -69,6 +69,9 @@ __device__ __forceinline__ int64_t seg_search(const int64_t* off, int64_t lo, in
 constexpr int kFillTile = 2048;   // wedges per CTA
 constexpr int kFillCache = 2048;  // segment offsets staged in shared memory per CTA
 
+// ROWS = false: interleaved (a, b) pairs, the [T,2] buffer get_ei2 returns transposed; ROWS = true: two contiguous rows
+// out_ab[0 .. n) = a, out_ab[n .. 2n) = b (n = t_end - t_begin), the fresh [2,T'] tensor blockei2's boolean indexing returns.
+template <bool ROWS>
 __global__ void __launch_bounds__(kThreads) k_ei2_fill(const int64_t* __restrict__ in_ptr, const int32_t* __restrict__ in_ids,
                                                        const int64_t* __restrict__ out_ptr, const int32_t* __restrict__ out_ids,
                                                        const int64_t* __restrict__ off, int64_t n_node, int64_t t_begin,
@@ -120,7 +123,13 @@ __global__ void __launch_bounds__(kThreads) k_ei2_fill(const int64_t* __restrict
     longlong2 v;
     v.x = (int64_t)__ldg(in_ids + ib0 + ia);
     v.y = (int64_t)__ldg(out_ids + ob + ib);
-    __stcs(out_ab + (t - t_begin), v);  // one 128-bit streaming store per wedge
+    if (ROWS) {
+      int64_t* __restrict__ o = reinterpret_cast<int64_t*>(out_ab);
+      __stcs(o + (t - t_begin), (long long)v.x);
+      __stcs(o + (t_end - t_begin) + (t - t_begin), (long long)v.y);
+    } else {
+      __stcs(out_ab + (t - t_begin), v);  // one 128-bit streaming store per wedge
+    }
   }
 }
 
@@ -386,8 +395,21 @@ extern "C" int twowl_ei2_fill(const int64_t* in_ptr, const int32_t* in_ids, cons
   TW_CHECK_ARG(aligned16(out_ab), "ei2_fill: out_ab must be 16-byte aligned");
   const int64_t tiles = cdiv(t_end - t_begin, kFillTile);
   TW_CHECK_ARG(tiles < 0x7fffffffLL, "ei2_fill: range too large for one launch; split [t_begin,t_end)");
-  k_ei2_fill<<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(in_ptr, in_ids, out_ptr, out_ids, off, n_node, t_begin,
-                                                                    t_end, (longlong2*)out_ab);
+  k_ei2_fill<false><<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(in_ptr, in_ids, out_ptr, out_ids, off, n_node, t_begin,
+                                                                           t_end, (longlong2*)out_ab);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_ei2_fill_rows(const int64_t* in_ptr, const int32_t* in_ids, const int64_t* out_ptr, const int32_t* out_ids,
+                                   const int64_t* off, int64_t n_node, int64_t t_begin, int64_t t_end, int64_t* out_rows,
+                                   void* stream) {
+  TW_CHECK_ARG(t_begin >= 0 && t_end >= t_begin, "ei2_fill_rows: bad range [%lld,%lld)", (long long)t_begin, (long long)t_end);
+  if (t_end == t_begin || n_node == 0) return 0;
+  const int64_t tiles = cdiv(t_end - t_begin, kFillTile);
+  TW_CHECK_ARG(tiles < 0x7fffffffLL, "ei2_fill_rows: range too large for one launch; split [t_begin,t_end)");
+  k_ei2_fill<true><<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(in_ptr, in_ids, out_ptr, out_ids, off, n_node, t_begin,
+                                                                          t_end, (longlong2*)out_rows);
   TW_LAUNCH_CHECK();
   return 0;
 }

@@ -158,6 +158,15 @@ def ei2_fill(in_ptr, in_ids, out_ptr, out_ids, off, n_node: int, t_begin: int, t
     return out
 
 
+def ei2_fill_rows(in_ptr, in_ids, out_ptr, out_ids, off, n_node: int, T: int) -> torch.Tensor:
+    """-> the same wedges as a fresh contiguous int64 [2,T] tensor (rows a, b): the layout blockei2 returns."""
+    out = torch.empty((2, T), dtype=torch.int64, device=in_ptr.device)
+    check(lib.twowl_ei2_fill_rows(in_ptr.data_ptr(), in_ids.data_ptr(), out_ptr.data_ptr(), out_ids.data_ptr(),
+                                  off.data_ptr(), n_node, 0, int(T), out.data_ptr(), _stream()), "ei2_fill_rows")
+    _count()
+    return out
+
+
 def mask_from_idx(idx: torch.Tensor, num: int) -> torch.Tensor:
     _need_cuda(idx)
     idx = idx.reshape(-1)
