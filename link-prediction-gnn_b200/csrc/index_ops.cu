@@ -97,21 +97,46 @@ __global__ void __launch_bounds__(kThreads) k_ei2_fill(const int64_t* __restrict
     cout1 = out_ptr[n_lo + 1] - ob1;
     ib1 = in_ptr[n_lo];
   }
-  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    int64_t node = node1, base = base1, ob = ob1, cout = cout1, ib0 = ib1;
-    if (!one) {
-      if (cached) {
-        const int64_t j = seg_search(s_off, 0, n_hi - n_lo, t);
-        node = n_lo + j;
-        base = s_off[j];
-      } else {
-        node = seg_search(off, n_lo, n_hi, t);
-        base = off[node];
-      }
-      ob = out_ptr[node];
-      cout = out_ptr[node + 1] - ob;
-      ib0 = in_ptr[node];
+  auto emit = [&](int64_t t, int32_t a, int32_t b) {
+    if (ROWS) {
+      int64_t* __restrict__ o = reinterpret_cast<int64_t*>(out_ab);
+      __stcs(o + (t - t_begin), (long long)a);
+      __stcs(o + (t_end - t_begin) + (t - t_begin), (long long)b);
+    } else {
+      __stcs(out_ab + (t - t_begin), make_longlong2((long long)a, (long long)b));  // one 128-bit streaming store per wedge
     }
+  };
+  if (one) {
+    // (ia, ib) = divmod(t - base, cout) once per thread, then stepped by the block stride: the kernel was issue-bound (80 % of the
+    // issue slots, ncu) on a divide per wedge. cout < 2^31 (pair rows), ia < cin < 2^31.
+    const uint32_t cout = (uint32_t)cout1;
+    const uint32_t qs = (uint32_t)blockDim.x / cout, rs = (uint32_t)blockDim.x % cout;
+    int64_t t = t0 + threadIdx.x;
+    if (t < t1) {
+      const int64_t local = t - base1;
+      uint32_t ia = (uint32_t)(local / (int64_t)cout), ib = (uint32_t)(local - (int64_t)ia * (int64_t)cout);
+      const int32_t* __restrict__ ina = in_ids + ib1;
+      const int32_t* __restrict__ outb = out_ids + ob1;
+      for (; t < t1; t += blockDim.x) {
+        emit(t, __ldg(ina + ia), __ldg(outb + ib));
+        ia += qs, ib += rs;
+        if (ib >= cout) ib -= cout, ++ia;
+      }
+    }
+    return;
+  }
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    int64_t node, base;
+    if (cached) {
+      const int64_t j = seg_search(s_off, 0, n_hi - n_lo, t);
+      node = n_lo + j;
+      base = s_off[j];
+    } else {
+      node = seg_search(off, n_lo, n_hi, t);
+      base = off[node];
+    }
+    const int64_t ob = out_ptr[node];
+    const int64_t cout = out_ptr[node + 1] - ob;
     const int64_t local = t - base;
     int64_t ia, ib;
     if ((uint64_t)local < 0x100000000ull && (uint64_t)cout < 0x100000000ull) {   // 32-bit divide: ~10x cheaper than the 64-bit one
@@ -120,16 +145,7 @@ __global__ void __launch_bounds__(kThreads) k_ei2_fill(const int64_t* __restrict
     } else {
       ia = local / cout, ib = local - ia * cout;
     }
-    longlong2 v;
-    v.x = (int64_t)__ldg(in_ids + ib0 + ia);
-    v.y = (int64_t)__ldg(out_ids + ob + ib);
-    if (ROWS) {
-      int64_t* __restrict__ o = reinterpret_cast<int64_t*>(out_ab);
-      __stcs(o + (t - t_begin), (long long)v.x);
-      __stcs(o + (t_end - t_begin) + (t - t_begin), (long long)v.y);
-    } else {
-      __stcs(out_ab + (t - t_begin), v);  // one 128-bit streaming store per wedge
-    }
+    emit(t, __ldg(in_ids + in_ptr[node] + ia), __ldg(out_ids + ob + ib));
   }
 }
 
