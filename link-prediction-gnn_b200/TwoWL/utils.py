@@ -16,7 +16,7 @@ from twowl_b200 import ops
 from twowl_b200.graph import WedgeIndex, WedgeStruct, build_wedge_struct
 
 __all__ = ["degree", "set_mul", "check_in_set", "get_ei2", "blockei2", "idx2mask", "sample_block", "reverse",
-           "double", "random_split_edges", "get_ei2_implicit", "WedgeIndex", "torch", "Tensor", "math"]
+           "double", "random_split_edges", "get_ei2_implicit", "get_ei2_shard", "WedgeIndex", "torch", "Tensor", "math"]
 
 
 def _tag(t: Tensor, struct: WedgeStruct) -> Tensor:
@@ -77,6 +77,20 @@ def get_ei2(n_node: int, pos_edge, pred_edge):
     Returns int64 [2,T] as the same transposed view of a [T,2] buffer the reference returns."""
     struct = build_wedge_struct(int(n_node), pos_edge, pred_edge)
     return _tag(_materialize(struct), struct)
+
+
+def get_ei2_shard(n_node: int, pos_edge, pred_edge, rank: int, world: int):
+    """Rank `rank`'s contiguous slice of get_ei2's columns when `world` ranks build the index together (extension):
+    every rank holds the small int edge lists and fills only wedges [T*rank/world, T*(rank+1)/world) - equal work whatever the
+    degree skew, no exchange - and the slices concatenated in rank order ARE get_ei2(n_node, pos_edge, pred_edge), because the
+    layout is one global prefix sum. Returns (int64 [2, T_rank] in the reference's transposed layout, first column index, T)."""
+    struct = build_wedge_struct(int(n_node), pos_edge, pred_edge)
+    n = struct.n_node
+    off = ops.ei2_offsets(struct.in_ptr, struct.out_ptr, n)
+    T = int(off[-1].item())
+    t0, t1 = T * int(rank) // int(world), T * (int(rank) + 1) // int(world)
+    part = ops.ei2_fill(struct.in_ptr, struct.in_ids, struct.out_ptr, struct.out_ids, off, n, t0, t1).t()
+    return part, t0, T
 
 
 def get_ei2_implicit(n_node: int, pos_edge, pred_edge) -> WedgeIndex:

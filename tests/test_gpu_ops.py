@@ -120,6 +120,22 @@ def test_get_ei2_random_vs_oracle(U, n, e, p, seed):
         assert same(r1, o1) and same(r2, o2)
 
 
+@pytest.mark.parametrize("world", [2, 3, 7])
+def test_get_ei2_rank_slices_concatenate_to_the_reference_order(U, world):
+    """every rank fills its own wedge range; the rank-order concatenation is get_ei2 bit for bit."""
+    rng = np.random.default_rng(world)
+    n = 500
+    und = np.concatenate([rng.integers(0, n, size=(2, 2500)), np.stack([np.zeros(300, np.int64), rng.integers(1, n, 300)])], axis=1)
+    pos, pred = O.synthetic_split(n, und, seed=world)                 # node 0 is a hub: its segment spans several ranks' ranges
+    dpos, dpred = dev(pos), dev(pred)
+    full = U.get_ei2(n, dpos, dpred)
+    parts = [U.get_ei2_shard(n, dpos, dpred, r, world) for r in range(world)]
+    assert all(p[2] == full.shape[1] for p in parts)
+    assert [p[1] for p in parts] == [full.shape[1] * r // world for r in range(world)]
+    assert torch.equal(torch.cat([p[0] for p in parts], dim=1), full)
+    assert np.array_equal(full.cpu().numpy(), O.get_ei2(n, pos, pred))
+
+
 def test_check_in_set_duplicates_and_degree(U):
     rng = np.random.default_rng(7)
     t = rng.integers(0, 500, size=10000)
