@@ -191,13 +191,15 @@ class LocalWLNet(nn.Module):
 
         self.pred = nn.Linear(channels_2wl, 1)
 
-    def _wedges(self, ei2, R: int):
+    def _wedges(self, ei2, R: int, pt=None):
         """Pick the representation of ei2 the pair-level kernels read.
         structured: ei2 came from this package's get_ei2 / blockei2 / sample_block (or is a WedgeIndex) and
                     matches the pair table -> the factorised kernels, O(E + R) instead of O(T);
         explicit:   any int64 [2,T] tensor -> two CSRs over the wedges (built once per tensor, cached)."""
         struct = ei2.struct if isinstance(ei2, G.WedgeIndex) else _struct_of(ei2)
         ok = struct is not None and struct.R == R and struct.E % 2 == 0 and R % 2 == 0
+        if ok and pt is not None:
+            ok = G.wedges_match_table(struct, pt)      # the index was built for THIS pair table
         if self.pair_path == "structured" and not ok:
             raise RuntimeError("pair_path='structured' needs an ei2 produced by TwoWL.utils.get_ei2/sample_block "
                                "for this pair table")
@@ -224,7 +226,7 @@ class LocalWLNet(nn.Module):
             from twowl_b200 import rowshard
             return rowshard.forward_pairs(self, x, pos, idx, ei2)
         pt = G.pair_table(pos, x.shape[0])
-        wedges = self._wedges(ei2, pt.R) if len(self.conv2s) else None
+        wedges = self._wedges(ei2, pt.R, pt) if len(self.conv2s) else None
         if self.pair_locality and isinstance(wedges, G.WedgeStruct) and pt.mated and idx is not None:
             lv = G.locality_view(wedges, pos)
             pt = G.pair_table(lv.pos, x.shape[0])

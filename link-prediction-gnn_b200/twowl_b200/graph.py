@@ -231,6 +231,19 @@ def build_wedge_struct(n_node: int, pos_edge: torch.Tensor, pred_edge: torch.Ten
                        out_ptr, out_ids, ops.seg_plan(in_ptr, int(n_node), E), ops.seg_plan(out_ptr, int(n_node), E + P))
 
 
+def wedges_match_table(struct: "WedgeStruct", pt: PairTable) -> bool:
+    """Does the factored wedge index describe THIS pair table - pos = [pos_edge^T ; pred_edge^T], the layout of
+    datasets.py:95-99 - so that the factorised kernels (which read the centre / target nodes from the index and the pair
+    endpoints from the table) compute what the explicit [2,T] tensor says? One device comparison per (index, table), cached;
+    a mismatch sends the model to the explicit path, which follows the tensor whatever it holds."""
+    def build():
+        if struct.R != pt.R or struct.n_node > pt.n:
+            return False
+        same = torch.equal(struct.src, pt.src) and torch.equal(struct.dst_e, pt.dst[: struct.E])
+        return bool(same)
+    return _cache.get(struct.src, ("match", pt.src.data_ptr(), pt.R), build)
+
+
 @dataclass
 class LocalityView:
     """The same pair table with its PAIRS (rows 2k, 2k+1 together) regrouped by their higher-degree endpoint, observed edges

@@ -251,7 +251,7 @@ def forward_pairs(model, x, pos, idx, ei2):
     if idx is None:
         raise RuntimeError("row-sharded forward needs idx (the target links)")
     pt = G.pair_table(pos, x.shape[0])
-    wedges = model._wedges(ei2, pt.R)
+    wedges = model._wedges(ei2, pt.R, pt)
     why = supported(model, wedges, x.shape[1])
     if why is None and not pt.mated:
         why = "row sharding needs the doubled pair layout (rows 2k / 2k+1 = (u,v) / (v,u))"
