@@ -290,7 +290,6 @@ def pair_layer(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tensor, gmf:
                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (h_next, O_f, O_r, stats_f, stats_r, SH_f, SH_r); only h_next is differentiable, the rest is saved state."""
     h = h.contiguous()
-    outs = []
     # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
     SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
                               src_scale2=dinv[0])
@@ -373,7 +372,6 @@ def pair_layer_readout(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tens
                        seed_f: int, seed_r: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (pred [L,1], O_f, O_r, stats_f, stats_r, SH_f, SH_r); only pred is differentiable, the rest is saved state."""
     h = h.contiguous()
-    outs = []
     # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
     SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
                               src_scale2=dinv[0])
