@@ -226,6 +226,9 @@ size_t twowl_graphnorm_stats_workspace_bytes(int64_t M, int32_t C);
 int twowl_graphnorm_stats(const float* x, int64_t M, int32_t C, const float* mean_scale, float eps, float* stats,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* Dropout seeds (every `seed*` argument below): a counter-based hash of (seed, element index) decides each element, so the
+ * backward regenerates the forward's mask from the same seed. A seed with bit 63 set is the ADDRESS (low 63 bits) of a device
+ * uint64 holding the seed: a step captured as a CUDA graph keeps its seeds in device memory and refreshes them between replays. */
 /* y = weight*(x - mean_scale*mean)*inv_std + bias ; then dropout(p, seed) if p > 0 ; then ReLU if relu.
  * out = y + (addend ? addend : 0)  - addend carries the other branch of the conv2s + conv2s_r sum of
  * model.py:77; it may alias out. */

@@ -21,7 +21,7 @@ from twowl_b200 import ops
 
 def _seed() -> int:
     # drawn from torch's default CPU generator: reproducible under torch.manual_seed, no device sync
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
+    return ops.next_seed()
 
 
 class _Lin(nn.Module):

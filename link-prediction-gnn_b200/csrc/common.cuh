@@ -119,8 +119,15 @@ __device__ __forceinline__ void f4_add(float4& a, const float4& x) {
 __device__ __forceinline__ float4 f4_mul(const float4& a, const float4& b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
+// A seed argument with bit 63 set is not the seed but the ADDRESS (low 63 bits) of a device uint64 that holds it: a step
+// captured as a CUDA graph bakes its scalar arguments in, so its dropout seeds live in device memory and are refreshed
+// between replays (twowl_b200/graphed.py). Host-drawn seeds are below 2^62.
+__device__ __forceinline__ uint64_t resolve_seed(uint64_t seed) {
+  return (seed >> 63) ? __ldg(reinterpret_cast<const unsigned long long*>(seed & 0x7fffffffffffffffull)) : seed;
+}
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
   // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the dropout mask
+  seed = resolve_seed(seed);
   uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

@@ -442,7 +442,7 @@ def pair_layer_apply(x, wedges, seq_f, seq_r, training: bool):
     cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
     cr, gr = seq_r.modlist[0], seq_r.modlist[1]
     p = dpf.p if (training and dpf.p > 0.0) else 0.0
-    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(2)] if p > 0.0 else [0, 0]
+    seeds = [ops.next_seed() for _ in range(2)] if p > 0.0 else [0, 0]
     _, centre, dinv, selfw, bnode = wedges.prepared()
     out = pair_layer(x, cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight, gr.bias,
                      gr.mean_scale, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr, wedges.out_ids,
@@ -455,7 +455,7 @@ def pair_layer_readout_apply(x, wedges, seq_f, seq_r, training: bool, idx, pred)
     cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
     cr, gr = seq_r.modlist[0], seq_r.modlist[1]
     p = dpf.p if (training and dpf.p > 0.0) else 0.0
-    seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(2)] if p > 0.0 else [0, 0]
+    seeds = [ops.next_seed() for _ in range(2)] if p > 0.0 else [0, 0]
     _, centre, dinv, selfw, bnode = wedges.prepared()
     out = pair_layer_readout(x, cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight,
                              gr.bias, gr.mean_scale, idx, pred.weight, pred.bias, wedges.in_ptr, wedges.in_ids, wedges.in_plan,

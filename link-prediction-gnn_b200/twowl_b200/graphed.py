@@ -8,8 +8,10 @@ reads the device from the host, so the whole step is capturable; the 
 graph with a per-entry mask (graph.MaskedEdges), and the degree feature is the full degree minus the blocked edges' sources.
 
 Replay-time inputs are copied into static buffers (blocked edge ids, readout row ids, labels); outputs are the static loss /
-logits tensors and the parameters' `.grad`. Dropout seeds are drawn on the host at capture time, so a captured step repeats its
-masks: capture with dropout 0 / eval mode, or re-capture per epoch.
+logits tensors and the parameters' `.grad`. Dropout: scalar kernel arguments are baked into a captured graph, so during capture
+the seeds are handed out as ADDRESSES of slots of a device buffer (the kernels read a seed with bit 63 set through that address,
+include/twowl.h), and every replay first refills the buffer with fresh random numbers on the device: new masks per step, forward
+and backward of one step still see the same seeds.
 """
 from __future__ import annotations
 
@@ -17,6 +19,31 @@ import torch
 
 from . import graph as G
 from . import ops
+
+
+class DeviceSeeds:
+    """Dropout seeds in device memory: `provider` hands out the tagged address of the next slot (as the signed int a torch custom
+    op accepts); `refresh()` redraws every slot on the device (no host sync)."""
+    SLOTS = 256
+
+    def __init__(self, device):
+        self.buf = torch.zeros(self.SLOTS, dtype=torch.int64, device=device)
+        self.used = 0
+        self.refresh()
+
+    def provider(self) -> int:
+        if self.used >= self.SLOTS:
+            raise RuntimeError("more dropout seeds in one step than DeviceSeeds.SLOTS")
+        addr = self.buf.data_ptr() + 8 * self.used
+        self.used += 1
+        return addr - (1 << 63)          # bit 63 set, as a signed 64-bit integer
+
+    def refresh(self):
+        self.buf.random_(0, 2 ** 62)
+
+    def values(self):
+        """Host copy of the current seeds (tests: replaying the same step eagerly)."""
+        return [int(v) for v in self.buf.cpu().tolist()]
 
 
 class GraphedTrainStep:
@@ -39,8 +66,17 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = self.logits = None
         self._warmup = warmup
+        self.seeds = DeviceSeeds(dev)
 
     def _body(self):
+        self.seeds.used = 0
+        prev = ops.set_seed_provider(self.seeds.provider)
+        try:
+            self._step()
+        finally:
+            ops.set_seed_provider(prev)
+
+    def _step(self):
         mask = ops.mask_from_idx(self.s_block, self.E)
         x_new = self.deg_src.clone()
         x_new.index_add_(0, self.ei[0].index_select(0, self.s_block), torch.full_like(self.s_block, -1))
@@ -83,6 +119,7 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture(blocked_ids, idx, y)
         self._load(blocked_ids, idx, y)
+        self.seeds.refresh()
         self.graph.replay()
         ops.add_launches(self.launches_per_step)
         for p, g in zip(self.params, self.static_grads):       # the caller may have cleared .grad (optimizer.zero_grad)

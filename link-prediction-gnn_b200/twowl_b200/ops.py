@@ -63,6 +63,24 @@ def _count(n: int = 1):
     _launches += n
 
 
+# ---- dropout seeds: host-drawn by default (reproducible under torch.manual_seed, no device sync); a provider can hand out
+#      device-resident seeds instead (CUDA-graph capture, twowl_b200.graphed)
+_seed_provider = None
+
+
+def next_seed() -> int:
+    if _seed_provider is not None:
+        return _seed_provider()
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def set_seed_provider(fn):
+    """fn() -> int per call (or None to restore the host RNG). Returns the previous provider."""
+    global _seed_provider
+    prev, _seed_provider = _seed_provider, fn
+    return prev
+
+
 def add_launches(n: int):
     """Kernels launched outside the Python wrappers: a CUDA-graph replay of a captured step (twowl_b200.graphed)."""
     _count(int(n))

@@ -282,7 +282,7 @@ def forward_pairs(model, x, pos, idx, ei2):
         cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
         cr, gr = seq_r.modlist[0], seq_r.modlist[1]
         p = dpf.p if (model.training and dpf.p > 0.0) else 0.0
-        seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) for _ in range(2)] if p > 0.0 else [0, 0]
+        seeds = [ops.next_seed() for _ in range(2)] if p > 0.0 else [0, 0]
         par = (cf.lin.weight, cf.bias, gf.weight, gf.bias, gf.mean_scale, cr.lin.weight, cr.bias, gr.weight, gr.bias, gr.mean_scale)
         if i < last:
             H = _ShardedPairLayer.apply(H, *par, shard, loc, rows, blocked_l, pt.R, wedges.n_node, gf.eps, p, seeds[0], seeds[1])
