@@ -63,7 +63,8 @@ def work(args, device="cuda"):
         lr = setting.pop("lr")
         mod = LocalWLNet(max_degree, use_node_attr, trn_ds.na, **setting).to(device)
         opt = Adam(mod.parameters(), lr=lr)
-        val = train.train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, args.epoch, verbose=True, record_dir=record_dir)
+        val = train.train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, args.epoch, verbose=True, record_dir=record_dir,
+                                  cuda_graph=getattr(args, "cuda_graph", False))
         os.makedirs(time_dir, exist_ok=True)
         with open(os.path.join(time_dir, "time_twowl.txt"), "a") as f:
             f.write("Time:" + str(round(time.time() - time_start, 4)) + "\n")
@@ -98,5 +99,6 @@ if __name__ == "__main__":
     ap.add_argument("--trials", type=int, default=10)
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--device", default="cuda")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the training step as one captured CUDA graph")
     a = ap.parse_args()
     print(work(a, a.device))

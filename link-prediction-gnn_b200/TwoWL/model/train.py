@@ -24,10 +24,12 @@ PATH_SAVE_TEST_AUC = "records_auc/"   # constant.py:8 of the reference
 _state = {}
 
 
-def train(mod, opt, dataset, batch_size, i):
+def train(mod, opt, dataset, batch_size, i, step=None):
     """train.py:11-47: one batch = batch_size/2 positive + batch_size/2 negative undirected target links, their edges
     blocked from the graph (sample_block), forward, BCE-with-logits, backward, optimizer step.
-    -> (loss: float, train AUC: float, next batch index: int)."""
+    -> (loss: float, train AUC: float, next batch index: int).
+    step: an optional twowl_b200.graphed.GraphedTrainStep for this dataset / batch size - edge blocking, forward, loss and
+    backward are then ONE replayed CUDA graph (the small graphs are launch-bound otherwise)."""
     mod.train()
     if i == 0:
         _state["pos_bs"] = batch_size // 2
@@ -40,13 +42,17 @@ def train(mod, opt, dataset, batch_size, i):
     y = torch.cat((torch.ones_like(idx1, dtype=torch.float), torch.zeros_like(idx2, dtype=torch.float)), dim=0).unsqueeze(-1)
     idx1 = double(idx1, for_index=True)
     idx2 = double(idx2, for_index=True) + dataset.ei.shape[1]
-    ei_new, x_new, ei2_new = sample_block(idx1, dataset.x.shape[0], dataset.ei, dataset.ei2)
     pos2 = torch.cat((idx1, idx2), dim=0)
 
     opt.zero_grad()
-    pred = mod(x_new, ei_new, dataset.pos1, pos2, ei2_new)
-    loss = F.binary_cross_entropy_with_logits(pred, y)
-    loss.backward()
+    if step is not None:
+        loss = step(idx1, pos2, y)
+        pred = step.logits
+    else:
+        ei_new, x_new, ei2_new = sample_block(idx1, dataset.x.shape[0], dataset.ei, dataset.ei2)
+        pred = mod(x_new, ei_new, dataset.pos1, pos2, ei2_new)
+        loss = F.binary_cross_entropy_with_logits(pred, y)
+        loss.backward()
     opt.step()
 
     with torch.no_grad():
@@ -76,7 +82,7 @@ def test(mod, dataset, test=False, curve=True):
     return result, fpr, tpr
 
 
-def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True, record_dir=PATH_SAVE_TEST_AUC):
+def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True, record_dir=PATH_SAVE_TEST_AUC, cuda_graph=False):
     """train.py:71-135: one batch per epoch (the reference resets train_idx every epoch, train.py:87), validation every
     epoch, test on every validation improvement, early stop after 800 epochs without one; appends
     'AUC:<auc>   Time:<s>   ' to <record_dir><dsname>_auc_record_twowl.txt and keeps fpr.json / tpr.json of the best run."""
@@ -89,6 +95,11 @@ def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True,
     tst_ds.pos1 = tst_ds.pos1.to(torch.long)
     batch_size = val_ds.y.shape[0]
     vprint(f"batch size{batch_size}")
+    step = None
+    if cuda_graph:   # the training step as one replayed CUDA graph (dropout included: device-resident seeds)
+        from twowl_b200.graphed import GraphedTrainStep
+        pb = batch_size // 2
+        step = GraphedTrainStep(mod, trn_ds.x.shape[0], trn_ds.ei, trn_ds.pos1, trn_ds.ei2, n_block=2 * pb, n_links=2 * pb)
 
     best_val, tst_score, early_stop, early_stop_thd = 0, 0, 0, 800
     fpr = tpr = None
@@ -96,7 +107,7 @@ def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True,
     for i in range(epoch):
         train_idx = 0
         t0 = time.time()
-        loss, trn_score, train_idx = train(mod, opt, trn_ds, batch_size, train_idx)
+        loss, trn_score, train_idx = train(mod, opt, trn_ds, batch_size, train_idx, step)
         t1 = time.time()
         val_score, _, _ = test(mod, val_ds, curve=False)
         vprint(f"epoch: {i:03d}, trn: time {t1 - t0:.2f} s, loss {loss:.4f}, trn {trn_score:.4f}, val {val_score:.4f}", end=" ")

@@ -81,3 +81,22 @@ def test_headless_driver_trains_and_writes_the_reference_record_files(cuda, tmp_
     a, fpr, tpr = T.test(mod, tst)
     assert abs(a - sk_auc(fpr, tpr)) < 1e-9
     assert T.test(mod, tst, curve=False)[1] is None
+
+
+def test_train_routine_with_the_step_replayed_as_a_cuda_graph_learns(cuda, tmp_path, monkeypatch):
+    """train_routine(cuda_graph=True): blocking + forward + BCE + backward of every epoch is one replayed graph (dropout on, seeds
+    in device memory); the planted communities must be learned as on the eager path."""
+    import TwoWL.TwoWL_work as W
+    import TwoWL.model.train as T
+    from torch.optim import Adam
+    csv = tmp_path / "edges.csv"
+    _planted_partition_csv(csv)
+    monkeypatch.chdir(tmp_path)
+    args = argparse.Namespace(pattern="2wl_l", csv=str(csv), dataset="planted", seed=0)
+    torch.manual_seed(0)
+    bg, trn, val, tst = W._datasets(args, torch.device("cuda"))
+    mod = W.LocalWLNet(int(bg.x[2].max()), False, None, channels_1wl=64, channels_2wl=32, depth1=2, depth2=1, dp_lin0=0.1,
+                       dp_lin1=0.1, dp_emb=0.1, dp_1wl0=0.1, dp_2wl=0.1, dp_1wl1=0.1).cuda()
+    opt = Adam(mod.parameters(), lr=0.05)
+    best = T.train_routine("planted", mod, opt, trn, val, tst, 300, verbose=False, record_dir=None, cuda_graph=True)
+    assert best > 0.6, best
