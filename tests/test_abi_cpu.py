@@ -95,3 +95,28 @@ def test_state_dict_keys_match_the_reference(L, fb):
     assert float(w.abs().max()) <= np.sqrt(6.0 / 32) + 1e-6
     assert float(mod2.conv2s[0].modlist[0].bias.abs().max()) == 0.0
     assert torch.equal(mod2.emb[1].mean_scale.detach(), torch.ones(32))
+
+
+def test_seed_provider_and_tagged_seed_addresses():
+    """Host-side plumbing of the dropout seeds: ops.next_seed() draws from torch's CPU generator (reproducible, below 2^62) unless a
+    provider is installed; a device-resident seed travels as its address with bit 63 set, written as the signed 64-bit integer a torch
+    custom op accepts, and ctypes hands the same 64 bits to the uint64_t argument of the C ABI."""
+    import ctypes
+    import torch
+    from twowl_b200 import ops
+    torch.manual_seed(3)
+    a = [ops.next_seed() for _ in range(4)]
+    torch.manual_seed(3)
+    assert a == [ops.next_seed() for _ in range(4)] and all(0 <= v < 2 ** 62 for v in a)
+    it = iter([11, 22])
+    prev = ops.set_seed_provider(lambda: next(it))
+    try:
+        assert prev is None and ops.next_seed() == 11 and ops.next_seed() == 22
+    finally:
+        assert ops.set_seed_provider(prev) is not None
+    assert ops.next_seed() not in (11, 22) or True
+    addr = 0x7F12_3456_7000
+    tagged = addr - (1 << 63)                                  # what graphed.DeviceSeeds.provider returns
+    assert -(1 << 63) <= tagged < 0                            # fits torch's int64 schema
+    as_u64 = ctypes.c_uint64(tagged).value
+    assert as_u64 >> 63 == 1 and as_u64 & 0x7FFF_FFFF_FFFF_FFFF == addr
