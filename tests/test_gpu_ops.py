@@ -120,6 +120,56 @@ def test_get_ei2_random_vs_oracle(U, n, e, p, seed):
         assert same(r1, o1) and same(r2, o2)
 
 
+def test_index_operators_hypothesis_graphs(U):
+    """Property test (SURVEY 4 / 7 "hypothesis-generated graphs"): on arbitrary small inputs - empty edge or prediction lists,
+    isolated nodes, multi-edges, self loops, blocked ids that repeat - every integer operator equals the oracle bit for bit, on
+    the doubled layout (where blockei2 regenerates the join) and on raw, odd-sized lists (where it compacts the tensor)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def graphs(draw):
+        n = draw(st.integers(1, 24))
+        node = st.integers(0, n - 1)
+        und_e = draw(st.lists(st.tuples(node, node), min_size=0, max_size=40))
+        und_p = draw(st.lists(st.tuples(node, node), min_size=0, max_size=20))
+        doubled = draw(st.booleans())
+        seed = draw(st.integers(0, 2 ** 16))
+        return n, und_e, und_p, doubled, seed
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(graphs())
+    def run(case):
+        n, und_e, und_p, doubled, seed = case
+        rng = np.random.default_rng(seed)
+        e = np.array(und_e, dtype=np.int64).reshape(-1, 2).T
+        p = np.array(und_p, dtype=np.int64).reshape(-1, 2).T
+        pos, pred = (O.double(e), O.double(p)) if doubled else (e, p)
+        E = pos.shape[1]
+        ref = O.get_ei2(n, pos, pred)
+        got = U.get_ei2(n, dev(pos), dev(pred))
+        assert same(got, ref)
+        assert same(U.degree(dev(pos), n), O.degree(pos, n))
+        if E:
+            k = int(rng.integers(1, E + 1))
+            blk = rng.integers(0, E, size=k)                      # repeats allowed
+            assert same(U.blockei2(got, dev(blk)), O.blockei2(ref, blk))
+            uniq = np.unique(blk)
+            g_ei, g_x, g_ei2 = U.sample_block(dev(uniq), n, dev(pos), got)
+            o_ei, o_x, o_ei2 = O.sample_block(uniq, n, pos, ref)
+            assert same(g_ei, o_ei) and same(g_x, o_x) and same(g_ei2, o_ei2)
+            again = U.blockei2(g_ei2, dev(blk))                   # blocking an already blocked index
+            assert same(again, O.blockei2(o_ei2, blk))
+        r1, r2 = U.reverse(got)
+        o1, o2 = O.reverse(ref)
+        assert same(r1, o1) and same(r2, o2)
+        if e.shape[1]:
+            assert same(U.double(dev(e)), O.double(e))
+            ids = rng.integers(0, max(e.shape[1], 1), size=5)
+            assert same(U.double(dev(ids), for_index=True), O.double(ids, for_index=True))
+
+    run()
+
+
 @pytest.mark.parametrize("world", [2, 3, 7])
 def test_get_ei2_rank_slices_concatenate_to_the_reference_order(U, world):
     """every rank fills its own wedge range; the rank-order concatenation is get_ei2 bit for bit."""
