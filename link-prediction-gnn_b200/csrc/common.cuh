@@ -126,8 +126,8 @@ __device__ __forceinline__ uint64_t resolve_seed(uint64_t seed) {
   return (seed >> 63) ? __ldg(reinterpret_cast<const unsigned long long*>(seed & 0x7fffffffffffffffull)) : seed;
 }
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
-  // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the dropout mask
-  seed = resolve_seed(seed);
+  // splitmix64 finaliser over (seed, element index): counter-based, so the backward regenerates the dropout mask.
+  // `seed` is the VALUE: kernels resolve a tagged seed once at entry (resolve_seed), never per element.
   uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

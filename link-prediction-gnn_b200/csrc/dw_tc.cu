@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
   float* cs = reinterpret_cast<float*>(bars + 16);   // GN: [2 branches][P, Q][C] column constants
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // dropout seeds as VALUES, read once: a tagged seed is the address of a device uint64 (common.cuh). Resolving inside the split
+  // pass - a load the compiler must keep ordered against that pass's stores - cost 3.4 ms of the 14.6 (measured).
+  uint64_t seed_f = 0, seed_r = 0;
+  if (GN && p.thresh) seed_f = resolve_seed(p.seed_f), seed_r = resolve_seed(p.seed_r);
   const int64_t ntiles = (p.M + kDwTileK - 1) / kDwTileK;
   const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   float g = da[c], keep = 1.f;
-                  if (p.thresh) keep = drop_scale(br ? p.seed_r : p.seed_f, e0 + c, p.thresh, p.inv_keep);
+                  if (p.thresh) keep = drop_scale(br ? seed_r : seed_f, e0 + c, p.thresh, p.inv_keep);
                   g *= keep;
                   if (p.relu && !(fmaf(sa[c], xa[c], oa[c]) * keep > 0.f)) g = 0.f;
                   add[c] = sa[c] * g;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_apply(const float* __restri
                                                            const float* __restrict__ bias, const float* __restrict__ mean_scale,
                                                            uint32_t thresh, float inv_keep, uint64_t seed, int relu,
                                                            const float* addend, float* out) {
+  seed = resolve_seed(seed);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   if (rm.slot < 0) return;
   const int c0 = rm.c4 * 4;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
                                                                  const float* __restrict__ mean_scale, uint32_t thresh,
                                                                  float inv_keep, uint64_t seed, int relu,
                                                                  double* __restrict__ part) {
+  seed = resolve_seed(seed);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[2] = {f4_zero(), f4_zero()};
   if (rm.slot >= 0) {
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_dx(const float* __restr
                                                             const float* __restrict__ bias, const float* __restrict__ mean_scale,
                                                             uint32_t thresh, float inv_keep, uint64_t seed, int relu,
                                                             const float* __restrict__ sums, float* __restrict__ dx) {
+  seed = resolve_seed(seed);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   if (rm.slot < 0) return;
   const int c0 = rm.c4 * 4;
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_apply2(const float* __restr
                                                             const float* __restrict__ br, const float* __restrict__ mr,
                                                             uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
                                                             int relu, float* __restrict__ out) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   if (rm.slot < 0) return;
   const int c0 = rm.c4 * 4;
@@ -287,6 +291,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_partial(const float* _
                                                                   const float* __restrict__ br, const float* __restrict__ mr,
                                                                   uint32_t thresh, float inv_keep, uint64_t seed_f, uint64_t seed_r,
                                                                   int relu, double* __restrict__ part) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
   if (rm.slot >= 0) {
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx(const float* __rest
                                                              int relu, const float* __restrict__ sums_f,
                                                              const float* __restrict__ sums_r, float* __restrict__ dxf,
                                                              float* __restrict__ dxr) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   if (rm.slot < 0) return;
   const int c0 = rm.c4 * 4;
@@ -387,6 +393,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float*
                                                                     int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     float* __restrict__ pred) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   constexpr int kPer = 32 / GW;
   const int lane = threadIdx.x & 31, sub = lane / GW, c4 = lane % GW;
   const int cv = C >> 2;
@@ -441,6 +448,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* _
                                                                   int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
                                                                   const float* __restrict__ w, const float* __restrict__ b,
                                                                   float* __restrict__ pred) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const int lane = threadIdx.x & 31;
   const int cv = C >> 2;
   const float4* __restrict__ xf4 = reinterpret_cast<const float4*>(xf);
@@ -480,6 +488,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
                                                                        int relu, const int64_t* __restrict__ idx, int64_t sidx, int64_t L,
                                                                        const float* __restrict__ w, const float* __restrict__ dpred,
                                                                        float* __restrict__ G, double* __restrict__ part) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[6] = {f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero()};
   if (rm.slot >= 0) {
@@ -538,6 +547,7 @@ __global__ void __launch_bounds__(kNormThreads, 3) k_gn_bwd2_dx_rows(const float
                                                                   int relu, const float* __restrict__ sums_f,
                                                                   const float* __restrict__ sums_r, float* __restrict__ dxf,
                                                                   float* __restrict__ dxr) {
+  seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   if (rm.slot < 0) return;
   const int c0 = rm.c4 * 4;
