@@ -71,6 +71,27 @@ def _worker(rank, world, port, out):
         assert N == 101
         assert torch.allclose(mu, full.mean(0), rtol=1e-12, atol=1e-12)
         assert torch.allclose(M2 / N, full.var(0, unbiased=False), rtol=1e-12, atol=1e-12)
+        # 5. row-sharded readout plumbing (twowl_b200.rowshard): every rank contributes the logits of the target links inside
+        #    its row block, ends with the full [L,1] tensor, and gets back the gradient of its own links only; the complete
+        #    GraphNorm / readout parameter gradients stay on rank 0 so that the caller's SUM over ranks is exact
+        sys.path.insert(0, os.path.join(ROOT, "link-prediction-gnn_b200"))
+        from twowl_b200 import rowshard as RS
+        shard = RS.RowShard()
+        assert (shard.rank, shard.world) == (rank, world)
+        L = 11
+        links = torch.arange(L)[rank::world]                                    # this rank's target links
+        pred_l = (links.double() * 10 + rank).reshape(-1, 1).requires_grad_(True)
+        full = RS._ScatterLogits.apply(pred_l, links, L, shard)
+        want = torch.stack([torch.tensor([float(l * 10 + l % world)]) for l in range(L)]).double()
+        assert torch.equal(full.detach(), want)
+        (full * torch.arange(1.0, L + 1).double().reshape(-1, 1)).sum().backward()
+        assert torch.equal(pred_l.grad.reshape(-1), (links + 1).double())
+        C = 3
+        dpf, dpr = torch.arange(4.0 * C), torch.arange(4.0 * C) + 100
+        gf, gr = RS._param_grads(shard, C, dpf.clone(), dpr.clone())
+        tot = torch.cat(gf + gr).clone()
+        dist.all_reduce(tot)
+        assert torch.equal(tot, torch.cat((dpf[3 * C:], dpf[:3 * C], dpr[3 * C:], dpr[:3 * C])))   # counted once
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         out.put((rank, f"{type(e).__name__}: {e}"))
