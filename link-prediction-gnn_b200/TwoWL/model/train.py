@@ -21,7 +21,39 @@ from twowl_b200 import ops
 
 PATH_SAVE_TEST_AUC = "records_auc/"   # constant.py:8 of the reference
 
-_state = {}
+
+class _BatchCursor:
+    """The reference's module-level batch state (train.py:12-23): one permutation of the positive and of the negative undirected
+    pairs per pass over the data, cut into consecutive slices of pos_bs / neg_bs ids. Redrawn whenever train() is called with
+    i == 0 - which train_routine does every epoch (train.py:87)."""
+
+    def __init__(self):
+        self.pos_bs = self.neg_bs = 0
+        self.perm_pos = self.perm_neg = None
+
+    def reset(self, dataset, batch_size):
+        n_edges = dataset.ei.shape[1]
+        dev = dataset.x.device
+        self.pos_bs = self.neg_bs = batch_size // 2
+        self.perm_pos = torch.randperm(n_edges // 2, device=dev)
+        self.perm_neg = torch.randperm((dataset.pos1.shape[0] - n_edges) // 2, device=dev)
+
+    def take(self, dataset, i):
+        """-> (blocked edge ids = the positive pairs' two directions, readout rows [positives | negatives], labels)."""
+        und_pos = self.perm_pos[i * self.pos_bs:(i + 1) * self.pos_bs]
+        und_neg = self.perm_neg[i * self.neg_bs:(i + 1) * self.neg_bs]
+        rows_pos = double(und_pos, for_index=True)
+        rows_neg = double(und_neg, for_index=True) + dataset.ei.shape[1]
+        labels = torch.cat((torch.ones(und_pos.numel(), device=und_pos.device),
+                            torch.zeros(und_neg.numel(), device=und_pos.device))).unsqueeze(-1)
+        return rows_pos, torch.cat((rows_pos, rows_neg)), labels
+
+    def advance(self, i):
+        i += 1
+        return 0 if (i + 1) * self.pos_bs > self.perm_pos.shape[0] else i
+
+
+_cursor = _BatchCursor()
 
 
 def train(mod, opt, dataset, batch_size, i, step=None):
@@ -32,37 +64,24 @@ def train(mod, opt, dataset, batch_size, i, step=None):
     backward are then ONE replayed CUDA graph (the small graphs are launch-bound otherwise)."""
     mod.train()
     if i == 0:
-        _state["pos_bs"] = batch_size // 2
-        _state["neg_bs"] = batch_size // 2
-        _state["perm1"] = torch.randperm(dataset.ei.shape[1] // 2, device=dataset.x.device)
-        _state["perm2"] = torch.randperm((dataset.pos1.shape[0] - dataset.ei.shape[1]) // 2, device=dataset.x.device)
-    pb, nb, perm1, perm2 = _state["pos_bs"], _state["neg_bs"], _state["perm1"], _state["perm2"]
-    idx1 = perm1[i * pb:(i + 1) * pb]
-    idx2 = perm2[i * nb:(i + 1) * nb]
-    y = torch.cat((torch.ones_like(idx1, dtype=torch.float), torch.zeros_like(idx2, dtype=torch.float)), dim=0).unsqueeze(-1)
-    idx1 = double(idx1, for_index=True)
-    idx2 = double(idx2, for_index=True) + dataset.ei.shape[1]
-    pos2 = torch.cat((idx1, idx2), dim=0)
+        _cursor.reset(dataset, batch_size)
+    blocked, rows, y = _cursor.take(dataset, i)
 
     opt.zero_grad()
-    if step is not None:
-        loss = step(idx1, pos2, y)
-        pred = step.logits
-    else:
-        ei_new, x_new, ei2_new = sample_block(idx1, dataset.x.shape[0], dataset.ei, dataset.ei2)
-        pred = mod(x_new, ei_new, dataset.pos1, pos2, ei2_new)
+    if step is None:
+        ei_new, x_new, ei2_new = sample_block(blocked, dataset.x.shape[0], dataset.ei, dataset.ei2)
+        pred = mod(x_new, ei_new, dataset.pos1, rows, ei2_new)
         loss = F.binary_cross_entropy_with_logits(pred, y)
         loss.backward()
+    else:
+        loss = step(blocked, rows, y)
+        pred = step.logits
     opt.step()
 
     with torch.no_grad():
-        # sigmoid is monotone: the AUC of the logits is the AUC of the probabilities (ties included up to fp32 saturation,
-        # so rank the probabilities like the reference does)
-        res = torch.cat((loss.detach().double().reshape(1), ops.auc(pred.sigmoid(), y)[:1])).cpu()
-    i += 1
-    if (i + 1) * pb > perm1.shape[0]:
-        i = 0
-    return float(res[0]), float(res[1]), i
+        # ONE host read for loss and score; the AUC ranks the probabilities like the reference does (train.py:41-43)
+        both = torch.cat((loss.detach().double().reshape(1), ops.auc(pred.sigmoid(), y)[:1])).cpu()
+    return float(both[0]), float(both[1]), _cursor.advance(i)
 
 
 @torch.no_grad()
@@ -70,75 +89,71 @@ def test(mod, dataset, test=False, curve=True):
     """train.py:50-68: full-graph inference, every prediction pair is a target; AUC over one label per undirected pair.
     -> (auc, fpr, tpr); fpr / tpr are None with curve=False (no device->host copy of the scores then)."""
     mod.eval()
-    pred = mod(dataset.x, dataset.ei, dataset.pos1,
-               dataset.ei.shape[1] + torch.arange(dataset.y.shape[0], device=dataset.x.device), dataset.ei2, True)
-    sig = pred.sigmoid()
-    yy = dataset.y.reshape(-1)[0::2][: sig.shape[0]]          # the reference's interleaved True/False mask (train.py:62-64)
-    result = float(ops.auc(sig, yy)[0].item())
-    fpr = tpr = None
-    if curve:
-        from sklearn.metrics import roc_curve
-        fpr, tpr, _ = roc_curve(yy.cpu().numpy(), sig.cpu().numpy().reshape(-1))
-    return result, fpr, tpr
+    n_edges = dataset.ei.shape[1]
+    targets = n_edges + torch.arange(dataset.y.shape[0], device=dataset.x.device)
+    prob = mod(dataset.x, dataset.ei, dataset.pos1, targets, dataset.ei2, True).sigmoid()
+    labels = dataset.y.reshape(-1)[0::2][: prob.shape[0]]     # the reference's interleaved True/False mask (train.py:62-64)
+    score = float(ops.auc(prob, labels)[0].item())
+    if not curve:
+        return score, None, None
+    from sklearn.metrics import roc_curve
+    fpr, tpr, _ = roc_curve(labels.cpu().numpy(), prob.cpu().numpy().reshape(-1))
+    return score, fpr, tpr
+
+
+def _record_run(record_dir, dsname, tst_score, seconds, fpr, tpr):
+    """train.py:108-134: append 'AUC:<auc>   Time:<s>   ' to the dataset's record file; when this run's (unrounded) score is not
+    below any recorded (rounded) one, keep its ROC curve in fpr.json / tpr.json in the working directory."""
+    os.makedirs(record_dir, exist_ok=True)
+    path = os.path.join(record_dir, f"{dsname}_auc_record_twowl.txt")
+    with open(path, "a") as f:
+        f.write(f"AUC:{round(tst_score, 4)}   Time:{round(seconds, 4)}   \n")
+    with open(path) as f:
+        recorded = [float(ln.split()[0].split(":")[1]) for ln in (raw.strip() for raw in f) if ln]
+    if fpr is not None and recorded and tst_score >= max(recorded):
+        for name, curve in (("fpr.json", fpr), ("tpr.json", tpr)):
+            with open(name, "w") as f:
+                json.dump(curve.tolist(), f)
 
 
 def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True, record_dir=PATH_SAVE_TEST_AUC, cuda_graph=False):
     """train.py:71-135: one batch per epoch (the reference resets train_idx every epoch, train.py:87), validation every
     epoch, test on every validation improvement, early stop after 800 epochs without one; appends
     'AUC:<auc>   Time:<s>   ' to <record_dir><dsname>_auc_record_twowl.txt and keeps fpr.json / tpr.json of the best run."""
-    def vprint(*args, **kwargs):
-        if verbose:
-            print(*args, **kwargs)
-
-    trn_ds.pos1 = trn_ds.pos1.to(torch.long)
-    val_ds.pos1 = val_ds.pos1.to(torch.long)
-    tst_ds.pos1 = tst_ds.pos1.to(torch.long)
+    say = print if verbose else (lambda *a, **k: None)
+    for ds in (trn_ds, val_ds, tst_ds):
+        ds.pos1 = ds.pos1.to(torch.long)
     batch_size = val_ds.y.shape[0]
-    vprint(f"batch size{batch_size}")
+    say(f"batch size{batch_size}")
     step = None
     if cuda_graph:   # the training step as one replayed CUDA graph (dropout included: device-resident seeds)
         from twowl_b200.graphed import GraphedTrainStep
-        pb = batch_size // 2
-        step = GraphedTrainStep(mod, trn_ds.x.shape[0], trn_ds.ei, trn_ds.pos1, trn_ds.ei2, n_block=2 * pb, n_links=2 * pb)
+        half = batch_size // 2
+        step = GraphedTrainStep(mod, trn_ds.x.shape[0], trn_ds.ei, trn_ds.pos1, trn_ds.ei2, n_block=2 * half, n_links=2 * half)
 
-    best_val, tst_score, early_stop, early_stop_thd = 0, 0, 0, 800
+    patience = 800                       # epochs without a validation improvement before giving up (train.py:83)
+    best_val = tst_score = 0
+    since_best = 0
     fpr = tpr = None
-    t0 = t1 = 0.0
-    for i in range(epoch):
-        train_idx = 0
-        t0 = time.time()
-        loss, trn_score, train_idx = train(mod, opt, trn_ds, batch_size, train_idx, step)
-        t1 = time.time()
-        val_score, _, _ = test(mod, val_ds, curve=False)
-        vprint(f"epoch: {i:03d}, trn: time {t1 - t0:.2f} s, loss {loss:.4f}, trn {trn_score:.4f}, val {val_score:.4f}", end=" ")
-        early_stop += 1
+    started = finished = 0.0
+    for ep in range(epoch):
+        started = time.time()
+        loss, trn_score, _ = train(mod, opt, trn_ds, batch_size, 0, step)
+        finished = time.time()
+        val_score = test(mod, val_ds, curve=False)[0]
+        line = f"epoch: {ep:03d}, trn: time {finished - started:.2f} s, loss {loss:.4f}, trn {trn_score:.4f}, val {val_score:.4f} "
+        since_best += 1
         if val_score > best_val:
-            early_stop = 0
-            best_val = val_score
+            best_val, since_best = val_score, 0
             if verbose:
-                t0 = time.time()
+                started = time.time()
                 tst_score, fpr, tpr = test(mod, tst_ds, True)
-                t1 = time.time()
-            vprint(f"tst {tst_score:.4f}")
-        else:
-            vprint()
-        if early_stop > early_stop_thd:
+                finished = time.time()
+            line += f"tst {tst_score:.4f}"
+        say(line)
+        if since_best > patience:
             break
-    vprint(f"end test {tst_score:.3f}")
+    say(f"end test {tst_score:.3f}")
     if verbose and record_dir is not None:
-        os.makedirs(record_dir, exist_ok=True)
-        rec = os.path.join(record_dir, f"{dsname}_auc_record_twowl.txt")
-        with open(rec, "a") as f:
-            f.write("AUC:" + str(round(tst_score, 4)) + "   " + "Time:" + str(round(t1 - t0, 4)) + "   " + "\n")
-        values_auc = []
-        with open(rec) as f1:
-            for line in f1:
-                line = line.strip()
-                if line:
-                    values_auc.append(float(line.split()[0].split(":")[1]))
-        if fpr is not None and values_auc and tst_score >= max(values_auc):
-            with open("fpr.json", "w") as f:
-                json.dump(fpr.tolist(), f)
-            with open("tpr.json", "w") as f:
-                json.dump(tpr.tolist(), f)
+        _record_run(record_dir, dsname, tst_score, finished - started, fpr, tpr)
     return best_val
