@@ -54,6 +54,52 @@ def test_index_operators_random_graphs(ref, seed):
     assert np.array_equal(O.double(k, True), ref.utils.double(torch.from_numpy(k), True).numpy())
 
 
+def test_index_operators_hypothesis_graphs(ref):
+    """The same pin over hypothesis-generated inputs: multi-edges, self loops, isolated nodes, an empty prediction list, blocked ids
+    that repeat - the oracle must equal the UNMODIFIED reference functions (TorchScript, utils.py:8-90) bit for bit."""
+    import warnings
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def graphs(draw):
+        n = draw(st.integers(1, 20))
+        node = st.integers(0, n - 1)
+        und_e = draw(st.lists(st.tuples(node, node), min_size=1, max_size=30))
+        und_p = draw(st.lists(st.tuples(node, node), min_size=0, max_size=15))
+        return n, und_e, und_p, draw(st.booleans()), draw(st.integers(0, 2 ** 16))
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(graphs())
+    def run(case):
+        n, und_e, und_p, doubled, seed = case
+        rng = np.random.default_rng(seed)
+        e = np.array(und_e, dtype=np.int64).reshape(-1, 2).T
+        p = np.array(und_p, dtype=np.int64).reshape(-1, 2).T
+        pos, pred = (O.double(e), O.double(p)) if doubled else (e, p)
+        tp, tq = torch.from_numpy(pos), torch.from_numpy(pred)
+        ei2_ref = ref.utils.get_ei2(n, tp, tq)
+        ei2 = O.get_ei2(n, pos, pred)
+        assert np.array_equal(ei2, ei2_ref.numpy().reshape(2, -1))
+        assert np.array_equal(O.degree(pos, n), ref.utils.degree(tp, n).numpy())
+        blk = rng.integers(0, pos.shape[1], size=int(rng.integers(1, pos.shape[1] + 1)))      # repeats allowed
+        if ei2.shape[1]:
+            assert np.array_equal(O.blockei2(ei2, blk), ref.utils.blockei2(ei2_ref, torch.from_numpy(blk)).numpy())
+            a, b = O.reverse(ei2)
+            ra, rb = ref.utils.reverse(ei2_ref)
+            assert np.array_equal(a, ra.numpy()) and np.array_equal(b, rb.numpy())
+        uniq = np.unique(blk)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r_ei, r_x, r_ei2 = ref.utils.sample_block(torch.from_numpy(uniq), n, tp, ei2_ref if ei2.shape[1] else None)
+        o_ei, o_x, o_ei2 = O.sample_block(uniq, n, pos, ei2 if ei2.shape[1] else None)
+        assert np.array_equal(o_ei, r_ei.numpy()) and np.array_equal(o_x, r_x.numpy())
+        if o_ei2 is not None:
+            assert np.array_equal(o_ei2, r_ei2.numpy())
+        assert np.array_equal(O.double(e), ref.utils.double(torch.from_numpy(e)).numpy())
+
+    run()
+
+
 @pytest.mark.parametrize("cfg", [dict(c1=32, c2=16, d1=1, d2=1, a0=True, a1=True),
                                  dict(c1=24, c2=24, d1=3, d2=2, a0=False, a1=True)])
 def test_model_forward_backward_matches_reference_module(ref, cfg):
