@@ -86,6 +86,12 @@ int twowl_ei2_fill_rows(const int64_t* in_ptr, const int32_t* in_ids, const int6
 /* idx2mask (utils.py:53-57): mask[0..num) = 0 then mask[idx[j]] = 1 (uint8). */
 int twowl_mask_from_idx(const int64_t* idx, int64_t k, uint8_t* mask, int64_t num, void* stream);
 
+/* The bounds rule of the reference's advanced indexing `x[idx]` (model.py:78 readout rows, model.py:75 pair endpoints): an id
+ * in [-num, 0) wraps to id + num, anything else outside [0, num) is an IndexError there. out[i] (int64[k], contiguous) = the
+ * wrapped id, or 0 for an invalid one so that no consumer kernel can read out of bounds; bad[0] (int32, zeroed by the call) =
+ * the number of invalid ids, which the caller turns into an error (a device-side assertion on the Python side: no host sync). */
+int twowl_index_guard(const int64_t* idx, int64_t stride, int64_t k, int64_t num, int64_t* out, int32_t* bad, void* stream);
+
 /* Order-preserving column selection of a [2,T] int64 matrix (blockei2 utils.py:48-50; the ei filter of
  * sample_block utils.py:62-63):
  *   mode 0: keep column t iff !mask[t]            mode 1: keep column t iff !mask[row0[t]]

@@ -1,6 +1,7 @@
 """Headless replacement for the reference's TwoWL/TwoWL_work.py: the same ``work(args, device)`` /
 ``read_results_twowl()`` entry points and the same result files (records_auc/<ds>_auc_record_twowl.txt,
-<time_dir>/time_twowl.txt, logs.json), without Streamlit widgets and without Optuna (neither is installable offline):
+<time_dir>/time_twowl.txt, logs.json = the best trial's parameters as one flat dict, as `json.dump(study.best_params)` writes it
+at TwoWL_work.py:140-144), without Streamlit widgets and without Optuna (neither is installable offline):
 hyper-parameters are drawn from the reference's search space (TwoWL_work.py:67-79) with a seeded ``random.Random``.
 
     python -m TwoWL.TwoWL_work --csv raw_data/fb-pages-food/fb-pages-food.csv --trials 10 --epoch 1000 --device cuda
@@ -70,13 +71,22 @@ def work(args, device="cuda"):
             f.write("Time:" + str(round(time.time() - time_start, 4)) + "\n")
         if val > best["value"]:
             best = {"value": val, "params": params}
-    with open("logs.json", "w") as f:                # TwoWL_work.py:140-144
-        json.dump({"best_params": best["params"], "best_value": best["value"]}, f)
+    with open("logs.json", "w") as f:                # TwoWL_work.py:140-144: study.best_params, dumped flat
+        json.dump(best["params"], f)
     return {"best_params": best["params"], "best_val": best["value"]}
 
 
+def read_results(dsname="fb-pages-food", record_dir=train.PATH_SAVE_TEST_AUC, time_dir=PATH_TIME_TWOWL, log_file="logs.json"):
+    """TwoWL_work.py:152-176 with the reference's return value: (best parameters from logs.json, best test AUC of the record
+    file, average trial wall time)."""
+    with open(log_file) as f:
+        logs = json.load(f)
+    aucs, _, walls = read_results_twowl(dsname, record_dir, time_dir)
+    return logs, max(aucs, default=0.0), sum(walls) / len(walls)
+
+
 def read_results_twowl(dsname="fb-pages-food", record_dir=train.PATH_SAVE_TEST_AUC, time_dir=PATH_TIME_TWOWL):
-    """TwoWL_work.py:152-176 without the plotting: (test AUCs, inference times, trial wall times) from the record files."""
+    """The raw series behind read_results: (test AUCs, inference times, trial wall times) from the record files."""
     aucs, infer, walls = [], [], []
     rec = os.path.join(record_dir, f"{dsname}_auc_record_twowl.txt")
     if os.path.isfile(rec):

@@ -225,7 +225,10 @@ class LocalWLNet(nn.Module):
         if self.row_shard is not None and self.row_shard.world > 1:
             from twowl_b200 import rowshard
             return rowshard.forward_pairs(self, x, pos, idx, ei2)
-        pt = G.pair_table(pos, x.shape[0])
+        pt = G.pair_table(pos, x.shape[0])             # validates pos against x's rows once per table (IndexError as model.py:75)
+        if idx is not None:
+            # x[idx] of model.py:78: ids in [-R, 0) wrap, anything else out of range is a device-side assertion (no host sync)
+            idx = ops.index_guard(idx, pt.R, "idx")
         wedges = self._wedges(ei2, pt.R, pt) if len(self.conv2s) else None
         if self.pair_locality and isinstance(wedges, G.WedgeStruct) and pt.mated and idx is not None:
             lv = G.locality_view(wedges, pos)

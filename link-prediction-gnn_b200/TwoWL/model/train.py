@@ -119,7 +119,11 @@ def _record_run(record_dir, dsname, tst_score, seconds, fpr, tpr):
 def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True, record_dir=PATH_SAVE_TEST_AUC, cuda_graph=False):
     """train.py:71-135: one batch per epoch (the reference resets train_idx every epoch, train.py:87), validation every
     epoch, test on every validation improvement, early stop after 800 epochs without one; appends
-    'AUC:<auc>   Time:<s>   ' to <record_dir><dsname>_auc_record_twowl.txt and keeps fpr.json / tpr.json of the best run."""
+    'AUC:<auc>   Time:<s>   ' to <record_dir><dsname>_auc_record_twowl.txt and keeps fpr.json / tpr.json of the best run.
+    One deliberate deviation: the reference's `fpr, tpr` are overwritten by every epoch's VALIDATION call (train.py:91), so its
+    fpr.json / tpr.json hold the last epoch's validation curve (the checked-in files have 1/96 steps); here the
+    validation call skips the curve (no device->host copy of the scores per epoch) and the files hold the TEST curve of the
+    best validation epoch - the curve the recorded AUC belongs to."""
     say = print if verbose else (lambda *a, **k: None)
     for ds in (trn_ds, val_ds, tst_ds):
         ds.pos1 = ds.pos1.to(torch.long)

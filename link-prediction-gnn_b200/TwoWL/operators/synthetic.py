@@ -42,7 +42,9 @@ def sample_non_edges(keys_sorted: torch.Tensor, n: int, count: int, generator: t
     dev = keys_sorted.device
     m = keys_sorted.numel()
     neg = torch.empty(0, dtype=torch.int64, device=dev)
-    while neg.numel() < count:
+    for _ in range(64):      # bounded, like datasets.negative_sampling: a near-complete graph cannot supply `count` non-edges
+        if neg.numel() >= count:
+            break
         k = int(1.2 * (count - neg.numel())) + 64
         r = torch.randint(0, n, (k,), generator=generator, device=dev)
         c = torch.randint(0, n, (k,), generator=generator, device=dev)
@@ -52,6 +54,8 @@ def sample_non_edges(keys_sorted: torch.Tensor, n: int, count: int, generator: t
             p = torch.searchsorted(keys_sorted, cand).clamp_(max=m - 1)
             cand = cand[keys_sorted[p] != cand]
         neg = torch.unique(torch.cat((neg, cand)))
+    if neg.numel() < count:
+        raise ValueError(f"only {neg.numel()} of the {count} requested non-edges exist / were found in 64 rounds")
     return neg[torch.randperm(neg.numel(), generator=generator, device=dev)[:count]]
 
 

@@ -11,11 +11,12 @@
 // One persistent CTA per SM, 14 warps, warp-specialised:
 //   warp  0    TMA producer: raw fp32 tiles of dO_f, dO_r, H with cp.async.bulk.tensor (SWIZZLE_128B_ATOM_32B tensor maps
 //                            = the one MN-major layout the tensor core accepts for tf32, see below), L2 evict-first
-//   warps 2-9  split       : A: v = selfw[row] * raw written back in place (the tensor core truncates it to tf32 = the `hi`
-//                            operand) and lo = v - trunc(v) into a second buffer; B: lo only (raw H is its own hi)
-//   warp  1    MMA issuer  : 3 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
-//   warps 10-13 drain      : TMEM -> fp32 registers (1024-row partial sums), per-CTA partials to global memory; a second
-//                            kernel adds them in double in CTA order: deterministic.
+//   warps 2-9  split       : A: v = selfw[row] * raw, hi = rn_tf32(v) written back in place, lo = rn_tf32(v - hi) into a second
+//                            buffer; B: the same split of the H tile (hi in place)
+//   warp  1    MMA issuer  : 4 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
+//   warps 10-13 drain      : TMEM -> fp32 registers after every tile (C <= 64), 64 tiles per addition into the CTA's double
+//                            partials in global memory; a second kernel adds the partials in double in CTA order:
+//                            deterministic.
 #include "common.cuh"
 
 namespace twowl {
@@ -30,16 +31,21 @@ constexpr int kDwStages = 2;
 // TMEM between drains (1024 rows)
 __host__ __device__ constexpr int dw_tile_k(int C) { return C <= 64 ? 64 : 32; }
 __host__ __device__ constexpr int dw_nacc(int C) { return C <= 64 ? 1 : 2; }
-// (the tensor core's fp32 accumulate TRUNCATES: the error of a TMEM-resident sum grows linearly with the number of
-// accumulate steps - 2048 rows at C = 128 measured 1.6e-5 relative - so both widths drain after 384 MMA steps)
-__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? 16 : 32; }
+// The tensor core's fp32 accumulate TRUNCATES: a TMEM-resident sum loses about half an ulp of its own magnitude per
+// accumulate step, always towards zero (2048 rows at C = 128 measured 1.6e-5 relative in round 1, when both widths drained
+// after 384 steps). C <= 64 therefore drains after EVERY tile: the accumulator restarts at zero, the three small products
+// (lo*lo, lo*hi, hi*lo) are added while it is still small, and only the 8 hi*hi steps run at full magnitude (~5e-7
+// relative); the drain warps add the tiles in fp32 registers, 64 tiles at a time, into per-CTA DOUBLE partials. C = 128
+// (two 128 x 128 accumulators, no room in registers: the running sums live in `part`) drains every 4 tiles.
+__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? 1 : 4; }
+constexpr int kDwRegTiles = 64;   // C <= 64: tiles added in fp32 registers between two additions into the double partials
 __host__ __device__ constexpr int dw_part_rows(int C) { return C <= 64 ? 128 : 2 * C; }
 
 struct DwParams {
   const float* rsf;
   const float* rsr;
   int64_t M;
-  float* part;  // [gridDim.x][dw_part_rows(C)][C]
+  float* part;  // [gridDim.x][dw_part_rows(C)][C]: fp32 running sums (C = 128), or the same shape in double (C <= 64)
   // GN = true: the A tiles are the OUTPUTS O_f, O_r of the last pair layer and the gradients are made on the fly
   // (twowl_pair_dw_gn): dO = P * O + Q (+ sc * g_y on the rows the readout selected), written to dOf / dOr as well
   const float* consts;   // [2 branches][4][C] = (P, Q, sc, of), twowl_gn2_readout_bwd_prepare
@@ -129,12 +135,22 @@ __device__ __forceinline__ bool dw_elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ float dw_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// tf32 split of both operands, round-to-nearest: x = hi + lo + r, hi = rn_tf32(x), lo = rn_tf32(x - hi), |r| <= 2^-22 |x|
+// (see pair_conv.cu); four products hi*hi + hi*lo + lo*hi + lo*lo.
+__device__ __forceinline__ float dw_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo) {
+  hi.x = dw_rna(v.x), hi.y = dw_rna(v.y), hi.z = dw_rna(v.z), hi.w = dw_rna(v.w);
+  lo.x = dw_rna(v.x - hi.x), lo.y = dw_rna(v.y - hi.y), lo.z = dw_rna(v.z - hi.z), lo.w = dw_rna(v.w - hi.w);
+}
 
 // C = width of dO_f, dO_r and H (32, 64 or 128). One stage:
 //   A_hi: AG groups of 32 M-elements ([f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
 template <int C, bool GN>
-__global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
+__global__ void __maxnreg__(144) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
                                                          const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmH) {
   constexpr int GS = C / 32;                          // 32-column groups per source
   constexpr int kDwTileK = dw_tile_k(C), NACC = dw_nacc(C), kDwFlush = dw_flush(C);
@@ -246,9 +262,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
 #pragma unroll
         for (int ac = 0; ac < NACC; ++ac) {   // C = 128: D_f from the f groups of A, D_r from the r groups
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint64_t Ap = ((pass == 0) ? Alo : Ahi) + (uint64_t)(ac * GS * (kDwLbo >> 4));
-            const uint64_t Bp = (pass == 1) ? Blo : Bhi;
+          for (int pass = 0; pass < 4; ++pass) {   // lo*lo, lo*hi, hi*lo, hi*hi: small terms first
+            const uint64_t Ap = ((pass < 2) ? Alo : Ahi) + (uint64_t)(ac * GS * (kDwLbo >> 4));
+            const uint64_t Bp = (pass == 0 || pass == 2) ? Blo : Bhi;
 #pragma unroll
             for (int k = 0; k < kDwTileK / 8; ++k)   // one group of 8 k-rows per K-step
               dw_mma(tmem_base + (uint32_t)(a * TB + ac * C), Ap + (uint64_t)(k * (kDwKStep >> 4)), Bp + (uint64_t)(k * (kDwKStep >> 4)),
@@ -326,7 +342,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
       load_heads(row0 + 2 * tstride, it + 2 < my_tiles, hdnn);
       float4* Ahi = reinterpret_cast<float4*>(smem + st * kStage);
       float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
-      const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
+      float4* Bhi = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf);
       float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
       // one branch (f, then r) at a time: RPT rows x GS column groups per thread
 #pragma unroll
@@ -404,16 +420,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
             }
             const float sc = br ? sr[q] : sf[q];
             x.x *= sc, x.y *= sc, x.z *= sc, x.w *= sc;
-            Ahi[j * kSplitThreads + t] = x;
-            Alo[j * kSplitThreads + t] = make_float4(dw_lo(x.x), dw_lo(x.y), dw_lo(x.z), dw_lo(x.w));
+            float4 hi, lo;
+            dw_split(x, hi, lo);
+            Ahi[j * kSplitThreads + t] = hi;
+            Alo[j * kSplitThreads + t] = lo;
           }
         }
       }
 #pragma unroll 4
       for (int j = 0; j < kBIter; ++j) {
         const int i = j * kSplitThreads + t;
-        const float4 v = Bhi[i];
-        Blo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
+        float4 hi, lo;
+        dw_split(Bhi[i], hi, lo);
+        Bhi[i] = hi;
+        Blo[i] = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       dw_mbar_arrive(&split_done[st]);
@@ -426,6 +446,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
       float acc[C];
 #pragma unroll
       for (int i = 0; i < C; ++i) acc[i] = 0.f;
+      // this thread's row of the CTA's double partials: written by this thread only, L2-resident
+      double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.part) + ((size_t)blockIdx.x * 128 + ew * 32 + lane) * C);
+      bool first = true;
+      int since = 0;
       for (int64_t grp = 0; grp < ngroups; ++grp) {
         const int a = (int)(grp & 1);
         dw_mbar_wait(&tfull[a], (uint32_t)((grp >> 1) & 1));
@@ -440,10 +464,24 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         dw_mbar_arrive(&tempty[a]);
-      }
-      float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.x * 128 + ew * 32 + lane) * C);
+        if (++since == kDwRegTiles || grp + 1 == ngroups) {
 #pragma unroll
-      for (int q = 0; q < C / 4; ++q) dst[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+          for (int q = 0; q < C / 2; ++q) {
+            double2 o = make_double2((double)acc[2 * q], (double)acc[2 * q + 1]);
+            if (!first) {
+              const double2 prev = dst[q];
+              o.x += prev.x, o.y += prev.y;
+            }
+            dst[q] = o;
+            acc[2 * q] = 0.f, acc[2 * q + 1] = 0.f;
+          }
+          first = false, since = 0;
+        }
+      }
+      if (ngroups == 0) {   // a CTA without tiles still owns a slice of the partials
+#pragma unroll
+        for (int q = 0; q < C / 2; ++q) dst[q] = make_double2(0.0, 0.0);
+      }
     } else {
       // two 128 x C accumulators do not fit a thread's registers: the running sums live in this CTA's slice of `part`
       // (L2-resident: read-add-write by the owning thread every kDwFlush tiles)
@@ -486,7 +524,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
 }
 
 // dW_f[co][ci] = sum_cta part[cta][co][ci], dW_r = rows C..2C-1, added in CTA order in double
-__global__ void k_dw_tc_final(const float* __restrict__ part, int nparts, int C, int prows, float* __restrict__ dWf,
+template <typename T>
+__global__ void k_dw_tc_final(const T* __restrict__ part, int nparts, int C, int prows, float* __restrict__ dWf,
                               float* __restrict__ dWr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * C * C) return;
@@ -534,14 +573,18 @@ static int dw_dispatch(const DwParams& p, int C, const float* Af, const float* A
                  : C == 64 ? dw_launch<64, GN>(p, Af, Ar, H, s, ldA, ldH)
                            : dw_launch<128, GN>(p, Af, Ar, H, s, ldA, ldH);
   if (rc) return rc;
-  k_dw_tc_final<<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>(p.part, dw_grid(p.M, C), C, dw_part_rows(C), dWf, dWr);
+  if (dw_nacc(C) == 1)
+    k_dw_tc_final<double><<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>(reinterpret_cast<const double*>(p.part), dw_grid(p.M, C), C,
+                                                                   dw_part_rows(C), dWf, dWr);
+  else
+    k_dw_tc_final<float><<<(int)cdiv(2 * C * C, 256), 256, 0, s>>>(p.part, dw_grid(p.M, C), C, dw_part_rows(C), dWf, dWr);
   TW_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" size_t twowl_pair_dw_workspace_bytes(int64_t M, int32_t C) {
   (void)M;
-  return align_up((size_t)kNumSMs * (size_t)dw_part_rows(C) * (size_t)C * sizeof(float));
+  return align_up((size_t)kNumSMs * (size_t)dw_part_rows(C) * (size_t)C * (dw_nacc(C) == 1 ? sizeof(double) : sizeof(float)));
 }
 
 extern "C" int twowl_pair_dw(const float* dOf, const float* dOr, const float* rsf, const float* rsr, const float* H, int64_t M,

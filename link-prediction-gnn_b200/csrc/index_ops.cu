@@ -159,6 +159,23 @@ __global__ void __launch_bounds__(kThreads) k_mask_scatter(const int64_t* __rest
   }
 }
 
+// x[idx] semantics of the reference's advanced indexing (model.py:78, utils.py:55): an id in [-num, 0) wraps, anything else
+// outside [0, num) is an error. out[i] = the wrapped id (0 for an invalid one, so that no consumer can read out of bounds) and
+// bad[0] counts the invalid ids - the caller turns a non-zero count into a device-side assertion / an IndexError.
+__global__ void __launch_bounds__(kThreads) k_index_guard(const int64_t* __restrict__ idx, int64_t stride, int64_t k, int64_t num,
+                                                          int64_t* __restrict__ out, int32_t* __restrict__ bad) {
+  int nbad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = idx[i * stride];
+    if (v < 0) v += num;
+    const bool ok = v >= 0 && v < num;
+    nbad += !ok;
+    out[i] = ok ? v : 0;
+  }
+  nbad = __reduce_add_sync(0xffffffffu, nbad);
+  if ((threadIdx.x & 31) == 0 && nbad) atomicAdd(bad, nbad);
+}
+
 // tile = 2048 columns = 8 rounds of 256 threads (round r, thread i -> column base + r*256 + i: coalesced). All rounds' keys are
 // requested before any mask byte is looked up, and the order-preserving ranks come from ONE block-wide prefix over the 8 x 8
 // (round, warp) ballot counts - two barriers per tile instead of three per round.
@@ -435,6 +452,18 @@ extern "C" int twowl_mask_from_idx(const int64_t* idx, int64_t k, uint8_t* mask,
   if (num > 0) TW_CUDA(cudaMemsetAsync(mask, 0, (size_t)num, s));
   if (k > 0 && num > 0) {
     k_mask_scatter<<<grid_for(k, kThreads), kThreads, 0, s>>>(idx, k, mask, num);
+    TW_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int twowl_index_guard(const int64_t* idx, int64_t stride, int64_t k, int64_t num, int64_t* out, int32_t* bad,
+                                 void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  TW_CHECK_ARG(bad != nullptr && (k == 0 || (idx && out)), "index_guard: null argument");
+  TW_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), s));
+  if (k > 0) {
+    k_index_guard<<<grid_for(k, kThreads), kThreads, 0, s>>>(idx, stride, k, num, out, bad);
     TW_LAUNCH_CHECK();
   }
   return 0;

@@ -13,10 +13,10 @@
 //   warp  0    TMA producer: one lane streams raw fp32 128-row tiles of A_s into a ring of shared-memory stages with
 //                            cp.async.bulk.tensor (SWIZZLE_128B tensor map = the UMMA canonical K-major layout, L2
 //                            evict-first), 2-3 tiles in flight per SM
-//   warps 2-3  split       : lo = x - trunc_tf32(x) of a landed tile into a second buffer (smem -> smem). The tensor
-//                            core TRUNCATES fp32 operands to tf32 (measured, tools/mma_probe.cu), so the raw tile IS
-//                            the `hi` operand of the 3xTF32 scheme and is never rewritten
-//   warp  1    MMA issuer  : one lane issues 3 x Kd/8 tcgen05.mma kind::tf32 per source (lo*hi, hi*lo, hi*hi) into that
+//   warps 2-3  split       : hi = rn_tf32(x) written back IN PLACE, lo = rn_tf32(x - hi) into a second buffer (smem -> smem):
+//                            both exactly representable in tf32, so the tensor core's truncation of fp32 operands
+//                            (measured, tools/mma_probe.cu) loses nothing
+//   warp  1    MMA issuer  : one lane issues 4 x Kd/8 tcgen05.mma kind::tf32 per source (lo*lo, lo*hi, hi*lo, hi*hi) into that
 //                            source's TMEM accumulator (double buffered); tcgen05.commit releases the stages / publishes
 //   warps 4-11 epilogue    : (4 TMEM lane quarters x 2 column halves) gathered rows requested before the accumulator
 //                            is waited for; tcgen05.ld -> row scale, source sum -> per-warp smem transpose -> coalesced
@@ -124,13 +124,18 @@ __device__ __forceinline__ float4 pc_ldg_keep(const float4* p, uint64_t policy) 
 }
 __device__ __forceinline__ void pc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pc_sw128(int r, int c) { return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4)); }
-__device__ __forceinline__ float pc_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// The tf32 split of both GEMM operands: x = hi + lo + r with hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32),
+// |r| <= 2^-11 |x - hi| <= 2^-22 |x|, unbiased. Both parts are tf32 numbers, so the tensor core (which TRUNCATES fp32 operands
+// to tf32, tools/mma_probe.cu) reads them exactly, and the four products hi*hi + hi*lo + lo*hi + lo*lo carry a relative error
+// <= 2^-21 per product - against 3 * 2^-20, biased, for the truncating three-product scheme this replaces (round 1).
+__device__ __forceinline__ float pc_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
+  hi.x = pc_rna(v.x), hi.y = pc_rna(v.y), hi.z = pc_rna(v.z), hi.w = pc_rna(v.w);
+  lo.x = pc_rna(v.x - hi.x), lo.y = pc_rna(v.y - hi.y), lo.z = pc_rna(v.z - hi.z), lo.w = pc_rna(v.w - hi.w);
 }
 // One lane of a converged warp. The single-thread instructions (TMA, tcgen05.mma / commit) are issued under this predicate
 // with the WHOLE warp running the surrounding loop on warp-uniform values: the compiler then keeps descriptors and
@@ -303,22 +308,23 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
             if (ns == 1 && Kd - kb * 32 >= 32) {
               // one full slab per stage (the 16 KB ring of the wide two-source launches)
 #pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 1) ? blo : bhi;
+              for (int pass = 0; pass < 4; ++pass) {
+                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   pc_mma(tacc, Ap + (uint64_t)(k * 2), Bp + (uint64_t)(k * 2), idesc, acc);
                   acc = 1;
                 }
-                if (pass == 0) pc_commit(&lo_empty[l.slot]);
+                if (pass == 1) pc_commit(&lo_empty[l.slot]);
               }
             } else if (ns == kPcGroup && Kd - kb * 32 >= kPcGroup * 32) {
-              // full stage: 3 passes (lo*hi, hi*lo, hi*hi: small terms first) x 2 slabs x 4 k-steps, back to back
+              // full stage: 4 passes (lo*lo, lo*hi, hi*lo, hi*hi: small terms first - the accumulator's own truncation is
+              // relative to its magnitude) x 2 slabs x 4 k-steps, back to back
 #pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 1) ? blo : bhi;
+              for (int pass = 0; pass < 4; ++pass) {
+                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
 #pragma unroll
                 for (int j = 0; j < kPcGroup; ++j) {
 #pragma unroll
@@ -327,12 +333,12 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
                     acc = 1;
                   }
                 }
-                if (pass == 0) pc_commit(&lo_empty[l.slot]);  // the lo stage is free once the first pass has read it
+                if (pass == 1) pc_commit(&lo_empty[l.slot]);  // the lo stage is free once the two passes that read it are done
               }
             } else {
-              for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 1) ? blo : bhi;
+              for (int pass = 0; pass < 4; ++pass) {
+                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
                 for (int j = 0; j < ns; ++j) {
                   const int rem = Kd - (kb + j) * 32;
                   const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;   // 8 k-values per tf32 MMA; the padding is zero on both sides
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
                     acc = 1;
                   }
                 }
-                if (pass == 0) pc_commit(&lo_empty[l.slot]);
+                if (pass == 1) pc_commit(&lo_empty[l.slot]);
               }
             }
             pc_commit(&raw_empty[r.slot]);  // stage reusable once these MMAs have read it
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
       __syncwarp();
     }
   } else if (warp < kPcFirstEpi) {
-    // ===================================================== split: lo = x - trunc_tf32(x), same (swizzled) offsets
+    // ===================================================== split: hi in place, lo into the lo ring, same (swizzled) offsets
     const int t = tid - kPcFirstSplit * 32;  // 0..63
     constexpr int kSplitThreads = kPcSplitWarps * 32;
     constexpr int kBatch = (int)(kPcSlab / 16u) / kSplitThreads;     // 16 float4 per thread per slab
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
       for (int gi = 0; gi < ngroups; ++gi) {
         const int ns = KB - gi * G < G ? KB - gi * G : G;
         pc_mbar_wait(&raw_full[r.slot], r.phase);
-        const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)r.slot * kStage);
+        float4* __restrict__ src = reinterpret_cast<float4*>(As + (size_t)r.slot * kStage);
         float4* __restrict__ dst = reinterpret_cast<float4*>(Ls + (size_t)l.slot * kStage);
         float4 x[kBatch];
 #pragma unroll
@@ -373,8 +379,12 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         pc_mbar_wait(&lo_empty[l.slot], l.phase ^ 1u);
         for (int b = 0; b < ns; ++b) {
 #pragma unroll
-          for (int j = 0; j < kBatch; ++j)
-            dst[(b * kBatch + j) * kSplitThreads + t] = make_float4(pc_lo(x[j].x), pc_lo(x[j].y), pc_lo(x[j].z), pc_lo(x[j].w));
+          for (int j = 0; j < kBatch; ++j) {
+            float4 hi, lo;
+            pc_split(x[j], hi, lo);
+            src[(b * kBatch + j) * kSplitThreads + t] = hi;   // in place: the MMA reads the stage only after lo_full
+            dst[(b * kBatch + j) * kSplitThreads + t] = lo;
+          }
           if (b + 1 < ns) {
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) x[j] = src[((b + 1) * kBatch + j) * kSplitThreads + t];
@@ -571,6 +581,19 @@ __global__ void k_pc_stats_final(const double* __restrict__ part, int nparts, in
   stats[C + c] = (float)(1.0 / sqrt(var + (1.0 - a) * (1.0 - a) * mean * mean + (double)eps));
 }
 
+// tuning knobs from the environment (TWOWL_PC_STAGES, TWOWL_PC_NSPLIT), read ONCE per process - not on every launch
+struct PcEnv {
+  int stages = 0, nsplit = 0;
+  PcEnv() {
+    if (const char* e = getenv("TWOWL_PC_STAGES")) stages = atoi(e);
+    if (const char* e = getenv("TWOWL_PC_NSPLIT")) nsplit = atoi(e);
+  }
+};
+static const PcEnv& pc_env() {
+  static const PcEnv env;
+  return env;
+}
+
 // How one launch is cut: column windows of Nsub (multiple of 16) output columns per CTA, raw / lo ring depths.
 struct PcConfig {
   int nsplit = 0, Nsub = 0, stages = 0, lo_stages = 0, tmem_cols = 0, group = kPcGroup;
@@ -606,18 +629,14 @@ static PcConfig pc_config(int Kd, int Nd, int nsrc, bool with_stats, int force_n
       if (pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo, grp) > cap) continue;
     }
     while (st < kPcMaxStages && pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st + 1, lo, grp) <= cap) ++st;
-    if (const char* e = getenv("TWOWL_PC_STAGES")) st = atoi(e) < st ? (atoi(e) < 2 ? 2 : atoi(e)) : st;   // tuning knob
-    if (const char* e = getenv("TWOWL_PC_LO")) lo = atoi(e) >= 2 ? lo : 1;
+    if (pc_env().stages > 0) st = pc_env().stages < st ? (pc_env().stages < 2 ? 2 : pc_env().stages) : st;   // tuning knob
     best.nsplit = ns, best.Nsub = Nsub, best.stages = st, best.lo_stages = lo, best.group = grp;
     best.tmem_cols = pc_tmem_cols(Nsub, nsrc);
     best.smem = pc_smem_bytes(Kd, Nsub, nsrc, with_stats, st, lo, grp);
   }
   return best;
 }
-static int pc_force_nsplit() {
-  const char* e = getenv("TWOWL_PC_NSPLIT");
-  return e ? atoi(e) : 0;
-}
+static int pc_force_nsplit() { return pc_env().nsplit; }
 static bool pc_supported(int Kd, int Nd, int nsrc) { return pc_config(Kd, Nd, nsrc, nsrc == 1).nsplit > 0; }
 static int pc_grid(int64_t M, int nsplit) {
   const int64_t ntiles = cdiv(M, kPcTileM);

@@ -45,10 +45,15 @@ class _Cache:
 
 
 _cache = _Cache()
+# structures built from tensors that a training loop may recreate every step (an untagged edge tensor, an explicit [2,T']
+# wedge tensor): their own small cache, so that one entry per step can neither pin 24 steps' worth of index memory nor evict
+# the dataset-lifetime entries above (pair tables, regrouped views, row-shard blocks)
+_step_cache = _Cache(cap=4)
 
 
 def clear_cache():
     _cache.clear()
+    _step_cache.clear()
 
 
 def _i64(t: torch.Tensor) -> torch.Tensor:
@@ -86,7 +91,7 @@ class MaskedEdges:
         return self.ei.device
 
 
-def node_graph(edge1, n: int) -> NodeGraph:
+def node_graph(edge1, n: int, _base: bool = False) -> NodeGraph:
     """CSR by target / by source + gcn_norm degrees of an int64 [2,E] edge tensor, cached per tensor. An edge tensor that
     sample_block produced (utils.py:61-64: the whole graph minus the sampled edge ids) reuses the cached CSRs of the
     whole graph with a per-entry mask instead of sorting its E' edges again every step."""
@@ -97,7 +102,7 @@ def node_graph(edge1, n: int) -> NodeGraph:
         if tag is not None and not (tag[2] == edge1._version and tag[0].shape[1] >= edge1.shape[1]):
             tag = None
     if tag is not None:
-        base = node_graph(tag[0], n)
+        base = node_graph(tag[0], n, _base=True)
         emask, temask = ops.gather_u8(tag[1], base.ids), ops.gather_u8(tag[1], base.tids)
         return NodeGraph(n, base.ptr, base.col, base.tptr, base.tcol, ops.gcn_dinv_entries(base.ptr, base.col, n, emask),
                          base.plan, base.tplan, base.ids, base.tids, emask, temask)
@@ -111,7 +116,8 @@ def node_graph(edge1, n: int) -> NodeGraph:
         m = ei.shape[1]
         return NodeGraph(n, ptr, col, tptr, tcol, ops.gcn_dinv(ptr, col, n), ops.seg_plan(ptr, n, m),
                          ops.seg_plan(tptr, n, m), ids, tids)
-    return _cache.get(edge1, ("node", n), build)
+    # the base graph of a sample_block result / MaskedEdges is a dataset tensor; a bare tensor may be a per-step one
+    return (_cache if _base else _step_cache).get(edge1, ("node", n), build)
 
 
 # ------------------------------------------------------------------------------ pair table (pos)
@@ -138,9 +144,16 @@ def pair_table(pos: torch.Tensor, n: int) -> PairTable:
         ptr_d, ids_d = ops.csr_build(p[:, 1], n)
         R = p.shape[0]
         mated = False
-        if R % 2 == 0 and R > 0:   # one host read per pair table (cached): does the doubled layout hold?
-            q = p.reshape(R // 2, 2, 2)
-            mated = bool(((q[:, 0, 0] == q[:, 1, 1]) & (q[:, 0, 1] == q[:, 1, 0])).all().item())
+        if R > 0:   # ONE host read per pair table (cached): the endpoints' range, and whether the doubled layout holds
+            lo_hi = torch.stack((p.min(), p.max()))
+            if R % 2 == 0:
+                q = p.reshape(R // 2, 2, 2)
+                lo_hi = torch.cat((lo_hi, ((q[:, 0, 0] == q[:, 1, 1]) & (q[:, 0, 1] == q[:, 1, 0])).all().reshape(1).to(p.dtype)))
+            vals = lo_hi.tolist()
+            if vals[0] < 0 or vals[1] >= n:
+                # x[pos[:, 0]] of model.py:75 raises IndexError in the reference; the gather kernels do no bounds checks
+                raise IndexError(f"pos holds node ids in [{vals[0]}, {vals[1]}] but the features have {n} rows")
+            mated = len(vals) == 3 and bool(vals[2])
         return PairTable(n, R, ops.narrow_i32(p[:, 0]), ops.narrow_i32(p[:, 1]), ptr_s, ids_s, ptr_d, ids_d,
                          ops.seg_plan(ptr_s, n, R), ops.seg_plan(ptr_d, n, R), mated)
     return _cache.get(pos, ("pos", n), build)
@@ -176,7 +189,7 @@ def explicit_wedges(ei2: torch.Tensor, R: int) -> ExplicitWedges:
         d1 = ops.gcn_dinv(ptr_b, col_b, R, flip=0, row_flip=1)
         T = e.shape[1]
         return ExplicitWedges(R, ptr_b, col_b, ptr_a, col_a, (d0, d1), ops.seg_plan(ptr_b, R, T), ops.seg_plan(ptr_a, R, T))
-    return _cache.get(ei2, ("ei2", R), build)
+    return _step_cache.get(ei2, ("ei2", R), build)
 
 
 # ------------------------------------------------------------------------------ structured wedge index
@@ -238,10 +251,12 @@ def wedges_match_table(struct: "WedgeStruct", pt: PairTable) -> bool:
     a mismatch sends the model to the explicit path, which follows the tensor whatever it holds."""
     def build():
         if struct.R != pt.R or struct.n_node > pt.n:
-            return False
+            return (pt, False)
         same = torch.equal(struct.src, pt.src) and torch.equal(struct.dst_e, pt.dst[: struct.E])
-        return bool(same)
-    return _cache.get(struct.src, ("match", pt.src.data_ptr(), pt.R), build)
+        return (pt, bool(same))
+    # keyed on BOTH tensors' identity (pointer, shape, strides, version); the entry holds struct.src (as its key tensor) and pt
+    # (in its value), so neither address can be recycled for another table while the verdict is cached
+    return _cache.get(struct.src, ("match",) + _Cache.key(pt.src), build)[1]
 
 
 @dataclass

@@ -78,8 +78,9 @@ class GraphedTrainStep:
 
     def _step(self):
         mask = ops.mask_from_idx(self.s_block, self.E)
-        x_new = self.deg_src.clone()
-        x_new.index_add_(0, self.ei[0].index_select(0, self.s_block), torch.full_like(self.s_block, -1))
+        # degree by source of the edges the MASK keeps (utils.py:62-67): an id that occurs twice in the blocked list removes its
+        # edge once, exactly like sample_block's ei[:, ~mask]
+        x_new = self.deg_src - torch.zeros_like(self.deg_src).index_add_(0, self.ei[0], mask.to(self.deg_src.dtype))
         edges = G.MaskedEdges(self.ei, mask)
         wedges = G.WedgeIndex(self.struct.with_blocked(mask))
         self.logits = self.mod(x_new, edges, self.pos1, self.s_idx, wedges)

@@ -197,6 +197,23 @@ def mask_from_idx(idx: torch.Tensor, num: int) -> torch.Tensor:
     return mask
 
 
+def index_guard(idx: torch.Tensor, num: int, what: str = "index") -> torch.Tensor:
+    """The bounds rule of the reference's `x[idx]` on the device, without a host sync: ids in [-num, 0) wrap, any other id
+    outside [0, num) trips a device-side assertion (the way torch's own CUDA indexing reports it: the next synchronising call
+    raises). Returns the wrapped ids as a contiguous int64 tensor the kernels can consume without bounds checks."""
+    _need_cuda(idx)
+    idx = idx.reshape(-1)
+    if idx.dtype != torch.int64:
+        idx = idx.to(torch.int64)
+    out = torch.empty(idx.numel(), dtype=torch.int64, device=idx.device)
+    bad = torch.empty(1, dtype=torch.int32, device=idx.device)
+    p, s = _row(idx) if idx.numel() else (0, 1)
+    check(lib.twowl_index_guard(p, s, idx.numel(), int(num), out.data_ptr(), bad.data_ptr(), _stream()), "index_guard")
+    _count()
+    torch._assert_async(bad == 0, f"twowl_b200: {what} out of range for {int(num)} rows (IndexError in the reference)")
+    return out
+
+
 def select_columns(mat: torch.Tensor, mask: torch.Tensor, mode: int) -> torch.Tensor:
     """Order-preserving column selection of an int64 [2,T] matrix (any strides).
     mode 0: keep column t iff !mask[t]; mode 1: keep iff !mask[mat[0,t]]."""

@@ -78,9 +78,10 @@ def _local(struct: G.WedgeStruct, pt: G.PairTable, lo: int, hi: int) -> _Local:
         hiE = max(lo, min(hi, struct.E))
         in_ptr, in_ids = ops.csr_build(struct.dst_e[lo:hiE].to(torch.int64), n)
         out_ptr, out_ids = ops.csr_build(struct.src[lo:hi].to(torch.int64), n)
-        return _Local(lo, hi, hiE - lo, pt.src[lo:hi].contiguous(), pt.dst[lo:hi].contiguous(), in_ptr, in_ids,
-                      ops.seg_plan(in_ptr, n, hiE - lo), out_ptr, out_ids, ops.seg_plan(out_ptr, n, hi - lo))
-    return G._cache.get(struct.src, ("rowshard", lo, hi, pt.src.data_ptr()), build)
+        return (pt, _Local(lo, hi, hiE - lo, pt.src[lo:hi].contiguous(), pt.dst[lo:hi].contiguous(), in_ptr, in_ids,
+                           ops.seg_plan(in_ptr, n, hiE - lo), out_ptr, out_ids, ops.seg_plan(out_ptr, n, hi - lo)))
+    # the entry holds struct.src (key tensor) and pt (value): neither address can be recycled while the block is cached
+    return G._cache.get(struct.src, ("rowshard", lo, hi) + G._Cache.key(pt.src), build)[1]
 
 
 def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr):
@@ -257,7 +258,7 @@ def forward_pairs(model, x, pos, idx, ei2):
         why = "row sharding needs the doubled pair layout (rows 2k / 2k+1 = (u,v) / (v,u))"
     if why is not None:
         raise NotImplementedError(why)
-    idx = idx.reshape(-1)
+    idx = ops.index_guard(idx, pt.R, "idx")      # x[idx] of model.py:78: negative ids wrap, anything else out of range asserts
     if getattr(model, "pair_locality", False):
         # the blocks are cut from the pair table regrouped by hub (graph.LocalityView): same rows, streaming per-node gathers
         lv = G.locality_view(wedges, pos)

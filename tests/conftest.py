@@ -31,3 +31,23 @@ def fb(golden):
     """fb-pages-food seed-0 split as produced by the reference (oracle/gen_golden.py)."""
     g = golden("fb_pages_food_seed0.npz")
     return {k: g[k] for k in g.files}
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the parity ledger (tests/helpers.parity): how many elements of every end-to-end tensor passed by which clause."""
+    from helpers import LEDGER
+    if LEDGER.rows:
+        try:
+            LEDGER.dump(os.environ.get("TWOWL_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", "parity_report.json")))
+        except OSError:
+            pass
+
+
+def pytest_terminal_summary(terminalreporter):
+    from helpers import LEDGER
+    if LEDGER.rows:
+        t = LEDGER.totals()
+        terminalreporter.write_line(f"parity ledger ({len(LEDGER.rows)} tensors): " + ", ".join(f"{k}={v}" for k, v in t.items()))
+        for r in LEDGER.rows:
+            if r["ref_error_clause"] or r["scale_floor"]:
+                terminalreporter.write_line(f"  relaxed: {r}")

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, fb_split, sha
+from helpers import assert_close, fb_split, r32, sha
 from oracle import twowl_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -97,6 +97,45 @@ def test_fb_pages_food_index_golden(U, fb):
     wi = U.blockei2(U.get_ei2_implicit(n, dev(ei), dev(pred)), idx1)
     assert wi.num_wedges() == ei2_new.shape[1]
     assert sha(wi.materialize()) == str(fb["sb_ei2_sha"])
+
+
+def test_basegraph_preprocess_split_degree_feature_golden(U, fb):
+    """the PRODUCT BaseGraph (TwoWL/operators/datasets.py) built from the reference's own split
+    (golden edge_pos / edge_neg / num_pos / num_neg), through preprocess() and setPosDegreeFeature(), against what the reference's
+    BaseGraph produced from the same inputs (datasets.py:44-114, frozen by oracle/gen_golden.py): pos1s and ei2s by sha256 of
+    the int64 bytes, x / ys / max_x / edge_indexs directly, and the split() / dataset() containers."""
+    import TwoWL.operators.datasets as D
+    n = int(fb["num_nodes"][0])
+    ep, en = dev(fb["edge_pos"].astype(np.int64)), dev(fb["edge_neg"].astype(np.int64))
+    num_pos, num_neg = torch.from_numpy(fb["num_pos"]), torch.from_numpy(fb["num_neg"])
+    for pattern in ("2wl_l", "2wl_l_implicit"):
+        bg = D.BaseGraph(torch.zeros((n, 0), device="cuda"), None, ep, en, num_pos, num_neg, pattern)
+        assert bg.num_nodes == n and bg.max_x is None
+        bg.preprocess()
+        bg.setPosDegreeFeature()
+        assert bg.max_x == int(fb["max_x"][0])
+        for s in range(3):
+            ei, pred, pos1 = fb_split(fb, s)
+            assert same(bg.edge_indexs[s], ei)
+            assert tuple(bg.pos1s[s].shape) == pos1.shape and bg.pos1s[s].dtype == torch.int64
+            assert sha(bg.pos1s[s]) == str(fb[f"pos1_{s}_sha"])
+            assert same(bg.x[s], fb[f"x{s}"].astype(np.int64)) and bg.x[s].dtype == torch.int64
+            assert bg.edge_attrs[s].dtype == torch.float32 and bool((bg.edge_attrs[s] == 1).all())
+            assert bg.edge_attrs[s].shape[0] == ei.shape[1]
+            ei2 = bg.ei2s[s] if pattern == "2wl_l" else bg.ei2s[s].materialize()
+            assert tuple(ei2.shape) == tuple(fb[f"ei2_{s}_shape"]) and sha(ei2) == str(fb[f"ei2_{s}_sha"])
+            assert np.array_equal(ei2[:, :64].cpu().numpy(), fb[f"ei2_{s}_head"])
+            assert np.array_equal(ei2[:, -64:].cpu().numpy(), fb[f"ei2_{s}_tail"])
+        # labels: train = zeros for the negatives only (datasets.py:84), val / test = ones then zeros
+        assert bg.ys[0].shape == (int(fb["num_neg"][0]), 1) and not bool(bg.ys[0].any())
+        assert bg.ys[1].shape == (int(fb["num_pos"][1] + fb["num_neg"][1]), 1)
+        assert bg.ys[2].dtype == torch.float32 and np.array_equal(bg.ys[2].cpu().numpy(), fb["test_y"])
+        # containers: split(i) -> dataset(x, na, ei, ea, pos1, y, ei2) exactly as train.py / TwoWL_work.py:40-46 use them
+        for s in range(3):
+            ds = D.dataset(*bg.split(s))
+            assert ds.x is bg.x[s] and ds.na is None and ds.ei is bg.edge_indexs[s] and ds.ea is bg.edge_attrs[s]
+            assert ds.pos1 is bg.pos1s[s] and ds.y is bg.ys[s] and ds.ei2 is bg.ei2s[s]
+        assert "BaseGraph object" in bg.toString()
 
 
 # ------------------------------------------------------------------------------ seeded random vs oracle
@@ -252,9 +291,9 @@ def test_seg_reduce_vs_fp64(U, C):
     rows = np.minimum((rng.pareto(1.0, size=nnz) * 40).astype(np.int64), M - 1)
     cols = rng.integers(0, M, size=nnz)
     ptr, col = _csr_from(rows, cols, M)
-    X = torch.randn(M, C, dtype=torch.float64)
-    sc = torch.rand(M, dtype=torch.float64) + 0.1
-    bias = torch.randn(C, dtype=torch.float64)
+    X = r32(torch.randn(M, C, dtype=torch.float64))       # exactly representable in fp32: no input rounding
+    sc = r32(torch.rand(M, dtype=torch.float64) + 0.1)
+    bias = r32(torch.randn(C, dtype=torch.float64))
     mask = rng.random(M) < 0.2
     order = np.argsort(rows, kind="stable")
     r_s, c_s = torch.from_numpy(rows[order]), torch.from_numpy(cols[order])
@@ -264,15 +303,20 @@ def test_seg_reduce_vs_fp64(U, C):
         keep = (s != tgt) & ~torch.from_numpy(mask)[c_s]
         ref = torch.zeros(M, C, dtype=torch.float64).index_add_(0, tgt[keep], sc[s[keep]].unsqueeze(1) * X[s[keep]])
         ref = sc.unsqueeze(1) * ref + (sc ** 2).unsqueeze(1) * X + bias
+        # the same sum over the absolute values of its terms, and the longest sum (+ the roundings inside one term): the fp32
+        # summation bound of helpers.assert_close - nothing relative to the tensor's largest element
+        absum = torch.zeros(M, C, dtype=torch.float64).index_add_(0, tgt[keep], sc[s[keep]].unsqueeze(1) * X[s[keep]].abs())
+        absum = sc.unsqueeze(1) * absum + (sc ** 2).unsqueeze(1) * X.abs() + bias.abs()
+        nterms = int(torch.bincount(tgt[keep], minlength=M).max()) + 6
         kw = dict(flip=flip, row_flip=row_flip, src_scale=sc.float().cuda(), dst_scale=sc.float().cuda(), skip_self=True,
                   self_mode=1, bias=bias.float().cuda(), skip_mask=dev(mask.astype(np.uint8)))
         got = ops.seg_reduce(ptr, col, M, X.float().cuda(), **kw)
-        assert_close(got, ref, rtol=1e-5, atol=2e-4, what=f"seg_reduce C={C} flip={flip} row_flip={row_flip}")
+        assert_close(got, ref, absum=absum, nterms=nterms, what=f"seg_reduce C={C} flip={flip} row_flip={row_flip}")
         # with the long-row plan (rows > TWOWL_LONG_ROW entries are cut into chunks): same values, and repeatable
         plan = ops.seg_plan(ptr, M, nnz)
         assert int(plan[0]) >= 1, "the test graph must contain long rows"
         got2 = ops.seg_reduce(ptr, col, M, X.float().cuda(), plan=plan, **kw)
-        assert_close(got2, ref, rtol=1e-5, atol=2e-4, what=f"seg_reduce planned C={C}")
+        assert_close(got2, ref, absum=absum, nterms=nterms, what=f"seg_reduce planned C={C}")
         assert torch.equal(got2, ops.seg_reduce(ptr, col, M, X.float().cuda(), plan=ops.seg_plan(ptr, M, nnz), **kw))
         # dinv: exact integer degree
         d = ops.gcn_dinv(ptr, col, M, flip=flip, row_flip=row_flip, skip_mask=dev(mask.astype(np.uint8)))
@@ -347,17 +391,20 @@ def test_linear_fwd_bwd(U, M, Ci, Co, impl, monkeypatch):
     from twowl_b200 import ops
     monkeypatch.setattr(ops, "LINEAR_IMPL", impl)
     torch.manual_seed(M)
-    x = torch.randn(M, Ci, dtype=torch.float64).requires_grad_(True)
-    w = torch.randn(Co, Ci, dtype=torch.float64).requires_grad_(True)
-    g = torch.randn(M, Co, dtype=torch.float64)
+    x = r32(torch.randn(M, Ci, dtype=torch.float64)).requires_grad_(True)
+    w = r32(torch.randn(Co, Ci, dtype=torch.float64)).requires_grad_(True)
+    g = r32(torch.randn(M, Co, dtype=torch.float64))
     (x @ w.t()).backward(g)
     gx, gw = x.detach().float().cuda().requires_grad_(True), w.detach().float().cuda().requires_grad_(True)
     z = F2.linear(gx, gw)
     z.backward(g.float().cuda())
-    k = lambda t: 1e-6 * float(t.abs().max()) * 4
-    assert_close(z, (x @ w.t()).detach(), atol=k(x @ w.t()), what="linear fwd")
-    assert_close(gx.grad, x.grad, atol=k(x.grad), what="linear dX")
-    assert_close(gw.grad, w.grad, atol=k(w.grad), what="linear dW")
+    # sums of Ci / Co / M products: fp32 summation bound over the absolute terms (+ the split-tf32 product bound on the tensor
+    # cores; the weight gradient always runs the SIMT split-K kernel)
+    xa, wa, ga = x.detach().abs(), w.detach().abs(), g.abs()
+    mma = impl != 0
+    assert_close(z, (x @ w.t()).detach(), absum=xa @ wa.t(), nterms=Ci + 2, mma=mma, what="linear fwd")
+    assert_close(gx.grad, x.grad, absum=ga @ wa, nterms=Co + 2, mma=mma, what="linear dX")
+    assert_close(gw.grad, w.grad, absum=ga.t() @ xa, nterms=M + 2, what="linear dW")
 
 
 @pytest.mark.parametrize("mated", [False, True])
@@ -366,23 +413,33 @@ def test_pair_init_readout_embedding(U, mated):
     from twowl_b200 import graph as G
     torch.manual_seed(3)
     N, R, C, V, L = 500, 4000, 24, 37, 300
-    X = torch.randn(N, C, dtype=torch.float64).requires_grad_(True)
+    X = r32(torch.randn(N, C, dtype=torch.float64)).requires_grad_(True)
     pos = torch.randint(0, N, (R, 2))
     if mated:   # the doubled layout of utils.py:81-90: rows 2k / 2k+1 = (u,v) / (v,u) -> one-pass backward
         pos[1::2] = pos[0::2].flip(1)
     idx = torch.randint(0, R, (2 * L,))
     idx[5] = idx[4]
     idx[10] = idx[2]                                   # duplicates: gradients must add up
-    w = torch.randn(1, C, dtype=torch.float64).requires_grad_(True)
-    b = torch.randn(1, dtype=torch.float64).requires_grad_(True)
-    emb = torch.randn(V, C, dtype=torch.float64).requires_grad_(True)
+    w = r32(torch.randn(1, C, dtype=torch.float64)).requires_grad_(True)
+    b = r32(torch.randn(1, dtype=torch.float64)).requires_grad_(True)
+    emb = r32(torch.randn(V, C, dtype=torch.float64)).requires_grad_(True)
     deg = torch.randint(0, V, (N,))
-    h0 = emb[deg] + X
-    H = h0[pos[:, 0]] * h0[pos[:, 1]]
-    h = H[idx]
-    ref = (h[0::2] * h[1::2]) @ w.t() + b
-    gout = torch.randn(L, 1, dtype=torch.float64)
+
+    def graph(X, w, b, emb):
+        h0 = emb[deg] + X
+        H = h0[pos[:, 0]] * h0[pos[:, 1]]
+        h = H[idx]
+        return (h[0::2] * h[1::2]) @ w.t() + b
+    ref = graph(X, w, b, emb)
+    gout = r32(torch.randn(L, 1, dtype=torch.float64))
     ref.backward(gout)
+    # the same graph on the absolute values: every op is a product or a sum with coefficient +1, so its outputs / gradients
+    # are the sums of the ABSOLUTE terms of the outputs / gradients above - the `absum` of helpers.assert_close
+    leaves = [t.detach().abs().requires_grad_(True) for t in (X, w, b, emb)]
+    aref = graph(*leaves)
+    aref.backward(gout.abs())
+    cnt = torch.bincount(pos.reshape(-1), minlength=N) * int(torch.bincount(idx, minlength=R).max())
+    nt = {"dX": int(cnt.max()) + 8, "dw": L + 8, "db": L, "demb": int(torch.bincount(deg, weights=cnt.double(), minlength=V).max()) + 8}
 
     c = lambda t: t.detach().float().cuda().requires_grad_(True)
     gX, gw, gb, gemb = c(X), c(w), c(b), c(emb)
@@ -392,9 +449,9 @@ def test_pair_init_readout_embedding(U, mated):
     gH = F2.pair_init(g0, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
     out = F2.readout(gH, idx.cuda(), gw, gb)
     out.backward(gout.float().cuda())
-    assert_close(out, ref.detach(), atol=1e-4, what="readout fwd")
-    for name, g, r in (("dX", gX, X), ("dw", gw, w), ("db", gb, b), ("demb", gemb, emb)):
-        assert_close(g.grad, r.grad, atol=1e-5 * max(float(r.grad.abs().max()), 1.0), what=name)
+    assert_close(out, ref.detach(), absum=aref.detach(), nterms=C + 8, what="readout fwd")
+    for (name, g, r), a in zip((("dX", gX, X), ("dw", gw, w), ("db", gb, b), ("demb", gemb, emb)), leaves):
+        assert_close(g.grad, r.grad, absum=a.grad, nterms=nt[name], what=name)
 
 
 @pytest.mark.parametrize("M,Kd,Nd,nsrc,ngather,stats", [
@@ -413,19 +470,23 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
         pytest.skip("shape not covered by the tcgen05 kernel")
     torch.manual_seed(M + Kd + Nd)
     NT = 777
-    A = [torch.randn(M, Kd, dtype=torch.float64) for _ in range(nsrc)]
-    rs = [torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3) for _ in range(nsrc)]   # zeros occur (selfw = 0 rows)
-    W = [torch.randn(Kd, Nd, dtype=torch.float64) / Kd ** 0.5 for _ in range(nsrc)]          # stored [Kd, Nd]: w_kn = 1
-    T = [torch.randn(NT, Nd, dtype=torch.float64) for _ in range(ngather)]
+    A = [r32(torch.randn(M, Kd, dtype=torch.float64)) for _ in range(nsrc)]
+    rs = [r32(torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3)) for _ in range(nsrc)]   # zeros occur (selfw = 0 rows)
+    W = [r32(torch.randn(Kd, Nd, dtype=torch.float64) / Kd ** 0.5) for _ in range(nsrc)]          # stored [Kd, Nd]: w_kn = 1
+    T = [r32(torch.randn(NT, Nd, dtype=torch.float64)) for _ in range(ngather)]
     idx = [torch.randint(-1, NT, (M,)) for _ in range(ngather)]
-    coef = [torch.rand(M, dtype=torch.float64) for _ in range(ngather)]
-    bias = torch.randn(Nd, dtype=torch.float64)
+    coef = [r32(torch.rand(M, dtype=torch.float64)) for _ in range(ngather)]
+    bias = r32(torch.randn(Nd, dtype=torch.float64))
     ref = bias.expand(M, Nd).clone()
+    absum = bias.abs().expand(M, Nd).clone()            # the same sum over the absolute values of its terms
     for s in range(nsrc):
         ref += (rs[s].unsqueeze(1) * A[s]) @ W[s]
+        absum += (rs[s].unsqueeze(1) * A[s].abs()) @ W[s].abs()
     for g in range(ngather):
         ok = idx[g] >= 0
         ref[ok] += coef[g][ok].unsqueeze(1) * T[g][idx[g][ok]]
+        absum[ok] += coef[g][ok].unsqueeze(1) * T[g][idx[g][ok]].abs()
+    nterms = nsrc * Kd + ngather + 4
     c = lambda t: t.float().cuda().contiguous()
     for w_kn in (1, 0):
         Wd = [c(w) if w_kn else c(w.t()) for w in W]
@@ -434,12 +495,17 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
                             gathers=[(c(T[g]), idx[g].int().cuda(), c(coef[g])) for g in range(ngather)], bias=c(bias),
                             stats_mean_scale=ms.cuda() if stats else None, eps=1e-5)
         out = res[0] if stats else res
-        assert_close(out, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()), what=f"pair_conv out w_kn={w_kn}")
+        assert_close(out, ref, absum=absum, nterms=nterms, mma=True, what=f"pair_conv out w_kn={w_kn}")
         if stats:
             mean = ref.mean(0)
             var = ((ref - mean * ms.double()) ** 2).mean(0)
-            assert_close(res[1][:Nd], mean, rtol=1e-5, atol=1e-5, what="pair_conv mean")
-            assert_close(res[1][Nd:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what="pair_conv inv_std")
+            # the column mean inherits the mean of the elements' bounds (its own accumulation runs in double)
+            assert_close(res[1][:Nd], mean, absum=absum.mean(0), nterms=nterms, mma=True, what="pair_conv mean")
+            # d(inv_std)/inv_std = -d(var) / (2 (var + eps)), |d var| <= 2 mean(|o - a*mean| * bound): first-order propagation of the same bounds
+            dev_ = (ref - mean * ms.double()).abs()
+            dvar = 2 * (dev_ * absum).mean(0) + 2 * dev_.mean(0) * ms.double() * absum.mean(0)
+            inv = (var + 1e-5).rsqrt()
+            assert_close(res[1][Nd:], inv, absum=inv * dvar / (2 * (var + 1e-5)), nterms=nterms, mma=True, what="pair_conv inv_std")
 
 
 @pytest.mark.parametrize("M,Kd,C", [(3, 64, 64), (129, 32, 32), (5000, 64, 64), (70001, 64, 64), (30011, 128, 128), (9000, 24, 32),
@@ -450,15 +516,15 @@ def test_pair_conv_dual_vs_fp64(U, M, Kd, C):
     from twowl_b200 import ops
     torch.manual_seed(M + C)
     NT = 777
-    A = torch.randn(M, Kd, dtype=torch.float64)
-    W = [torch.randn(C, Kd, dtype=torch.float64) / Kd ** 0.5 for _ in range(2)]
-    T = [torch.randn(NT, C, dtype=torch.float64) for _ in range(2)]
+    A = r32(torch.randn(M, Kd, dtype=torch.float64))
+    W = [r32(torch.randn(C, Kd, dtype=torch.float64) / Kd ** 0.5) for _ in range(2)]
+    T = [r32(torch.randn(NT, C, dtype=torch.float64)) for _ in range(2)]
     idx = [torch.randint(0, NT, (M,)) for _ in range(2)]
     idx[1][::7] = -1                                     # rows without a gathered term
-    coef = [torch.rand(M, dtype=torch.float64) for _ in range(2)]
-    rs = [torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.2) for _ in range(2)]
-    bias = [torch.randn(C, dtype=torch.float64) for _ in range(2)]
-    ms = [torch.rand(C, dtype=torch.float64) + 0.5 for _ in range(2)]
+    coef = [r32(torch.rand(M, dtype=torch.float64)) for _ in range(2)]
+    rs = [r32(torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.2)) for _ in range(2)]
+    bias = [r32(torch.randn(C, dtype=torch.float64)) for _ in range(2)]
+    ms = [r32(torch.rand(C, dtype=torch.float64) + 0.5) for _ in range(2)]
     c = lambda t: t.float().cuda().contiguous()          # noqa: E731
     ci = lambda t: t.to(torch.int32).cuda()              # noqa: E731
     assert ops.pair_conv_dual_supported(Kd, C)
@@ -469,14 +535,18 @@ def test_pair_conv_dual_vs_fp64(U, M, Kd, C):
     for d, (O, st, mom) in enumerate(((Of, sf, mf), (Or, sr, mr))):
         g = T[d][idx[d].clamp(min=0)] * (idx[d] >= 0).double().unsqueeze(1)
         ref = rs[d].unsqueeze(1) * (A @ W[d].t()) + coef[d].unsqueeze(1) * g + bias[d]
-        tol = 4e-6 * max(float(ref.abs().max()), 1.0)
-        assert_close(O, ref, rtol=1e-5, atol=tol, what=f"dual out {d}")
+        absum = rs[d].unsqueeze(1) * (A.abs() @ W[d].abs().t()) + coef[d].unsqueeze(1) * g.abs() + bias[d].abs()
+        kw = dict(nterms=Kd + 5, mma=True)              # fp32 summation + split-tf32 product bounds over the absolute terms
+        assert_close(O, ref, absum=absum, what=f"dual out {d}", **kw)
         mean = ref.mean(0)
         var = ((ref - ms[d] * mean) ** 2).mean(0)
-        assert_close(st[:C], mean, rtol=1e-5, atol=tol, what=f"dual mean {d}")
-        assert_close(st[C:], (var + 1e-5).rsqrt(), rtol=2e-5, atol=1e-6, what=f"dual inv_std {d}")
-        assert_close(mom[:C], ref.sum(0), rtol=1e-5, atol=tol * M, what=f"dual moment sum {d}")
-        assert_close(mom[C:], (ref ** 2).sum(0), rtol=2e-5, atol=tol * M, what=f"dual moment sumsq {d}")
+        assert_close(st[:C], mean, absum=absum.mean(0), what=f"dual mean {d}", **kw)
+        dev_ = (ref - mean * ms[d]).abs()               # first-order propagation of the elements' bounds into inv_std
+        dvar = 2 * (dev_ * absum).mean(0) + 2 * dev_.mean(0) * ms[d] * absum.mean(0)
+        inv = (var + 1e-5).rsqrt()
+        assert_close(st[C:], inv, absum=inv * dvar / (2 * (var + 1e-5)), what=f"dual inv_std {d}", **kw)
+        assert_close(mom[:C], ref.sum(0), absum=absum.sum(0), what=f"dual moment sum {d}", **kw)
+        assert_close(mom[C:], (ref ** 2).sum(0), absum=(2 * ref.abs() * absum).sum(0), what=f"dual moment sumsq {d}", **kw)
         one, st1 = ops.pair_conv([c(A)], [c(W[d])], [0], row_scale=[c(rs[d])], gathers=[(c(T[d]), ci(idx[d]), c(coef[d]))], bias=c(bias[d]),
                                  stats_mean_scale=c(ms[d]))
         assert torch.equal(one, O), f"dual launch differs from the single-direction launch, direction {d}"
@@ -488,16 +558,19 @@ def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     """[dW_f; dW_r] = [selfw_f*dO_f | selfw_r*dO_r]^T H with MN-major tcgen05 operands."""
     from twowl_b200 import ops
     torch.manual_seed(M + C)
-    dOf, dOr, H = (torch.randn(M, C, dtype=torch.float64) for _ in range(3))
-    rsf = torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3)
-    rsr = torch.rand(M, dtype=torch.float64)
+    dOf, dOr, H = (r32(torch.randn(M, C, dtype=torch.float64)) for _ in range(3))
+    rsf = r32(torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3))
+    rsr = r32(torch.rand(M, dtype=torch.float64))
     ref_f = (rsf.unsqueeze(1) * dOf).t() @ H
     ref_r = (rsr.unsqueeze(1) * dOr).t() @ H
     c = lambda t: t.float().cuda().contiguous()
     gf, gr = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
-    tol = 4e-6 * max(float(ref_f.abs().max()), float(ref_r.abs().max()), 1.0)
-    assert_close(gf, ref_f, rtol=1e-5, atol=tol, what="pair_dw f")
-    assert_close(gr, ref_r, rtol=1e-5, atol=tol, what="pair_dw r")
+    # a sum over M rows (dw_tc.cu): C <= 64: one tile's 8 truncating accumulate steps (<= 2u each), then 64 tiles in fp32
+    # registers, then double; C = 128: 4 tiles x 16 truncating steps, then one fp32 read-add-write per 4 tiles per CTA
+    # (+ the roundings of the scaled operand); + the split-tf32 product bound
+    kw = dict(nterms=(96 if C <= 64 else 136 + M // (32 * 148 * 4)), mma=True)
+    assert_close(gf, ref_f, absum=(rsf.unsqueeze(1) * dOf.abs()).t() @ H.abs(), what="pair_dw f", **kw)
+    assert_close(gr, ref_r, absum=(rsr.unsqueeze(1) * dOr.abs()).t() @ H.abs(), what="pair_dw r", **kw)
     gf2, gr2 = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
     assert torch.equal(gf, gf2) and torch.equal(gr, gr2)      # deterministic
 
@@ -507,17 +580,17 @@ def test_pair_dw_wide_tiles_vs_fp64(U, M, Co, Ci):
     """Layers wider than 128: the weight gradients tiled into 128-column blocks through pitched TMA tensor maps (twowl_pair_dw_ld)."""
     from twowl_b200 import ops
     torch.manual_seed(M + Co)
-    dOf, dOr = (torch.randn(M, Co, dtype=torch.float64) for _ in range(2))
-    H = torch.randn(M, Ci, dtype=torch.float64)
-    rsf = torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3)
-    rsr = torch.rand(M, dtype=torch.float64)
+    dOf, dOr = (r32(torch.randn(M, Co, dtype=torch.float64)) for _ in range(2))
+    H = r32(torch.randn(M, Ci, dtype=torch.float64))
+    rsf = r32(torch.rand(M, dtype=torch.float64) * (torch.rand(M) > 0.3))
+    rsr = r32(torch.rand(M, dtype=torch.float64))
     c = lambda t: t.float().cuda().contiguous()          # noqa: E731
     assert ops.pair_dw_wide_supported(Co, Ci)
     gf, gr = ops.pair_dw_wide(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
     ref_f, ref_r = (rsf.unsqueeze(1) * dOf).t() @ H, (rsr.unsqueeze(1) * dOr).t() @ H
-    tol = 4e-6 * max(float(ref_f.abs().max()), float(ref_r.abs().max()), 1.0)
-    assert_close(gf, ref_f, rtol=1e-5, atol=tol, what="pair_dw_wide f")
-    assert_close(gr, ref_r, rtol=1e-5, atol=tol, what="pair_dw_wide r")
+    kw = dict(nterms=136 + M // (32 * 148 * 4), mma=True)      # the 128-column launches, as test_pair_dw_tcgen05_vs_fp64
+    assert_close(gf, ref_f, absum=(rsf.unsqueeze(1) * dOf.abs()).t() @ H.abs(), what="pair_dw_wide f", **kw)
+    assert_close(gr, ref_r, absum=(rsr.unsqueeze(1) * dOr.abs()).t() @ H.abs(), what="pair_dw_wide r", **kw)
 
 
 @pytest.mark.parametrize("M,C,L,p", [(64, 64, 10, 0.0), (5000, 32, 700, 0.3), (70001, 64, 9000, 0.0), (70001, 64, 9000, 0.5),

@@ -68,7 +68,12 @@ def test_headless_driver_trains_and_writes_the_reference_record_files(cuda, tmp_
     assert all(0.4 < a <= 1.0 for a in aucs) and all(t >= 0 for t in infer)
     line = open(os.path.join(args.record_dir, "planted_auc_record_twowl.txt")).readline()
     assert line.startswith("AUC:") and "   Time:" in line           # train.py:110-112 format
-    assert os.path.isfile("logs.json")
+    # logs.json = the best trial's parameters as ONE FLAT dict, as json.dump(study.best_params) writes it (TwoWL_work.py:140-144),
+    # and read_results returns the reference's triple (TwoWL_work.py:152-176)
+    import json
+    assert json.load(open("logs.json")) == res["best_params"]
+    logs, best_auc, avg_time = W.read_results("planted", args.record_dir, args.time_dir)
+    assert logs == res["best_params"] and best_auc == max(aucs) and abs(avg_time - sum(walls) / 2) < 1e-9
     # train.py:126 of the reference compares the UNROUNDED test score with the records rounded to 4 decimals, so the curve files
     # appear only when the best trial's score happened to round down - mirrored as is: both files or neither
     assert os.path.isfile("fpr.json") == os.path.isfile("tpr.json")
