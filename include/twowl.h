@@ -187,6 +187,13 @@ typedef struct twowl_seg_args {
   const float* src_scale2;
   float* out2;
   float* partial2;
+  /* output rows [row_begin, row_end) only (row_end = 0: all M rows): one node block of a row-sharded multi-GPU job. ptr / col /
+   * the plan / out are those of the WHOLE CSR; rows outside the range are neither read nor written. */
+  int64_t row_begin;
+  int64_t row_end;
+  /* dual output with the mates' rows taken from a SECOND matrix: out2[m] = sum src_scale2[s^1] * X_mate[s^1] (NULL = X). One pass
+   * over a node's out-list then gives both directions' gradient sums dS_f (from dO_f) and dS_r (from dO_r) of the pair layer. */
+  const float* X_mate;
 } twowl_seg_args;
 int twowl_seg_reduce(const twowl_seg_args* h_args, void* stream);
 size_t twowl_sizeof_seg_args(void);   /* binding guard: a foreign-language mirror of the struct must have this size */
@@ -433,6 +440,12 @@ int twowl_wedge_prepare(const int32_t* src /*[R]*/, const int32_t* dst_e /*[E]*/
                         const uint8_t* blocked /*[E] or NULL*/, const int64_t* in_ptr /*[N+1]*/, int32_t* cnt /*[N]*/,
                         int32_t* centre /*[2,R]*/, float* dinv /*[2,R]*/, float* selfw /*[2,R]*/,
                         int32_t* bnode /*[2,R]: node whose S row r feeds (backward gather), -1 if none*/, void* stream);
+/* The same constants for the pair rows [row_lo, row_hi) only (even bounds: rows 2k / 2k+1 stay together): one rank's block of
+ * a row-sharded step (twowl_b200.rowshard). cnt[N] is still the count over ALL live in-edges (every rank holds the int edge
+ * lists); centre / dinv / selfw / bnode are [2, row_hi - row_lo]. */
+int twowl_wedge_prepare_rows(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N, const uint8_t* blocked,
+                             const int64_t* in_ptr, int64_t row_lo, int64_t row_hi, int32_t* cnt, int32_t* centre, float* dinv,
+                             float* selfw, int32_t* bnode, void* stream);
 /* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias   (centre < 0: no S term) */
 int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,
                           const float* selfw, const float* bias, int64_t R, int32_t C, float* out, void* stream);

@@ -164,8 +164,8 @@ class LocalWLNet(nn.Module):
         # the LAST pair layer only feeds x[idx] (model.py:77-83): fuse it with the readout so its GraphNorm / ReLU run
         # on the selected rows only (needs fused_pair_layer and an idx)
         self.fused_readout = True
-        # a twowl_b200.rowshard.RowShard: forward / backward run on this rank's block of pair rows (multi-GPU, one step cut
-        # over the ranks; node-level part replicated). None = the whole pair table on this GPU.
+        # a twowl_b200.rowshard.RowShard: forward / backward run on this rank's block of pair rows and node block (multi-GPU,
+        # one step cut over the ranks). None = the whole pair table on this GPU.
         self.row_shard = None
         # regroup the pair rows internally by their higher-degree endpoint (graph.LocalityView): same terms, streaming gathers
         self.pair_locality = True
@@ -213,6 +213,9 @@ class LocalWLNet(nn.Module):
         """model.py:68-84. x: int64 [N] degrees; edge1: int64 [2,E']; pos: int64 [R,2]; idx: int64 [2L];
         ei2: int64 [2,T'] (or a WedgeIndex). Returns fp32 [L,1] logits. ``test`` is unused, as in the
         reference. reverse(ei2) (model.py:69) is folded into the aggregation kernels."""
+        if self.row_shard is not None and self.row_shard.world > 1:
+            from twowl_b200 import rowshard
+            return rowshard.forward(self, x, edge1, pos, idx, ei2)
         if self.use_node_feat:
             x = self.lin1(self.node_feat)
         else:
@@ -222,9 +225,6 @@ class LocalWLNet(nn.Module):
         for conv1 in self.conv1s:
             x = conv1(x, edge1)
 
-        if self.row_shard is not None and self.row_shard.world > 1:
-            from twowl_b200 import rowshard
-            return rowshard.forward_pairs(self, x, pos, idx, ei2)
         pt = G.pair_table(pos, x.shape[0])             # validates pos against x's rows once per table (IndexError as model.py:75)
         if idx is not None:
             # x[idx] of model.py:78: ids in [-R, 0) wrap, anything else out of range is a device-side assertion (no host sync)

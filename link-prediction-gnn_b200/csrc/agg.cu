@@ -28,6 +28,7 @@ struct SegParams {
   int C;
   int flip;
   int row_flip;
+  int64_t row_lo, row_hi;      // output rows [row_lo, row_hi) only (a node block of a row-sharded job); the rest is untouched
   const float* src_scale;
   const uint8_t* skip_mask;
   const uint8_t* row_skip_mask;
@@ -46,6 +47,7 @@ struct SegParams {
   const float* src_scale2;
   float* out2;
   float* partial2;
+  const float* Xm;             // dual mode: the mates' rows come from this matrix instead of X (NULL = X)
   // long-row plan (all NULL/0 when the CSR has no plan)
   const int32_t* plan_counts;  // [0] = number of long rows, [1] = number of chunks
   const int32_t* long_row;     // CSR row of each long row
@@ -78,6 +80,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
                                                float4 (&acc)[VEC], float4 (&acc2)[(MODE & 4) ? VEC : 1]) {
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
+  const float4* __restrict__ Xm4 = ((MODE & 4) && p.Xm) ? reinterpret_cast<const float4*>(p.Xm) : X4;
   if (kb >= ke) return;
   auto load_col = [&](int64_t k0) -> int {
     const int64_t k = k0 + g.gl;
@@ -131,7 +134,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
           const int c4 = g.gl + v * G;
           const bool on = sj[u] >= 0 && c4 < g.cv;
           x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
-          if (MODE & 6) xm[u][v] = on ? ldg_cached(X4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
+          if (MODE & 6) xm[u][v] = on ? ldg_cached(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
           if (MODE & 1) y[u][v] = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
         }
       }
@@ -201,8 +204,8 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
   };
   int64_t kb_n, ke_n;
   bool masked_n;
-  row_range(group0, kb_n, ke_n, masked_n);
-  for (int64_t m = group0; m < p.M; m += ngroups) {
+  row_range(p.row_lo + group0, kb_n, ke_n, masked_n);
+  for (int64_t m = p.row_lo + group0; m < p.row_hi; m += ngroups) {
     const int64_t kb = kb_n;
     int64_t ke = ke_n;
     const bool masked = masked_n;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
     const int slot = p.chunk_owner[ch];
     const int64_t r = p.long_row[slot];
     const int64_t m = r ^ (int64_t)p.row_flip;
+    if (m < p.row_lo || m >= p.row_hi) continue;
     const int64_t c = ch - p.long_base[slot];
     int64_t kb = p.ptr[r] + c * TWOWL_ROW_CHUNK;
     int64_t ke = kb + TWOWL_ROW_CHUNK < p.ptr[r + 1] ? kb + TWOWL_ROW_CHUNK : p.ptr[r + 1];
@@ -268,23 +272,41 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + gid;
   const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
   auto chunks_of = [&](int64_t r) { return (p.ptr[r + 1] - p.ptr[r] + TWOWL_ROW_CHUNK - 1) / TWOWL_ROW_CHUNK; };
+  // the chunk partials of a row are added in DOUBLE: a hub's row has ~1000 of them (degree 62 745), the "degree 1" row of the
+  // embedding backward thousands, and an fp32 chain of that length would put ~sqrt(n) * 2^-24 of relative error into every
+  // per-node sum that feeds all pairs centred on the hub; the 64 entries inside a chunk stay an fp32 chain
   auto add_chunks = [&](int64_t base, int64_t c0, int64_t cstep, int64_t nch, float4 (&acc)[VEC], float4 (&acc2)[DUAL ? VEC : 1]) {
+    double d[VEC][4], d2[DUAL ? VEC : 1][4];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) d[v][0] = d[v][1] = d[v][2] = d[v][3] = 0.0;
+#pragma unroll
+    for (int v = 0; v < (DUAL ? VEC : 1); ++v) d2[v][0] = d2[v][1] = d2[v][2] = d2[v][3] = 0.0;
     for (int64_t c = c0; c < nch; c += cstep) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int c4 = g.gl + v * G;
         if (c4 < g.cv) {
-          f4_add(acc[v], reinterpret_cast<const float4*>(p.partial)[(base + c) * g.cv + c4]);
-          if constexpr (DUAL) f4_add(acc2[v], reinterpret_cast<const float4*>(p.partial2)[(base + c) * g.cv + c4]);
+          const float4 t = reinterpret_cast<const float4*>(p.partial)[(base + c) * g.cv + c4];
+          d[v][0] += (double)t.x, d[v][1] += (double)t.y, d[v][2] += (double)t.z, d[v][3] += (double)t.w;
+          if constexpr (DUAL) {
+            const float4 u = reinterpret_cast<const float4*>(p.partial2)[(base + c) * g.cv + c4];
+            d2[v][0] += (double)u.x, d2[v][1] += (double)u.y, d2[v][2] += (double)u.z, d2[v][3] += (double)u.w;
+          }
         }
       }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = make_float4((float)d[v][0], (float)d[v][1], (float)d[v][2], (float)d[v][3]);
+    if constexpr (DUAL) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc2[v] = make_float4((float)d2[v][0], (float)d2[v][1], (float)d2[v][2], (float)d2[v][3]);
     }
   };
   // (a) short lists: one group per row
   for (int64_t slot = group0; slot < nlong; slot += ngroups) {
     const int64_t r = p.long_row[slot];
     const int64_t nch = chunks_of(r);
-    if (nch > kLongWide) continue;
+    if (nch > kLongWide || (r ^ (int64_t)p.row_flip) < p.row_lo || (r ^ (int64_t)p.row_flip) >= p.row_hi) continue;
     float4 acc[VEC], acc2[DUAL ? VEC : 1];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   for (int64_t slot = blockIdx.x; slot < nlong; slot += gridDim.x) {
     const int64_t r = p.long_row[slot];
     const int64_t nch = chunks_of(r);
-    if (nch <= kLongWide) continue;
+    if (nch <= kLongWide || (r ^ (int64_t)p.row_flip) < p.row_lo || (r ^ (int64_t)p.row_flip) >= p.row_hi) continue;   // block-uniform
     float4 acc[VEC], acc2[DUAL ? VEC : 1];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
 template <int G, int VEC, int MODE>
 static void launch_seg_mode(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
   constexpr int kGroupsPerCta = kAggThreads / G;
-  k_seg_rows<G, VEC, MODE><<<grid_for(p.M, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
+  k_seg_rows<G, VEC, MODE><<<grid_for(p.row_hi - p.row_lo, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   if (p.plan_counts && chunk_cap > 0) {
     k_seg_chunks<G, VEC, MODE><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
     const size_t lsm = (size_t)kGroupsPerCta * ((MODE & 4) ? 2 : 1) * (size_t)(p.C / 4) * sizeof(float4);
@@ -485,15 +507,21 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   TW_CHECK_ARG(!planned || (a->long_row && a->long_base && a->chunk_owner && (a->partial || a->chunk_cap == 0) &&
                             (!a->out2 || a->partial2 || a->chunk_cap == 0)),
                "seg_reduce: incomplete long-row plan");
+  TW_CHECK_ARG(a->row_begin >= 0 && a->row_end >= 0 && a->row_end <= a->M && (a->row_end == 0 || a->row_begin <= a->row_end),
+               "seg_reduce: row range [%lld, %lld) outside [0, M]", (long long)a->row_begin, (long long)a->row_end);
+  TW_CHECK_ARG(!(a->row_end && a->row_flip && ((a->row_begin | a->row_end) & 1)), "seg_reduce: a row range under row_flip needs even bounds");
   if (a->M == 0) return 0;
   SegParams p;
+  p.row_lo = a->row_end ? a->row_begin : 0, p.row_hi = a->row_end ? a->row_end : a->M;   // row_end = 0: every row
+  if (p.row_hi <= p.row_lo) return 0;
   p.ptr = a->ptr, p.col = a->col, p.M = a->M, p.X = a->X, p.C = a->C, p.flip = a->flip, p.row_flip = a->row_flip;
   p.src_scale = a->src_scale, p.skip_mask = a->skip_mask, p.row_skip_mask = a->row_skip_mask;
   p.skip_self = a->skip_self, p.self_mode = a->self_mode, p.dst_scale = a->dst_scale, p.bias = a->bias;
   p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum, p.entry_mask = a->entry_mask;
   p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
   p.partial = a->partial;
-  p.src_scale2 = a->src_scale2, p.out2 = a->out2, p.partial2 = a->partial2;
+  p.src_scale2 = a->src_scale2, p.out2 = a->out2, p.partial2 = a->partial2, p.Xm = a->X_mate;
+  TW_CHECK_ARG(!a->X_mate || (a->out2 && aligned16(a->X_mate)), "seg_reduce: X_mate goes with the dual output");
   cudaStream_t s = (cudaStream_t)stream;
   const int cv = a->C >> 2;
   const int64_t cc = a->chunk_cap, lc = a->long_cap;

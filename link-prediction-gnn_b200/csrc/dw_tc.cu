@@ -12,12 +12,16 @@
 //   warp  0    TMA producer: raw fp32 tiles of dO_f, dO_r, H with cp.async.bulk.tensor (SWIZZLE_128B_ATOM_32B tensor maps
 //                            = the one MN-major layout the tensor core accepts for tf32, see below), L2 evict-first
 //   warps 2-9  split       : A: v = selfw[row] * raw, hi = rn_tf32(v) written back in place, lo = rn_tf32(v - hi) into a second
-//                            buffer; B: the same split of the H tile (hi in place)
-//   warp  1    MMA issuer  : 4 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
+//                            buffer; B: lo = rn_tf32(h - trunc_tf32(h)) only (the tensor core reads raw H as its own hi)
+//   warp  1    MMA issuer  : 3 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
 //   warps 10-13 drain      : TMEM -> fp32 registers after every tile (C <= 64), 64 tiles per addition into the CTA's double
 //                            partials in global memory; a second kernel adds the partials in double in CTA order:
 //                            deterministic.
 #include "common.cuh"
+
+#ifndef TWOWL_DW_FLUSH
+#define TWOWL_DW_FLUSH 1
+#endif
 
 namespace twowl {
 
@@ -37,7 +41,7 @@ __host__ __device__ constexpr int dw_nacc(int C) { return C <= 64 ? 1 : 2; }
 // (lo*lo, lo*hi, hi*lo) are added while it is still small, and only the 8 hi*hi steps run at full magnitude (~5e-7
 // relative); the drain warps add the tiles in fp32 registers, 64 tiles at a time, into per-CTA DOUBLE partials. C = 128
 // (two 128 x 128 accumulators, no room in registers: the running sums live in `part`) drains every 4 tiles.
-__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? 1 : 4; }
+__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? TWOWL_DW_FLUSH : 4; }
 constexpr int kDwRegTiles = 64;   // C <= 64: tiles added in fp32 registers between two additions into the double partials
 __host__ __device__ constexpr int dw_part_rows(int C) { return C <= 64 ? 128 : 2 * C; }
 
@@ -135,13 +139,10 @@ __device__ __forceinline__ bool dw_elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// tf32 split of both operands, round-to-nearest: x = hi + lo + r, hi = rn_tf32(x), lo = rn_tf32(x - hi), |r| <= 2^-22 |x|
-// (see pair_conv.cu); four products hi*hi + hi*lo + lo*hi + lo*lo.
-__device__ __forceinline__ float dw_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// tf32 split (see pair_conv.cu): A = selfw * dO is written back by the split warps anyway, so its hi is rn_tf32(v) and
+// lo = rn_tf32(v - hi); B = the raw H tile, read by the tensor core as hi = trunc_tf32(h), lo = rn_tf32(h - hi). Three products.
+__device__ __forceinline__ float dw_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float dw_lo(float x) { return dw_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
 __device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo) {
   hi.x = dw_rna(v.x), hi.y = dw_rna(v.y), hi.z = dw_rna(v.z), hi.w = dw_rna(v.w);
   lo.x = dw_rna(v.x - hi.x), lo.y = dw_rna(v.y - hi.y), lo.z = dw_rna(v.z - hi.z), lo.w = dw_rna(v.w - hi.w);
@@ -150,7 +151,7 @@ __device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo
 // C = width of dO_f, dO_r and H (32, 64 or 128). One stage:
 //   A_hi: AG groups of 32 M-elements ([f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
 template <int C, bool GN>
-__global__ void __maxnreg__(144) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
+__global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const __grid_constant__ CUtensorMap tmF,
                                                          const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmH) {
   constexpr int GS = C / 32;                          // 32-column groups per source
   constexpr int kDwTileK = dw_tile_k(C), NACC = dw_nacc(C), kDwFlush = dw_flush(C);
@@ -262,9 +263,9 @@ __global__ void __maxnreg__(144) k_dw_tc(const DwParams p, const __grid_constant
 #pragma unroll
         for (int ac = 0; ac < NACC; ++ac) {   // C = 128: D_f from the f groups of A, D_r from the r groups
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {   // lo*lo, lo*hi, hi*lo, hi*hi: small terms first
-            const uint64_t Ap = ((pass < 2) ? Alo : Ahi) + (uint64_t)(ac * GS * (kDwLbo >> 4));
-            const uint64_t Bp = (pass == 0 || pass == 2) ? Blo : Bhi;
+          for (int pass = 0; pass < 3; ++pass) {   // lo*hi, hi*lo, hi*hi: small terms first
+            const uint64_t Ap = ((pass == 0) ? Alo : Ahi) + (uint64_t)(ac * GS * (kDwLbo >> 4));
+            const uint64_t Bp = (pass == 1) ? Blo : Bhi;
 #pragma unroll
             for (int k = 0; k < kDwTileK / 8; ++k)   // one group of 8 k-rows per K-step
               dw_mma(tmem_base + (uint32_t)(a * TB + ac * C), Ap + (uint64_t)(k * (kDwKStep >> 4)), Bp + (uint64_t)(k * (kDwKStep >> 4)),
@@ -342,7 +343,7 @@ __global__ void __maxnreg__(144) k_dw_tc(const DwParams p, const __grid_constant
       load_heads(row0 + 2 * tstride, it + 2 < my_tiles, hdnn);
       float4* Ahi = reinterpret_cast<float4*>(smem + st * kStage);
       float4* Alo = reinterpret_cast<float4*>(smem + st * kStage + kAHalf);
-      float4* Bhi = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf);
+      const float4* Bhi = reinterpret_cast<const float4*>(smem + st * kStage + 2 * kAHalf);
       float4* Blo = reinterpret_cast<float4*>(smem + st * kStage + 2 * kAHalf + kBHalf);
       // one branch (f, then r) at a time: RPT rows x GS column groups per thread
 #pragma unroll
@@ -430,10 +431,8 @@ __global__ void __maxnreg__(144) k_dw_tc(const DwParams p, const __grid_constant
 #pragma unroll 4
       for (int j = 0; j < kBIter; ++j) {
         const int i = j * kSplitThreads + t;
-        float4 hi, lo;
-        dw_split(Bhi[i], hi, lo);
-        Bhi[i] = hi;
-        Blo[i] = lo;
+        const float4 v = Bhi[i];
+        Blo[i] = make_float4(dw_lo(v.x), dw_lo(v.y), dw_lo(v.z), dw_lo(v.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       dw_mbar_arrive(&split_done[st]);

@@ -411,8 +411,13 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float*
   for (int64_t l0 = grp0; l0 < L; l0 += 2 * ngrp) {
     const int64_t l1 = l0 + ngrp;
     const bool two = l1 < L;
-    const int64_t a0 = idx[(2 * l0) * sidx], a1 = idx[(2 * l0 + 1) * sidx];
-    const int64_t b0 = two ? idx[(2 * l1) * sidx] : a0, b1 = two ? idx[(2 * l1 + 1) * sidx] : a1;
+    // a negative row id = "this link is not mine" (a row-sharded caller masks the links outside its block): its logit is 0
+    // and nothing is gathered for it (the loads below then read row 0)
+    int64_t a0 = idx[(2 * l0) * sidx], a1 = idx[(2 * l0 + 1) * sidx];
+    int64_t b0 = two ? idx[(2 * l1) * sidx] : a0, b1 = two ? idx[(2 * l1 + 1) * sidx] : a1;
+    const bool va = a0 >= 0 && a1 >= 0, vb = b0 >= 0 && b1 >= 0;
+    if (!va) a0 = a1 = 0;
+    if (!vb) b0 = b1 = 0;
     const int64_t ea0 = a0 * cv + cc, ea1 = a1 * cv + cc, eb0 = b0 * cv + cc, eb1 = b1 * cv + cc;
     const float4 fa0 = ldg_cached(xf4 + ea0), ra0 = ldg_cached(xr4 + ea0), fa1 = ldg_cached(xf4 + ea1), ra1 = ldg_cached(xr4 + ea1);
     const float4 fb0 = ldg_cached(xf4 + eb0), rb0 = ldg_cached(xr4 + eb0), fb1 = ldg_cached(xf4 + eb1), rb1 = ldg_cached(xr4 + eb1);
@@ -432,8 +437,8 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float*
       acc1 += __shfl_xor_sync(gmask, acc1, d);
     }
     if (c4 == 0) {
-      pred[l0] = acc0 + bias;
-      if (two) pred[l1] = acc1 + bias;
+      pred[l0] = va ? acc0 + bias : 0.f;
+      if (two) pred[l1] = vb ? acc1 + bias : 0.f;
     }
   }
 }
@@ -458,6 +463,10 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* _
   const int64_t nwarps = ((int64_t)gridDim.x * kNormThreads) >> 5;
   for (int64_t l = warp0; l < L; l += nwarps) {
     const int64_t i0 = idx[(2 * l) * sidx], i1 = idx[(2 * l + 1) * sidx];
+    if (i0 < 0 || i1 < 0) {   // not this rank's link (see k_gn2_readout_fwd_g); warp-uniform
+      if (lane == 0) pred[l] = 0.f;
+      continue;
+    }
     float acc = 0.f;
     for (int c4 = lane; c4 < cv; c4 += 32) {
       const GnCols cf(C, c4 * 4, stf, wf, bf, mf), cr(C, c4 * 4, str_, wr, br, mr);
@@ -500,6 +509,10 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
     float4* __restrict__ G4 = reinterpret_cast<float4*>(G);
     for (int64_t j = (int64_t)blockIdx.x * rm.slots + rm.slot; j < 2 * L; j += (int64_t)gridDim.x * rm.slots) {
       const int64_t ra = idx[j * sidx], rb = idx[(j ^ 1) * sidx];
+      if (ra < 0 || rb < 0) {   // not this rank's link: no gradient row, no contribution to the column sums
+        G4[j * rm.cv + rm.c4] = f4_zero();
+        continue;
+      }
       const float g = dpred[j >> 1];
       const int64_t ea = ra * rm.cv + rm.c4, eb = rb * rm.cv + rm.c4;
       const float4 af = ldg_cached(xf4 + ea), ar = ldg_cached(xr4 + ea);

@@ -13,10 +13,10 @@
 //   warp  0    TMA producer: one lane streams raw fp32 128-row tiles of A_s into a ring of shared-memory stages with
 //                            cp.async.bulk.tensor (SWIZZLE_128B tensor map = the UMMA canonical K-major layout, L2
 //                            evict-first), 2-3 tiles in flight per SM
-//   warps 2-3  split       : hi = rn_tf32(x) written back IN PLACE, lo = rn_tf32(x - hi) into a second buffer (smem -> smem):
-//                            both exactly representable in tf32, so the tensor core's truncation of fp32 operands
-//                            (measured, tools/mma_probe.cu) loses nothing
-//   warp  1    MMA issuer  : one lane issues 4 x Kd/8 tcgen05.mma kind::tf32 per source (lo*lo, lo*hi, hi*lo, hi*hi) into that
+//   warps 2-3  split       : lo = rn_tf32(x - trunc_tf32(x)) of a landed tile into a second buffer (smem -> smem). The tensor
+//                            core TRUNCATES fp32 operands to tf32 (measured, tools/mma_probe.cu), so the raw tile IS
+//                            the `hi` operand of the split-tf32 scheme and is never rewritten
+//   warp  1    MMA issuer  : one lane issues 3 x Kd/8 tcgen05.mma kind::tf32 per source (lo*hi, hi*lo, hi*hi) into that
 //                            source's TMEM accumulator (double buffered); tcgen05.commit releases the stages / publishes
 //   warps 4-11 epilogue    : (4 TMEM lane quarters x 2 column halves) gathered rows requested before the accumulator
 //                            is waited for; tcgen05.ld -> row scale, source sum -> per-warp smem transpose -> coalesced
@@ -124,16 +124,21 @@ __device__ __forceinline__ float4 pc_ldg_keep(const float4* p, uint64_t policy) 
 }
 __device__ __forceinline__ void pc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pc_sw128(int r, int c) { return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4)); }
-// The tf32 split of both GEMM operands: x = hi + lo + r with hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32),
-// |r| <= 2^-11 |x - hi| <= 2^-22 |x|, unbiased. Both parts are tf32 numbers, so the tensor core (which TRUNCATES fp32 operands
-// to tf32, tools/mma_probe.cu) reads them exactly, and the four products hi*hi + hi*lo + lo*hi + lo*lo carry a relative error
-// <= 2^-21 per product - against 3 * 2^-20, biased, for the truncating three-product scheme this replaces (round 1).
-__device__ __forceinline__ float pc_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo) {
+// The tf32 split of the GEMM operands. The tensor core TRUNCATES fp32 operands to tf32 (tools/mma_probe.cu), so
+//   A (streamed): the raw tile is read as hi = trunc_tf32(x) for free; the split warps add lo = rn_tf32(x - hi) in a second
+//                 buffer (x - hi is exact, < 2^-10 |x|; rounding it to NEAREST instead of letting the tensor core truncate it
+//                 halves the error and removes its bias: |x - hi - lo| <= 2^-21 |x|);
+//   W (resident): hi = rn_tf32(w), lo = rn_tf32(w - hi): |w - hi - lo| <= 2^-22 |w|, |lo| <= 2^-11 |w|.
+// Three products hi*hi + hi*lo + lo*hi are issued; the dropped lo*lo is <= 2^-21 |a*w|. Per product the relative error is
+// <= 2^-21 + 2^-22 + 2^-21 = 1.25 * 2^-20, unbiased (round 1: 3 * 2^-20 with every term biased towards zero). A fourth
+// product and a round-to-nearest hi written back in place were measured: 4x smaller GEMM error, no change of the end-to-end
+// error (which is dominated by the conditioning of the fp32 chain, tools/diag_parity.py) and +11 % step time - not kept.
+// round to nearest tf32 (ties away from zero, = cvt.rna.tf32.f32) with two integer-pipe instructions: half an ulp of the
+// 10-bit mantissa added to the magnitude bits, the 13 low bits cleared (a carry into the exponent is the correct result). The
+// cvt instruction itself issues on the quarter-rate conversion pipe, which the latency-bound split warps feel.
+__device__ __forceinline__ float pc_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float pc_lo(float x) { return pc_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+__device__ __forceinline__ void pc_split(const float4& v, float4& hi, float4& lo) {   // resident weights
   hi.x = pc_rna(v.x), hi.y = pc_rna(v.y), hi.z = pc_rna(v.z), hi.w = pc_rna(v.w);
   lo.x = pc_rna(v.x - hi.x), lo.y = pc_rna(v.y - hi.y), lo.z = pc_rna(v.z - hi.z), lo.w = pc_rna(v.w - hi.w);
 }
@@ -308,23 +313,23 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
             if (ns == 1 && Kd - kb * 32 >= 32) {
               // one full slab per stage (the 16 KB ring of the wide two-source launches)
 #pragma unroll
-              for (int pass = 0; pass < 4; ++pass) {
-                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   pc_mma(tacc, Ap + (uint64_t)(k * 2), Bp + (uint64_t)(k * 2), idesc, acc);
                   acc = 1;
                 }
-                if (pass == 1) pc_commit(&lo_empty[l.slot]);
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);
               }
             } else if (ns == kPcGroup && Kd - kb * 32 >= kPcGroup * 32) {
-              // full stage: 4 passes (lo*lo, lo*hi, hi*lo, hi*hi: small terms first - the accumulator's own truncation is
-              // relative to its magnitude) x 2 slabs x 4 k-steps, back to back
+              // full stage: 3 passes (lo*hi, hi*lo, hi*hi: small terms first - the accumulator's own truncation is relative to
+              // its magnitude) x 2 slabs x 4 k-steps, back to back
 #pragma unroll
-              for (int pass = 0; pass < 4; ++pass) {
-                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
 #pragma unroll
                 for (int j = 0; j < kPcGroup; ++j) {
 #pragma unroll
@@ -333,12 +338,12 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
                     acc = 1;
                   }
                 }
-                if (pass == 1) pc_commit(&lo_empty[l.slot]);  // the lo stage is free once the two passes that read it are done
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);  // the lo stage is free once the first pass has read it
               }
             } else {
-              for (int pass = 0; pass < 4; ++pass) {
-                const uint64_t Ap = (pass < 2) ? Alo : Ahi;
-                const uint64_t Bp = (pass == 0 || pass == 2) ? blo : bhi;
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t Ap = (pass == 0) ? Alo : Ahi;
+                const uint64_t Bp = (pass == 1) ? blo : bhi;
                 for (int j = 0; j < ns; ++j) {
                   const int rem = Kd - (kb + j) * 32;
                   const int ksteps = rem >= 32 ? 4 : (rem + 7) >> 3;   // 8 k-values per tf32 MMA; the padding is zero on both sides
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
                     acc = 1;
                   }
                 }
-                if (pass == 1) pc_commit(&lo_empty[l.slot]);
+                if (pass == 0) pc_commit(&lo_empty[l.slot]);
               }
             }
             pc_commit(&raw_empty[r.slot]);  // stage reusable once these MMAs have read it
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
       __syncwarp();
     }
   } else if (warp < kPcFirstEpi) {
-    // ===================================================== split: hi in place, lo into the lo ring, same (swizzled) offsets
+    // ===================================================== split: lo = rn_tf32(x - trunc_tf32(x)), same (swizzled) offsets
     const int t = tid - kPcFirstSplit * 32;  // 0..63
     constexpr int kSplitThreads = kPcSplitWarps * 32;
     constexpr int kBatch = (int)(kPcSlab / 16u) / kSplitThreads;     // 16 float4 per thread per slab
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
       for (int gi = 0; gi < ngroups; ++gi) {
         const int ns = KB - gi * G < G ? KB - gi * G : G;
         pc_mbar_wait(&raw_full[r.slot], r.phase);
-        float4* __restrict__ src = reinterpret_cast<float4*>(As + (size_t)r.slot * kStage);
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(As + (size_t)r.slot * kStage);
         float4* __restrict__ dst = reinterpret_cast<float4*>(Ls + (size_t)l.slot * kStage);
         float4 x[kBatch];
 #pragma unroll
@@ -379,12 +384,8 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
         pc_mbar_wait(&lo_empty[l.slot], l.phase ^ 1u);
         for (int b = 0; b < ns; ++b) {
 #pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            float4 hi, lo;
-            pc_split(x[j], hi, lo);
-            src[(b * kBatch + j) * kSplitThreads + t] = hi;   // in place: the MMA reads the stage only after lo_full
-            dst[(b * kBatch + j) * kSplitThreads + t] = lo;
-          }
+          for (int j = 0; j < kBatch; ++j)
+            dst[(b * kBatch + j) * kSplitThreads + t] = make_float4(pc_lo(x[j].x), pc_lo(x[j].y), pc_lo(x[j].z), pc_lo(x[j].w));
           if (b + 1 < ns) {
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) x[j] = src[((b + 1) * kBatch + j) * kSplitThreads + t];

@@ -150,12 +150,20 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_cnt_block(const int32_t* 
     if (blocked[a] && i >= 0 && i < N) atomicSub(&cnt[i], 1);  // integer atomics: order-independent result
   }
 }
+// rows [row_lo, row_hi) of the pair table -> entries [0, row_hi - row_lo) of the [2, Rout] outputs (Rout = row_hi - row_lo;
+// the whole table: row_lo = 0, row_hi = Rout = R)
 __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __restrict__ src, const int32_t* __restrict__ dst_e,
                                                             int64_t E, int64_t R, int64_t N, const uint8_t* __restrict__ blocked,
-                                                            const int32_t* __restrict__ cnt, int32_t* __restrict__ centre,
-                                                            float* __restrict__ dinv, float* __restrict__ selfw,
-                                                            int32_t* __restrict__ bnode) {
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < R; b += (int64_t)gridDim.x * blockDim.x) {
+                                                            const int32_t* __restrict__ cnt, int64_t row_lo, int64_t row_hi,
+                                                            int32_t* __restrict__ centre_, float* __restrict__ dinv_,
+                                                            float* __restrict__ selfw_, int32_t* __restrict__ bnode_) {
+  // the outputs are addressed as if they covered the whole table: [q * Rout + (b - row_lo)] = base[q * Rout - row_lo + b]
+  const int64_t Rout = row_hi - row_lo;
+  int32_t* const centre = centre_ - row_lo;
+  float* const dinv = dinv_ - row_lo;
+  float* const selfw = selfw_ - row_lo;
+  int32_t* const bnode = bnode_ - row_lo;
+  for (int64_t b = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < row_hi; b += (int64_t)gridDim.x * blockDim.x) {
     // direction 0 (edge2 = [a^1; b]): row b is fed by the in-list of src[b]; its id-self-loop is a = b^1
     // direction 1 (edge2_r = [a; b^1]): row b is fed by the in-list of src[b^1]; its id-self-loop is a = b
     const int64_t mate = b ^ 1;
@@ -168,11 +176,11 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __res
     const float d0 = rsqrtf_exact((float)(n0 - (self0 ? 1 : 0) + 1));
     const float d1 = rsqrtf_exact((float)(n1 - (self1 ? 1 : 0) + 1));
     centre[b] = (c0 >= 0 && c0 < N) ? c0 : -1;
-    centre[R + b] = (c1 >= 0 && c1 < N) ? c1 : -1;
+    centre[Rout + b] = (c1 >= 0 && c1 < N) ? c1 : -1;
     dinv[b] = d0;
-    dinv[R + b] = d1;
+    dinv[Rout + b] = d1;
     selfw[b] = self0 ? 0.f : d0 * d0;
-    selfw[R + b] = self1 ? 0.f : d1 * d1;
+    selfw[Rout + b] = self1 ? 0.f : d1 * d1;
     // backward: row b is a source of S_d[node] iff its feeding edge (b^1 for direction 0, b for direction 1) is live
     int32_t n0b = -1, n1b = -1;
     if (mate < E && !(blocked && blocked[mate])) {
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __res
       if (nd >= 0 && nd < N) n1b = nd;
     }
     bnode[b] = n0b;
-    bnode[R + b] = n1b;
+    bnode[Rout + b] = n1b;
   }
 }
 
@@ -314,7 +322,24 @@ extern "C" int twowl_wedge_prepare(const int32_t* src, const int32_t* dst_e, int
   cudaStream_t s = (cudaStream_t)stream;
   if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
   if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
-  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, centre, dinv, selfw, bnode);
+  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, 0, R, centre, dinv, selfw, bnode);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_wedge_prepare_rows(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N,
+                                        const uint8_t* blocked, const int64_t* in_ptr, int64_t row_lo, int64_t row_hi, int32_t* cnt,
+                                        int32_t* centre, float* dinv, float* selfw, int32_t* bnode, void* stream) {
+  TW_CHECK_ARG(E >= 0 && R >= E && N >= 0, "wedge_prepare_rows: need 0 <= E <= R and N >= 0");
+  TW_CHECK_ARG(row_lo >= 0 && row_lo <= row_hi && row_hi <= R && !((row_lo | row_hi) & 1),
+               "wedge_prepare_rows: [%lld, %lld) must be an even-bounded range of the %lld pair rows", (long long)row_lo,
+               (long long)row_hi, (long long)R);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
+  if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
+  if (row_hi > row_lo)
+    k_wedge_rows<<<grid_for(row_hi - row_lo, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, row_lo, row_hi, centre,
+                                                                                dinv, selfw, bnode);
   TW_LAUNCH_CHECK();
   return 0;
 }

@@ -34,6 +34,7 @@ class SegArgs(ctypes.Structure):
         ("chunk_owner", ctypes.c_void_p), ("partial", ctypes.c_void_p), ("chunk_cap", ctypes.c_int64),
         ("long_cap", ctypes.c_int64), ("pair_sum", ctypes.c_int32), ("entry_mask", ctypes.c_void_p),
         ("src_scale2", ctypes.c_void_p), ("out2", ctypes.c_void_p), ("partial2", ctypes.c_void_p),
+        ("row_begin", ctypes.c_int64), ("row_end", ctypes.c_int64), ("X_mate", ctypes.c_void_p),
     ]
 
 

@@ -319,12 +319,15 @@ def _pl_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)   # no zero-filled [R,C] gradients for the saved-state outputs
 
 
-def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars, dWs=None):
+def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars, dWs=None, dh_out=None):
     """Backward of the structured pair-level GCNConv pair from the gradients dO_f, dO_r of its two outputs:
     -> dh and, per direction, (dW, dbias, d gn.weight, d gn.bias, d gn.mean_scale).
     dWs: the (selfw_d * dO_d)^T H parts when the caller already has them (pair_dw_gn)."""
     C = wf.shape[0]
-    dSs = [ops.seg_reduce(out_ptr, out_ids, n_node, dOs[d], plan=out_plan, flip=d, src_scale=dinv[d]) for d in range(2)]
+    # both directions' gradient sums from ONE pass over every node's out-list: entry b contributes dinv_f[b] * dO_f[b] to dS_f and
+    # dinv_r[b^1] * dO_r[b^1] to dS_r (bit-identical to the two passes with flip = 0 / 1)
+    dSs = list(ops.seg_reduce(out_ptr, out_ids, n_node, dOs[0].contiguous(), plan=out_plan, src_scale=dinv[0], dual=True,
+                              src_scale2=dinv[1], X_mate=dOs[1].contiguous()))
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d ;  the gathered part of dH goes through (dS_d W_d)
     if dWs is not None:
         pass
@@ -341,7 +344,7 @@ def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf,
         dpar = dpars[d]
         res.append((dW, dpar[3 * C:], dpar[:C], dpar[C:2 * C], dpar[2 * C:3 * C]))
     dh = ops.pair_conv(dOs, [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
-                       gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])])
+                       gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])], out=dh_out)
     return dh, res
 
 
@@ -411,14 +414,17 @@ def _plr_bwd(ctx, g, *_unused):
         G, head, nxt, consts, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd_prepare(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr),
                                                                                p_drop, seed_f, seed_r, True, idx, pw.contiguous(),
                                                                                g.reshape(-1))
-        dOf, dOr, dWf, dWr = ops.pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop, seed_f, seed_r, True, selfw[0], selfw[1], h)
+        inplace = ops.INPLACE_BACKWARD and wf.shape[0] == wf.shape[1]
+        dOf, dOr, dWf, dWr = ops.pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop, seed_f, seed_r, True, selfw[0], selfw[1], h,
+                                            inplace=inplace)
         dWs = [dWf, dWr]
     else:
+        inplace = False
         dOf, dOr, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r,
                                                            True, idx, pw.contiguous(), g.reshape(-1))
         dWs = None
     dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr],
-                           dWs=dWs)
+                           dWs=dWs, dh_out=h if inplace else None)      # h is not read by that launch: dH may take its place
     return (dh,) + res[0] + res[1] + (None, dpw.reshape(pw.shape), dpb) + (None,) * 16
 
 

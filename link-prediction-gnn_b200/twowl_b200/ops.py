@@ -346,8 +346,9 @@ def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
 
 def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
                row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
-               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None):
-    """dual=True -> (out, out2): out2[m] = sum src_scale2[s^1] * X[s^1] over the same entries (see twowl_seg_args)."""
+               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None, rows=None, X_mate=None):
+    """dual=True -> (out, out2): out2[m] = sum src_scale2[s^1] * X[s^1] over the same entries (see twowl_seg_args).
+    rows=(lo, hi): only output rows [lo, hi) are computed (and written into `out`, which keeps its full [M, C] shape)."""
     _need_cuda(ptr, col, X)
     assert X.dtype == torch.float32 and X.is_contiguous()
     C = X.shape[1]
@@ -358,6 +359,10 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
                 mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate), pair_sum=int(pair_sum), entry_mask=_p(entry_mask))
+    if rows is not None:
+        a.row_begin, a.row_end = int(rows[0]), int(rows[1])
+        if a.row_end <= a.row_begin:
+            return (out, out2) if dual else out
     partial = None
     if plan is not None:
         nnz = col.numel()
@@ -372,8 +377,13 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
             a.partial2 = partial2.data_ptr()
     if dual:
         a.src_scale2, a.out2 = _p(src_scale2), out2.data_ptr()
+        if X_mate is not None:      # the mates' rows come from a second matrix of the same shape (dO_r next to dO_f)
+            assert X_mate.shape == X.shape and X_mate.is_contiguous() and X_mate.dtype == torch.float32
+            a.X_mate = X_mate.data_ptr()
     nbytes = col.numel() * (4 * C * (1 + int(pair_sum) + int(X2 is not None) + int(dual)) + 8 + 4 * int(dual)) + \
         M * (4 * C + 8) * (1 + int(dual))
+    if rows is not None:      # a node block: its share of the entries is not known on the host - charged by its share of the rows
+        nbytes = nbytes * (int(rows[1]) - int(rows[0])) // max(M, 1)
     with _P("seg_reduce", nbytes):
         check(lib.twowl_seg_reduce(ctypes.byref(a), _stream()), "seg_reduce")
     _count(1 if plan is None else 3)
@@ -674,6 +684,22 @@ def wedge_prepare(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr):
     return cnt, centre, dinv, selfw, bnode
 
 
+def wedge_prepare_rows(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr, lo: int, hi: int):
+    """wedge_prepare for the pair rows [lo, hi) only -> (cnt [N], centre, dinv, selfw, bnode [2, hi - lo])."""
+    dev = src32.device
+    Rl = hi - lo
+    cnt = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    centre = torch.empty((2, Rl), dtype=torch.int32, device=dev)
+    dinv = torch.empty((2, Rl), dtype=torch.float32, device=dev)
+    selfw = torch.empty((2, Rl), dtype=torch.float32, device=dev)
+    bnode = torch.empty((2, Rl), dtype=torch.int32, device=dev)
+    check(lib.twowl_wedge_prepare_rows(src32.data_ptr(), dst_e32.data_ptr(), E, R, N, _p(blocked), in_ptr.data_ptr(), int(lo), int(hi),
+                                       cnt.data_ptr(), centre.data_ptr(), dinv.data_ptr(), selfw.data_ptr(), bnode.data_ptr(),
+                                       _stream()), "wedge_prepare_rows")
+    _count(3)
+    return cnt, centre, dinv, selfw, bnode
+
+
 def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
     R, C = Z.shape
     out = torch.empty_like(Z)
@@ -702,7 +728,7 @@ def pair_conv_supported(Kd: int, Nd: int, nsrc: int) -> bool:
 
 
 def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_scale=None, eps: float = 1e-5,
-              want_moments: bool = False):
+              want_moments: bool = False, out=None):
     """out = sum_s (row_scale_s * A_s) B_s^T + sum_g coef_g * T_g[idx_g] + bias on tcgen05 (3xTF32).
     A, W, w_kn, row_scale: sequences of length nsrc; gathers: sequence of (T, idx int32, coef).
     Returns out, or (out, stats[2*Nd]) when stats_mean_scale is given (GraphNorm mean / inv_std of out), or
@@ -712,7 +738,10 @@ def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_s
     Nd = W[0].shape[1] if w_kn[0] else W[0].shape[0]
     dev = A[0].device
     _need_cuda(*A, *W)
-    out = torch.empty((M, Nd), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((M, Nd), dtype=torch.float32, device=dev)
+    else:   # a caller-owned [M, Nd] buffer that is none of this launch's inputs (the in-place backward, see INPLACE_BACKWARD)
+        assert out.shape == (M, Nd) and out.is_contiguous() and all(out.data_ptr() != x.data_ptr() for x in A)
     a = ConvArgs(nsrc=nsrc, ngather=len(gathers), Kd=Kd, Nd=Nd, M=M, bias=_p(bias), out=out.data_ptr(), eps=float(eps))
     keep = []
     for s in range(nsrc):
@@ -840,12 +869,19 @@ def pair_dw_wide(dOf, dOr, rsf, rsr, H):
     return dWf, dWr
 
 
-def pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop: float, seed_f: int, seed_r: int, relu: bool, rsf, rsr, H):
+# The backward of the last pair layer may reuse the forward's buffers: dO_f / dO_r are written over O_f / O_r (every 64-row
+# tile is read by the CTA that overwrites it) and dH over H (which that launch does not read). 3 live [R,C] tensors instead of 6:
+# hidden 128 at R = 60 M pair rows fits one 180 GB GPU. The saved activations are gone afterwards, so backward(retain_graph=True)
+# is not possible in this mode - opt in with TWOWL_INPLACE_BACKWARD=1 or ops.INPLACE_BACKWARD = True.
+INPLACE_BACKWARD = os.environ.get("TWOWL_INPLACE_BACKWARD", "0") != "0"
+
+
+def pair_dw_gn(Of, Or, consts, G, head, nxt, p_drop: float, seed_f: int, seed_r: int, relu: bool, rsf, rsr, H, inplace: bool = False):
     """pair_dw with the gradients made on the fly from the last pair layer's outputs (after gn2_readout_bwd_prepare):
-    -> (dOf, dOr [M,C], dWf, dWr [C,C]). One pass: reads Of, Or, H, writes dOf, dOr."""
+    -> (dOf, dOr [M,C], dWf, dWr [C,C]). One pass: reads Of, Or, H, writes dOf, dOr (over Of, Or with inplace=True)."""
     _need_cuda(Of, Or, H)
     M, C = H.shape
-    dOf, dOr = torch.empty_like(Of), torch.empty_like(Or)
+    dOf, dOr = (Of, Or) if inplace else (torch.empty_like(Of), torch.empty_like(Or))
     dWf = torch.empty((C, C), dtype=torch.float32, device=H.device)
     dWr = torch.empty((C, C), dtype=torch.float32, device=H.device)
     nb = lib.twowl_pair_dw_workspace_bytes(M, C)

@@ -1,9 +1,9 @@
 """Row-block sharding of the pair table over several GPUs: ONE TwoWL step cut over the ranks.
 
-Rank g owns the contiguous block [lo, hi) of pair rows (even boundaries: rows 2k / 2k+1 are the two directions of one pair,
-utils.py:81-90, and stay together), i.e. its rows of every [R, C] activation of model.py:75-83, the observed edges and the
-target links that fall into the block. The node-level part of the model (model.py:71-73, [N, C] tensors) is replicated.
-On the factorised wedge path a pair row only talks to the other rows through per-NODE sums, so the exchange per step is
+Pair level (model.py:75-83). Rank g owns the contiguous block [lo, hi) of pair rows (even boundaries: rows 2k / 2k+1 are the
+two directions of one pair, utils.py:81-90, and stay together), i.e. its rows of every [R, C] activation, the observed edges
+and the target links that fall into the block. On the factorised wedge path a pair row only talks to the other rows through
+per-NODE sums, so the exchange per pair layer is
 
     forward   all_reduce  SH_f, SH_r   [2, N, C] fp32      in-list sums of the pair layer (partial over the rank's edges)
               all_reduce  moments      [2, 2C]   fp64      GraphNorm column (sum, sum of squares) of both branches
@@ -11,15 +11,32 @@ On the factorised wedge path a pair row only talks to the other rows through per
     backward  all_reduce  colsums      [6, C]    fp64      GraphNorm-backward / readout column sums over the selected rows
                                                            ([4, C] over all rows for a layer that is not the last)
               all_reduce  dS_f, dS_r   [2, N, C] fp32      gradient of the per-node sums
-    (+ the caller's ONE all-reduce of the flat parameter gradients, dist.allreduce_grads)
 
-instead of the all-gather / reduce-scatter of [R, C] an explicit wedge index would need. Every rank computes the same numbers
-as the single-GPU path up to the summation order of those five reductions. Gradients that are complete on every rank after an
-all-reduce (GraphNorm / readout parameters) are kept on rank 0 only, so that the caller's gradient SUM is exact.
+instead of the all-gather / reduce-scatter of [R, C] an explicit wedge index would need.
 
-Covers any depth2 >= 1 on the structured wedge path with the doubled pair layout and widths the tensor-core kernels take
-(32 / 64 / 128); every non-last layer adds its own SH / moments / GraphNorm-backward column sums / dS exchanges. Dropout masks are keyed by the LOCAL row id: statistically the
-same as the single-GPU run, not the same bits (parity tests run with dropout 0 / eval mode).
+Node level (model.py:71-73). The node-level GCNConv aggregations - the only node-level work that is not a cheap streaming pass -
+are cut into NODE blocks [g*B, (g+1)*B), B = ceil(N / world): a rank reduces the in-lists (forward) / out-lists (backward) of
+its own nodes only (twowl_seg_args.row_begin / row_end on the whole graph's CSR) and the blocks are exchanged:
+
+    forward   all_gather  conv output  [N, C]    fp32      per node layer
+    backward  all_reduce  d(x)         [N, C]    fp32      once: the pair-init backward leaves every rank a PARTIAL dx
+              all_gather  d(z)         [N, C]    fp32      per node layer
+              all_reduce  d(emb)       [V, C]    fp32      the embedding gradient, summed over node blocks
+
+Everything else at node level (embedding lookup, GraphNorm, the [N, C] x [C, C] linear layers) is a streaming pass of a few
+hundred MB and stays replicated. Gradient bookkeeping: upstream of the dx all-reduce every rank holds COMPLETE gradients, so the
+parameter gradients made there (and every other gradient that is complete on all ranks after a reduction: GraphNorm / readout
+column sums) are kept on rank 0 only - the caller's ONE all-reduce (sum) of the flat parameter gradients is then exact
+(dist.allreduce_grads); gradients made from a rank's own rows stay partial and are summed by that same all-reduce.
+
+No step of this path reads device data on the host: the target links of a block are selected by a mask (links outside the block
+carry row id -1, which the readout kernels skip), not by a compaction whose size the host would have to know.
+
+Every rank computes the same numbers as the single-GPU path up to the summation order of those reductions. Covers any
+depth1 >= 1, depth2 >= 1 on the structured wedge path with the doubled pair layout and widths the tensor-core kernels take
+(32 / 64 / 128). Dropout masks are keyed by the LOCAL row id: statistically the same as the single-GPU run, not the same bits
+(parity tests run with dropout 0 / eval mode); the replicated node-level dropout draws the same host seeds on every rank
+(seed every rank's torch generator alike).
 """
 from __future__ import annotations
 
@@ -29,6 +46,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from . import functional as F2
 from . import graph as G
 from . import ops
 
@@ -41,20 +59,180 @@ def block_of(R: int, rank: int, world: int) -> Tuple[int, int]:
     return 2 * (pairs * rank // world), 2 * (pairs * (rank + 1) // world)
 
 
+def node_block(N: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """(lo, hi, B): rank's node block [lo, hi) of equal-size blocks B = ceil(N / world) (the last ones may be short or empty)."""
+    B = -(-N // world)
+    return min(rank * B, N), min((rank + 1) * B, N), B
+
+
+_last_shard = None
+
+
 class RowShard:
-    """Assign to ``LocalWLNet.row_shard`` to run forward / backward on this rank's block of pair rows."""
+    """Assign to ``LocalWLNet.row_shard`` to run forward / backward on this rank's block of pair rows (and node block)."""
 
     def __init__(self, group=None, rank: Optional[int] = None, world: Optional[int] = None):
+        global _last_shard
         self.group = group
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank, self.world = int(rank), int(world)
+        self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self.log = {}            # collective name -> [calls, bytes] since construction
+        self.steps = 0
+        _last_shard = self
 
-    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+    def _account(self, what: str, t: torch.Tensor):
+        e = self.log.setdefault(what, [0, 0])
+        e[0] += 1
+        e[1] += t.numel() * t.element_size()
+
+    def all_reduce(self, t: torch.Tensor, what: str = "all_reduce") -> torch.Tensor:
         if self.world > 1:
-            dist.all_reduce(t, group=self.group)
+            self._account("all_reduce " + what, t)
+            with ops._P("nccl_all_reduce", 2 * t.numel() * t.element_size()):
+                dist.all_reduce(t, group=self.group)
         return t
+
+    def all_gather_blocks(self, full: torch.Tensor, B: int, what: str = "all_gather") -> torch.Tensor:
+        """full: [world * B, C] whose block [rank*B, (rank+1)*B) this rank has filled -> every block filled, in place."""
+        if self.world > 1:
+            self._account("all_gather " + what, full)
+            mine = full[self.rank * B:(self.rank + 1) * B]
+            with ops._P("nccl_all_gather", full.numel() * full.element_size()):
+                if self.nccl:
+                    dist.all_gather_into_tensor(full, mine, group=self.group)     # in place: input = this rank's slice of output
+                else:   # gloo (the CPU / single-device tests): blocks of the other ranks zeroed, then a sum
+                    full[:self.rank * B].zero_()
+                    full[(self.rank + 1) * B:].zero_()
+                    dist.all_reduce(full, group=self.group)
+        return full
+
+
+def comm_summary():
+    """Collectives of the most recent RowShard per step: {name: {"calls_per_step", "MB_per_step"}} (bench.py)."""
+    s = _last_shard
+    if s is None or not s.steps:
+        return None
+    out = {k: {"calls_per_step": round(v[0] / s.steps, 2), "MB_per_step": round(v[1] / s.steps / 1e6, 2)} for k, v in sorted(s.log.items())}
+    out["total_MB_per_step"] = round(sum(v[1] for v in s.log.values()) / s.steps / 1e6, 1)
+    return out
+
+
+# ------------------------------------------------------------------------------ node level
+
+
+class _Rank0Grad(torch.autograd.Function):
+    """Identity on a parameter whose gradient is COMPLETE on every rank: keep it on rank 0 so that the caller's sum is exact."""
+
+    @staticmethod
+    def forward(ctx, p, shard):
+        ctx.keep = shard.rank == 0
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if ctx.keep else torch.zeros_like(g)), None
+
+
+class _ShardedEmbedding(torch.autograd.Function):
+    """nn.Embedding lookup by degree (model.py:71), replicated; backward = the segmented row sum by degree over this rank's
+    NODE block of a gradient that is complete on every rank, summed over the ranks, kept on rank 0."""
+
+    @staticmethod
+    def forward(ctx, weight, deg, shard):
+        ctx.save_for_backward(deg)
+        ctx.meta = (weight.shape[0], shard)
+        return ops.gather_rows(weight.contiguous(), deg)
+
+    @staticmethod
+    def backward(ctx, g):
+        (deg,) = ctx.saved_tensors
+        V, shard = ctx.meta
+        deg = deg.reshape(-1)
+        lo, hi, _ = node_block(deg.numel(), shard.rank, shard.world)
+        g = g.contiguous()
+        if hi > lo:
+            ptr, ids = ops.csr_build(deg[lo:hi], V)     # rows = degree values: extremely skewed, so plan it
+            plan = ops.seg_plan(ptr, V, hi - lo)
+            dW = ops.seg_reduce(ptr, ids, V, g[lo:hi], plan=plan)
+        else:
+            dW = g.new_zeros((V, g.shape[1]))
+        shard.all_reduce(dW, "d(emb) [V,C]")
+        if shard.rank != 0:
+            dW.zero_()
+        return dW, None, None
+
+
+class _ShardedNodeAggregate(torch.autograd.Function):
+    """GCNConv.propagate + bias of a node layer (model.py:73; functional.gcn_aggregate) with the output rows cut into node blocks:
+    this rank reduces the in-lists of its own nodes and the blocks are all-gathered. Backward: (all-reduce of the incoming
+    gradient when it is partial, i.e. for the layer that feeds the pair level), the out-lists of the rank's own nodes, all-gather
+    -> d(z) complete on every rank; d(bias) complete, kept on rank 0."""
+
+    @staticmethod
+    def forward(ctx, z, bias, gr, shard, grad_is_partial):
+        z = z.contiguous()
+        N, C = z.shape
+        lo, hi, B = node_block(N, shard.rank, shard.world)
+        full = torch.empty((B * shard.world, C), dtype=z.dtype, device=z.device)
+        ops.seg_reduce(gr.ptr, gr.col, N, z, plan=gr.plan, src_scale=gr.dinv, dst_scale=gr.dinv, skip_self=True, self_mode=1, bias=bias,
+                       entry_mask=gr.emask, out=full[:N], rows=(lo, hi))
+        shard.all_gather_blocks(full, B, "node conv out [N,C]")
+        ctx.gr, ctx.shard, ctx.partial = gr, shard, bool(grad_is_partial)
+        return full[:N]
+
+    @staticmethod
+    def backward(ctx, g):
+        gr, shard = ctx.gr, ctx.shard
+        N, C = g.shape
+        lo, hi, B = node_block(N, shard.rank, shard.world)
+        if ctx.partial:
+            g = shard.all_reduce(g.clone(memory_format=torch.contiguous_format), "d(x) [N,C]")
+        else:
+            g = g.contiguous()
+        dbias = ops.colsum(g) if shard.rank == 0 else g.new_zeros((C,))
+        full = torch.empty((B * shard.world, C), dtype=g.dtype, device=g.device)
+        ops.seg_reduce(gr.tptr, gr.tcol, N, g, plan=gr.tplan, src_scale=gr.dinv, dst_scale=gr.dinv, skip_self=True, self_mode=1,
+                       entry_mask=gr.temask, out=full[:N], rows=(lo, hi))
+        shard.all_gather_blocks(full, B, "node d(z) [N,C]")
+        return full[:N], dbias, None, None, None
+
+
+def forward_nodes(model, x, edge1):
+    """model.py:71-73 with the aggregations cut into node blocks: x int64 [N] degrees -> [N, C] (complete on every rank)."""
+    shard: RowShard = model.row_shard
+    if model.use_node_feat:
+        raise NotImplementedError("row sharding covers the degree-embedding input (use_node_feat=False)")
+    N = x.numel()
+
+    def r0(p):
+        return _Rank0Grad.apply(p, shard)
+
+    def gn_act(gn, dp, act, h):
+        p = dp.p if (model.training and dp.p > 0.0) else 0.0
+        seed = ops.next_seed() if p > 0.0 else 0
+        return F2.graphnorm_act(h, r0(gn.weight), r0(gn.bias), r0(gn.mean_scale), None, gn.eps, p, seed, isinstance(act, torch.nn.ReLU))[0]
+
+    emb, gn0, dp0 = model.emb[0], model.emb[1], model.emb[2]
+    h = _ShardedEmbedding.apply(emb.weight, x, shard)
+    h = gn_act(gn0, dp0, None, h)
+    last = len(model.conv1s) - 1
+    for k, seq in enumerate(model.conv1s):
+        conv, gn, dp, act = seq.modlist[0], seq.modlist[1], seq.modlist[2], seq.modlist[3]
+        gr = G.node_graph(edge1, N)
+        z = F2.linear(h, r0(conv.lin.weight))
+        out = _ShardedNodeAggregate.apply(z, conv.bias, gr, shard, k == last)
+        if k == last:     # its GraphNorm sees the partial gradients of the pair level: ordinary (partial) parameter gradients
+            p = dp.p if (model.training and dp.p > 0.0) else 0.0
+            h = gn.fused(out, p, isinstance(act, torch.nn.ReLU), None)
+        else:
+            h = gn_act(gn, dp, act, out)
+    return h
+
+
+# ------------------------------------------------------------------------------ pair level
 
 
 @dataclass
@@ -93,7 +271,7 @@ def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr)
                               src_scale2=dinv[0])
     SH = torch.stack((SHf, SHr))
     del SHf, SHr
-    shard.all_reduce(SH)
+    shard.all_reduce(SH, "SH [2,N,C]")
     Sf, Sr = ops.linear_fwd(SH[0], wf), ops.linear_fwd(SH[1], wr)
     if ops.PAIR_CONV_DUAL and ops.pair_conv_dual_supported(H.shape[1], wf.shape[0]):
         Of, Or, mf, mr = ops.pair_conv_dual(H, wf, wr, selfw[0], selfw[1], (Sf, centre[0], dinv[0]), (Sr, centre[1], dinv[1]), bf, br,
@@ -106,7 +284,7 @@ def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr)
                                    stats_mean_scale=gm, eps=eps, want_moments=True)
             Os.append(O)
             moms.append(mom)
-    mom = shard.all_reduce(torch.stack(moms))
+    mom = shard.all_reduce(torch.stack(moms), "GraphNorm moments [2,2C] f64")
     sf = ops.graphnorm_stats_from_moments(mom[0], R_total, gmf, eps)
     sr = ops.graphnorm_stats_from_moments(mom[1], R_total, gmr, eps)
     return Os[0], Os[1], sf, sr, SH
@@ -117,12 +295,12 @@ def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
     (dH, dW_f, dW_r) on this block: the dS exchange and the input-gradient pass."""
     _, dinv, selfw, bnode = rows
     dOs = (dOf, dOr)
-    dS = torch.stack([ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOs[d], plan=loc.out_plan, flip=d, src_scale=dinv[d])
-                      for d in range(2)])
+    dS = torch.stack(ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOs[0].contiguous(), plan=loc.out_plan, src_scale=dinv[0], dual=True,
+                                    src_scale2=dinv[1], X_mate=dOs[1].contiguous()))
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d: with THIS rank's partial dS the sum over ranks is the full product
     dWf = dWf + ops.linear_bwd_weight(dS[0], SH[0])
     dWr = dWr + ops.linear_bwd_weight(dS[1], SH[1])
-    shard.all_reduce(dS)
+    shard.all_reduce(dS, "dS [2,N,C]")
     dSW = [ops.linear_bwd_input(dS[0], wf), ops.linear_bwd_input(dS[1], wr)]
     dh = ops.pair_conv([dOf, dOr], [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
                        gathers=[(dSW[0], bnode[0], dinv[0]), (dSW[1], bnode[1], dinv[1])])
@@ -175,7 +353,8 @@ class _ShardedPairLayer(torch.autograd.Function):
         shard, loc, R_total, n_node, p_drop, seed_f, seed_r = ctx.meta
         C = wf.shape[0]
         dOf, dOr, dpf, dpr = ops.graphnorm_bwd2_sharded(Of, Or, g.contiguous(), sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f,
-                                                        seed_r, True, R_total, shard.all_reduce)
+                                                        seed_r, True, R_total,
+                                                        lambda t: shard.all_reduce(t, "GraphNorm-backward column sums [4,C] f64"))
         dWf, dWr = ops.pair_dw(dOf, dOr, rows[2][0], rows[2][1], H)
         dh, dWf, dWr = _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
         gf, gr = _param_grads(shard, C, dpf, dpr)
@@ -183,8 +362,8 @@ class _ShardedPairLayer(torch.autograd.Function):
 
 
 class _ShardedLastLayer(torch.autograd.Function):
-    """The last conv2s / conv2s_r layer (model.py:77) + readout (model.py:78-83) on one row block: H [Rl, C] -> logits of the
-    target links inside the block."""
+    """The last conv2s / conv2s_r layer (model.py:77) + readout (model.py:78-83) on one row block: H [Rl, C] -> [L, 1] with the
+    logits of the target links inside the block and 0 for the others (idx_l = -1 there)."""
 
     @staticmethod
     def forward(ctx, H, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, pw, pb, shard, loc, rows, idx_l, blocked_l, R_total, n_node,
@@ -208,7 +387,7 @@ class _ShardedLastLayer(torch.autograd.Function):
         pf, pr = (gwf, gbf, gmf), (gwr, gbr, gmr)
         Gp, head, nxt, colsums = ops.gn2_readout_bwd_rows(Of, Or, sf, sr, pf, pr, p_drop, seed_f, seed_r, True, idx_l, pw.contiguous(),
                                                           g.reshape(-1))
-        shard.all_reduce(colsums)
+        shard.all_reduce(colsums, "readout / GraphNorm-backward column sums [6,C] f64")
         consts, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd_finish(colsums, R_total, sf, sr, pf, pr)
         dOf, dOr, dWf, dWr = ops.pair_dw_gn(Of, Or, consts, Gp, head, nxt, p_drop, seed_f, seed_r, True, rows[2][0], rows[2][1], H)
         dh, dWf, dWr = _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
@@ -216,27 +395,21 @@ class _ShardedLastLayer(torch.autograd.Function):
         return (dh, dWf) + gf + (dWr,) + gr + (dpw.reshape(pw.shape), dpb) + (None,) * 11
 
 
-class _ScatterLogits(torch.autograd.Function):
-    """Every rank's [L_loc, 1] logits -> the full [L, 1] tensor of model.py:83 on every rank (one all-reduce of L floats);
-    backward hands each rank the gradient of its own links."""
+class _SumLogits(torch.autograd.Function):
+    """Every rank's [L, 1] logits (its own links filled, 0 elsewhere) -> the full [L, 1] tensor of model.py:83 on every rank (one
+    all-reduce of L floats). Backward: the whole gradient to every rank - the masked readout backward uses its own links' only."""
 
     @staticmethod
-    def forward(ctx, pred_l, links_l, L, shard):
-        full = pred_l.new_zeros((L, 1))
-        full[links_l] = pred_l
-        shard.all_reduce(full)
-        ctx.save_for_backward(links_l)
-        return full
+    def forward(ctx, pred_l, shard):
+        return shard.all_reduce(pred_l.clone(), "logits [L]")
 
     @staticmethod
     def backward(ctx, g):
-        (links_l,) = ctx.saved_tensors
-        return g[links_l].contiguous(), None, None, None
+        return g, None
 
 
 def supported(model, wedges, C: int) -> Optional[str]:
     """None if the sharded path covers this model / input, else the reason."""
-    from . import functional as F2
     if len(model.conv2s) < 1:
         return "row sharding needs at least one pair layer"
     if not isinstance(wedges, G.WedgeStruct):
@@ -244,6 +417,22 @@ def supported(model, wedges, C: int) -> Optional[str]:
     if not all(F2.pair_layer_supported(wedges, C, f, r) for f, r in zip(model.conv2s, model.conv2s_r)) or not ops.pair_dw_supported(C):
         return f"pair width {C} is not covered by the tensor-core pair kernels"
     return None
+
+
+def mask_links(idx: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """Readout row ids [2L] -> block-local ids for the rows inside [lo, hi), -1 for the others; both rows of a link are the two
+    directions of one pair (double(.., for_index=True)), so they are inside or outside together (asserted on the device)."""
+    inb = (idx >= lo) & (idx < hi)
+    torch._assert_async((inb[0::2] == inb[1::2]).all(),
+                        "row-sharded readout: idx[2l] and idx[2l+1] must be the two rows of one pair (double(.., for_index=True))")
+    return torch.where(inb, idx - lo, torch.full_like(idx, -1))
+
+
+def forward(model, x, edge1, pos, idx, ei2):
+    """LocalWLNet.forward (model.py:68-84) cut over the ranks: node blocks for the node-level aggregations, row blocks of the pair
+    table for the pair level; returns the full [L, 1] logits on every rank."""
+    model.row_shard.steps += 1
+    return forward_pairs(model, forward_nodes(model, x, edge1), pos, idx, ei2)
 
 
 def forward_pairs(model, x, pos, idx, ei2):
@@ -268,15 +457,12 @@ def forward_pairs(model, x, pos, idx, ei2):
         idx = lv.newid[idx]
     lo, hi = block_of(pt.R, shard.rank, shard.world)
     loc = _local(wedges, pt, lo, hi)
-    _, centre, dinv, selfw, bnode = wedges.prepared()
-    rows = tuple(t[:, lo:hi].contiguous() for t in (centre, dinv, selfw, bnode))
+    # per-row constants of THIS block only (the degree counts are global: every rank holds the int edge lists)
+    _, centre, dinv, selfw, bnode = ops.wedge_prepare_rows(wedges.src, wedges.dst_e, wedges.E, wedges.R, wedges.n_node, wedges.blocked,
+                                                           wedges.in_ptr, lo, hi)
+    rows = (centre, dinv, selfw, bnode)
     blocked_l = wedges.blocked[lo:lo + loc.E_loc] if wedges.blocked is not None else None
-    L = idx.numel() // 2
-    inb = ((idx >= lo) & (idx < hi)).reshape(L, 2)
-    links_l = torch.nonzero(inb[:, 0]).reshape(-1)          # one host read: the block's target links
-    if bool((inb[:, 0] ^ inb[:, 1]).any().item()):
-        raise RuntimeError("row-sharded readout: idx[2l] and idx[2l+1] must be the two rows of one pair (double(.., for_index=True))")
-    idx_l = (idx.reshape(L, 2)[links_l] - lo).reshape(-1).contiguous()
+    idx_l = mask_links(idx, lo, hi)
     H = _ShardedPairInit.apply(x, loc, wedges.n_node)
     last = len(model.conv2s) - 1
     for i, (seq_f, seq_r) in enumerate(zip(model.conv2s, model.conv2s_r)):
@@ -290,4 +476,4 @@ def forward_pairs(model, x, pos, idx, ei2):
         else:
             pred_l = _ShardedLastLayer.apply(H, *par, model.pred.weight, model.pred.bias, shard, loc, rows, idx_l, blocked_l, pt.R,
                                              wedges.n_node, gf.eps, p, seeds[0], seeds[1])
-    return _ScatterLogits.apply(pred_l, links_l, L, shard)
+    return _SumLogits.apply(pred_l, shard)

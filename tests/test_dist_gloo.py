@@ -79,13 +79,44 @@ def _worker(rank, world, port, out):
         shard = RS.RowShard()
         assert (shard.rank, shard.world) == (rank, world)
         L = 11
-        links = torch.arange(L)[rank::world]                                    # this rank's target links
-        pred_l = (links.double() * 10 + rank).reshape(-1, 1).requires_grad_(True)
-        full = RS._ScatterLogits.apply(pred_l, links, L, shard)
-        want = torch.stack([torch.tensor([float(l * 10 + l % world)]) for l in range(L)]).double()
-        assert torch.equal(full.detach(), want)
-        (full * torch.arange(1.0, L + 1).double().reshape(-1, 1)).sum().backward()
-        assert torch.equal(pred_l.grad.reshape(-1), (links + 1).double())
+        # the readout rows of a batch: link l selects the mates (2*r_l, 2*r_l + 1); a rank keeps the links whose rows fall into
+        # its block as block-local ids and masks the others with -1 (no compaction, hence no device->host size read)
+        R = 40
+        lo, hi = RS.block_of(R, rank, world)
+        rows_of_link = torch.tensor([3, 17, 0, 19, 8, 12, 5, 11, 15, 2, 9])
+        idx = torch.stack((2 * rows_of_link, 2 * rows_of_link + 1), dim=1).reshape(-1)
+        idx_l = RS.mask_links(idx, lo, hi)
+        mine = (2 * rows_of_link >= lo) & (2 * rows_of_link < hi)
+        assert torch.equal(idx_l.reshape(L, 2)[mine], idx.reshape(L, 2)[mine] - lo) and bool((idx_l.reshape(L, 2)[~mine] == -1).all())
+        counted = mine.to(torch.int64).clone()
+        dist.all_reduce(counted)
+        assert bool((counted == 1).all())                                       # every link belongs to exactly one rank
+        # logits: own links filled, 0 elsewhere -> one all-reduce gives every rank the full [L,1]; the gradient comes back whole
+        pred_l = (torch.where(mine, torch.arange(L) * 10 + rank, torch.zeros(L, dtype=torch.int64))).double().reshape(-1, 1).requires_grad_(True)
+        full = RS._SumLogits.apply(pred_l, shard)
+        owner = torch.tensor([next(r for r in range(world) if RS.block_of(R, r, world)[0] <= 2 * int(v) < RS.block_of(R, r, world)[1])
+                              for v in rows_of_link])
+        assert torch.equal(full.detach().reshape(-1), (torch.arange(L) * 10 + owner).double())
+        w = torch.arange(1.0, L + 1).double().reshape(-1, 1)
+        (full * w).sum().backward()
+        assert torch.equal(pred_l.grad, w)
+        # node blocks: equal size B, cover [0, N), the last may be short
+        N = 37
+        blocks = [RS.node_block(N, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == N and all(b[2] * world >= N for b in blocks)
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        # all_gather_blocks: every rank fills its own block of a [world*B, C] buffer; afterwards all blocks are filled everywhere
+        B = blocks[0][2]
+        buf = torch.full((B * world, 3), -7.0)
+        buf[rank * B:(rank + 1) * B] = float(rank + 1)
+        shard.all_gather_blocks(buf, B)
+        assert torch.equal(buf, torch.arange(1.0, world + 1).repeat_interleave(B).reshape(-1, 1).expand(-1, 3))
+        # a gradient that is complete on every rank is kept on rank 0 only (the caller sums over ranks)
+        prm = torch.ones(4, dtype=torch.float64, requires_grad=True)
+        (RS._Rank0Grad.apply(prm, shard) * torch.arange(4.0).double()).sum().backward()
+        tot = prm.grad.clone()
+        dist.all_reduce(tot)
+        assert torch.equal(tot, torch.arange(4.0).double())
         C = 3
         dpf, dpr = torch.arange(4.0 * C), torch.arange(4.0 * C) + 100
         gf, gr = RS._param_grads(shard, C, dpf.clone(), dpr.clone())

@@ -341,6 +341,55 @@ def test_seg_reduce_dual_output(U, C):
         b = ops.seg_reduce(ptr, col, N, X, plan=plan, flip=1, src_scale=s_f, skip_mask=mask)
         a2, b2 = ops.seg_reduce(ptr, col, N, X, plan=plan, src_scale=s_r, skip_mask=mask, dual=True, src_scale2=s_f)
         assert torch.equal(a, a2) and torch.equal(b, b2)
+        # the mates' rows from a SECOND matrix (dS_f from dO_f and dS_r from dO_r in one pass over a node's out-list)
+        Y = torch.randn(R, C).cuda()
+        c = ops.seg_reduce(ptr, col, N, Y, plan=plan, flip=1, src_scale=s_f)
+        a3, c3 = ops.seg_reduce(ptr, col, N, X, plan=plan, src_scale=s_r, dual=True, src_scale2=s_f, X_mate=Y)
+        assert torch.equal(ops.seg_reduce(ptr, col, N, X, plan=plan, flip=0, src_scale=s_r), a3) and torch.equal(c, c3)
+
+
+@pytest.mark.parametrize("C", [24, 64])
+def test_seg_reduce_row_range_is_the_full_result_on_that_range(U, C):
+    """twowl_seg_args.row_begin / row_end (a node block of a row-sharded job): the rows inside the range equal the full launch's
+    bit for bit - long rows included - and the rows outside are not touched."""
+    from twowl_b200 import ops
+    rng = np.random.default_rng(C + 7)
+    M, nnz = 3000, 50000
+    rows = np.minimum((rng.pareto(1.0, size=nnz) * 40).astype(np.int64), M - 1)
+    cols = rng.integers(0, M, size=nnz)
+    ptr, col = _csr_from(rows, cols, M)
+    X = torch.randn(M, C).cuda()
+    sc = (torch.rand(M) + 0.1).cuda()
+    bias = torch.randn(C).cuda()
+    plan = ops.seg_plan(ptr, M, nnz)
+    assert int(plan[0]) >= 1
+    kw = dict(plan=plan, src_scale=sc, dst_scale=sc, skip_self=True, self_mode=1, bias=bias)
+    full = ops.seg_reduce(ptr, col, M, X, **kw)
+    for lo, hi in ((0, 1000), (1000, 2001), (2001, M), (5, 5), (0, M)):
+        out = torch.full((M, C), -123.0, device="cuda")
+        ops.seg_reduce(ptr, col, M, X, out=out, rows=(lo, hi), **kw)
+        assert torch.equal(out[lo:hi], full[lo:hi])
+        assert bool((out[:lo] == -123.0).all()) and bool((out[hi:] == -123.0).all())
+
+
+def test_index_guard_wraps_negative_ids_and_asserts_on_the_rest(U):
+    """x[idx] of model.py:78 / utils.py:55: ids in [-num, 0) wrap, anything else outside [0, num) is an IndexError in the
+    reference - here a device-side assertion (no host sync on the good path); checked in a subprocess, the assertion poisons the
+    CUDA context."""
+    import subprocess
+    import sys
+    from twowl_b200 import ops
+    idx = torch.tensor([0, 5, -1, -6, 3], device="cuda")
+    assert ops.index_guard(idx, 6).tolist() == [0, 5, 5, 0, 3]
+    assert ops.index_guard(idx[::2], 6).tolist() == [0, 5, 3]          # strided view
+    code = ("import sys, torch; sys.path[:0] = %r; from twowl_b200 import ops; "
+            "ops.index_guard(torch.tensor([0, 6], device='cuda'), 6); torch.cuda.synchronize()" % (sys.path[:4],))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and ("out of range" in r.stderr or "device-side assert" in r.stderr or "Assertion" in r.stderr), r.stderr[-2000:]
+    import TwoWL.model.model  # noqa: F401  (pos out of range -> IndexError once per pair table)
+    from twowl_b200 import graph as G
+    with pytest.raises(IndexError):
+        G.pair_table(torch.tensor([[0, 7], [7, 0]], device="cuda"), 7)
 
 
 @pytest.mark.parametrize("M,C,p,relu", [(1, 4, 0.0, True), (620, 64, 0.0, False), (6576, 24, 0.0, True),
