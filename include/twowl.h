@@ -92,6 +92,18 @@ int twowl_mask_from_idx(const int64_t* idx, int64_t k, uint8_t* mask, int64_t nu
  * the number of invalid ids, which the caller turns into an error (a device-side assertion on the Python side: no host sync). */
 int twowl_index_guard(const int64_t* idx, int64_t stride, int64_t k, int64_t num, int64_t* out, int32_t* bad, void* stream);
 
+/* Seeded uniform sampling of `count` DISTINCT non-edges (the negatives of utils.py:129-146 / datasets.py:176-197) without the
+ * reference's dense N x N mask: one open-addressing hash set over the keys row*N + col holds the edges and the accepted samples;
+ * slot i draws candidates from a counter-based generator keyed by (seed, i, round) and the smallest slot proposing a key wins
+ * it, so the result depends on (seed, edges) only. undirected = 1: edges and samples are unordered pairs, returned with
+ * row < col (the upper triangle random_split_edges keeps); 0: ordered pairs. Self loops are never sampled.
+ * out_row / out_col int64[count]; done uint8[count] (or NULL) marks the slots that were filled; unresolved[0] = the number that
+ * were not after `rounds` rounds (more non-edges asked for than exist, or a nearly complete graph). */
+size_t twowl_nonedge_sample_workspace_bytes(int64_t n_edges, int64_t count);
+int twowl_nonedge_sample(const int64_t* row, int64_t s_row, const int64_t* col, int64_t s_col, int64_t n_edges, int64_t num_nodes,
+                         int64_t count, int32_t undirected, uint64_t seed, int32_t rounds, int64_t* out_row, int64_t* out_col,
+                         uint8_t* done, int32_t* unresolved, void* ws, size_t ws_bytes, void* stream);
+
 /* Order-preserving column selection of a [2,T] int64 matrix (blockei2 utils.py:48-50; the ei filter of
  * sample_block utils.py:62-63):
  *   mode 0: keep column t iff !mask[t]            mode 1: keep column t iff !mask[row0[t]]
@@ -454,6 +466,19 @@ int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre,
 int twowl_wedge_apply_bwd(const float* dS, const float* dO, const int32_t* dst_e, const uint8_t* blocked, int64_t E,
                           int64_t N, const float* dinv, const float* selfw, int32_t direction, int64_t R, int32_t C,
                           float* dZ, void* stream);
+
+/* ------------------------------------------------------------------ node-attribute input (model.py:47-51) ------ */
+
+/* nn.Dropout(p): out[i] = x[i] / (1 - p) or 0, the mask a counter hash of (seed, i); applying it to a gradient with the same
+ * seed is the backward. */
+int twowl_dropout(const float* x, int64_t n, float p, uint64_t seed, float* out, void* stream);
+/* bias + nn.LayerNorm(C, elementwise_affine=False, eps) + nn.Dropout(p) in one row pass (the tail of relu_lin, model.py:27-33):
+ * y[m] = dropout((u - mean(u)) / sqrt(var(u) + eps)), u = z[m] + bias; stats[m] = (mean, inv_std) for the backward, which
+ * returns dz = du (d bias = its column sum). */
+int twowl_bias_layernorm_fwd(const float* z, const float* bias, int64_t M, int32_t C, float eps, float p, uint64_t seed, float* y,
+                             float* stats, void* stream);
+int twowl_bias_layernorm_bwd(const float* g, const float* z, const float* bias, const float* stats, int64_t M, int32_t C, float p,
+                             uint64_t seed, float* dz, void* stream);
 
 #ifdef __cplusplus
 }

@@ -217,7 +217,14 @@ class LocalWLNet(nn.Module):
             from twowl_b200 import rowshard
             return rowshard.forward(self, x, edge1, pos, idx, ei2)
         if self.use_node_feat:
-            x = self.lin1(self.node_feat)
+            # model.py:47-51: lin1 = [Dropout(dp_lin0), [Linear, LayerNorm(no affine), Dropout(dp_lin1), Identity]] - the modules keep
+            # the parameters (state_dict keys lin1.1.0.{weight,bias}); the arithmetic is one fused op on this package's kernels
+            dp0, blk = self.lin1[0], self.lin1[1]
+            lin, ln, dp1 = blk[0], blk[1], blk[2]
+            p0 = dp0.p if (self.training and dp0.p > 0.0) else 0.0
+            p1 = dp1.p if (self.training and dp1.p > 0.0) else 0.0
+            x = F2.node_feat_input(self.node_feat, lin.weight, lin.bias, ln.eps, p0, _seed() if p0 > 0.0 else 0, p1,
+                                   _seed() if p1 > 0.0 else 0)[0]
         else:
             emb, gn, dp = self.emb[0], self.emb[1], self.emb[2]
             x = F2.embedding(emb.weight, x)

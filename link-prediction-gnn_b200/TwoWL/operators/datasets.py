@@ -95,22 +95,13 @@ class _Data:
 
 
 def negative_sampling(edge_index, num_nodes: int, num_neg_samples: int):
-    """Uniform directed non-edges (u,v), not in edge_index - the contract of PyG's negative_sampling as
-    called at datasets.py:176-197 - by rejection against the sorted edge keys, on the tensor's device."""
-    dev = edge_index.device
-    keys = torch.unique(edge_index[0].to(torch.int64) * num_nodes + edge_index[1].to(torch.int64))
-    got = torch.empty(0, dtype=torch.int64, device=dev)
-    for _ in range(64):
-        if got.numel() >= num_neg_samples:
-            break
-        m = int(1.3 * (num_neg_samples - got.numel())) + 64
-        k = torch.randint(0, num_nodes, (m,), device=dev) * num_nodes + torch.randint(0, num_nodes, (m,), device=dev)
-        if keys.numel():
-            p = torch.searchsorted(keys, k).clamp_(max=keys.numel() - 1)
-            k = k[keys[p] != k]
-        got = torch.unique(torch.cat((got, k)))
-    got = got[torch.randperm(got.numel(), device=dev)[:num_neg_samples]]
-    return torch.stack((got // num_nodes, got % num_nodes))
+    """Uniform directed non-edges (u,v), not in edge_index, distinct - the contract of PyG's negative_sampling as called at
+    datasets.py:176-197 (which passes the graph with its self loops added, so no self loop is ever drawn) - from the seeded
+    hash-set sampler kernel (csrc/sampler.cu, twowl_nonedge_sample)."""
+    from twowl_b200 import ops
+    r, c = ops.sample_non_edges(edge_index[0].to(torch.int64), edge_index[1].to(torch.int64), num_nodes, num_neg_samples,
+                                undirected=False)
+    return torch.stack((r, c))
 
 
 def do_edge_split(data, val_ratio=0.05, test_ratio=0.1, neg_pool_max=False):

@@ -1,7 +1,8 @@
 """Input formats and generators either side of the hot path: seeded on-device R-MAT / uniform graphs in
 the reference's edge-list conventions, and an edge-list reader for CSV (datasets.py:154-168's format), .npy and raw binary.
 
-Everything here is plain torch on whatever device it is given (input generation, not the measured path); the outputs feed
+The generators are plain torch on the device they are given (input generation, not the measured path); the negative draw is
+the package's hash-set sampler kernel (CUDA only, like every operator here). The outputs feed
 ``TwoWL.utils.double`` / ``get_ei2`` / ``operators.datasets.graph_from_split`` exactly like the reference's CSV does.
 """
 from __future__ import annotations
@@ -37,26 +38,16 @@ def canonical_undirected(src: torch.Tensor, dst: torch.Tensor, n: int) -> torch.
 
 
 def sample_non_edges(keys_sorted: torch.Tensor, n: int, count: int, generator: torch.Generator) -> torch.Tensor:
-    """`count` distinct uniform undirected non-edges (keys lo*n + hi, lo < hi) by rejection against the sorted edge keys - the
-    contract of the reference's negative draw (utils.py:127-139) without its dense N x N mask."""
+    """`count` distinct uniform undirected non-edges (keys lo*n + hi, lo < hi) - the contract of the reference's negative draw
+    (utils.py:127-139) without its dense N x N mask - from the hash-set sampler kernel (twowl_nonedge_sample), seeded from
+    `generator`."""
+    from twowl_b200 import ops
     dev = keys_sorted.device
-    m = keys_sorted.numel()
-    neg = torch.empty(0, dtype=torch.int64, device=dev)
-    for _ in range(64):      # bounded, like datasets.negative_sampling: a near-complete graph cannot supply `count` non-edges
-        if neg.numel() >= count:
-            break
-        k = int(1.2 * (count - neg.numel())) + 64
-        r = torch.randint(0, n, (k,), generator=generator, device=dev)
-        c = torch.randint(0, n, (k,), generator=generator, device=dev)
-        lo, hi = torch.minimum(r, c), torch.maximum(r, c)
-        cand = (lo * n + hi)[lo != hi]
-        if m:
-            p = torch.searchsorted(keys_sorted, cand).clamp_(max=m - 1)
-            cand = cand[keys_sorted[p] != cand]
-        neg = torch.unique(torch.cat((neg, cand)))
-    if neg.numel() < count:
-        raise ValueError(f"only {neg.numel()} of the {count} requested non-edges exist / were found in 64 rounds")
-    return neg[torch.randperm(neg.numel(), generator=generator, device=dev)[:count]]
+    seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=dev).item())
+    r, c = ops.sample_non_edges(keys_sorted // n, keys_sorted % n, n, count, seed=seed, undirected=True)
+    if r.numel() < count:
+        raise ValueError(f"only {r.numel()} of the {count} requested non-edges exist")
+    return r * n + c
 
 
 def synthetic_link_graph(n: int, src: torch.Tensor, dst: torch.Tensor, seed: int) -> Dict[str, torch.Tensor]:

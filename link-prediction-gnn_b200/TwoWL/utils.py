@@ -148,8 +148,8 @@ def double(x, for_index=False):
 def random_split_edges(data, val_ratio: float = 0.05, test_ratio: float = 0.1):
     """utils.py:93-147 - keep row<col, random train/val/test split of the positives, and n_v+n_t negatives
     drawn uniformly from the non-edges of the upper triangle. Same attribute names and shapes as the
-    reference; the dense N x N mask of utils.py:130 (1 TB at 1M nodes) is replaced by rejection sampling
-    against the sorted edge keys, and ``train_neg_adj_mask`` (never read by the TwoWL path) is omitted."""
+    reference; the dense N x N mask of utils.py:130 (1 TB at 1M nodes) is replaced by the hash-set sampler kernel
+    (csrc/sampler.cu), and ``train_neg_adj_mask`` (never read by the TwoWL path) is omitted."""
     num_nodes = int(data.num_nodes)
     row, col = data.edge_index
     edge_attr = getattr(data, "edge_attr", None)
@@ -171,22 +171,9 @@ def random_split_edges(data, val_ratio: float = 0.05, test_ratio: float = 0.1):
         data.val_pos_edge_attr = edge_attr[:n_v]
         data.test_pos_edge_attr = edge_attr[n_v:n_v + n_t]
 
-    need = n_v + n_t
-    keys = torch.unique(row.to(torch.int64) * num_nodes + col.to(torch.int64))
-    got = torch.empty(0, dtype=torch.int64, device=row.device)
-    for _ in range(64):      # bounded: a (near-)complete graph has fewer non-edges than asked for; the reference returns what exists
-        if got.numel() >= need:
-            break
-        m = int(1.3 * (need - got.numel())) + 64
-        r = torch.randint(0, num_nodes, (m,), device=row.device)
-        c = torch.randint(0, num_nodes, (m,), device=row.device)
-        lo, hi = torch.minimum(r, c), torch.maximum(r, c)
-        k = (lo * num_nodes + hi)[lo != hi]
-        pos = torch.searchsorted(keys, k).clamp_(max=max(keys.numel() - 1, 0))
-        k = k[keys[pos] != k] if keys.numel() else k
-        got = torch.unique(torch.cat((got, k)))
-    got = got[torch.randperm(got.numel(), device=row.device)[:need]]
-    neg_row, neg_col = got // num_nodes, got % num_nodes
+    # n_v + n_t distinct uniform non-edges of the upper triangle (utils.py:127-139): twowl_nonedge_sample, a seeded hash-set
+    # sampler, instead of the dense N x N mask; a graph with fewer non-edges than that returns what exists, like the reference
+    neg_row, neg_col = ops.sample_non_edges(row.to(torch.int64), col.to(torch.int64), num_nodes, n_v + n_t, undirected=True)
     data.val_neg_edge_index = torch.stack([neg_row[:n_v], neg_col[:n_v]], dim=0)
     data.test_neg_edge_index = torch.stack([neg_row[n_v:n_v + n_t], neg_col[n_v:n_v + n_t]], dim=0)
     return data

@@ -164,6 +164,66 @@ def _gn_bwd(ctx, g, _g_stats):
 
 graphnorm_act.register_autograd(_gn_bwd, setup_context=_gn_setup)
 
+# ------------------------------------------------------------------------------ node-attribute input (model.py:47-51,71)
+
+_K_CHUNK = 1024   # widest reduction dimension one linear launch takes
+
+
+def _chunks(F: int):
+    return [(k, min(k + _K_CHUNK, F)) for k in range(0, F, _K_CHUNK)]
+
+
+def _pad4(t: Tensor) -> Tensor:
+    """[rows, F] -> contiguous [rows, F rounded up to a multiple of 4] (zero columns: they add nothing to a product)."""
+    F = t.shape[1]
+    if F % 4 == 0:
+        return t.contiguous()
+    out = t.new_zeros((t.shape[0], F + (4 - F % 4)))
+    out[:, :F] = t
+    return out
+
+
+@torch.library.custom_op("twowl::node_feat_input", mutates_args=())
+def node_feat_input(node_feat: Tensor, weight: Tensor, bias: Tensor, eps: float, p_in: float, seed_in: int, p_out: float,
+                    seed_out: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Dropout(p_out)(LayerNorm(Linear(Dropout(p_in)(node_feat)))) of model.py:47-51 -> (x [N, c], z = the Linear's product before
+    the bias [N, c], stats [N, 2]); any feature width F (padded to a multiple of 4, cut into <= 1024-column slabs)."""
+    xin = _pad4(node_feat if p_in == 0.0 else ops.dropout(node_feat, p_in, seed_in))
+    w = _pad4(weight)
+    z = None
+    for lo, hi in _chunks(xin.shape[1]):
+        part = ops.linear_fwd(xin[:, lo:hi].contiguous(), w[:, lo:hi].contiguous())
+        z = part if z is None else z.add_(part)
+    y, stats = ops.bias_layernorm_fwd(z, bias.contiguous(), eps, p_out, seed_out)
+    return y, z, stats
+
+
+@node_feat_input.register_fake
+def _(node_feat, weight, bias, eps, p_in, seed_in, p_out, seed_out):
+    y = node_feat.new_empty((node_feat.shape[0], weight.shape[0]))
+    return y, torch.empty_like(y), node_feat.new_empty((node_feat.shape[0], 2))
+
+
+def _nf_setup(ctx, inputs, output):
+    node_feat, weight, bias, eps, p_in, seed_in, p_out, seed_out = inputs
+    ctx.save_for_backward(node_feat, bias, output[1], output[2])
+    ctx.meta = (weight.shape[1], p_in, seed_in, p_out, seed_out)
+    ctx.mark_non_differentiable(output[1], output[2])
+    ctx.set_materialize_grads(False)
+
+
+def _nf_bwd(ctx, g, *_unused):
+    node_feat, bias, z, stats = ctx.saved_tensors
+    F, p_in, seed_in, p_out, seed_out = ctx.meta
+    dz = ops.bias_layernorm_bwd(g.contiguous(), z, bias.contiguous(), stats, p_out, seed_out)
+    dbias = ops.colsum(dz)
+    xin = _pad4(node_feat if p_in == 0.0 else ops.dropout(node_feat, p_in, seed_in))      # the mask is regenerated from its seed
+    dW = torch.cat([ops.linear_bwd_weight(dz, xin[:, lo:hi].contiguous()) for lo, hi in _chunks(xin.shape[1])], dim=1)[:, :F]
+    return None, dW.contiguous(), dbias, None, None, None, None, None
+
+
+node_feat_input.register_autograd(_nf_bwd, setup_context=_nf_setup)
+
 # ------------------------------------------------------------------------------ embedding lookup
 
 

@@ -214,6 +214,36 @@ def index_guard(idx: torch.Tensor, num: int, what: str = "index") -> torch.Tenso
     return out
 
 
+def sample_non_edges(row: torch.Tensor, col: torch.Tensor, num_nodes: int, count: int, seed: Optional[int] = None,
+                     undirected: bool = True, rounds: int = 16):
+    """`count` distinct uniform non-edges of the graph (row[e], col[e]) on `num_nodes` nodes -> (neg_row, neg_col) int64, row < col
+    when undirected (utils.py:129-146), ordered pairs otherwise (datasets.py:176-197). Deterministic under `seed` (drawn from
+    torch's default generator when None, so torch.manual_seed reproduces it). Fewer than `count` pairs come back only when the
+    graph does not have that many non-edges (the reference returns what exists, too) - one host read tells."""
+    _need_cuda(row, col)
+    row, col = row.reshape(-1), col.reshape(-1)
+    assert row.dtype == torch.int64 and col.dtype == torch.int64 and row.numel() == col.numel()
+    dev = row.device
+    n_edges, count = row.numel(), int(count)
+    out_row = torch.empty(count, dtype=torch.int64, device=dev)
+    out_col = torch.empty(count, dtype=torch.int64, device=dev)
+    done = torch.empty(max(count, 1), dtype=torch.uint8, device=dev)
+    unresolved = torch.empty(1, dtype=torch.int32, device=dev)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    nb = lib.twowl_nonedge_sample_workspace_bytes(n_edges, count)
+    ws = _ws(nb, dev)
+    (pr, sr), (pc, sc) = (_row(row), _row(col)) if n_edges else ((0, 1), (0, 1))
+    check(lib.twowl_nonedge_sample(pr, sr, pc, sc, n_edges, int(num_nodes), count, int(undirected), int(seed), int(rounds),
+                                   out_row.data_ptr(), out_col.data_ptr(), done.data_ptr(), unresolved.data_ptr(), ws.data_ptr(), nb,
+                                   _stream()), "nonedge_sample")
+    _count(1 + 2 * int(rounds))
+    if count and int(unresolved.item()):        # rare: a (nearly) complete graph - keep the slots that were filled
+        keep = done[:count].bool()
+        out_row, out_col = out_row[keep], out_col[keep]
+    return out_row, out_col
+
+
 def select_columns(mat: torch.Tensor, mask: torch.Tensor, mode: int) -> torch.Tensor:
     """Order-preserving column selection of an int64 [2,T] matrix (any strides).
     mode 0: keep column t iff !mask[t]; mode 1: keep iff !mask[mat[0,t]]."""
@@ -666,6 +696,41 @@ def linear_bwd_weight(dZ, X, row_scale=None) -> torch.Tensor:
                                                  ws.data_ptr(), nb, _stream()), "linear_bwd_weight")
     _count(2)
     return dW
+
+
+# ------------------------------------------------------------------------------ node-attribute input (model.py:47-51)
+
+def dropout(x, p: float, seed: int) -> torch.Tensor:
+    """nn.Dropout(p) with the mask a counter hash of (seed, flat index): the same call on a gradient is the backward."""
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib.twowl_dropout(x.data_ptr(), x.numel(), float(p), int(seed), out.data_ptr(), _stream()), "dropout")
+    _count()
+    return out
+
+
+def bias_layernorm_fwd(z, bias, eps: float, p_drop: float, seed: int):
+    """dropout(LayerNorm(z + bias)) without affine parameters -> (y [M,C], stats [M,2] = (mean, inv_std))."""
+    _need_cuda(z, bias)
+    M, C = z.shape
+    y = torch.empty_like(z)
+    stats = torch.empty((M, 2), dtype=torch.float32, device=z.device)
+    with _P("bias_layernorm_fwd", 8 * M * C):
+        check(lib.twowl_bias_layernorm_fwd(z.data_ptr(), _p(bias), M, C, float(eps), float(p_drop), int(seed), y.data_ptr(),
+                                           stats.data_ptr(), _stream()), "bias_layernorm_fwd")
+    _count()
+    return y, stats
+
+
+def bias_layernorm_bwd(g, z, bias, stats, p_drop: float, seed: int) -> torch.Tensor:
+    M, C = z.shape
+    dz = torch.empty_like(z)
+    with _P("bias_layernorm_bwd", 12 * M * C):
+        check(lib.twowl_bias_layernorm_bwd(g.data_ptr(), z.data_ptr(), _p(bias), stats.data_ptr(), M, C, float(p_drop), int(seed),
+                                           dz.data_ptr(), _stream()), "bias_layernorm_bwd")
+    _count()
+    return dz
 
 
 # ------------------------------------------------------------------------------ structured wedge path

@@ -193,16 +193,22 @@ def _seq(sd, prefix, x, edge_index, act: bool):
     return torch.relu(x) if act else x
 
 
-def local_wl_forward(sd, x, edge1, pos, idx, ei2, act0: bool = True, act1: bool = True):
-    """LocalWLNet.forward (TwoWL/model/model.py:68-84), use_node_feat=False branch, eval
-    mode. ``sd`` maps the reference's state_dict keys to (possibly requires_grad) tensors."""
+def local_wl_forward(sd, x, edge1, pos, idx, ei2, act0: bool = True, act1: bool = True, node_feat=None):
+    """LocalWLNet.forward (TwoWL/model/model.py:68-84), eval mode / dropout 0. ``sd`` maps the reference's
+    state_dict keys to (possibly requires_grad) tensors. node_feat (use_node_feat=True, model.py:47-51,71):
+    x = LayerNorm(no affine)(Linear(node_feat)) with the parameters lin1.1.0.{weight,bias}; otherwise the
+    degree embedding + GraphNorm of model.py:53-55."""
     depth1 = len({k.split(".")[1] for k in sd if k.startswith("conv1s.")})
     depth2 = len({k.split(".")[1] for k in sd if k.startswith("conv2s.")})
     e = torch.as_tensor(_np(ei2)).to(torch.long)
     edge2 = torch.stack([e[0] ^ 1, e[1]])
     edge2_r = torch.stack([e[0], e[1] ^ 1])
-    h = sd["emb.0.weight"].index_select(0, x)
-    h = graph_norm(h, sd["emb.1.weight"], sd["emb.1.bias"], sd["emb.1.mean_scale"])
+    if node_feat is not None:
+        u = node_feat.to(sd["lin1.1.0.weight"].dtype) @ sd["lin1.1.0.weight"].t() + sd["lin1.1.0.bias"]
+        h = torch.nn.functional.layer_norm(u, (u.shape[1],), None, None, 1e-5)
+    else:
+        h = sd["emb.0.weight"].index_select(0, x)
+        h = graph_norm(h, sd["emb.1.weight"], sd["emb.1.bias"], sd["emb.1.mean_scale"])
     for k in range(depth1):
         act = act0 if k < depth1 - 1 else act1
         h = _seq(sd, f"conv1s.{k}.", h, edge1, act)
@@ -247,11 +253,11 @@ def init_state_dict(max_x: int, channels_1wl: int, channels_2wl: int, depth1: in
     return sd
 
 
-def fwd_bwd(sd, x, edge1, pos, idx, ei2, y, act0=True, act1=True):
+def fwd_bwd(sd, x, edge1, pos, idx, ei2, y, act0=True, act1=True, node_feat=None):
     """One reference train step minus the optimiser (TwoWL/model/train.py:36-38):
     forward, BCE-with-logits, backward. Returns (logits, loss, {name: grad})."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    pred = local_wl_forward(leaf, x, edge1, pos, idx, ei2, act0, act1)
+    pred = local_wl_forward(leaf, x, edge1, pos, idx, ei2, act0, act1, node_feat)
     loss = torch.nn.functional.binary_cross_entropy_with_logits(pred, y)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}

@@ -382,8 +382,10 @@ def test_index_guard_wraps_negative_ids_and_asserts_on_the_rest(U):
     idx = torch.tensor([0, 5, -1, -6, 3], device="cuda")
     assert ops.index_guard(idx, 6).tolist() == [0, 5, 5, 0, 3]
     assert ops.index_guard(idx[::2], 6).tolist() == [0, 5, 3]          # strided view
-    code = ("import sys, torch; sys.path[:0] = %r; from twowl_b200 import ops; "
-            "ops.index_guard(torch.tensor([0, 6], device='cuda'), 6); torch.cuda.synchronize()" % (sys.path[:4],))
+    import os
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "link-prediction-gnn_b200")
+    code = ("import sys, torch; sys.path.insert(0, %r); from twowl_b200 import ops; "
+            "ops.index_guard(torch.tensor([0, 6], device='cuda'), 6); torch.cuda.synchronize()" % (pkg,))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and ("out of range" in r.stderr or "device-side assert" in r.stderr or "Assertion" in r.stderr), r.stderr[-2000:]
     import TwoWL.model.model  # noqa: F401  (pos out of range -> IndexError once per pair table)

@@ -130,3 +130,32 @@ def test_model_forward_backward_matches_reference_module(ref, cfg):
     # init_state_dict produces the reference's key set and shapes
     mine = O.init_state_dict(int(x_new.max()), cfg["c1"], cfg["c2"], cfg["d1"], cfg["d2"])
     assert {k: tuple(v.shape) for k, v in mine.items()} == {k: tuple(v.shape) for k, v in sd.items()}
+
+
+def test_node_feature_branch_matches_reference_module(ref):
+    """use_node_feat=True (model.py:47-51,71): x = lin1(node_feat) = Dropout -> Linear -> LayerNorm(no affine) -> Dropout; with the
+    dropouts at 0 the oracle's node_feat branch must reproduce the reference module's logits and gradients."""
+    rng = np.random.default_rng(11)
+    n, F = 40, 13
+    pos_e, pred_e = O.synthetic_split(n, rng.integers(0, n, size=(2, 120)), seed=5)
+    ei2 = O.get_ei2(n, pos_e, pred_e)
+    blk = O.double(rng.choice(pos_e.shape[1] // 2, size=8, replace=False), True)
+    ei_new, x_new, ei2_new = O.sample_block(blk, n, pos_e, ei2)
+    negs = O.double(rng.choice(pred_e.shape[1] // 2, size=8, replace=False), True) + pos_e.shape[1]
+    idx = torch.from_numpy(np.concatenate([blk, negs]))
+    pos1 = torch.from_numpy(np.concatenate([pos_e.T, pred_e.T]))
+    y = torch.cat((torch.ones(8), torch.zeros(8))).unsqueeze(-1)
+    torch.manual_seed(1)
+    feat = torch.randn(n, F)
+    mod = ref.model.LocalWLNet(0, True, feat, channels_1wl=24, channels_2wl=16, depth1=2, depth2=1, dp_lin0=0., dp_lin1=0., dp_emb=0.,
+                               dp_1wl0=0., dp_2wl=0., dp_1wl1=0.)
+    x, e1 = torch.from_numpy(x_new), torch.from_numpy(ei_new)
+    pred = mod(x, e1, pos1, idx, torch.from_numpy(ei2_new))
+    torch.nn.functional.binary_cross_entropy_with_logits(pred, y).backward()
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    assert "lin1.1.0.weight" in sd and "lin1.1.0.bias" in sd and not any(k.startswith("emb.") for k in sd)
+    o_pred, _, o_grads = O.fwd_bwd(sd, x, e1, pos1, idx, ei2_new, y, True, True, node_feat=feat)
+    assert torch.allclose(o_pred, pred.detach(), rtol=1e-5, atol=1e-6)
+    for k, p in mod.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert torch.allclose(o_grads[k], g, rtol=1e-5, atol=1e-6), k

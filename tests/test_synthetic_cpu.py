@@ -1,37 +1,21 @@
-"""Input generators and edge-list reader - plain torch / numpy, run on CPU."""
+"""Input generators and edge-list reader - plain torch / numpy, run on CPU (the negative draw is a CUDA kernel:
+tests/test_gpu_sampler.py)."""
 import numpy as np
 import pytest
 import torch
 
-from TwoWL.operators.synthetic import canonical_undirected, load_edge_list, rmat_edges, sample_non_edges, synthetic_link_graph
+from TwoWL.operators.synthetic import canonical_undirected, load_edge_list, rmat_edges
 
 
-def test_rmat_graph_is_seeded_simple_and_skewed():
+def test_rmat_edge_samples_are_seeded_in_range_and_skewed():
     s, d, n = rmat_edges(12, 60000, (0.57, 0.19, 0.19, 0.05), 0, "cpu")
     s2, d2, _ = rmat_edges(12, 60000, (0.57, 0.19, 0.19, 0.05), 0, "cpu")
     assert n == 4096 and torch.equal(s, s2) and torch.equal(d, d2)                  # seeded
     assert int(s.min()) >= 0 and int(s.max()) < n and int(d.max()) < n
-    g = synthetic_link_graph(n, s, d, 0)
-    pos, neg = g["pos_und"], g["neg_und"]
-    assert pos.shape == neg.shape and pos.shape[0] == 2
-    assert bool((pos[0] < pos[1]).all()) and bool((neg[0] < neg[1]).all())           # canonical, no self loops
-    kp, kn = pos[0] * n + pos[1], neg[0] * n + neg[1]
-    assert kp.unique().numel() == kp.numel() and kn.unique().numel() == kn.numel()   # simple graph, distinct negatives
-    assert not bool(torch.isin(kn, kp).any())                                        # negatives are non-edges
-    assert torch.equal(torch.sort(kp).values, canonical_undirected(s, d, n))
-    deg = torch.bincount(torch.cat((pos[0], pos[1])), minlength=n)
+    keys = canonical_undirected(s, d, n)
+    assert bool((keys[1:] > keys[:-1]).all()) and bool((keys // n < keys % n).all())  # sorted, unique, lo < hi, no self loops
+    deg = torch.bincount(torch.cat((keys // n, keys % n)), minlength=n)
     assert int(deg.max()) > 20 * float(deg.float().mean())                           # R-MAT skew: hubs exist
-    assert not torch.equal(kp, torch.sort(kp).values)                                # rows are shuffled like a dataset's
-
-
-def test_non_edge_sampler_on_a_dense_graph():
-    n = 12
-    iu = torch.triu_indices(n, n, 1)
-    keys = (iu[0] * n + iu[1])[:-5]                                                  # all but 5 pairs are edges
-    gen = torch.Generator().manual_seed(1)
-    neg = sample_non_edges(torch.sort(keys).values, n, 5, gen)
-    assert torch.equal(torch.sort(neg).values, torch.sort((iu[0] * n + iu[1])[-5:]).values)
-    assert sample_non_edges(torch.empty(0, dtype=torch.int64), 4, 6, gen).unique().numel() == 6   # empty graph: every pair is free
 
 
 def test_edge_list_formats_agree(tmp_path):
