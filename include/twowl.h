@@ -480,6 +480,20 @@ int twowl_bias_layernorm_fwd(const float* z, const float* bias, int64_t M, int32
 int twowl_bias_layernorm_bwd(const float* g, const float* z, const float* bias, const float* stats, int64_t M, int32_t C, float p,
                              uint64_t seed, float* dz, void* stream);
 
+/* ------------------------------------------------------------------ loss + optimiser (train.py:37-39) ---------- */
+
+/* F.binary_cross_entropy_with_logits(logits, labels) (mean reduction) forward AND backward in one pass:
+ * loss[0] = mean(max(x,0) - x*y + log1p(exp(-|x|))); dlogits[i] = (sigmoid(x_i) - y_i) / n (or NULL); prob[i] = sigmoid(x_i)
+ * (or NULL; what the train AUC ranks, train.py:41-43). Block partials in double, added in block order: deterministic. */
+size_t twowl_bce_logits_workspace_bytes(int64_t n);
+int twowl_bce_logits(const float* logits, const float* labels, int64_t n, float* loss, float* dlogits, float* prob, void* ws,
+                     size_t ws_bytes, void* stream);
+/* torch.optim.Adam.step() (amsgrad = False) over ONE flat fp32 buffer of n parameters; step[0] (int64, device memory: the call
+ * is capturable in a CUDA graph) is the number of steps taken so far and is incremented. grad_scale (or NULL) = a device scalar
+ * the gradient is multiplied by first (the 1/world of an averaged data-parallel gradient). */
+int twowl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, const float* grad_scale, int64_t* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,11 +13,11 @@ import random
 import time
 
 import torch
-from torch.optim import Adam
 
 from TwoWL.model import train
 from TwoWL.model.model import LocalWLNet
 from TwoWL.operators.datasets import load_dataset, dataset
+from twowl_b200.optim import FusedAdam
 
 PATH_TIME_TWOWL = "./assets/"          # constant.py:10 of the reference
 SEARCH_SPACE = {                        # TwoWL_work.py:67-79
@@ -63,7 +63,7 @@ def work(args, device="cuda"):
         params = dict(setting)
         lr = setting.pop("lr")
         mod = LocalWLNet(max_degree, use_node_attr, trn_ds.na, **setting).to(device)
-        opt = Adam(mod.parameters(), lr=lr)
+        opt = FusedAdam(mod.parameters(), lr=lr)       # Adam(mod.parameters(), lr) of TwoWL_work.py:100 as one kernel per step
         val = train.train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, args.epoch, verbose=True, record_dir=record_dir,
                                   cuda_graph=getattr(args, "cuda_graph", False))
         os.makedirs(time_dir, exist_ok=True)

@@ -6,6 +6,8 @@ What changes underneath:
   * ROC-AUC is computed on the device (``ops.auc``: radix sort + tie-aware rank sum) instead of
     ``pred.sigmoid().cpu().numpy()`` + sklearn every step (train.py:41-43, :61-66); ``train`` makes ONE host read per step
     (loss and score together) where the reference makes two.
+  * the loss is ``twowl::bce_with_logits`` (forward + gradient in one kernel pass) and the optimiser may be
+    ``twowl_b200.optim.FusedAdam`` (one kernel over a flat parameter buffer; any torch optimizer works as well).
   * ``test`` computes the ROC curve points only when asked (``curve=True``, the default, keeps the reference's
     ``(auc, fpr, tpr)`` return value); ``train_routine`` asks for them only where the reference uses them.
 """
@@ -17,6 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from TwoWL.utils import sample_block, double
+from twowl_b200 import functional as F2
 from twowl_b200 import ops
 
 PATH_SAVE_TEST_AUC = "records_auc/"   # constant.py:8 of the reference
@@ -71,12 +74,13 @@ def train(mod, opt, dataset, batch_size, i, step=None):
     if step is None:
         ei_new, x_new, ei2_new = sample_block(blocked, dataset.x.shape[0], dataset.ei, dataset.ei2)
         pred = mod(x_new, ei_new, dataset.pos1, rows, ei2_new)
-        loss = F.binary_cross_entropy_with_logits(pred, y)
+        loss = F2.bce_with_logits(pred, y)      # F.binary_cross_entropy_with_logits + its gradient in one pass (train.py:37)
         loss.backward()
     else:
         loss = step(blocked, rows, y)
         pred = step.logits
-    opt.step()
+    if step is None or getattr(step, "optimizer", None) is None:     # a captured step may contain the optimiser's update
+        opt.step()
 
     with torch.no_grad():
         # ONE host read for loss and score; the AUC ranks the probabilities like the reference does (train.py:41-43)
@@ -133,7 +137,9 @@ def train_routine(dsname, mod, opt, trn_ds, val_ds, tst_ds, epoch, verbose=True,
     if cuda_graph:   # the training step as one replayed CUDA graph (dropout included: device-resident seeds)
         from twowl_b200.graphed import GraphedTrainStep
         half = batch_size // 2
-        step = GraphedTrainStep(mod, trn_ds.x.shape[0], trn_ds.ei, trn_ds.pos1, trn_ds.ei2, n_block=2 * half, n_links=2 * half)
+        from twowl_b200.optim import FusedAdam
+        step = GraphedTrainStep(mod, trn_ds.x.shape[0], trn_ds.ei, trn_ds.pos1, trn_ds.ei2, n_block=2 * half, n_links=2 * half,
+                                optimizer=opt if isinstance(opt, FusedAdam) else None)
 
     patience = 800                       # epochs without a validation improvement before giving up (train.py:83)
     best_val = tst_score = 0

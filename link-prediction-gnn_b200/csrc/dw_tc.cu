@@ -11,8 +11,8 @@
 // One persistent CTA per SM, 14 warps, warp-specialised:
 //   warp  0    TMA producer: raw fp32 tiles of dO_f, dO_r, H with cp.async.bulk.tensor (SWIZZLE_128B_ATOM_32B tensor maps
 //                            = the one MN-major layout the tensor core accepts for tf32, see below), L2 evict-first
-//   warps 2-9  split       : A: v = selfw[row] * raw, hi = rn_tf32(v) written back in place, lo = rn_tf32(v - hi) into a second
-//                            buffer; B: lo = rn_tf32(h - trunc_tf32(h)) only (the tensor core reads raw H as its own hi)
+//   warps 2-9  split       : A: v = selfw[row] * raw written back in place (the tensor core truncates it to tf32 = the `hi`
+//                            operand) and lo = v - trunc(v) into a second buffer; B: lo only (raw H is its own hi)
 //   warp  1    MMA issuer  : 3 x 8 tcgen05.mma per tile into a TMEM accumulator that is drained every kDwFlush tiles
 //   warps 10-13 drain      : TMEM -> fp32 registers after every tile (C <= 64), 64 tiles per addition into the CTA's double
 //                            partials in global memory; a second kernel adds the partials in double in CTA order:
@@ -20,7 +20,7 @@
 #include "common.cuh"
 
 #ifndef TWOWL_DW_FLUSH
-#define TWOWL_DW_FLUSH 1
+#define TWOWL_DW_FLUSH 2
 #endif
 
 namespace twowl {
@@ -37,10 +37,11 @@ __host__ __device__ constexpr int dw_tile_k(int C) { return C <= 64 ? 64 : 32; }
 __host__ __device__ constexpr int dw_nacc(int C) { return C <= 64 ? 1 : 2; }
 // The tensor core's fp32 accumulate TRUNCATES: a TMEM-resident sum loses about half an ulp of its own magnitude per
 // accumulate step, always towards zero (2048 rows at C = 128 measured 1.6e-5 relative in round 1, when both widths drained
-// after 384 steps). C <= 64 therefore drains after EVERY tile: the accumulator restarts at zero, the three small products
-// (lo*lo, lo*hi, hi*lo) are added while it is still small, and only the 8 hi*hi steps run at full magnitude (~5e-7
-// relative); the drain warps add the tiles in fp32 registers, 64 tiles at a time, into per-CTA DOUBLE partials. C = 128
-// (two 128 x 128 accumulators, no room in registers: the running sums live in `part`) drains every 4 tiles.
+// after 384 steps - above the 1e-5 band of a weight gradient). C <= 64 therefore drains every TWOWL_DW_FLUSH = 2 tiles (the
+// first tile's small products are added while the accumulator is still small: ~32 steps at full magnitude, < 2e-6
+// relative; every tile: 0.5 ms slower for 5e-7); the drain warps add the drains in fp32 registers, 64 at a time, into
+// per-CTA DOUBLE partials. C = 128 (two 128 x 128 accumulators, no room in registers: the running sums live in `part`)
+// drains every 4 tiles.
 __host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? TWOWL_DW_FLUSH : 4; }
 constexpr int kDwRegTiles = 64;   // C <= 64: tiles added in fp32 registers between two additions into the double partials
 __host__ __device__ constexpr int dw_part_rows(int C) { return C <= 64 ? 128 : 2 * C; }
@@ -139,14 +140,10 @@ __device__ __forceinline__ bool dw_elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// tf32 split (see pair_conv.cu): A = selfw * dO is written back by the split warps anyway, so its hi is rn_tf32(v) and
-// lo = rn_tf32(v - hi); B = the raw H tile, read by the tensor core as hi = trunc_tf32(h), lo = rn_tf32(h - hi). Three products.
-__device__ __forceinline__ float dw_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ float dw_lo(float x) { return dw_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
-__device__ __forceinline__ void dw_split(const float4& v, float4& hi, float4& lo) {
-  hi.x = dw_rna(v.x), hi.y = dw_rna(v.y), hi.z = dw_rna(v.z), hi.w = dw_rna(v.w);
-  lo.x = dw_rna(v.x - hi.x), lo.y = dw_rna(v.y - hi.y), lo.z = dw_rna(v.z - hi.z), lo.w = dw_rna(v.w - hi.w);
-}
+// tf32 split (see pair_conv.cu): the tensor core reads an fp32 operand as hi = trunc_tf32(x); lo = x - hi goes into a second
+// buffer for both operands, three products. (Rounding hi / lo to nearest as pair_conv does for its lo was measured here: the
+// extra integer work sits on the split warps' critical path - +1.0 ms of 15 - for no change of any end-to-end error.)
+__device__ __forceinline__ float dw_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // C = width of dO_f, dO_r and H (32, 64 or 128). One stage:
 //   A_hi: AG groups of 32 M-elements ([f cols | r cols | zero padding when C = 32]), A_lo: the same, B_hi: C/32 groups, B_lo
@@ -421,10 +418,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_dw_tc(const DwParams p, const
             }
             const float sc = br ? sr[q] : sf[q];
             x.x *= sc, x.y *= sc, x.z *= sc, x.w *= sc;
-            float4 hi, lo;
-            dw_split(x, hi, lo);
-            Ahi[j * kSplitThreads + t] = hi;
-            Alo[j * kSplitThreads + t] = lo;
+            Ahi[j * kSplitThreads + t] = x;
+            Alo[j * kSplitThreads + t] = make_float4(dw_lo(x.x), dw_lo(x.y), dw_lo(x.z), dw_lo(x.w));
           }
         }
       }

@@ -509,10 +509,8 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
     float4* __restrict__ G4 = reinterpret_cast<float4*>(G);
     for (int64_t j = (int64_t)blockIdx.x * rm.slots + rm.slot; j < 2 * L; j += (int64_t)gridDim.x * rm.slots) {
       const int64_t ra = idx[j * sidx], rb = idx[(j ^ 1) * sidx];
-      if (ra < 0 || rb < 0) {   // not this rank's link: no gradient row, no contribution to the column sums
-        G4[j * rm.cv + rm.c4] = f4_zero();
-        continue;
-      }
+      if (ra < 0 || rb < 0) continue;   // not this rank's link: no contribution to the column sums; its G row is never read
+                                        // (the row chains hold valid positions only), so it is not written either
       const float g = dpred[j >> 1];
       const int64_t ea = ra * rm.cv + rm.c4, eb = rb * rm.cv + rm.c4;
       const float4 af = ldg_cached(xf4 + ea), ar = ldg_cached(xr4 + ea);

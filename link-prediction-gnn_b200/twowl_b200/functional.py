@@ -528,3 +528,37 @@ def pair_layer_readout_apply(x, wedges, seq_f, seq_r, training: bool, idx, pred)
                              wedges.out_ptr, wedges.out_ids, wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked,
                              wedges.n_node, gf.eps, p, seeds[0], seeds[1])
     return out[0]
+
+
+# ------------------------------------------------------------------------------ loss (train.py:37)
+
+
+@torch.library.custom_op("twowl::bce_with_logits", mutates_args=())
+def _bce_with_logits(logits: Tensor, labels: Tensor) -> Tuple[Tensor, Tensor]:
+    loss, dx, _ = ops.bce_logits(logits, labels, want_grad=True)
+    return loss.reshape(()), dx
+
+
+@_bce_with_logits.register_fake
+def _(logits, labels):
+    return logits.new_empty(()), torch.empty_like(logits)
+
+
+def _bce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.mark_non_differentiable(output[1])
+    ctx.set_materialize_grads(False)
+
+
+def _bce_bwd(ctx, g, _g_dx):
+    (dx,) = ctx.saved_tensors
+    return dx * g, None
+
+
+_bce_with_logits.register_autograd(_bce_bwd, setup_context=_bce_setup)
+
+
+def bce_with_logits(logits: Tensor, labels: Tensor) -> Tensor:
+    """F.binary_cross_entropy_with_logits(logits, labels) (mean reduction, train.py:37) with its gradient made in the same pass:
+    two launches for loss forward + backward instead of torch's chain."""
+    return _bce_with_logits(logits, labels)[0]

@@ -48,9 +48,13 @@ class DeviceSeeds:
 
 class GraphedTrainStep:
     def __init__(self, mod, n_node: int, ei: torch.Tensor, pos1: torch.Tensor, ei2, n_block: int, n_links: int,
-                 loss_fn=torch.nn.functional.binary_cross_entropy_with_logits, warmup: int = 3):
+                 loss_fn=None, warmup: int = 3, optimizer=None):
         """mod: LocalWLNet; ei: int64 [2,E] observed edges; pos1: int64 [R,2]; ei2: what get_ei2 / get_ei2_implicit returned for
-        them; n_block: blocked edge ids per step (= 2 x positive undirected links); n_links: target links per step."""
+        them; n_block: blocked edge ids per step (= 2 x positive undirected links); n_links: target links per step.
+        loss_fn: default = twowl::bce_with_logits (train.py:37 in two launches). optimizer: a twowl_b200.optim.FusedAdam whose
+        update (train.py:39) is then part of the captured step - the caller must not call its step() again."""
+        if loss_fn is None:
+            from .functional import bce_with_logits as loss_fn
         from TwoWL.utils import _struct_of
         self.mod, self.n, self.ei, self.pos1, self.loss_fn = mod, int(n_node), ei, pos1, loss_fn
         self.struct = ei2.struct if isinstance(ei2, G.WedgeIndex) else _struct_of(ei2)
@@ -63,6 +67,7 @@ class GraphedTrainStep:
         self.s_idx = torch.zeros(2 * n_links, dtype=torch.int64, device=dev)
         self.s_y = torch.zeros((n_links, 1), dtype=torch.float32, device=dev)
         self.params = [p for p in mod.parameters() if p.requires_grad]
+        self.optimizer = optimizer
         self.graph = None
         self.loss = self.logits = None
         self._warmup = warmup
@@ -86,6 +91,8 @@ class GraphedTrainStep:
         self.logits = self.mod(x_new, edges, self.pos1, self.s_idx, wedges)
         self.loss = self.loss_fn(self.logits, self.s_y)
         self.loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
 
     def _load(self, blocked_ids, idx, y):
         self.s_block.copy_(blocked_ids.reshape(-1), non_blocking=True)
@@ -95,6 +102,8 @@ class GraphedTrainStep:
     def capture(self, blocked_ids, idx, y):
         """Warm up on a side stream (builds every cached index structure), then capture one step."""
         self._load(blocked_ids, idx, y)
+        # the warm-up iterations must leave no trace in the optimiser: its state and the parameters are restored afterwards
+        snap = None if self.optimizer is None else {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state_dict().items()}
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -105,6 +114,8 @@ class GraphedTrainStep:
                 self._body()
                 self.loss = self.logits = None      # drop the autograd graph before the next iteration / the capture
         cur.wait_stream(side)
+        if snap is not None:
+            self.optimizer.load_state_dict(snap)
         for p in self.params:
             p.grad = None
         self.graph = torch.cuda.CUDAGraph()

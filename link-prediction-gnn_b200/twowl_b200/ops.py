@@ -1018,6 +1018,39 @@ def graphnorm_bwd2_sharded(xf, xr, dout, sf, sr, pf, pr, p_drop: float, seed_f: 
     return dxf, dxr, dpf, dpr
 
 
+# ------------------------------------------------------------------------------ loss + optimiser (train.py:37-39)
+
+def bce_logits(logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True, want_prob: bool = False):
+    """F.binary_cross_entropy_with_logits (mean) forward and backward in one pass -> (loss [1], dlogits like logits | None,
+    sigmoid(logits) | None)."""
+    _need_cuda(logits, labels)
+    x = logits.detach().reshape(-1).contiguous()
+    y = labels.detach().reshape(-1).to(torch.float32).contiguous()
+    n = x.numel()
+    assert y.numel() == n and x.dtype == torch.float32, "bce_logits: fp32 logits and as many labels"
+    dev = x.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x) if want_grad else None
+    prob = torch.empty_like(x) if want_prob else None
+    nb = lib.twowl_bce_logits_workspace_bytes(n)
+    ws = _ws(nb, dev)
+    check(lib.twowl_bce_logits(x.data_ptr(), y.data_ptr(), n, loss.data_ptr(), _p(dx), _p(prob), ws.data_ptr(), nb, _stream()), "bce_logits")
+    _count(2)
+    return loss, (None if dx is None else dx.view_as(logits)), (None if prob is None else prob.view_as(logits))
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float = 0.0,
+              grad_scale=None):
+    """torch.optim.Adam.step() over one flat fp32 buffer, in place; `step` = int64 device scalar (incremented)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, step)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n and step.dtype == torch.int64
+    assert all(t.is_contiguous() and t.dtype == torch.float32 for t in (param, grad, exp_avg, exp_avg_sq))
+    check(lib.twowl_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n, float(lr), float(beta1),
+                              float(beta2), float(eps), float(weight_decay), _p(grad_scale), step.data_ptr(), _stream()), "adam_step")
+    _count(2)
+
+
 # ------------------------------------------------------------------------------ metrics
 
 def auc(score: torch.Tensor, label: torch.Tensor) -> torch.Tensor:

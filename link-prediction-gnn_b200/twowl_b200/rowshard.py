@@ -12,7 +12,7 @@ per-NODE sums, so the exchange per pair layer is
                                                            ([4, C] over all rows for a layer that is not the last)
               all_reduce  dS_f, dS_r   [2, N, C] fp32      gradient of the per-node sums
 
-instead of the all-gather / reduce-scatter of [R, C] an explicit wedge index would need.
+(N here = the nodes that have observed in-edges: graph.locality_view compacts the node ids of the wedge structure) instead of the all-gather / reduce-scatter of [R, C] an explicit wedge index would need.
 
 Node level (model.py:71-73). The node-level GCNConv aggregations - the only node-level work that is not a cheap streaming pass -
 are cut into NODE blocks [g*B, (g+1)*B), B = ceil(N / world): a rank reduces the in-lists (forward) / out-lists (backward) of
@@ -200,6 +200,28 @@ class _ShardedNodeAggregate(torch.autograd.Function):
         return full[:N], dbias, None, None, None
 
 
+class _NodeLinear(torch.autograd.Function):
+    """z = h W^T of a node layer, replicated (a streaming pass). Its input gradient is complete on every rank; the weight gradient
+    dz^T h runs over the N nodes, so every rank takes its node block and the caller's gradient sum completes it."""
+
+    @staticmethod
+    def forward(ctx, h, w, shard):
+        h = h.contiguous()
+        ctx.save_for_backward(h, w)
+        ctx.shard = shard
+        return ops.linear_fwd(h, w.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.saved_tensors
+        shard = ctx.shard
+        g = g.contiguous()
+        lo, hi, _ = node_block(h.shape[0], shard.rank, shard.world)
+        dh = ops.linear_bwd_input(g, w.contiguous()) if ctx.needs_input_grad[0] else None
+        dw = ops.linear_bwd_weight(g[lo:hi], h[lo:hi]) if hi > lo else torch.zeros_like(w)
+        return dh, dw, None
+
+
 def forward_nodes(model, x, edge1):
     """model.py:71-73 with the aggregations cut into node blocks: x int64 [N] degrees -> [N, C] (complete on every rank)."""
     shard: RowShard = model.row_shard
@@ -222,7 +244,7 @@ def forward_nodes(model, x, edge1):
     for k, seq in enumerate(model.conv1s):
         conv, gn, dp, act = seq.modlist[0], seq.modlist[1], seq.modlist[2], seq.modlist[3]
         gr = G.node_graph(edge1, N)
-        z = F2.linear(h, r0(conv.lin.weight))
+        z = _NodeLinear.apply(h, conv.lin.weight, shard)
         out = _ShardedNodeAggregate.apply(z, conv.bias, gr, shard, k == last)
         if k == last:     # its GraphNorm sees the partial gradients of the pair level: ordinary (partial) parameter gradients
             p = dp.p if (model.training and dp.p > 0.0) else 0.0
@@ -245,9 +267,12 @@ class _Local:
     in_ptr: torch.Tensor   # the block's observed edges grouped by target node (local ids)
     in_ids: torch.Tensor
     in_plan: torch.Tensor
-    out_ptr: torch.Tensor  # the block's pair rows grouped by source node (local ids) = pair_init's backward CSR
+    out_ptr: torch.Tensor  # the block's pair rows grouped by source node (local ids), in the wedge structure's node ids
     out_ids: torch.Tensor
     out_plan: torch.Tensor
+    xout_ptr: torch.Tensor  # the same grouping by the pair TABLE's (original) node ids = pair_init's backward CSR
+    xout_ids: torch.Tensor
+    xout_plan: torch.Tensor
 
 
 def _local(struct: G.WedgeStruct, pt: G.PairTable, lo: int, hi: int) -> _Local:
@@ -256,8 +281,10 @@ def _local(struct: G.WedgeStruct, pt: G.PairTable, lo: int, hi: int) -> _Local:
         hiE = max(lo, min(hi, struct.E))
         in_ptr, in_ids = ops.csr_build(struct.dst_e[lo:hiE].to(torch.int64), n)
         out_ptr, out_ids = ops.csr_build(struct.src[lo:hi].to(torch.int64), n)
+        xout_ptr, xout_ids = ops.csr_build(pt.src[lo:hi].to(torch.int64), pt.n)
         return (pt, _Local(lo, hi, hiE - lo, pt.src[lo:hi].contiguous(), pt.dst[lo:hi].contiguous(), in_ptr, in_ids,
-                           ops.seg_plan(in_ptr, n, hiE - lo), out_ptr, out_ids, ops.seg_plan(out_ptr, n, hi - lo)))
+                           ops.seg_plan(in_ptr, n, hiE - lo), out_ptr, out_ids, ops.seg_plan(out_ptr, n, hi - lo),
+                           xout_ptr, xout_ids, ops.seg_plan(xout_ptr, pt.n, hi - lo)))
     # the entry holds struct.src (key tensor) and pt (value): neither address can be recycled while the block is cached
     return G._cache.get(struct.src, ("rowshard", lo, hi) + G._Cache.key(pt.src), build)[1]
 
@@ -297,10 +324,13 @@ def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
     dOs = (dOf, dOr)
     dS = torch.stack(ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOs[0].contiguous(), plan=loc.out_plan, src_scale=dinv[0], dual=True,
                                     src_scale2=dinv[1], X_mate=dOs[1].contiguous()))
-    # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d: with THIS rank's partial dS the sum over ranks is the full product
-    dWf = dWf + ops.linear_bwd_weight(dS[0], SH[0])
-    dWr = dWr + ops.linear_bwd_weight(dS[1], SH[1])
     shard.all_reduce(dS, "dS [2,N,C]")
+    # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d: the second product runs over the N nodes - every rank takes its NODE block of
+    # the (now complete) dS and SH, and the caller's gradient sum over the ranks completes the product
+    lo, hi, _ = node_block(n_node, shard.rank, shard.world)
+    if hi > lo:
+        dWf = dWf + ops.linear_bwd_weight(dS[0, lo:hi], SH[0, lo:hi])
+        dWr = dWr + ops.linear_bwd_weight(dS[1, lo:hi], SH[1, lo:hi])
     dSW = [ops.linear_bwd_input(dS[0], wf), ops.linear_bwd_input(dS[1], wr)]
     dh = ops.pair_conv([dOf, dOr], [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
                        gathers=[(dSW[0], bnode[0], dinv[0]), (dSW[1], bnode[1], dinv[1])])
@@ -330,7 +360,7 @@ class _ShardedPairInit(torch.autograd.Function):
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         loc, n_node = ctx.meta
-        dx = ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, g.contiguous(), plan=loc.out_plan, X2=x, mul_idx=loc.dst, pair_sum=True)
+        dx = ops.seg_reduce(loc.xout_ptr, loc.xout_ids, x.shape[0], g.contiguous(), plan=loc.xout_plan, X2=x, mul_idx=loc.dst, pair_sum=True)
         return dx, None, None
 
 

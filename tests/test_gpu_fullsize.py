@@ -95,8 +95,10 @@ def test_full_size_step_vs_fp64(workload, hidden):
     # than this fp32 evaluation's own worst element of the tensor.
     lg32, l32, g32 = ref64.step(sd, x_new, ei_plain, pos1, idx, E, blocked, y, dtype=torch.float32)
     tag = f"{workload}/hidden{hidden} "
-    parity(out, lg32, lg64, tag + "logits", allow_relaxed=out.numel())
+    # at this size (sums over up to 6e7 rows, logits up to ~100) a larger share of the elements sits outside the 1e-5 band in ANY
+    # fp32 evaluation - the plain torch one included: up to 15 % of a tensor may pass through the relaxation clauses (observed:
+    # 9.6 % of the 3.0 M logits at rmat / hidden 64, 7 % at collab / hidden 256, see the ledger)
+    parity(out, lg32, lg64, tag + "logits", allow_relaxed=out.numel() * 15 // 100)
     parity(loss, l32, l64, tag + "loss")
     for k in sorted(grads):
-        # allow_relaxed: the number of elements of this gradient tensor that may pass through the relaxation clauses
-        parity(grads[k], g32[k], g64[k], tag + "grad " + k, scale_floor=1e-5, allow_relaxed=grads[k].numel())
+        parity(grads[k], g32[k], g64[k], tag + "grad " + k, scale_floor=1e-5, allow_relaxed=max(8, grads[k].numel() * 15 // 100))

@@ -5,6 +5,15 @@ import numpy as np
 import pytest
 import torch
 
+
+class _F2:
+    def __getattr__(self, k):
+        from twowl_b200 import functional
+        return getattr(functional, k)
+
+
+F2 = _F2()
+
 from helpers import fb_split
 
 pytestmark = pytest.mark.gpu
@@ -42,7 +51,7 @@ def test_graphed_step_replays_bit_identical_to_eager(fb, implicit):
             p.grad = None
         ei_new, x_new, ei2_new = U.sample_block(idx1, n, dei, ei2)
         out = mod(x_new, ei_new, dpos, idx, ei2_new)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+        loss = F2.bce_with_logits(out, y)     # the loss the captured step uses (twowl::bce_with_logits, train.py:37)
         loss.backward()
         assert torch.equal(out, logits_g) and torch.equal(loss, loss_g), f"batch {it}"
         for k, p in mod.named_parameters():
@@ -92,7 +101,7 @@ def test_graphed_step_with_dropout_redraws_its_masks_and_matches_eager(fb):
                 p.grad = None
             ei_new, x_new, ei2_new = U.sample_block(idx1, n, dei, ei2)
             out = mod(x_new, ei_new, dpos, idx, ei2_new)
-            loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+            loss = F2.bce_with_logits(out, y)     # the loss the captured step uses (twowl::bce_with_logits, train.py:37)
             loss.backward()
         finally:
             ops.set_seed_provider(prev)

@@ -105,3 +105,76 @@ def test_train_routine_with_the_step_replayed_as_a_cuda_graph_learns(cuda, tmp_p
     opt = Adam(mod.parameters(), lr=0.05)
     best = T.train_routine("planted", mod, opt, trn, val, tst, 300, verbose=False, record_dir=None, cuda_graph=True)
     assert best > 0.6, best
+
+
+@pytest.mark.parametrize("n", [1, 7, 384, 100003])
+def test_fused_bce_matches_torch(cuda, n):
+    """twowl::bce_with_logits (train.py:37): loss, gradient and probabilities of one pass against F.binary_cross_entropy_with_logits
+    evaluated in float64."""
+    from twowl_b200 import functional as F2
+    from twowl_b200 import ops
+    torch.manual_seed(n)
+    x = (torch.randn(n, 1) * 6).cuda().requires_grad_(True)
+    x.data[0] = 40.0          # saturated logits: the stable form must not overflow
+    y = (torch.rand(n, 1) > 0.5).float().cuda()
+    loss = F2.bce_with_logits(x, y)
+    (loss * 3.0).backward()
+    x64 = x.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(x64, y.double())
+    (ref * 3.0).backward()
+    assert loss.shape == () and abs(float(loss) - float(ref)) <= 1e-6 + 1e-6 * abs(float(ref))
+    assert torch.allclose(x.grad.double(), x64.grad, rtol=1e-5, atol=1e-9)
+    _, _, prob = ops.bce_logits(x, y, want_grad=False, want_prob=True)
+    assert torch.allclose(prob.double(), torch.sigmoid(x64.detach()), rtol=1e-6, atol=1e-7)
+    assert torch.equal(F2.bce_with_logits(x, y), loss.detach())               # deterministic
+
+
+def test_fused_adam_matches_torch_adam(cuda):
+    """twowl_b200.optim.FusedAdam (train.py:39 / TwoWL_work.py:100): twenty steps of the one-kernel update on a flat buffer against
+    torch.optim.Adam on the same gradients - with and without weight decay - and the parameters stay views of the flat buffer."""
+    from twowl_b200.optim import FusedAdam
+    for wd in (0.0, 0.01):
+        torch.manual_seed(0)
+        shapes = [(37, 64), (64,), (24, 24), (1, 24), (1,)]
+        mine = [torch.nn.Parameter(torch.randn(s).cuda()) for s in shapes]
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+        a, b = FusedAdam(mine, lr=0.01, weight_decay=wd), torch.optim.Adam(ref, lr=0.01, weight_decay=wd)
+        for t in range(20):
+            for p, q in zip(mine, ref):
+                g = torch.randn_like(p) * (10.0 ** (t % 3 - 1))
+                p.grad, q.grad = g.clone(), g.clone()
+            a.step()
+            b.step()
+        for p, q in zip(mine, ref):
+            assert torch.allclose(p, q, rtol=2e-6, atol=1e-7), float((p - q).abs().max())
+            assert p.data_ptr() >= a.flat.data_ptr() and p.data_ptr() < a.flat.data_ptr() + 4 * a.flat.numel()
+        assert int(a.step_count) == 20
+        a.zero_grad()
+        assert all(p.grad is None for p in mine)
+
+
+def test_train_with_fused_adam_inside_the_replayed_step_learns(cuda, tmp_path, monkeypatch):
+    """The whole train step of train.py:29-39 - edge blocking, forward, BCE, backward AND the Adam update - as one replayed CUDA
+    graph: the loss goes down, and the warm-up iterations of the capture leave no trace in the optimiser."""
+    import TwoWL.TwoWL_work as W
+    import TwoWL.model.train as T
+    from twowl_b200.graphed import GraphedTrainStep
+    from twowl_b200.optim import FusedAdam
+    csv = tmp_path / "edges.csv"
+    _planted_partition_csv(csv)
+    args = argparse.Namespace(pattern="2wl_l", csv=str(csv))
+    torch.manual_seed(0)
+    bg, trn, val, tst = W._datasets(args, torch.device("cuda"))
+    for ds in (trn, val, tst):
+        ds.pos1 = ds.pos1.to(torch.long)
+    mod = W.LocalWLNet(int(bg.x[2].max()), False, None, channels_1wl=32, channels_2wl=16, dp_lin0=0., dp_lin1=0., dp_emb=0.1, dp_1wl0=0.,
+                       dp_2wl=0.1, dp_1wl1=0.).cuda()
+    opt = FusedAdam(mod.parameters(), lr=0.02)
+    bs = val.y.shape[0]
+    half = bs // 2
+    step = GraphedTrainStep(mod, trn.x.shape[0], trn.ei, trn.pos1, trn.ei2, n_block=2 * half, n_links=2 * half, optimizer=opt)
+    before = opt.flat.clone()
+    losses = [T.train(mod, opt, trn, bs, 0, step)[0] for _ in range(60)]
+    assert int(opt.step_count) == 60                       # one update per call: neither the warm-up nor train() added any
+    assert not torch.equal(before, opt.flat)
+    assert sum(losses[-10:]) / 10 < sum(losses[:10]) / 10 - 0.02, (losses[:10], losses[-10:])
