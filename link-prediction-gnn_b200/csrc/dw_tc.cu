@@ -40,9 +40,10 @@ __host__ __device__ constexpr int dw_nacc(int C) { return C <= 64 ? 1 : 2; }
 // after 384 steps - above the 1e-5 band of a weight gradient). C <= 64 therefore drains every TWOWL_DW_FLUSH = 2 tiles (the
 // first tile's small products are added while the accumulator is still small: ~32 steps at full magnitude, < 2e-6
 // relative; every tile: 0.5 ms slower for 5e-7); the drain warps add the drains in fp32 registers, 64 at a time, into
-// per-CTA DOUBLE partials. C = 128 (two 128 x 128 accumulators, no room in registers: the running sums live in `part`)
-// drains every 4 tiles.
-__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? TWOWL_DW_FLUSH : 4; }
+// per-CTA DOUBLE partials. C = 128 (two 128 x 128 accumulators, no room in registers: the running sums live in `part`, a
+// 128 KB read-add-write per drain) drains every 8 tiles of 32 rows: ~96 steps, < 6e-6 relative (every 4 tiles was measured:
+// the read-add-write traffic made the kernel 1.7x slower at R = 60 M).
+__host__ __device__ constexpr int dw_flush(int C) { return C <= 64 ? TWOWL_DW_FLUSH : 8; }
 constexpr int kDwRegTiles = 64;   // C <= 64: tiles added in fp32 registers between two additions into the double partials
 __host__ __device__ constexpr int dw_part_rows(int C) { return C <= 64 ? 128 : 2 * C; }
 

@@ -376,7 +376,7 @@ def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
 
 def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
                row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
-               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None, rows=None, X_mate=None):
+               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None, rows=None, X_mate=None, out2=None):
     """dual=True -> (out, out2): out2[m] = sum src_scale2[s^1] * X[s^1] over the same entries (see twowl_seg_args).
     rows=(lo, hi): only output rows [lo, hi) are computed (and written into `out`, which keeps its full [M, C] shape)."""
     _need_cuda(ptr, col, X)
@@ -384,7 +384,8 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
     C = X.shape[1]
     if out is None:
         out = torch.empty((M, C), dtype=torch.float32, device=X.device)
-    out2 = torch.empty((M, C), dtype=torch.float32, device=X.device) if dual else None
+    if dual and out2 is None:
+        out2 = torch.empty((M, C), dtype=torch.float32, device=X.device)
     a = SegArgs(ptr=ptr.data_ptr(), col=col.data_ptr(), M=M, X=X.data_ptr(), C=C, flip=int(flip), row_flip=int(row_flip),
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),

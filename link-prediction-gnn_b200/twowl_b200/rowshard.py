@@ -40,6 +40,7 @@ depth1 >= 1, depth2 >= 1 on the structured wedge path with the doubled pair layo
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -81,6 +82,7 @@ class RowShard:
         self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.log = {}            # collective name -> [calls, bytes] since construction
         self.steps = 0
+        self.chunks = int(os.environ.get("TWOWL_ROWSHARD_CHUNKS", "4"))   # node-range chunks of the pipelined table exchanges
         _last_shard = self
 
     def _account(self, what: str, t: torch.Tensor):
@@ -94,6 +96,34 @@ class RowShard:
             with ops._P("nccl_all_reduce", 2 * t.numel() * t.element_size()):
                 dist.all_reduce(t, group=self.group)
         return t
+
+    def all_reduce_async(self, t: torch.Tensor, what: str):
+        """Start an all-reduce of a contiguous tensor on the communication stream (it waits for what the current stream has
+        enqueued so far); kernels launched next on the current stream overlap it. -> handle with .wait() (a stream wait)."""
+        if self.world == 1:
+            return None
+        self._account("all_reduce " + what, t)
+        return dist.all_reduce(t, group=self.group, async_op=True)
+
+    def reduce_in_chunks(self, M: int, produce, tensors, what: str):
+        """A per-node table made by a row-range kernel and summed over the ranks, pipelined: `produce(lo, hi)` fills rows
+        [lo, hi) of every tensor in `tensors` ([M, C] each); the all-reduce of a chunk runs on the communication stream while
+        the next chunk is produced. Only the last chunk's exchange is exposed."""
+        K = self.chunks if self.world > 1 else 1
+        bounds = [M * k // K for k in range(K + 1)]
+        handles = []
+        for k in range(K):
+            lo, hi = bounds[k], bounds[k + 1]
+            if hi <= lo:
+                continue
+            produce(lo, hi)
+            for t in tensors:
+                h = self.all_reduce_async(t[lo:hi], what)
+                if h is not None:
+                    handles.append(h)
+        with ops._P("nccl_all_reduce_wait", 0):
+            for h in handles:
+                h.wait()
 
     def all_gather_blocks(self, full: torch.Tensor, B: int, what: str = "all_gather") -> torch.Tensor:
         """full: [world * B, C] whose block [rank*B, (rank+1)*B) this rank has filled -> every block filled, in place."""
@@ -294,11 +324,13 @@ def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr)
     -> (O_f, O_r, stats_f, stats_r, SH [2,N,C])."""
     centre, dinv, selfw, _ = rows
     (wf, bf, gmf), (wr, br, gmr) = pf, pr
-    SHr, SHf = ops.seg_reduce(loc.in_ptr, loc.in_ids, n_node, H, plan=loc.in_plan, src_scale=dinv[1], skip_mask=blocked_l, dual=True,
-                              src_scale2=dinv[0])
-    SH = torch.stack((SHf, SHr))
-    del SHf, SHr
-    shard.all_reduce(SH, "SH [2,N,C]")
+    # both directions' in-list sums (SH[0] = forward, SH[1] = reverse) from one pass over the block's edges, produced one node
+    # range at a time so that the all-reduce of a range overlaps the gathers of the next
+    SH = torch.empty((2, n_node, H.shape[1]), dtype=H.dtype, device=H.device)
+    shard.reduce_in_chunks(n_node, lambda lo, hi: ops.seg_reduce(loc.in_ptr, loc.in_ids, n_node, H, plan=loc.in_plan, src_scale=dinv[1],
+                                                                 skip_mask=blocked_l, dual=True, src_scale2=dinv[0], out=SH[1], out2=SH[0],
+                                                                 rows=(lo, hi)),
+                           (SH[0], SH[1]), "SH [2,N,C]")
     Sf, Sr = ops.linear_fwd(SH[0], wf), ops.linear_fwd(SH[1], wr)
     if ops.PAIR_CONV_DUAL and ops.pair_conv_dual_supported(H.shape[1], wf.shape[0]):
         Of, Or, mf, mr = ops.pair_conv_dual(H, wf, wr, selfw[0], selfw[1], (Sf, centre[0], dinv[0]), (Sr, centre[1], dinv[1]), bf, br,
@@ -322,9 +354,12 @@ def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
     (dH, dW_f, dW_r) on this block: the dS exchange and the input-gradient pass."""
     _, dinv, selfw, bnode = rows
     dOs = (dOf, dOr)
-    dS = torch.stack(ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOs[0].contiguous(), plan=loc.out_plan, src_scale=dinv[0], dual=True,
-                                    src_scale2=dinv[1], X_mate=dOs[1].contiguous()))
-    shard.all_reduce(dS, "dS [2,N,C]")
+    dS = torch.empty((2, n_node, H.shape[1]), dtype=H.dtype, device=H.device)
+    dOf_c, dOr_c = dOs[0].contiguous(), dOs[1].contiguous()
+    shard.reduce_in_chunks(n_node, lambda lo, hi: ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOf_c, plan=loc.out_plan, src_scale=dinv[0],
+                                                                 dual=True, src_scale2=dinv[1], X_mate=dOr_c, out=dS[0], out2=dS[1],
+                                                                 rows=(lo, hi)),
+                           (dS[0], dS[1]), "dS [2,N,C]")
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d: the second product runs over the N nodes - every rank takes its NODE block of
     # the (now complete) dS and SH, and the caller's gradient sum over the ranks completes the product
     lo, hi, _ = node_block(n_node, shard.rank, shard.world)

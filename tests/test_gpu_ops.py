@@ -617,9 +617,9 @@ def test_pair_dw_tcgen05_vs_fp64(U, M, C):
     c = lambda t: t.float().cuda().contiguous()
     gf, gr = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
     # a sum over M rows (dw_tc.cu): C <= 64: two tiles' 2 x 24 truncating accumulate steps (<= 2u each), then 64 drains in fp32
-    # registers, then double; C = 128: 4 tiles x 12 truncating steps, then one fp32 read-add-write per 4 tiles per CTA
+    # registers, then double; C = 128: 8 tiles x 12 truncating steps, then one fp32 read-add-write per 8 tiles per CTA
     # (+ the roundings of the scaled operand); + the split-tf32 product bound (both operands truncated here: 3 * 2^-20)
-    kw = dict(nterms=(168 if C <= 64 else 136 + M // (32 * 148 * 4)), mma=True, mma_bound=3 * 2.0 ** -20)
+    kw = dict(nterms=(168 if C <= 64 else 264 + M // (32 * 148 * 8)), mma=True, mma_bound=3 * 2.0 ** -20)
     assert_close(gf, ref_f, absum=(rsf.unsqueeze(1) * dOf.abs()).t() @ H.abs(), what="pair_dw f", **kw)
     assert_close(gr, ref_r, absum=(rsr.unsqueeze(1) * dOr.abs()).t() @ H.abs(), what="pair_dw r", **kw)
     gf2, gr2 = ops.pair_dw(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
@@ -639,7 +639,7 @@ def test_pair_dw_wide_tiles_vs_fp64(U, M, Co, Ci):
     assert ops.pair_dw_wide_supported(Co, Ci)
     gf, gr = ops.pair_dw_wide(c(dOf), c(dOr), c(rsf), c(rsr), c(H))
     ref_f, ref_r = (rsf.unsqueeze(1) * dOf).t() @ H, (rsr.unsqueeze(1) * dOr).t() @ H
-    kw = dict(nterms=136 + M // (32 * 148 * 4), mma=True, mma_bound=3 * 2.0 ** -20)      # the 128-column launches, as test_pair_dw_tcgen05_vs_fp64
+    kw = dict(nterms=264 + M // (32 * 148 * 8), mma=True, mma_bound=3 * 2.0 ** -20)      # the 128-column launches, as test_pair_dw_tcgen05_vs_fp64
     assert_close(gf, ref_f, absum=(rsf.unsqueeze(1) * dOf.abs()).t() @ H.abs(), what="pair_dw_wide f", **kw)
     assert_close(gr, ref_r, absum=(rsr.unsqueeze(1) * dOr.abs()).t() @ H.abs(), what="pair_dw_wide r", **kw)
 

@@ -1,7 +1,8 @@
 """Row-block sharding of the pair table ("G-rank logits/grads == 1-rank within the same tolerance").
 
-World sizes 2 and 3 (uneven blocks; blocks that hold only prediction pairs and no observed edge) of one fb-pages-food train
-step run as separate processes on cuda:0 over gloo; rank 0's logits, loss and rank-summed parameter gradients are compared
+World sizes 2, 3 and 8 (uneven blocks; blocks that hold only prediction pairs and no observed edge; node blocks of 78 nodes) of
+one fb-pages-food train step (depth1 = 2: two node layers cut into node blocks; depth2 = 1 or 2) run as separate processes on
+cuda:0 over gloo; rank 0's logits, loss and rank-summed parameter gradients are compared
 with (a) the CPU oracle in fp32 / fp64 and (b) this package's single-GPU path, at the north_star tolerance.
 
 The weight seeds are chosen so that no pre-ReLU value of the pair layer at a selected row lies within 1e-5 of zero (checked
@@ -46,7 +47,7 @@ def _run_world(world, c2, seed, out, depth2=1):
     return dict(np.load(out))
 
 
-@pytest.mark.parametrize("world,c2,seed,depth2", [(2, 32, 7, 1), (3, 64, 5, 1), (2, 32, 4, 2)])
+@pytest.mark.parametrize("world,c2,seed,depth2", [(2, 32, 7, 1), (3, 64, 5, 1), (2, 32, 4, 2), (8, 32, 7, 1)])
 def test_row_sharded_step_matches_single_gpu_and_oracle(tmp_path, world, c2, seed, depth2):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
