@@ -559,6 +559,30 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
             assert_close(res[1][Nd:], inv, absum=inv * dvar / (2 * (var + 1e-5)), nterms=nterms, mma=True, what="pair_conv inv_std")
 
 
+@pytest.mark.parametrize("ratio,M", [(3.0, 40001), (10.0, 40001), (30.0, 300000)])
+def test_pair_conv_statistics_with_a_large_mean(U, ratio, M):
+    """GraphNorm statistics out of pair_conv's epilogue are raw moments: fp32 (sum, sum of squares) per 32-row block, added in
+    double, var = E[x^2] - mean^2 in double (SURVEY 7 hard part 4 warns about this form). The rounding of x^2 is relative to
+    mean^2, so the variance loses accuracy as |mean| / std grows: bounded here at the ratios a GCNConv output can plausibly
+    reach (bias-dominated columns): inv_std within 1e-5 + ratio^2 * 2^-22 relative. (The op-by-op GraphNorm kernel
+    twowl_graphnorm_stats uses shifted sums and has no such dependence.)"""
+    from twowl_b200 import ops
+    torch.manual_seed(int(ratio) + M)
+    Kd = Nd = 64
+    A = r32(torch.randn(M, Kd, dtype=torch.float64))
+    W = r32(torch.randn(Nd, Kd, dtype=torch.float64) / Kd ** 0.5)         # A W^T has unit variance per column
+    bias = r32(torch.full((Nd,), ratio, dtype=torch.float64) * (torch.rand(Nd, dtype=torch.float64) * 0.5 + 0.75))
+    ms = torch.ones(Nd)
+    ref = A @ W.t() + bias
+    c = lambda t: t.float().cuda().contiguous()          # noqa: E731
+    out, st = ops.pair_conv([c(A)], [c(W)], [0], bias=c(bias), stats_mean_scale=ms.cuda(), eps=1e-5)
+    mean = ref.mean(0)
+    inv = (((ref - mean) ** 2).mean(0) + 1e-5).rsqrt()
+    assert_close(st[:Nd], mean, rtol=1e-6, atol=1e-6, what="mean")
+    rel = ((st[Nd:].double().cpu() - inv) / inv).abs().max()
+    assert float(rel) <= 1e-5 + ratio ** 2 * 2.0 ** -22, (float(rel), ratio)
+
+
 @pytest.mark.parametrize("M,Kd,C", [(3, 64, 64), (129, 32, 32), (5000, 64, 64), (70001, 64, 64), (30011, 128, 128), (9000, 24, 32),
                                     (4000, 256, 256)])
 def test_pair_conv_dual_vs_fp64(U, M, Kd, C):
