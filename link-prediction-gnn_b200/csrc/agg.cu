@@ -56,6 +56,26 @@ struct SegParams {
   float* partial;              // [chunks, C]
 };
 
+// L2 policies of the gathers (measured with ncu at R-MAT 1M/16M: every seg_reduce launch moves 6.0-6.5 TB/s of DRAM traffic -
+// the kernels are at the DRAM roofline for the bytes they touch, so the only lever is touching fewer): rows of an [R, C]
+// activation are read once or twice per launch, megabytes apart (no reuse an L2 of 126 MB could serve) -> evict-first; rows of
+// a per-NODE table (x in the pair-init backward: 268 MB, re-read deg(n) times) -> evict-last, so that the stream does not
+// flush them (L2 hit rate of that launch: 3 % before).
+struct SegPolicies {
+  uint64_t stream, keep;
+  __device__ SegPolicies() {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  }
+};
+__device__ __forceinline__ float4 seg_ldg(const float4* p, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+
 template <int G>
 struct GroupCtx {
   int gl, gbase, cv;
@@ -76,8 +96,8 @@ struct GroupCtx {
 // MODE: 0 = plain gather, 1 = times X2[mul_idx], 3 = (X[s] + X[s^1]) times X2[mul_idx], 4 = dual (X[s] -> acc, X[s^1] -> acc2)
 // (compile-time, so that the plain path keeps its registers for gathers in flight)
 template <int G, int VEC, int MODE>
-__device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCtx<G>& g, int64_t m, int64_t kb, int64_t ke,
-                                               float4 (&acc)[VEC], float4 (&acc2)[(MODE & 4) ? VEC : 1]) {
+__device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCtx<G>& g, const SegPolicies& pol, int64_t m, int64_t kb,
+                                               int64_t ke, float4 (&acc)[VEC], float4 (&acc2)[(MODE & 4) ? VEC : 1]) {
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const float4* __restrict__ X24 = reinterpret_cast<const float4*>(p.X2);
   const float4* __restrict__ Xm4 = ((MODE & 4) && p.Xm) ? reinterpret_cast<const float4*>(p.Xm) : X4;
@@ -133,9 +153,11 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
         for (int v = 0; v < VEC; ++v) {
           const int c4 = g.gl + v * G;
           const bool on = sj[u] >= 0 && c4 < g.cv;
-          x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
-          if (MODE & 6) xm[u][v] = on ? ldg_cached(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
-          if (MODE & 1) y[u][v] = on ? ldg_cached(X24 + (int64_t)m2j[u] * g.cv + c4) : f4_zero();
+          // MODE 0 gathers a per-node / per-row table with reuse (default policy); the other modes stream [R, C] rows
+          if (MODE == 0) x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
+          else x[u][v] = on ? seg_ldg(X4 + (int64_t)sj[u] * g.cv + c4, pol.stream) : f4_zero();
+          if (MODE & 6) xm[u][v] = on ? seg_ldg(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4, pol.stream) : f4_zero();
+          if (MODE & 1) y[u][v] = on ? seg_ldg(X24 + (int64_t)m2j[u] * g.cv + c4, pol.keep) : f4_zero();
         }
       }
 #pragma unroll
@@ -191,6 +213,7 @@ template <int G, int VEC, int MODE>
 __global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
+  const SegPolicies pol;
   const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
   const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
   auto row_range = [&](int64_t m_, int64_t& kb_, int64_t& ke_, bool& masked_) {
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_rows(const SegParams p) {
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
 #pragma unroll
     for (int v = 0; v < ((MODE & 4) ? VEC : 1); ++v) acc2[v] = f4_zero();
-    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc, acc2);
+    seg_accumulate<G, VEC, MODE>(p, g, pol, m, kb, ke, acc, acc2);
     seg_finalize<G, VEC>(p, g, m, acc);
     if constexpr ((MODE & 4) != 0) seg_store2<G, VEC>(p, g, m, acc2);
   }
@@ -228,6 +251,7 @@ template <int G, int VEC, int MODE>
 __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
   constexpr int kGroupsPerCta = kAggThreads / G;
   const GroupCtx<G> g(p.C);
+  const SegPolicies pol;
   const int nchunks = p.plan_counts[1];
   const int64_t group0 = (int64_t)blockIdx.x * kGroupsPerCta + threadIdx.x / G;
   const int64_t ngroups = (int64_t)gridDim.x * kGroupsPerCta;
@@ -245,7 +269,7 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_chunks(const SegParams p) {
     for (int v = 0; v < VEC; ++v) acc[v] = f4_zero();
 #pragma unroll
     for (int v = 0; v < ((MODE & 4) ? VEC : 1); ++v) acc2[v] = f4_zero();
-    seg_accumulate<G, VEC, MODE>(p, g, m, kb, ke, acc, acc2);
+    seg_accumulate<G, VEC, MODE>(p, g, pol, m, kb, ke, acc, acc2);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const int c4 = g.gl + v * G;

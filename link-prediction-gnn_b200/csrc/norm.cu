@@ -416,6 +416,13 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float*
     int64_t a0 = idx[(2 * l0) * sidx], a1 = idx[(2 * l0 + 1) * sidx];
     int64_t b0 = two ? idx[(2 * l1) * sidx] : a0, b1 = two ? idx[(2 * l1 + 1) * sidx] : a1;
     const bool va = a0 >= 0 && a1 >= 0, vb = b0 >= 0 && b1 >= 0;
+    if (!va && !vb) {   // uniform over the lane group (its lanes share the two links): nothing to gather, nothing to reduce
+      if (c4 == 0) {
+        pred[l0] = 0.f;
+        if (two) pred[l1] = 0.f;
+      }
+      continue;
+    }
     if (!va) a0 = a1 = 0;
     if (!vb) b0 = b1 = 0;
     const int64_t ea0 = a0 * cv + cc, ea1 = a1 * cv + cc, eb0 = b0 * cv + cc, eb1 = b1 * cv + cc;

@@ -104,4 +104,4 @@ def test_full_size_step_vs_fp64(workload, hidden):
     for k in sorted(grads):
         # gradient floor 3e-5 x the tensor's largest magnitude: a weight / GraphNorm gradient here is a sum over up to 6e7 rows of
         # products of fp32 activations that each carry ~1e-6 of relative error, with ~10x cancellation between the terms
-        parity(grads[k], g32[k], g64[k], tag + "grad " + k, scale_floor=3e-5, allow_relaxed=max(8, grads[k].numel() * 15 // 100))
+        parity(grads[k], g32[k], g64[k], tag + "grad " + k, scale_floor=3e-5, allow_relaxed=max(16, grads[k].numel() * 15 // 100))

@@ -51,6 +51,8 @@ def rows_of(path):
 def op_of(name):
     if "k_pair_conv" in name:
         return "pair_conv"
+    if "k_dw_tc_final" in name:
+        return None
     if "k_dw_tc" in name:
         return "pair_dw_gn" if ("true" in name or ", 1>" in name or "(bool)1" in name) else "pair_dw"
     if "k_seg_rows" in name or "k_seg_chunks" in name or "k_seg_long" in name:
@@ -65,8 +67,8 @@ def main():
     calls = {}          # op -> list of [bytes, ns] per op call
     for r in rows:
         op = op_of(r["name"])
-        if op is None:
-            continue
+        if op is None or (op == "pair_conv" and "k_pair_conv<0" in r["name"]):
+            continue        # k_pair_conv<0, 0> = the plain linear layers (ops.linear_*), not the pair_conv op
         lst = calls.setdefault(op, [])
         if op == "seg_reduce" and "k_seg_rows" not in r["name"] and lst:
             lst[-1][0] += r["rd"] + r["wr"]
