@@ -56,11 +56,11 @@ struct SegParams {
   float* partial;              // [chunks, C]
 };
 
-// L2 policies of the gathers (measured with ncu at R-MAT 1M/16M: every seg_reduce launch moves 6.0-6.5 TB/s of DRAM traffic -
-// the kernels are at the DRAM roofline for the bytes they touch, so the only lever is touching fewer): rows of an [R, C]
-// activation are read once or twice per launch, megabytes apart (no reuse an L2 of 126 MB could serve) -> evict-first; rows of
-// a per-NODE table (x in the pair-init backward: 268 MB, re-read deg(n) times) -> evict-last, so that the stream does not
-// flush them (L2 hit rate of that launch: 3 % before).
+// L2 policies of the gathers. Measured with ncu at R-MAT 1M/16M: every big seg_reduce launch moves 5.5-6.5 TB/s of DRAM traffic -
+// the kernels are at the DRAM roofline for the bytes they touch, so the only lever is touching fewer. In the pair-init backward
+// the rows of the [R, C] gradient are a stream (read twice, megabytes apart) while the rows of the per-NODE table x (268 MB,
+// re-read deg(n) times) have reuse: stream = evict-first, table = evict-last (that launch: 44.8 -> 42.2 GB, 7.0 -> 6.7 ms).
+// The same hints on the two-output passes (no table there) made them 10 % slower and are not used.
 struct SegPolicies {
   uint64_t stream, keep;
   __device__ SegPolicies() {
@@ -153,11 +153,15 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
         for (int v = 0; v < VEC; ++v) {
           const int c4 = g.gl + v * G;
           const bool on = sj[u] >= 0 && c4 < g.cv;
-          // MODE 0 gathers a per-node / per-row table with reuse (default policy); the other modes stream [R, C] rows
-          if (MODE == 0) x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
-          else x[u][v] = on ? seg_ldg(X4 + (int64_t)sj[u] * g.cv + c4, pol.stream) : f4_zero();
-          if (MODE & 6) xm[u][v] = on ? seg_ldg(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4, pol.stream) : f4_zero();
-          if (MODE & 1) y[u][v] = on ? seg_ldg(X24 + (int64_t)m2j[u] * g.cv + c4, pol.keep) : f4_zero();
+          // with a second factor (pair-init backward): the [R, C] rows are a stream, the per-node table is what L2 should keep
+          if (MODE & 1) {
+            x[u][v] = on ? seg_ldg(X4 + (int64_t)sj[u] * g.cv + c4, pol.stream) : f4_zero();
+            if (MODE & 2) xm[u][v] = on ? seg_ldg(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4, pol.stream) : f4_zero();
+            y[u][v] = on ? seg_ldg(X24 + (int64_t)m2j[u] * g.cv + c4, pol.keep) : f4_zero();
+          } else {
+            x[u][v] = on ? ldg_cached(X4 + (int64_t)sj[u] * g.cv + c4) : f4_zero();
+            if (MODE & 6) xm[u][v] = on ? ldg_cached(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4) : f4_zero();
+          }
         }
       }
 #pragma unroll
