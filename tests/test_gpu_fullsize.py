@@ -99,7 +99,9 @@ def test_full_size_step_vs_fp64(workload, hidden):
     # at this size (sums over up to 6e7 rows, logits up to ~100) a larger share of the elements sits outside the 1e-5 band in ANY
     # fp32 evaluation - the plain torch one included: up to 15 % of a tensor may pass through the relaxation clauses (observed:
     # 9.6 % of the 3.0 M logits at rmat / hidden 64, 7 % at collab / hidden 256, see the ledger)
-    parity(out, lg32, lg64, tag + "logits", allow_relaxed=out.numel() * 15 // 100)
+    # (logits: additionally 1e-5 x the largest logit, ~1e-3 absolute here - the torch-fp32 evaluation's own worst element moves
+    #  between 5e-5 and 2e-4 from run to run with the order of its atomics, so "4 x its error" alone is not a stable yardstick)
+    parity(out, lg32, lg64, tag + "logits", scale_floor=1e-5, allow_relaxed=out.numel() * 15 // 100)
     parity(loss, l32, l64, tag + "loss")
     for k in sorted(grads):
         # gradient floor 3e-5 x the tensor's largest magnitude: a weight / GraphNorm gradient here is a sum over up to 6e7 rows of
