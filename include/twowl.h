@@ -458,6 +458,12 @@ int twowl_wedge_prepare(const int32_t* src /*[R]*/, const int32_t* dst_e /*[E]*/
 int twowl_wedge_prepare_rows(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N, const uint8_t* blocked,
                              const int64_t* in_ptr, int64_t row_lo, int64_t row_hi, int32_t* cnt, int32_t* centre, float* dinv,
                              float* selfw, int32_t* bnode, void* stream);
+/* The same for TWO ranges of pair rows [lo0, hi0) and [lo1, hi1) (even bounds, hi0 <= lo1), written one after the other into
+ * [2, (hi0 - lo0) + (hi1 - lo1)] outputs: a rank's block of the row-sharded step is its slice of the observed pairs (rows < E)
+ * followed by its slice of the prediction pairs (rows >= E), so that every rank carries the same share of both. */
+int twowl_wedge_prepare_ranges(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N, const uint8_t* blocked,
+                               const int64_t* in_ptr, int64_t lo0, int64_t hi0, int64_t lo1, int64_t hi1, int32_t* cnt,
+                               int32_t* centre, float* dinv, float* selfw, int32_t* bnode, void* stream);
 /* apply (forward):  out[b] = dinv[b]*S[centre[b]] + selfw[b]*Z[b] + bias   (centre < 0: no S term) */
 int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,
                           const float* selfw, const float* bias, int64_t R, int32_t C, float* out, void* stream);

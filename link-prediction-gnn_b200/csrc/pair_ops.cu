@@ -150,19 +150,20 @@ __global__ void __launch_bounds__(kRowThreads) k_wedge_cnt_block(const int32_t* 
     if (blocked[a] && i >= 0 && i < N) atomicSub(&cnt[i], 1);  // integer atomics: order-independent result
   }
 }
-// rows [row_lo, row_hi) of the pair table -> entries [0, row_hi - row_lo) of the [2, Rout] outputs (Rout = row_hi - row_lo;
-// the whole table: row_lo = 0, row_hi = Rout = R)
+// rows [row_lo, row_hi) of the pair table -> entries [out_off, out_off + row_hi - row_lo) of the [2, Rout] outputs
+// (the whole table: row_lo = 0, row_hi = Rout = R, out_off = 0; a rank's block of the row-sharded path is two ranges - its
+// slice of the observed pairs, then its slice of the prediction pairs - written one after the other)
 __global__ void __launch_bounds__(kRowThreads) k_wedge_rows(const int32_t* __restrict__ src, const int32_t* __restrict__ dst_e,
                                                             int64_t E, int64_t R, int64_t N, const uint8_t* __restrict__ blocked,
                                                             const int32_t* __restrict__ cnt, int64_t row_lo, int64_t row_hi,
-                                                            int32_t* __restrict__ centre_, float* __restrict__ dinv_,
-                                                            float* __restrict__ selfw_, int32_t* __restrict__ bnode_) {
-  // the outputs are addressed as if they covered the whole table: [q * Rout + (b - row_lo)] = base[q * Rout - row_lo + b]
-  const int64_t Rout = row_hi - row_lo;
-  int32_t* const centre = centre_ - row_lo;
-  float* const dinv = dinv_ - row_lo;
-  float* const selfw = selfw_ - row_lo;
-  int32_t* const bnode = bnode_ - row_lo;
+                                                            int64_t Rout, int64_t out_off, int32_t* __restrict__ centre_,
+                                                            float* __restrict__ dinv_, float* __restrict__ selfw_,
+                                                            int32_t* __restrict__ bnode_) {
+  // the outputs are addressed by the table's row id: [q * Rout + out_off + (b - row_lo)] = base[q * Rout + b]
+  int32_t* const centre = centre_ + (out_off - row_lo);
+  float* const dinv = dinv_ + (out_off - row_lo);
+  float* const selfw = selfw_ + (out_off - row_lo);
+  int32_t* const bnode = bnode_ + (out_off - row_lo);
   for (int64_t b = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < row_hi; b += (int64_t)gridDim.x * blockDim.x) {
     // direction 0 (edge2 = [a^1; b]): row b is fed by the in-list of src[b]; its id-self-loop is a = b^1
     // direction 1 (edge2_r = [a; b^1]): row b is fed by the in-list of src[b^1]; its id-self-loop is a = b
@@ -322,7 +323,29 @@ extern "C" int twowl_wedge_prepare(const int32_t* src, const int32_t* dst_e, int
   cudaStream_t s = (cudaStream_t)stream;
   if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
   if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
-  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, 0, R, centre, dinv, selfw, bnode);
+  if (R > 0) k_wedge_rows<<<grid_for(R, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, 0, R, R, 0, centre, dinv, selfw, bnode);
+  TW_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int twowl_wedge_prepare_ranges(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N,
+                                          const uint8_t* blocked, const int64_t* in_ptr, int64_t lo0, int64_t hi0, int64_t lo1,
+                                          int64_t hi1, int32_t* cnt, int32_t* centre, float* dinv, float* selfw, int32_t* bnode,
+                                          void* stream) {
+  TW_CHECK_ARG(E >= 0 && R >= E && N >= 0, "wedge_prepare_ranges: need 0 <= E <= R and N >= 0");
+  TW_CHECK_ARG(lo0 >= 0 && lo0 <= hi0 && hi0 <= lo1 && lo1 <= hi1 && hi1 <= R && !((lo0 | hi0 | lo1 | hi1) & 1),
+               "wedge_prepare_ranges: [%lld, %lld) and [%lld, %lld) must be even-bounded, ordered, disjoint ranges of the %lld pair rows",
+               (long long)lo0, (long long)hi0, (long long)lo1, (long long)hi1, (long long)R);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n0 = hi0 - lo0, n1 = hi1 - lo1;
+  if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
+  if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
+  if (n0 > 0)
+    k_wedge_rows<<<grid_for(n0, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, lo0, hi0, n0 + n1, 0, centre, dinv,
+                                                                   selfw, bnode);
+  if (n1 > 0)
+    k_wedge_rows<<<grid_for(n1, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, lo1, hi1, n0 + n1, n0, centre, dinv,
+                                                                   selfw, bnode);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -330,18 +353,11 @@ extern "C" int twowl_wedge_prepare(const int32_t* src, const int32_t* dst_e, int
 extern "C" int twowl_wedge_prepare_rows(const int32_t* src, const int32_t* dst_e, int64_t E, int64_t R, int64_t N,
                                         const uint8_t* blocked, const int64_t* in_ptr, int64_t row_lo, int64_t row_hi, int32_t* cnt,
                                         int32_t* centre, float* dinv, float* selfw, int32_t* bnode, void* stream) {
-  TW_CHECK_ARG(E >= 0 && R >= E && N >= 0, "wedge_prepare_rows: need 0 <= E <= R and N >= 0");
   TW_CHECK_ARG(row_lo >= 0 && row_lo <= row_hi && row_hi <= R && !((row_lo | row_hi) & 1),
                "wedge_prepare_rows: [%lld, %lld) must be an even-bounded range of the %lld pair rows", (long long)row_lo,
                (long long)row_hi, (long long)R);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (N > 0) k_wedge_cnt_init<<<grid_for(N, kRowThreads), kRowThreads, 0, s>>>(in_ptr, N, cnt);
-  if (blocked && E > 0 && N > 0) k_wedge_cnt_block<<<grid_for(E, kRowThreads), kRowThreads, 0, s>>>(dst_e, E, N, blocked, cnt);
-  if (row_hi > row_lo)
-    k_wedge_rows<<<grid_for(row_hi - row_lo, kRowThreads), kRowThreads, 0, s>>>(src, dst_e, E, R, N, blocked, cnt, row_lo, row_hi, centre,
-                                                                                dinv, selfw, bnode);
-  TW_LAUNCH_CHECK();
-  return 0;
+  return twowl_wedge_prepare_ranges(src, dst_e, E, R, N, blocked, in_ptr, row_lo, row_hi, row_hi, row_hi, cnt, centre, dinv, selfw, bnode,
+                                    stream);
 }
 
 extern "C" int twowl_wedge_apply_fwd(const float* S, const float* Z, const int32_t* centre, const float* dinv,

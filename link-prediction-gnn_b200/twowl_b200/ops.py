@@ -766,6 +766,23 @@ def wedge_prepare_rows(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr, 
     return cnt, centre, dinv, selfw, bnode
 
 
+def wedge_prepare_ranges(src32, dst_e32, E: int, R: int, N: int, blocked, in_ptr, r0, r1):
+    """wedge_prepare for the pair rows r0 = [lo0, hi0) followed by r1 = [lo1, hi1) -> (cnt [N], centre, dinv, selfw, bnode
+    [2, (hi0 - lo0) + (hi1 - lo1)]): one rank's block of the row-sharded step."""
+    dev = src32.device
+    Rl = (r0[1] - r0[0]) + (r1[1] - r1[0])
+    cnt = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    centre = torch.empty((2, Rl), dtype=torch.int32, device=dev)
+    dinv = torch.empty((2, Rl), dtype=torch.float32, device=dev)
+    selfw = torch.empty((2, Rl), dtype=torch.float32, device=dev)
+    bnode = torch.empty((2, Rl), dtype=torch.int32, device=dev)
+    check(lib.twowl_wedge_prepare_ranges(src32.data_ptr(), dst_e32.data_ptr(), E, R, N, _p(blocked), in_ptr.data_ptr(), int(r0[0]),
+                                         int(r0[1]), int(r1[0]), int(r1[1]), cnt.data_ptr(), centre.data_ptr(), dinv.data_ptr(),
+                                         selfw.data_ptr(), bnode.data_ptr(), _stream()), "wedge_prepare_ranges")
+    _count(4)
+    return cnt, centre, dinv, selfw, bnode
+
+
 def wedge_apply_fwd(S, Z, centre, dinv, selfw, bias) -> torch.Tensor:
     R, C = Z.shape
     out = torch.empty_like(Z)

@@ -1,8 +1,9 @@
 """Row-block sharding of the pair table over several GPUs: ONE TwoWL step cut over the ranks.
 
-Pair level (model.py:75-83). Rank g owns the contiguous block [lo, hi) of pair rows (even boundaries: rows 2k / 2k+1 are the
-two directions of one pair, utils.py:81-90, and stay together), i.e. its rows of every [R, C] activation, the observed edges
-and the target links that fall into the block. On the factorised wedge path a pair row only talks to the other rows through
+Pair level (model.py:75-83). Rank g owns a block of pair rows = its contiguous share of the observed pairs followed by its
+contiguous share of the prediction pairs (blocks_of; even boundaries: rows 2k / 2k+1 are the two directions of one pair,
+utils.py:81-90, and stay together), i.e. its rows of every [R, C] activation, the observed edges and the target links that fall
+into the block. On the factorised wedge path a pair row only talks to the other rows through
 per-NODE sums, so the exchange per pair layer is
 
     forward   all_reduce  SH_f, SH_r   [2, N, C] fp32      in-list sums of the pair layer (partial over the rank's edges)
@@ -53,11 +54,29 @@ from . import ops
 
 
 def block_of(R: int, rank: int, world: int) -> Tuple[int, int]:
-    """[lo, hi) of rank's block: equal numbers of undirected pairs (the factorised path costs the same for every row)."""
+    """[lo, hi) of rank's share of R rows cut into contiguous blocks of equal numbers of undirected pairs (even boundaries)."""
     if R % 2:
         raise ValueError("the pair table must have an even number of rows")
     pairs = R // 2
     return 2 * (pairs * rank // world), 2 * (pairs * (rank + 1) // world)
+
+
+def blocks_of(E: int, R: int, rank: int, world: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+    """rank's block of the pair table = ([olo, ohi), [plo, phi)): its share of the OBSERVED pairs (rows < E) followed by its
+    share of the PREDICTION pairs (rows >= E). The two kinds of rows cost differently - only observed edges feed the in-list
+    sums, only they can be blocked - so a contiguous cut of [0, R) would give the first ranks all of that work (measured at
+    world 8 on R-MAT 1M/16M: 15.4 ms of compute on the ranks holding observed edges against 12.6 ms on the others)."""
+    if E % 2 or R % 2 or not 0 <= E <= R:
+        raise ValueError("the pair table must hold E observed rows and R - E prediction rows, both even (doubled layout)")
+    olo, ohi = block_of(E, rank, world)
+    plo, phi = block_of(R - E, rank, world)
+    return (olo, ohi), (E + plo, E + phi)
+
+
+def take_ranges(t: torch.Tensor, ranges) -> torch.Tensor:
+    """rows of t inside the block's two ranges, observed share first (a copy)."""
+    (olo, ohi), (plo, phi) = ranges
+    return torch.cat((t[olo:ohi], t[plo:phi]))
 
 
 def node_block(N: int, rank: int, world: int) -> Tuple[int, int, int]:
@@ -72,9 +91,12 @@ _last_shard = None
 class RowShard:
     """Assign to ``LocalWLNet.row_shard`` to run forward / backward on this rank's block of pair rows (and node block)."""
 
-    def __init__(self, group=None, rank: Optional[int] = None, world: Optional[int] = None):
+    def __init__(self, group=None, rank: Optional[int] = None, world: Optional[int] = None, dry: bool = False):
+        """dry = True (tools/rowshard_dry.py only): the collectives are accounted but NOT run - one rank's compute of a
+        world-size-W step timed on a single device; the numbers it produces are partial sums, not results."""
         global _last_shard
         self.group = group
+        self.dry = bool(dry)
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
             world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -93,6 +115,8 @@ class RowShard:
     def all_reduce(self, t: torch.Tensor, what: str = "all_reduce") -> torch.Tensor:
         if self.world > 1:
             self._account("all_reduce " + what, t)
+            if self.dry:
+                return t
             with ops._P("nccl_all_reduce", 2 * t.numel() * t.element_size()):
                 dist.all_reduce(t, group=self.group)
         return t
@@ -103,6 +127,8 @@ class RowShard:
         if self.world == 1:
             return None
         self._account("all_reduce " + what, t)
+        if self.dry:
+            return None
         return dist.all_reduce(t, group=self.group, async_op=True)
 
     def reduce_in_chunks(self, M: int, produce, tensors, what: str):
@@ -129,6 +155,8 @@ class RowShard:
         """full: [world * B, C] whose block [rank*B, (rank+1)*B) this rank has filled -> every block filled, in place."""
         if self.world > 1:
             self._account("all_gather " + what, full)
+            if self.dry:
+                return full
             mine = full[self.rank * B:(self.rank + 1) * B]
             with ops._P("nccl_all_gather", full.numel() * full.element_size()):
                 if self.nccl:
@@ -289,9 +317,8 @@ def forward_nodes(model, x, edge1):
 
 @dataclass
 class _Local:
-    lo: int
-    hi: int
-    E_loc: int             # observed edges inside the block (rows [lo, min(hi, E)))
+    ranges: tuple          # ((olo, ohi), (plo, phi)) rows of the table this block holds, in this order
+    E_loc: int             # observed edges inside the block (its first ohi - olo rows)
     src: torch.Tensor      # int32 [Rl]
     dst: torch.Tensor
     in_ptr: torch.Tensor   # the block's observed edges grouped by target node (local ids)
@@ -305,18 +332,20 @@ class _Local:
     xout_plan: torch.Tensor
 
 
-def _local(struct: G.WedgeStruct, pt: G.PairTable, lo: int, hi: int) -> _Local:
+def _local(struct: G.WedgeStruct, pt: G.PairTable, ranges) -> _Local:
+    (olo, ohi), (plo, phi) = ranges
+
     def build():
         n = struct.n_node
-        hiE = max(lo, min(hi, struct.E))
-        in_ptr, in_ids = ops.csr_build(struct.dst_e[lo:hiE].to(torch.int64), n)
-        out_ptr, out_ids = ops.csr_build(struct.src[lo:hi].to(torch.int64), n)
-        xout_ptr, xout_ids = ops.csr_build(pt.src[lo:hi].to(torch.int64), pt.n)
-        return (pt, _Local(lo, hi, hiE - lo, pt.src[lo:hi].contiguous(), pt.dst[lo:hi].contiguous(), in_ptr, in_ids,
-                           ops.seg_plan(in_ptr, n, hiE - lo), out_ptr, out_ids, ops.seg_plan(out_ptr, n, hi - lo),
-                           xout_ptr, xout_ids, ops.seg_plan(xout_ptr, pt.n, hi - lo)))
+        El, Rl = ohi - olo, (ohi - olo) + (phi - plo)
+        src_l, dst_l = take_ranges(pt.src, ranges), take_ranges(pt.dst, ranges)
+        in_ptr, in_ids = ops.csr_build(struct.dst_e[olo:ohi].to(torch.int64), n)
+        out_ptr, out_ids = ops.csr_build(take_ranges(struct.src, ranges).to(torch.int64), n)
+        xout_ptr, xout_ids = ops.csr_build(src_l.to(torch.int64), pt.n)
+        return (pt, _Local(ranges, El, src_l, dst_l, in_ptr, in_ids, ops.seg_plan(in_ptr, n, El), out_ptr, out_ids,
+                           ops.seg_plan(out_ptr, n, Rl), xout_ptr, xout_ids, ops.seg_plan(xout_ptr, pt.n, Rl)))
     # the entry holds struct.src (key tensor) and pt (value): neither address can be recycled while the block is cached
-    return G._cache.get(struct.src, ("rowshard", lo, hi) + G._Cache.key(pt.src), build)[1]
+    return G._cache.get(struct.src, ("rowshard", olo, ohi, plo, phi) + G._Cache.key(pt.src), build)[1]
 
 
 def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr):
@@ -484,13 +513,17 @@ def supported(model, wedges, C: int) -> Optional[str]:
     return None
 
 
-def mask_links(idx: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
-    """Readout row ids [2L] -> block-local ids for the rows inside [lo, hi), -1 for the others; both rows of a link are the two
-    directions of one pair (double(.., for_index=True)), so they are inside or outside together (asserted on the device)."""
-    inb = (idx >= lo) & (idx < hi)
+def mask_links(idx: torch.Tensor, ranges) -> torch.Tensor:
+    """Readout row ids [2L] -> block-local ids for the rows inside the block's two ranges (observed share first, then the
+    prediction share), -1 for the others; both rows of a link are the two directions of one pair (double(.., for_index=True)),
+    so they are inside or outside together (asserted on the device)."""
+    (olo, ohi), (plo, phi) = ranges
+    in_o = (idx >= olo) & (idx < ohi)
+    in_p = (idx >= plo) & (idx < phi)
+    inb = in_o | in_p
     torch._assert_async((inb[0::2] == inb[1::2]).all(),
                         "row-sharded readout: idx[2l] and idx[2l+1] must be the two rows of one pair (double(.., for_index=True))")
-    return torch.where(inb, idx - lo, torch.full_like(idx, -1))
+    return torch.where(in_o, idx - olo, torch.where(in_p, idx - (plo - (ohi - olo)), torch.full_like(idx, -1)))
 
 
 def forward(model, x, edge1, pos, idx, ei2):
@@ -520,14 +553,14 @@ def forward_pairs(model, x, pos, idx, ei2):
         blocked = wedges.blocked
         wedges = lv.struct if blocked is None else lv.struct.with_blocked(ops.gather_u8(blocked, lv.perm[:wedges.E]))
         idx = lv.newid[idx]
-    lo, hi = block_of(pt.R, shard.rank, shard.world)
-    loc = _local(wedges, pt, lo, hi)
+    ranges = blocks_of(wedges.E, pt.R, shard.rank, shard.world)
+    loc = _local(wedges, pt, ranges)
     # per-row constants of THIS block only (the degree counts are global: every rank holds the int edge lists)
-    _, centre, dinv, selfw, bnode = ops.wedge_prepare_rows(wedges.src, wedges.dst_e, wedges.E, wedges.R, wedges.n_node, wedges.blocked,
-                                                           wedges.in_ptr, lo, hi)
+    _, centre, dinv, selfw, bnode = ops.wedge_prepare_ranges(wedges.src, wedges.dst_e, wedges.E, wedges.R, wedges.n_node, wedges.blocked,
+                                                             wedges.in_ptr, ranges[0], ranges[1])
     rows = (centre, dinv, selfw, bnode)
-    blocked_l = wedges.blocked[lo:lo + loc.E_loc] if wedges.blocked is not None else None
-    idx_l = mask_links(idx, lo, hi)
+    blocked_l = wedges.blocked[ranges[0][0]:ranges[0][1]] if wedges.blocked is not None else None
+    idx_l = mask_links(idx, ranges)
     H = _ShardedPairInit.apply(x, loc, wedges.n_node)
     last = len(model.conv2s) - 1
     for i, (seq_f, seq_r) in enumerate(zip(model.conv2s, model.conv2s_r)):

@@ -68,7 +68,7 @@ class _Dir:
         self.pre = "conv2s.0." if fwd else "conv2s_r.0."
 
 
-def step(sd, deg, ei, pos1, idx, E, blocked, y, chunk_rows=1 << 22, dtype=torch.float64):
+def step(sd, deg, ei, pos1, idx, E, blocked, y, chunk_rows=1 << 22, dtype=torch.float64, debug=None):
     """-> (logits [L,1], loss, {state_dict key: gradient}), all float64 (`dtype=torch.float32` evaluates the same program in
     fp32: what plain torch fp32 arithmetic - the reference's - makes of these formulas at this size). sd: state_dict of a depth-1/1 LocalWLNet;
     deg / ei: the node-level inputs AFTER sample_block (x_new, ei_new); pos1 int64 [R,2]; idx int64 [2L]; E = number of observed
@@ -153,6 +153,9 @@ def step(sd, deg, ei, pos1, idx, E, blocked, y, chunk_rows=1 << 22, dtype=torch.
         var = var + (v2[k] / R - var).detach()                              # the two-pass VALUE, the one-pass form's gradient
         branches.append(torch.relu(p[d.pre + "modlist.1.weight"] * (sel[k] - a * mean) / (var + EPS).sqrt() + p[d.pre + "modlist.1.bias"]))
     hsel = branches[0] + branches[1]
+    if debug is not None:       # intermediates for tools/diag_stages.py: where along the chain an implementation's error appears
+        debug.update(h=h.detach(), S=[t.detach() for t in S], mean=[(s1[k] / R).detach() for k in range(2)],
+                     var=[(v2[k] / R).detach() for k in range(2)], sel=[t.detach() for t in sel], hsel=hsel.detach())
     logits = (hsel[0::2] * hsel[1::2]) @ p["pred.weight"].t() + p["pred.bias"]            # model.py:78-83
     loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.to(dev, dt))
     loss.backward()

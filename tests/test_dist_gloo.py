@@ -81,20 +81,27 @@ def _worker(rank, world, port, out):
         L = 11
         # the readout rows of a batch: link l selects the mates (2*r_l, 2*r_l + 1); a rank keeps the links whose rows fall into
         # its block as block-local ids and masks the others with -1 (no compaction, hence no device->host size read)
-        R = 40
-        lo, hi = RS.block_of(R, rank, world)
+        # (a block = the rank's share of the observed rows [0, E) followed by its share of the prediction rows [E, R))
+        E, R = 24, 40
+        ranges = RS.blocks_of(E, R, rank, world)
+        (olo, ohi), (plo, phi) = ranges
         rows_of_link = torch.tensor([3, 17, 0, 19, 8, 12, 5, 11, 15, 2, 9])
         idx = torch.stack((2 * rows_of_link, 2 * rows_of_link + 1), dim=1).reshape(-1)
-        idx_l = RS.mask_links(idx, lo, hi)
-        mine = (2 * rows_of_link >= lo) & (2 * rows_of_link < hi)
-        assert torch.equal(idx_l.reshape(L, 2)[mine], idx.reshape(L, 2)[mine] - lo) and bool((idx_l.reshape(L, 2)[~mine] == -1).all())
+        idx_l = RS.mask_links(idx, ranges)
+        in_o = (2 * rows_of_link >= olo) & (2 * rows_of_link < ohi)
+        in_p = (2 * rows_of_link >= plo) & (2 * rows_of_link < phi)
+        mine = in_o | in_p
+        # block-local ids = positions in take_ranges(table, ranges)
+        local_of = torch.full((R,), -1, dtype=torch.int64)
+        local_of[RS.take_ranges(torch.arange(R), ranges)] = torch.arange((ohi - olo) + (phi - plo))
+        assert torch.equal(idx_l, local_of[idx]) and bool((idx_l.reshape(L, 2)[~mine] == -1).all()) and bool((idx_l.reshape(L, 2)[mine] >= 0).all())
         counted = mine.to(torch.int64).clone()
         dist.all_reduce(counted)
         assert bool((counted == 1).all())                                       # every link belongs to exactly one rank
         # logits: own links filled, 0 elsewhere -> one all-reduce gives every rank the full [L,1]; the gradient comes back whole
         pred_l = (torch.where(mine, torch.arange(L) * 10 + rank, torch.zeros(L, dtype=torch.int64))).double().reshape(-1, 1).requires_grad_(True)
         full = RS._SumLogits.apply(pred_l, shard)
-        owner = torch.tensor([next(r for r in range(world) if RS.block_of(R, r, world)[0] <= 2 * int(v) < RS.block_of(R, r, world)[1])
+        owner = torch.tensor([next(r for r in range(world) if any(lo_ <= 2 * int(v) < hi_ for lo_, hi_ in RS.blocks_of(E, R, r, world)))
                               for v in rows_of_link])
         assert torch.equal(full.detach().reshape(-1), (torch.arange(L) * 10 + owner).double())
         w = torch.arange(1.0, L + 1).double().reshape(-1, 1)
@@ -181,6 +188,20 @@ def test_row_shard_blocks_cover_the_pair_table_with_even_boundaries():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         block_of(7, 0, 2)
+    # a rank's block of the pair table: its share of the observed rows [0, E) + its share of the prediction rows [E, R) - the
+    # ranks' blocks tile both parts, every rank carries the same number of each kind (+- one pair)
+    from twowl_b200.rowshard import blocks_of
+    for E, R in ((0, 2), (4, 4), (24, 40), (30003804, 60007608)):
+        for world in (1, 2, 3, 8):
+            blocks = [blocks_of(E, R, r, world) for r in range(world)]
+            assert blocks[0][0][0] == 0 and blocks[-1][0][1] == E and blocks[0][1][0] == E and blocks[-1][1][1] == R
+            for k in (0, 1):
+                assert all(a[k][1] == b[k][0] for a, b in zip(blocks, blocks[1:]))
+                assert all(b[k][0] % 2 == 0 and b[k][1] % 2 == 0 and b[k][1] >= b[k][0] for b in blocks)
+                sizes = [(b[k][1] - b[k][0]) // 2 for b in blocks]
+                assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        blocks_of(3, 8, 0, 2)
     a = D.shard_batch(1000, 100, step=3, seed=1, replicate=True)
     b = D.shard_batch(1000, 100, step=3, seed=1)            # world size 1: the same draw
     assert torch.equal(a, b) and a.unique().numel() == 100
