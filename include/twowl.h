@@ -290,7 +290,10 @@ int twowl_graphnorm_bwd2(const float* xf, const float* xr, const float* dout, in
  *   bwd: from dpred[L]: dense dxf, dxr [M,C] (GraphNorm's statistics give every row a gradient), dparams_f / dparams_r [4C] as in
  *        twowl_graphnorm_bwd2, dw[C], db[1]. The incoming gradient is zero outside the selected rows, so the column reductions
  *        run over the 2L positions only and the dense pass reads xf, xr once. A row selected several times adds its positions in
- *        ascending order (deterministic). */
+ *        ascending order (deterministic).
+ *   Masked links: a NEGATIVE id in idx[2l] / idx[2l+1] masks link l (pred[l] = 0, no gradient) - a row-sharded caller marks the
+ *   links outside its row block that way; the id -2 additionally promises that every LATER link of the list is masked as well
+ *   (own links packed at the front), and the kernels stop scanning there. */
 int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M, int32_t C, const float* stats_f, const float* stats_r,
                           const float* wf, const float* bf, const float* mf, const float* wr, const float* br, const float* mr,
                           float p_drop, uint64_t seed_f, uint64_t seed_r, int32_t relu, const int64_t* idx, int64_t sidx, int64_t L,

@@ -12,6 +12,10 @@
 namespace twowl {
 
 constexpr int kNormThreads = 256;
+// Readout row ids (twowl_gn2_readout_*): any negative id = "this link is masked" (a row-sharded caller masks the links outside
+// its block); kMaskedTail additionally promises that EVERY later link of the list is masked as well (a caller that packed its
+// own links at the front, twowl_b200.rowshard.own_links_first) - the kernels stop there instead of scanning the tail.
+constexpr int64_t kMaskedTail = -2;
 constexpr int kNormMaxCtas = kNumSMs * 4;
 
 struct RowMap {
@@ -28,25 +32,49 @@ struct RowMap {
   }
 };
 
-// Reduce NV float4 values per thread over the CTA's row slots, in slot order, into doubles:
-// part[blockIdx.x][v][C].  smem: slots*cv float4 per value.
+// Column sums without long fp32 chains: a thread's fp32 running sums are folded into double accumulators every kFoldRows rows
+// (a grid-stride thread of a 1 M-row pass adds ~110 rows, of a 60 M-row pass ~6 000; as one fp32 chain that put ~1e-6 of
+// relative error into GraphNorm's mean / variance and into every column-sum gradient - 5-13 x what torch's cascaded fp32 sums
+// leave, measured stage by stage with tools/diag_node.py).
+constexpr int kFoldRows = 8;
+// The double accumulators live in shared memory, [value][component][thread] (conflict-free, no registers: in registers they
+// cost k_gn2_readout_bwd_rows its second CTA per SM).
 template <int NV>
-__device__ __forceinline__ void cta_col_reduce(const RowMap& rm, const float4 (&val)[NV], double* __restrict__ part, int C) {
-  extern __shared__ float4 s_red[];
+struct ColFold {
+  double* base;
+  int n;
+  __device__ __forceinline__ ColFold() : n(0) {
+    extern __shared__ double s_fold[];
+    base = s_fold + threadIdx.x;
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    if (rm.slot >= 0) s_red[(v * rm.slots + rm.slot) * rm.cv + rm.c4] = val[v];
+    for (int i = 0; i < NV * 4; ++i) base[i * kNormThreads] = 0.0;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NV * rm.cv; i += kNormThreads) {
-    const int v = i / rm.cv, c4 = i % rm.cv;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int s = 0; s < rm.slots; ++s) {
-      const float4 x = s_red[(v * rm.slots + s) * rm.cv + c4];
-      a0 += x.x, a1 += x.y, a2 += x.z, a3 += x.w;
+  __device__ __forceinline__ void flush(float4 (&val)[NV]) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double* o = base + (v * 4) * kNormThreads;
+      o[0] += (double)val[v].x, o[kNormThreads] += (double)val[v].y;
+      o[2 * kNormThreads] += (double)val[v].z, o[3 * kNormThreads] += (double)val[v].w;
+      val[v] = f4_zero();
     }
-    double* o = part + ((size_t)blockIdx.x * NV + v) * C + c4 * 4;
-    o[0] = a0, o[1] = a1, o[2] = a2, o[3] = a3;
+    n = 0;
+  }
+  __device__ __forceinline__ void tick(float4 (&val)[NV]) {
+    if (++n == kFoldRows) flush(val);
+  }
+};
+
+// The CTA's row slots added in slot order: part[blockIdx.x][v][C] (thread slot * cv + c4 holds columns 4 c4 .. 4 c4 + 3).
+template <int NV>
+__device__ __forceinline__ void cta_col_reduce_d(const RowMap& rm, const ColFold<NV>&, double* __restrict__ part, int C) {
+  extern __shared__ double s_fold[];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV * C; i += kNormThreads) {
+    const int v = i / C, c = i % C;
+    const double* col = s_fold + (size_t)(v * 4 + (c & 3)) * kNormThreads + (c >> 2);
+    double a = 0;
+    for (int sl = 0; sl < rm.slots; ++sl) a += col[sl * rm.cv];
+    part[((size_t)blockIdx.x * NV + v) * C + c] = a;
   }
 }
 
@@ -55,6 +83,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_stats_partial(const float* 
                                                                    double* __restrict__ part) {
   const RowMap rm(C);
   float4 v[2] = {f4_zero(), f4_zero()};
+  ColFold<2> fold;
   if (rm.slot >= 0) {
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
     const float4 sh = __ldg(x4 + rm.c4);  // shift = first row: keeps the squared sums well conditioned
@@ -64,9 +93,11 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_stats_partial(const float* 
       f4_add(v[0], a);
       v[1].x = fmaf(a.x, a.x, v[1].x), v[1].y = fmaf(a.y, a.y, v[1].y);
       v[1].z = fmaf(a.z, a.z, v[1].z), v[1].w = fmaf(a.w, a.w, v[1].w);
+      fold.tick(v);
     }
+    fold.flush(v);
   }
-  cta_col_reduce<2>(rm, v, part, C);
+  cta_col_reduce_d<2>(rm, fold, part, C);
 }
 
 __global__ void k_gn_stats_final(const double* __restrict__ part, int nparts, const float* __restrict__ x, int64_t M, int C,
@@ -170,6 +201,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
   seed = resolve_seed(seed);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[2] = {f4_zero(), f4_zero()};
+  ColFold<2> fold;
   if (rm.slot >= 0) {
     const GnCols cc(C, rm.c4 * 4, stats, weight, bias, mean_scale);
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
@@ -181,9 +213,11 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd_partial(const float* __
       v[0].x += gy[0], v[0].y += gy[1], v[0].z += gy[2], v[0].w += gy[3];
       v[1].x = fmaf(gy[0], n[0], v[1].x), v[1].y = fmaf(gy[1], n[1], v[1].y);
       v[1].z = fmaf(gy[2], n[2], v[1].z), v[1].w = fmaf(gy[3], n[3], v[1].w);
+      fold.tick(v);
     }
+    fold.flush(v);
   }
-  cta_col_reduce<2>(rm, v, part, C);
+  cta_col_reduce_d<2>(rm, fold, part, C);
 }
 
 // sums[0:C] = A = sum g_y, sums[C:2C] = B = sum g_y*n, sums[2C:3C] = (alpha/M) * sum g_o   (fp32, for pass 2)
@@ -294,6 +328,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_partial(const float* _
   seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+  ColFold<4> fold;
   if (rm.slot >= 0) {
     const int c0 = rm.c4 * 4;
     const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
@@ -312,9 +347,11 @@ __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_partial(const float* _
       v[2].x += gy[0], v[2].y += gy[1], v[2].z += gy[2], v[2].w += gy[3];
       v[3].x = fmaf(gy[0], n[0], v[3].x), v[3].y = fmaf(gy[1], n[1], v[3].y);
       v[3].z = fmaf(gy[2], n[2], v[3].z), v[3].w = fmaf(gy[3], n[3], v[3].w);
+      fold.tick(v);
     }
+    fold.flush(v);
   }
-  cta_col_reduce<4>(rm, v, part, C);
+  cta_col_reduce_d<4>(rm, fold, part, C);
 }
 
 __global__ void __launch_bounds__(kNormThreads) k_gn_bwd2_dx(const float* __restrict__ xf, const float* __restrict__ xr,
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd_g(const float*
     int64_t b0 = two ? idx[(2 * l1) * sidx] : a0, b1 = two ? idx[(2 * l1 + 1) * sidx] : a1;
     const bool va = a0 >= 0 && a1 >= 0, vb = b0 >= 0 && b1 >= 0;
     if (!va && !vb) {   // uniform over the lane group (its lanes share the two links): nothing to gather, nothing to reduce
+      if (a0 == kMaskedTail) break;   // packed list: every later link is masked too (their logits were zeroed by the launcher)
       if (c4 == 0) {
         pred[l0] = 0.f;
         if (two) pred[l1] = 0.f;
@@ -471,6 +509,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_fwd(const float* _
   for (int64_t l = warp0; l < L; l += nwarps) {
     const int64_t i0 = idx[(2 * l) * sidx], i1 = idx[(2 * l + 1) * sidx];
     if (i0 < 0 || i1 < 0) {   // not this rank's link (see k_gn2_readout_fwd_g); warp-uniform
+      if (i0 == kMaskedTail) break;
       if (lane == 0) pred[l] = 0.f;
       continue;
     }
@@ -507,6 +546,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
   seed_f = resolve_seed(seed_f); seed_r = resolve_seed(seed_r);   // a tagged seed is an address (common.cuh)
   const RowMap rm(C);
   float4 v[6] = {f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+  ColFold<6> fold;
   if (rm.slot >= 0) {
     const int c0 = rm.c4 * 4;
     const GnCols cf(C, c0, stf, wf, bf, mf), cr(C, c0, str_, wr, br, mr);
@@ -516,6 +556,7 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
     float4* __restrict__ G4 = reinterpret_cast<float4*>(G);
     for (int64_t j = (int64_t)blockIdx.x * rm.slots + rm.slot; j < 2 * L; j += (int64_t)gridDim.x * rm.slots) {
       const int64_t ra = idx[j * sidx], rb = idx[(j ^ 1) * sidx];
+      if (ra == kMaskedTail) break;     // packed list: every later position is masked too
       if (ra < 0 || rb < 0) continue;   // not this rank's link: no contribution to the column sums; its G row is never read
                                         // (the row chains hold valid positions only), so it is not written either
       const float g = dpred[j >> 1];
@@ -539,9 +580,11 @@ __global__ void __launch_bounds__(kNormThreads) k_gn2_readout_bwd_rows(const flo
         v[4].z = fmaf(g, ha.z * hb.z, v[4].z), v[4].w = fmaf(g, ha.w * hb.w, v[4].w);
         if (rm.c4 == 0) v[5].x += g;   // db = sum_l dpred[l], carried in column 0 of a sixth partial
       }
+      fold.tick(v);
     }
+    fold.flush(v);
   }
-  cta_col_reduce<6>(rm, v, part, C);
+  cta_col_reduce_d<6>(rm, fold, part, C);
 }
 
 // per-row chains of the positions that select it: head[row] -> position -> next[position] -> ... -> -1.
@@ -550,6 +593,7 @@ __global__ void __launch_bounds__(kNormThreads) k_row_chains(const int64_t* __re
                                                              int32_t* __restrict__ head, int32_t* __restrict__ next) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx[j * sidx];
+    if (r == kMaskedTail) break;   // packed list: no later position selects a row, and next[] is only read along the chains
     next[j] = (r >= 0 && r < M) ? atomicExch(&head[r], (int32_t)j) : -1;
   }
 }
@@ -655,12 +699,16 @@ __global__ void __launch_bounds__(kNormThreads) k_colsum_partial(const float* __
                                                                  double* __restrict__ part) {
   const RowMap rm(C);
   float4 v[1] = {f4_zero()};
+  ColFold<1> fold;
   if (rm.slot >= 0) {
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots)
+    for (int64_t r = (int64_t)blockIdx.x * rm.slots + rm.slot; r < M; r += (int64_t)gridDim.x * rm.slots) {
       f4_add(v[0], ldg_stream(x4 + r * rm.cv + rm.c4));
+      fold.tick(v);
+    }
+    fold.flush(v);
   }
-  cta_col_reduce<1>(rm, v, part, C);
+  cta_col_reduce_d<1>(rm, fold, part, C);
 }
 __global__ void k_colsum_final(const double* __restrict__ part, int nparts, int C, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -678,7 +726,11 @@ static int norm_grid(int64_t M, int C) {
   if (g < 1) g = 1;
   return (int)g;
 }
-static size_t red_smem(int C, int nv) { return (size_t)nv * (kNormThreads / (C >> 2)) * (C >> 2) * sizeof(float4); }
+// ColFold<nv>: nv x 4 doubles per thread
+static size_t red_smem(int C, int nv) {
+  (void)C;
+  return (size_t)nv * 4 * kNormThreads * sizeof(double);
+}
 static int check_mc(const char* op, int64_t M, int C) {
   TW_CHECK_ARG(M >= 0 && C >= 4 && (C & 3) == 0 && C <= 1024, "%s: C=%d must be a multiple of 4 in [4,1024]", op, C);
   return 0;
@@ -830,6 +882,7 @@ extern "C" int twowl_gn2_readout_fwd(const float* xf, const float* xr, int64_t M
   TW_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gn2_readout_fwd: dropout p=%f outside [0,1)", p_drop);
   if (L <= 0) return 0;
   const uint32_t thresh = p_drop > 0.f ? drop_thresh(p_drop) : 0u;
+  TW_CUDA(cudaMemsetAsync(pred, 0, (size_t)L * sizeof(float), (cudaStream_t)stream));   // logits of a masked tail (kMaskedTail)
 #define TW_RO_ARGS xf, xr, C, stats_f, stats_r, wf, bf, mf, wr, br, mr, thresh, 1.f / (1.f - p_drop), seed_f, seed_r, relu, idx, sidx, L, w, b, pred
   cudaStream_t s = (cudaStream_t)stream;
   const int cv = C >> 2;

@@ -361,6 +361,9 @@ def gather_u8(mask: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
+LONG_ROW = 64     # TWOWL_LONG_ROW of include/twowl.h: rows with more entries go through the long-row passes of seg_reduce
+
+
 def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
     """Long-row plan of a CSR as ONE int32 tensor: [counts(2) | long_row(lc) | long_base(lc) | chunk_owner(cc)],
     lc / cc being the capacities twowl_seg_plan_{long,chunk}_cap give for nnz (no host read needed)."""

@@ -79,6 +79,26 @@ def take_ranges(t: torch.Tensor, ranges) -> torch.Tensor:
     return torch.cat((t[olo:ohi], t[plo:phi]))
 
 
+def work_cuts(ptr_global: torch.Tensor, ptr_local: torch.Tensor, M: int, K: int):
+    """Cut the M rows of a CSR into K consecutive ranges of about equal work (entries + a per-row cost worth 4 entries):
+    -> [(lo, hi, has_long)]. The bounds come from the WHOLE graph's CSR `ptr_global`, which every rank holds - they must be the
+    same on all ranks (they size the collectives); has_long = this rank's own CSR `ptr_local` has rows longer than
+    TWOWL_LONG_ROW entries inside the range (a range without them runs the row pass only: no empty launches of the long-row
+    passes). Reads 2K numbers on the host: call it where the result is cached."""
+    if K <= 1 or M <= 1:
+        return [(0, M, True)]
+    p = ptr_global[:M + 1]
+    work = p + 4 * torch.arange(M + 1, device=p.device, dtype=p.dtype)
+    targets = (work[M] * torch.arange(1, K, device=p.device, dtype=p.dtype)) // K
+    inner = torch.searchsorted(work, targets).clamp_(0, M)
+    q = ptr_local[:M + 1]
+    is_long = ((q[1:] - q[:-1]) > ops.LONG_ROW).to(torch.int32)
+    csum = torch.cat((is_long.new_zeros(1), torch.cumsum(is_long, 0)))
+    bounds = [0] + inner.tolist() + [M]
+    longs = csum[torch.tensor(bounds, device=p.device)].tolist()
+    return [(bounds[k], bounds[k + 1], longs[k + 1] > longs[k]) for k in range(K)]
+
+
 def node_block(N: int, rank: int, world: int) -> Tuple[int, int, int]:
     """(lo, hi, B): rank's node block [lo, hi) of equal-size blocks B = ceil(N / world) (the last ones may be short or empty)."""
     B = -(-N // world)
@@ -131,18 +151,16 @@ class RowShard:
             return None
         return dist.all_reduce(t, group=self.group, async_op=True)
 
-    def reduce_in_chunks(self, M: int, produce, tensors, what: str):
-        """A per-node table made by a row-range kernel and summed over the ranks, pipelined: `produce(lo, hi)` fills rows
-        [lo, hi) of every tensor in `tensors` ([M, C] each); the all-reduce of a chunk runs on the communication stream while
-        the next chunk is produced. Only the last chunk's exchange is exposed."""
-        K = self.chunks if self.world > 1 else 1
-        bounds = [M * k // K for k in range(K + 1)]
+    def reduce_in_chunks(self, cuts, produce, tensors, what: str):
+        """A per-node table made by a row-range kernel and summed over the ranks, pipelined: `produce(lo, hi, has_long)` fills
+        rows [lo, hi) of every tensor in `tensors` ([M, C] each); the all-reduce of a chunk runs on the communication stream
+        while the next chunk is produced. `cuts` = work_cuts(...): node ranges of equal WORK, taken from the last (most nodes,
+        largest exchange) to the first (the hubs: fewest nodes), so that the one exchange nothing overlaps is the smallest."""
         handles = []
-        for k in range(K):
-            lo, hi = bounds[k], bounds[k + 1]
+        for lo, hi, has_long in reversed(cuts):
             if hi <= lo:
                 continue
-            produce(lo, hi)
+            produce(lo, hi, has_long)
             for t in tensors:
                 h = self.all_reduce_async(t[lo:hi], what)
                 if h is not None:
@@ -298,17 +316,12 @@ def forward_nodes(model, x, edge1):
     emb, gn0, dp0 = model.emb[0], model.emb[1], model.emb[2]
     h = _ShardedEmbedding.apply(emb.weight, x, shard)
     h = gn_act(gn0, dp0, None, h)
-    last = len(model.conv1s) - 1
     for k, seq in enumerate(model.conv1s):
         conv, gn, dp, act = seq.modlist[0], seq.modlist[1], seq.modlist[2], seq.modlist[3]
         gr = G.node_graph(edge1, N)
         z = _NodeLinear.apply(h, conv.lin.weight, shard)
-        out = _ShardedNodeAggregate.apply(z, conv.bias, gr, shard, k == last)
-        if k == last:     # its GraphNorm sees the partial gradients of the pair level: ordinary (partial) parameter gradients
-            p = dp.p if (model.training and dp.p > 0.0) else 0.0
-            h = gn.fused(out, p, isinstance(act, torch.nn.ReLU), None)
-        else:
-            h = gn_act(gn, dp, act, out)
+        out = _ShardedNodeAggregate.apply(z, conv.bias, gr, shard, False)
+        h = gn_act(gn, dp, act, out)      # the pair level hands back a COMPLETE dx (summed in _ShardedPairInit.backward)
     return h
 
 
@@ -330,9 +343,12 @@ class _Local:
     xout_ptr: torch.Tensor  # the same grouping by the pair TABLE's (original) node ids = pair_init's backward CSR
     xout_ids: torch.Tensor
     xout_plan: torch.Tensor
+    in_cuts: list           # work_cuts of the three CSRs: node ranges of the pipelined table exchanges
+    out_cuts: list
+    xout_cuts: list
 
 
-def _local(struct: G.WedgeStruct, pt: G.PairTable, ranges) -> _Local:
+def _local(struct: G.WedgeStruct, pt: G.PairTable, ranges, K: int = 1) -> _Local:
     (olo, ohi), (plo, phi) = ranges
 
     def build():
@@ -343,9 +359,11 @@ def _local(struct: G.WedgeStruct, pt: G.PairTable, ranges) -> _Local:
         out_ptr, out_ids = ops.csr_build(take_ranges(struct.src, ranges).to(torch.int64), n)
         xout_ptr, xout_ids = ops.csr_build(src_l.to(torch.int64), pt.n)
         return (pt, _Local(ranges, El, src_l, dst_l, in_ptr, in_ids, ops.seg_plan(in_ptr, n, El), out_ptr, out_ids,
-                           ops.seg_plan(out_ptr, n, Rl), xout_ptr, xout_ids, ops.seg_plan(xout_ptr, pt.n, Rl)))
+                           ops.seg_plan(out_ptr, n, Rl), xout_ptr, xout_ids, ops.seg_plan(xout_ptr, pt.n, Rl),
+                           work_cuts(struct.in_ptr, in_ptr, n, K), work_cuts(struct.out_ptr, out_ptr, n, K),
+                           work_cuts(pt.ptr_s, xout_ptr, pt.n, K)))
     # the entry holds struct.src (key tensor) and pt (value): neither address can be recycled while the block is cached
-    return G._cache.get(struct.src, ("rowshard", olo, ohi, plo, phi) + G._Cache.key(pt.src), build)[1]
+    return G._cache.get(struct.src, ("rowshard", olo, ohi, plo, phi, K) + G._Cache.key(pt.src), build)[1]
 
 
 def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr):
@@ -356,9 +374,10 @@ def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr)
     # both directions' in-list sums (SH[0] = forward, SH[1] = reverse) from one pass over the block's edges, produced one node
     # range at a time so that the all-reduce of a range overlaps the gathers of the next
     SH = torch.empty((2, n_node, H.shape[1]), dtype=H.dtype, device=H.device)
-    shard.reduce_in_chunks(n_node, lambda lo, hi: ops.seg_reduce(loc.in_ptr, loc.in_ids, n_node, H, plan=loc.in_plan, src_scale=dinv[1],
-                                                                 skip_mask=blocked_l, dual=True, src_scale2=dinv[0], out=SH[1], out2=SH[0],
-                                                                 rows=(lo, hi)),
+    shard.reduce_in_chunks(loc.in_cuts,
+                           lambda lo, hi, lg: ops.seg_reduce(loc.in_ptr, loc.in_ids, n_node, H, plan=loc.in_plan if lg else None,
+                                                             src_scale=dinv[1], skip_mask=blocked_l, dual=True, src_scale2=dinv[0],
+                                                             out=SH[1], out2=SH[0], rows=(lo, hi)),
                            (SH[0], SH[1]), "SH [2,N,C]")
     Sf, Sr = ops.linear_fwd(SH[0], wf), ops.linear_fwd(SH[1], wr)
     if ops.PAIR_CONV_DUAL and ops.pair_conv_dual_supported(H.shape[1], wf.shape[0]):
@@ -385,9 +404,10 @@ def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
     dOs = (dOf, dOr)
     dS = torch.empty((2, n_node, H.shape[1]), dtype=H.dtype, device=H.device)
     dOf_c, dOr_c = dOs[0].contiguous(), dOs[1].contiguous()
-    shard.reduce_in_chunks(n_node, lambda lo, hi: ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOf_c, plan=loc.out_plan, src_scale=dinv[0],
-                                                                 dual=True, src_scale2=dinv[1], X_mate=dOr_c, out=dS[0], out2=dS[1],
-                                                                 rows=(lo, hi)),
+    shard.reduce_in_chunks(loc.out_cuts,
+                           lambda lo, hi, lg: ops.seg_reduce(loc.out_ptr, loc.out_ids, n_node, dOf_c, plan=loc.out_plan if lg else None,
+                                                             src_scale=dinv[0], dual=True, src_scale2=dinv[1], X_mate=dOr_c,
+                                                             out=dS[0], out2=dS[1], rows=(lo, hi)),
                            (dS[0], dS[1]), "dS [2,N,C]")
     # dW_d = (selfw_d * dO_d)^T H + dS_d^T SH_d: the second product runs over the N nodes - every rank takes its NODE block of
     # the (now complete) dS and SH, and the caller's gradient sum over the ranks completes the product
@@ -411,20 +431,27 @@ def _param_grads(shard, C, dpf, dpr, extra=()):
 
 
 class _ShardedPairInit(torch.autograd.Function):
-    """model.py:75 on one row block: x [N, C] (replicated) -> H [Rl, C]; backward = this block's part of dx."""
+    """model.py:75 on one row block: x [N, C] (replicated) -> H [Rl, C]; backward = this block's part of dx, summed over the
+    ranks one node range at a time while the next range is gathered -> dx complete on every rank."""
 
     @staticmethod
-    def forward(ctx, x, loc, n_node):
+    def forward(ctx, x, loc, shard):
         x = x.contiguous()
         ctx.save_for_backward(x)
-        ctx.meta = (loc, n_node)
+        ctx.meta = (loc, shard)
         return ops.pair_init_fwd(x, loc.src, loc.dst)
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        loc, n_node = ctx.meta
-        dx = ops.seg_reduce(loc.xout_ptr, loc.xout_ids, x.shape[0], g.contiguous(), plan=loc.xout_plan, X2=x, mul_idx=loc.dst, pair_sum=True)
+        loc, shard = ctx.meta
+        g = g.contiguous()
+        N = x.shape[0]
+        dx = torch.empty_like(x)
+        shard.reduce_in_chunks(loc.xout_cuts,
+                               lambda lo, hi, lg: ops.seg_reduce(loc.xout_ptr, loc.xout_ids, N, g, plan=loc.xout_plan if lg else None, X2=x,
+                                                                 mul_idx=loc.dst, pair_sum=True, out=dx, rows=(lo, hi)),
+                               (dx,), "d(x) [N,C]")
         return dx, None, None
 
 
@@ -526,6 +553,25 @@ def mask_links(idx: torch.Tensor, ranges) -> torch.Tensor:
     return torch.where(in_o, idx - olo, torch.where(in_p, idx - (plo - (ohi - olo)), torch.full_like(idx, -1)))
 
 
+MASKED_TAIL = -2     # readout row id: this link and every later one is masked (include/twowl.h, twowl_gn2_readout_fwd)
+
+
+def own_links_first(idx_l: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Masked readout ids [2L] -> (the same links stably partitioned: this rank's first, the masked ones after them; dest [L] =
+    new position of link l). The readout kernels skip a masked link, but one lane group then meets its own links one at a
+    time between skipped ones and waits out a full gather latency for each (ncu, world 8: 0.36 + 0.65 ms at 1.2 TB/s for an
+    eighth of the links); with the rank's links packed at the front the groups work on them side by side, and the masked
+    links behind them carry the id MASKED_TAIL, at which the kernels stop. No size reaches the host: the count of own links stays a device scalar inside `dest`."""
+    L = idx_l.numel() // 2
+    valid = idx_l[0::2] >= 0
+    cv = torch.cumsum(valid, 0)
+    pos = torch.arange(L, device=idx_l.device)
+    dest = torch.where(valid, cv - 1, cv[-1] + (pos - cv))
+    packed = torch.empty_like(idx_l).view(L, 2)
+    packed[dest] = torch.where(valid.unsqueeze(1), idx_l.view(L, 2), torch.full_like(idx_l.view(L, 2), MASKED_TAIL))
+    return packed.view(-1), dest
+
+
 def forward(model, x, edge1, pos, idx, ei2):
     """LocalWLNet.forward (model.py:68-84) cut over the ranks: node blocks for the node-level aggregations, row blocks of the pair
     table for the pair level; returns the full [L, 1] logits on every rank."""
@@ -554,14 +600,14 @@ def forward_pairs(model, x, pos, idx, ei2):
         wedges = lv.struct if blocked is None else lv.struct.with_blocked(ops.gather_u8(blocked, lv.perm[:wedges.E]))
         idx = lv.newid[idx]
     ranges = blocks_of(wedges.E, pt.R, shard.rank, shard.world)
-    loc = _local(wedges, pt, ranges)
+    loc = _local(wedges, pt, ranges, shard.chunks if shard.world > 1 else 1)
     # per-row constants of THIS block only (the degree counts are global: every rank holds the int edge lists)
     _, centre, dinv, selfw, bnode = ops.wedge_prepare_ranges(wedges.src, wedges.dst_e, wedges.E, wedges.R, wedges.n_node, wedges.blocked,
                                                              wedges.in_ptr, ranges[0], ranges[1])
     rows = (centre, dinv, selfw, bnode)
     blocked_l = wedges.blocked[ranges[0][0]:ranges[0][1]] if wedges.blocked is not None else None
-    idx_l = mask_links(idx, ranges)
-    H = _ShardedPairInit.apply(x, loc, wedges.n_node)
+    idx_l, link_dest = own_links_first(mask_links(idx, ranges))
+    H = _ShardedPairInit.apply(x, loc, shard)
     last = len(model.conv2s) - 1
     for i, (seq_f, seq_r) in enumerate(zip(model.conv2s, model.conv2s_r)):
         cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
@@ -574,4 +620,4 @@ def forward_pairs(model, x, pos, idx, ei2):
         else:
             pred_l = _ShardedLastLayer.apply(H, *par, model.pred.weight, model.pred.bias, shard, loc, rows, idx_l, blocked_l, pt.R,
                                              wedges.n_node, gf.eps, p, seeds[0], seeds[1])
-    return _SumLogits.apply(pred_l, shard)
+    return _SumLogits.apply(pred_l.index_select(0, link_dest), shard)       # back to the caller's link order

@@ -202,6 +202,28 @@ def test_row_shard_blocks_cover_the_pair_table_with_even_boundaries():
                 assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         blocks_of(3, 8, 0, 2)
+    # own_links_first: the rank's links packed at the front in their original order, the masked ones behind them; dest maps a
+    # link to its new position (a permutation), so results gathered by dest come back in the caller's order
+    from twowl_b200.rowshard import own_links_first, work_cuts
+    idx_l = torch.tensor([-1, -1, 4, 5, -1, -1, 0, 1, 8, 9, -1, -1])
+    packed, dest = own_links_first(idx_l)
+    assert packed.tolist() == [4, 5, 0, 1, 8, 9, -2, -2, -2, -2, -2, -2] and sorted(dest.tolist()) == list(range(6))
+    assert torch.equal(packed.view(6, 2)[dest].clamp_min(-1), idx_l.view(6, 2))       # the masked tail carries -2 ("and all later")
+    packed, dest = own_links_first(torch.full((8,), -1))
+    assert bool((packed == -2).all()) and sorted(dest.tolist()) == [0, 1, 2, 3]
+    # work_cuts: consecutive node ranges covering [0, M) with about equal work; a range is flagged iff it holds a long row
+    lens = torch.tensor([200, 3, 1, 0, 0, 2, 70, 1, 1, 1, 5, 5, 5, 0, 9, 1])
+    ptr = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)))
+    for K in (1, 2, 4, 7):
+        cuts = work_cuts(ptr, ptr, lens.numel(), K)
+        assert cuts[0][0] == 0 and cuts[-1][1] == lens.numel() and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        for lo, hi, has_long in cuts:
+            assert has_long or not bool((lens[lo:hi] > 64).any())
+    assert work_cuts(ptr, ptr, lens.numel(), 4)[0][:2] == (0, 1)          # the 200-entry row is a range of its own
+    # the bounds come from the first (whole-graph) CSR only - identical on every rank; the flags from the rank's own
+    local = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(torch.minimum(lens, torch.tensor(3)), 0)))
+    assert [c[:2] for c in work_cuts(ptr, local, lens.numel(), 4)] == [c[:2] for c in work_cuts(ptr, ptr, lens.numel(), 4)]
+    assert not any(c[2] for c in work_cuts(ptr, local, lens.numel(), 4))
     a = D.shard_batch(1000, 100, step=3, seed=1, replicate=True)
     b = D.shard_batch(1000, 100, step=3, seed=1)            # world size 1: the same draw
     assert torch.equal(a, b) and a.unique().numel() == 100

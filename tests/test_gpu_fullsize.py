@@ -96,14 +96,15 @@ def test_full_size_step_vs_fp64(workload, hidden):
     # than this fp32 evaluation's own worst element of the tensor.
     lg32, l32, g32 = ref64.step(sd, x_new, ei_plain, pos1, idx, E, blocked, y, dtype=torch.float32)
     tag = f"{workload}/hidden{hidden} "
-    # at this size (sums over up to 6e7 rows, logits up to ~100) a larger share of the elements sits outside the 1e-5 band in ANY
-    # fp32 evaluation - the plain torch one included: up to 15 % of a tensor may pass through the relaxation clauses (observed:
-    # 9.6 % of the 3.0 M logits at rmat / hidden 64, 7 % at collab / hidden 256, see the ledger)
-    # (logits: additionally 1e-5 x the largest logit, ~1e-3 absolute here - the torch-fp32 evaluation's own worst element moves
-    #  between 5e-5 and 2e-4 from run to run with the order of its atomics, so "4 x its error" alone is not a stable yardstick)
-    parity(out, lg32, lg64, tag + "logits", scale_floor=1e-5, allow_relaxed=out.numel() * 15 // 100)
+    # Logits: at most 3 % of them may need a relaxation clause (observed at rmat / hidden 64: 0.55 % of the 3.0 M logits lie
+    # outside the float64 band - the torch-fp32 evaluation of the same program leaves 0.54-0.63 % outside; before the column sums
+    # of GraphNorm were folded into double every 8 rows it was 10.6 %, tools/diag_stages.py), and every one of those within
+    # 1e-5 x the largest logit (~1e-3 absolute at |logit| up to 98; observed worst 1.5e-4, torch-fp32's own 1.6-2.3e-4 - its
+    # atomics move its worst element from run to run, so "4 x its error" alone is not a stable yardstick).
+    parity(out, lg32, lg64, tag + "logits", scale_floor=1e-5, allow_relaxed=out.numel() * 3 // 100)
     parity(loss, l32, l64, tag + "loss")
     for k in sorted(grads):
         # gradient floor 3e-5 x the tensor's largest magnitude: a weight / GraphNorm gradient here is a sum over up to 6e7 rows of
         # products of fp32 activations that each carry ~1e-6 of relative error, with ~10x cancellation between the terms
+        # (observed worst over all tensors: 2.0e-5 x max; the torch-fp32 evaluation's own worst: 1.7e-4 x max on emb.0.weight)
         parity(grads[k], g32[k], g64[k], tag + "grad " + k, scale_floor=3e-5, allow_relaxed=max(16, grads[k].numel() * 15 // 100))
