@@ -14,8 +14,6 @@
 // are listed once per CSR by twowl_seg_plan; they are cut into chunks of TWOWL_ROW_CHUNK entries that
 // separate groups reduce into a partial buffer, and a third pass adds each row's partials in chunk order.
 // The order in which long rows were listed (an integer atomic counter) never influences a result.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace twowl {
@@ -392,23 +390,10 @@ __global__ void __launch_bounds__(kAggThreads) k_seg_long(const SegParams p) {
   }
 }
 
-// CTAs per SM of the row pass. Rows are dealt round-robin to lane groups, and their lengths differ by orders of magnitude: with
-// a grid of exactly the resident CTAs a group of a small launch (a node range of a row-sharded table: ~8 rows per group) is
-// stuck with whatever it was dealt and the SM idles behind its longest group (ncu: 30 % of the warp slots active). With several
-// times more CTAs than fit, the hardware hands out CTAs as others retire. TWOWL_SEG_ROWS_CTAS overrides (read once).
-static int seg_rows_ctas_per_sm() {
-  static const int v = [] {
-    const char* e = getenv("TWOWL_SEG_ROWS_CTAS");
-    const int x = e ? atoi(e) : 0;
-    return x > 0 ? x : 32;
-  }();
-  return v;
-}
-
 template <int G, int VEC, int MODE>
 static void launch_seg_mode(const SegParams& p, int64_t chunk_cap, int64_t long_cap, cudaStream_t s) {
   constexpr int kGroupsPerCta = kAggThreads / G;
-  k_seg_rows<G, VEC, MODE><<<grid_for(p.row_hi - p.row_lo, kGroupsPerCta, seg_rows_ctas_per_sm()), kAggThreads, 0, s>>>(p);
+  k_seg_rows<G, VEC, MODE><<<grid_for(p.row_hi - p.row_lo, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
   if (p.plan_counts && chunk_cap > 0) {
     k_seg_chunks<G, VEC, MODE><<<grid_for(chunk_cap, kGroupsPerCta, 8), kAggThreads, 0, s>>>(p);
     const size_t lsm = (size_t)kGroupsPerCta * ((MODE & 4) ? 2 : 1) * (size_t)(p.C / 4) * sizeof(float4);
@@ -568,12 +553,8 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int cv = a->C >> 2;
   const int64_t cc = a->chunk_cap, lc = a->long_cap;
-  // a row-range launch without a plan = a node range of a row-sharded table whose lists are short (1 / world of the graph's):
-  // half-width lane groups with two float4 per lane keep twice as many rows in flight per warp (TWOWL_SEG_NARROW, read once)
-  static const bool narrow = [] { const char* e = getenv("TWOWL_SEG_NARROW"); return e && atoi(e) > 0; }();
   if (cv <= 4) launch_seg<4, 1>(p, cc, lc, s);
   else if (cv <= 8) launch_seg<8, 1>(p, cc, lc, s);
-  else if (cv <= 16 && cv > 8 && narrow && a->row_end && !planned) launch_seg<8, 2>(p, cc, lc, s);
   else if (cv <= 16) launch_seg<16, 1>(p, cc, lc, s);
   else if (cv <= 32) launch_seg<32, 1>(p, cc, lc, s);
   else if (cv <= 64) launch_seg<32, 2>(p, cc, lc, s);

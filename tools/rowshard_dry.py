@@ -54,6 +54,27 @@ if os.environ.get("NCU"):      # under ncu --profile-from-start off: one step of
     torch.cuda.profiler.stop()
     sys.exit(0)
 
+if os.environ.get("DRY_KINETO"):      # every kernel of one step (torch glue included) and the idle time between them
+    from torch.profiler import profile, ProfilerActivity
+    mod.row_shard = RowShard(rank=ranks[0], world=world, dry=True)
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        a, b = step(3)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    per = {}
+    for e in evs:
+        k = per.setdefault(e.name[:70], [0, 0.0])
+        k[0] += 1
+        k[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    busy = sum(v[1] for v in per.values()) / 1e3
+    print(f"rank {ranks[0]}/{world}: step {a.elapsed_time(b):.2f} ms under the profiler, {len(evs)} device activities, {busy:.2f} ms busy")
+    for name, (cnt, us) in sorted(per.items(), key=lambda kv: -kv[1][1])[:45]:
+        print(f"   {us / 1e3:8.3f} ms {cnt:4d} x  {name}")
+    sys.exit(0)
+
 for r in ranks:
     mod.row_shard = RowShard(rank=r, world=world, dry=True)
     for i in range(3):
