@@ -359,7 +359,16 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's kernels on a high-priority stream: the row-sharded step overlaps the all-reduce of one node range with the
+        # gather kernel of the next, and a pending collective should take the SM resources a finished gather frees before the
+        # next gather's CTAs do (TWOWL_NCCL_HIGH_PRIO=0 turns it off)
+        opts = None
+        if os.environ.get("TWOWL_NCCL_HIGH_PRIO", "1") != "0":
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:   # noqa: BLE001 - an older torch without the option
+                opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     hidden = args.hidden or WORKLOADS[args.workload][3]
     args.warmup = max(args.warmup, 3)
     if args.inplace_backward or (args.workload == "rmat" and hidden >= 128 and not args.scale):

@@ -147,6 +147,10 @@ int twowl_gcn_dinv(const int64_t* ptr, const int32_t* col, int64_t M, int32_t fl
  * of one training step is the cached CSR of the whole graph minus the sampled edges (sample_block, utils.py:61-64). */
 int twowl_gcn_dinv_entries(const int64_t* ptr, const int32_t* col, int64_t M, const uint8_t* entry_mask, float* dinv,
                            void* stream);
+/* the same for the node rows [row_lo, row_hi) only (dinv keeps its [M] shape; the rest is untouched): one rank's node block of a
+ * row-sharded step, which then all-gathers the blocks (twowl_b200.rowshard). Only entry_mask[ptr[row_lo] .. ptr[row_hi]) is read. */
+int twowl_gcn_dinv_entries_rows(const int64_t* ptr, const int32_t* col, int64_t M, const uint8_t* entry_mask, int64_t row_lo,
+                                int64_t row_hi, float* dinv, void* stream);
 /* out[k] = mask[ids[k]] (uint8) - a per-edge mask carried to the entry order of a CSR built by twowl_csr_build. */
 int twowl_gather_u8(const uint8_t* mask, const int32_t* ids, int64_t n, uint8_t* out, void* stream);
 

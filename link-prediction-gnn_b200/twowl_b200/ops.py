@@ -352,13 +352,25 @@ def gcn_dinv_entries(ptr, col, M: int, entry_mask) -> torch.Tensor:
     return dinv
 
 
-def gather_u8(mask: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+def gather_u8(mask: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[k] = mask[ids[k]] (uint8): a per-edge mask in the entry order of a CSR."""
     _need_cuda(mask, ids)
-    out = torch.empty(ids.numel(), dtype=torch.uint8, device=mask.device)
+    if out is None:
+        out = torch.empty(ids.numel(), dtype=torch.uint8, device=mask.device)
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == ids.numel() and ids.is_contiguous()
     check(lib.twowl_gather_u8(mask.data_ptr(), ids.data_ptr(), ids.numel(), out.data_ptr(), _stream()), "gather_u8")
     _count()
     return out
+
+
+def gcn_dinv_entries_rows(ptr, col, M: int, entry_mask, lo: int, hi: int, dinv: torch.Tensor) -> torch.Tensor:
+    """gcn_dinv_entries for the node rows [lo, hi) only, written into dinv[lo:hi] (dinv: fp32, at least M elements)."""
+    _need_cuda(ptr, col, entry_mask, dinv)
+    assert dinv.dtype == torch.float32 and dinv.is_contiguous() and dinv.numel() >= M
+    check(lib.twowl_gcn_dinv_entries_rows(ptr.data_ptr(), col.data_ptr(), M, entry_mask.data_ptr(), int(lo), int(hi), dinv.data_ptr(),
+                                          _stream()), "gcn_dinv_entries_rows")
+    _count()
+    return dinv
 
 
 LONG_ROW = 64     # TWOWL_LONG_ROW of include/twowl.h: rows with more entries go through the long-row passes of seg_reduce

@@ -13,14 +13,17 @@ per-NODE sums, so the exchange per pair layer is
                                                            ([4, C] over all rows for a layer that is not the last)
               all_reduce  dS_f, dS_r   [2, N, C] fp32      gradient of the per-node sums
 
-(N here = the nodes that have observed in-edges: graph.locality_view compacts the node ids of the wedge structure) instead of the all-gather / reduce-scatter of [R, C] an explicit wedge index would need.
+(N here = the nodes that have observed in-edges: graph.locality_view compacts the node ids of the wedge structure) instead of
+the all-gather / reduce-scatter of [R, C] an explicit wedge index would need. The tables are produced and summed one node range
+at a time (reduce_in_chunks / work_cuts): the all-reduce of a range runs while the next one is gathered.
 
 Node level (model.py:71-73). The node-level GCNConv aggregations - the only node-level work that is not a cheap streaming pass -
 are cut into NODE blocks [g*B, (g+1)*B), B = ceil(N / world): a rank reduces the in-lists (forward) / out-lists (backward) of
 its own nodes only (twowl_seg_args.row_begin / row_end on the whole graph's CSR) and the blocks are exchanged:
 
     forward   all_gather  conv output  [N, C]    fp32      per node layer
-    backward  all_reduce  d(x)         [N, C]    fp32      once: the pair-init backward leaves every rank a PARTIAL dx
+    backward  all_reduce  d(x)         [N, C]    fp32      once, in the pair-init backward (its block's part of dx), pipelined by
+                                                           node range like the per-node tables: dx leaves it COMPLETE
               all_gather  d(z)         [N, C]    fp32      per node layer
               all_reduce  d(emb)       [V, C]    fp32      the embedding gradient, summed over node blocks
 
@@ -124,7 +127,9 @@ class RowShard:
         self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.log = {}            # collective name -> [calls, bytes] since construction
         self.steps = 0
-        self.chunks = int(os.environ.get("TWOWL_ROWSHARD_CHUNKS", "4"))   # node-range chunks of the pipelined table exchanges
+        # node ranges of the pipelined table exchanges (8 GPUs, R-MAT 1M/16M: 2 ranges 18.5 ms per step, 4 ranges 19.1 ms - every
+        # range is three more launches over short lists)
+        self.chunks = int(os.environ.get("TWOWL_ROWSHARD_CHUNKS", "2"))
         _last_shard = self
 
     def _account(self, what: str, t: torch.Tensor):
@@ -243,9 +248,10 @@ class _ShardedEmbedding(torch.autograd.Function):
 
 class _ShardedNodeAggregate(torch.autograd.Function):
     """GCNConv.propagate + bias of a node layer (model.py:73; functional.gcn_aggregate) with the output rows cut into node blocks:
-    this rank reduces the in-lists of its own nodes and the blocks are all-gathered. Backward: (all-reduce of the incoming
-    gradient when it is partial, i.e. for the layer that feeds the pair level), the out-lists of the rank's own nodes, all-gather
-    -> d(z) complete on every rank; d(bias) complete, kept on rank 0."""
+    this rank reduces the in-lists of its own nodes and the blocks are all-gathered. Backward: the out-lists of the rank's own
+    nodes, all-gather -> d(z) complete on every rank; d(bias) complete, kept on rank 0. (grad_is_partial=True first sums an
+    incoming gradient that is still partial over the ranks; the pair level now hands back a complete dx, so forward_nodes
+    passes False.)"""
 
     @staticmethod
     def forward(ctx, z, bias, gr, shard, grad_is_partial):
@@ -298,6 +304,38 @@ class _NodeLinear(torch.autograd.Function):
         return dh, dw, None
 
 
+def node_graph_block(edge1, N: int, shard: "RowShard") -> G.NodeGraph:
+    """graph.node_graph for ONE rank of a row-sharded step. The node graph of a step is the cached CSR of the whole graph minus
+    the edges sample_block took out (a per-entry mask) with the gcn_norm degrees recounted - E-sized work per step that every
+    rank would repeat (0.77 ms at R-MAT 1M/16M: two mask gathers + the degree count). A rank only ever reduces the lists of its
+    own node block, so it carries the mask to the entries of ITS block's rows in the two CSRs and counts ITS nodes' degrees; the
+    blocks of dinv (N floats) are all-gathered. Everything outside the block's entry ranges of emask / temask is unset and never
+    read (seg_reduce with rows = the block). Any other edge tensor takes the replicated graph.node_graph."""
+    if isinstance(edge1, G.MaskedEdges):
+        tag = (edge1.ei, edge1.mask)
+    else:
+        tag = getattr(edge1, "_twowl_edges", None)
+        if tag is not None and not (tag[2] == edge1._version and tag[0].shape[1] >= edge1.shape[1]):
+            tag = None
+    if tag is None or shard.world == 1:
+        return G.node_graph(edge1, N)
+    base = G.node_graph(tag[0], N, _base=True)
+    lo, hi, B = node_block(N, shard.rank, shard.world)
+    # entry ranges of the block's rows in the two CSRs: four numbers read once per whole graph and rank (cached with it)
+    e0, e1, t0, t1 = G._cache.get(base.ptr, ("rowshard-node-entries", lo, hi),
+                                  lambda: tuple(int(v) for v in torch.stack((base.ptr[lo], base.ptr[hi], base.tptr[lo], base.tptr[hi])).tolist()))
+    emask = torch.empty(base.ids.numel(), dtype=torch.uint8, device=base.ids.device)
+    temask = torch.empty(base.tids.numel(), dtype=torch.uint8, device=base.ids.device)
+    if e1 > e0:
+        ops.gather_u8(tag[1], base.ids[e0:e1], out=emask[e0:e1])
+    if t1 > t0:
+        ops.gather_u8(tag[1], base.tids[t0:t1], out=temask[t0:t1])
+    dinv = torch.empty(B * shard.world, dtype=torch.float32, device=base.ids.device)
+    ops.gcn_dinv_entries_rows(base.ptr, base.col, N, emask, lo, hi, dinv)
+    shard.all_gather_blocks(dinv.view(-1, 1), B, "node dinv [N]")
+    return G.NodeGraph(N, base.ptr, base.col, base.tptr, base.tcol, dinv[:N], base.plan, base.tplan, base.ids, base.tids, emask, temask)
+
+
 def forward_nodes(model, x, edge1):
     """model.py:71-73 with the aggregations cut into node blocks: x int64 [N] degrees -> [N, C] (complete on every rank)."""
     shard: RowShard = model.row_shard
@@ -316,9 +354,10 @@ def forward_nodes(model, x, edge1):
     emb, gn0, dp0 = model.emb[0], model.emb[1], model.emb[2]
     h = _ShardedEmbedding.apply(emb.weight, x, shard)
     h = gn_act(gn0, dp0, None, h)
+    gr = None
     for k, seq in enumerate(model.conv1s):
         conv, gn, dp, act = seq.modlist[0], seq.modlist[1], seq.modlist[2], seq.modlist[3]
-        gr = G.node_graph(edge1, N)
+        gr = gr if gr is not None else node_graph_block(edge1, N, shard)
         z = _NodeLinear.apply(h, conv.lin.weight, shard)
         out = _ShardedNodeAggregate.apply(z, conv.bias, gr, shard, False)
         h = gn_act(gn, dp, act, out)      # the pair level hands back a COMPLETE dx (summed in _ShardedPairInit.backward)
