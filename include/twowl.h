@@ -194,7 +194,9 @@ typedef struct twowl_seg_args {
   float* partial;                /* fp32 [chunk_cap, C] scratch */
   int64_t chunk_cap;
   int64_t long_cap;
-  int32_t pair_sum;              /* 1: gather X[s] + X[s ^ 1] (the two directions 2k / 2k+1 of one pair, utils.py:81-90) */
+  int32_t pair_sum;              /* 1: gather X[s] + X[s ^ 1] (the two directions 2k / 2k+1 of one pair, utils.py:81-90);
+                                    2: X has ONE row per pair that already holds that sum (twowl_conv_args.pair_sum_out): gather
+                                    X[s >> 1] - the same terms in the same order, half the rows read */
   const uint8_t* entry_mask;     /* indexed by CSR ENTRY k (not by col[k]) or NULL: entries removed from a cached CSR */
   /* dual output (out2 != NULL; plain gather, flip = row_flip = 0): one pass over the 2-row blocks (s, s^1) gives
    *   out[m]  = sum src_scale[s]    * X[s]        (edge2_r's in-list sum of the pair layer, model.py:77)
@@ -410,6 +412,9 @@ typedef struct twowl_conv_args {
   float* out2;                /* [M, Nd/2], dual launches */
   double* moments;            /* [2*Nd] or NULL (needs stats): the raw column (sum, sum of squares) of `out` over this call's
                                  M rows - what a row-sharded caller sums over ranks before twowl_graphnorm_stats_from_moments */
+  int32_t pair_sum_out;       /* 1: `out` is [M/2, Nd] and holds result[2k] + result[2k+1] - rows 2k / 2k+1 are the two directions
+                                 of one pair (utils.py:81-90) and the pair-init backward (model.py:75) only consumes their sum
+                                 (twowl_seg_args.pair_sum = 2). M even, ngather = 2, no stats, no dual. */
 } twowl_conv_args;
 int twowl_pair_conv_supported(int32_t Kd, int32_t Nd, int32_t nsrc);
 size_t twowl_pair_conv_workspace_bytes(int64_t M, int32_t Nd);

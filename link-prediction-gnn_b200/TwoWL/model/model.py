@@ -164,6 +164,8 @@ class LocalWLNet(nn.Module):
         # the LAST pair layer only feeds x[idx] (model.py:77-83): fuse it with the readout so its GraphNorm / ReLU run
         # on the selected rows only (needs fused_pair_layer and an idx)
         self.fused_readout = True
+        # depth2 = 1 on the doubled pair layout: the pair init joins that op too (twowl::pair_init_layer_readout)
+        self.fused_pair_init = True
         # a twowl_b200.rowshard.RowShard: forward / backward run on this rank's block of pair rows and node block (multi-GPU,
         # one step cut over the ranks). None = the whole pair table on this GPU.
         self.row_shard = None
@@ -243,6 +245,11 @@ class LocalWLNet(nn.Module):
             blocked = wedges.blocked
             wedges = lv.struct if blocked is None else lv.struct.with_blocked(ops.gather_u8(blocked, lv.perm[:wedges.E]))
             idx = lv.newid[idx.reshape(-1)]
+        if (self.fused_pair_init and len(self.conv2s) == 1 and self.fused_pair_layer and self.fused_readout and idx is not None
+                and pt.mated and F2.pair_layer_supported(wedges, x.shape[1], self.conv2s[0], self.conv2s_r[0])):
+            # depth2 = 1: pair init + the only pair layer + readout as ONE op - the gradient of the pair features never exists
+            # at full height (one row per pair: the sum of its two directions, which is all the pair-init backward reads)
+            return F2.pair_init_layer_readout_apply(x, pt, wedges, self.conv2s[0], self.conv2s_r[0], self.training, idx, self.pred)
         x = F2.pair_init(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, pt.ptr_d, pt.ids_d, pt.plan_d, pt.mated)
         if len(self.conv2s):
             last = len(self.conv2s) - 1

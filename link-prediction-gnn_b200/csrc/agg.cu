@@ -41,6 +41,7 @@ struct SegParams {
   float* out;
   int accumulate;
   int pair_sum;
+  int x_shift;                 // 1: X holds ONE row per pair (already X[2k] + X[2k+1]): entry s gathers X[s >> 1]
   const uint8_t* entry_mask;
   // dual mode (MODE & 4): one pass over the 2-row blocks (s, s^1) feeds TWO outputs: out += src_scale[s] * X[s],
   // out2 += src_scale2[s^1] * X[s^1] - both directions of the pair layer's in-list sum, H read as 512-byte blocks
@@ -155,7 +156,7 @@ __device__ __forceinline__ void seg_accumulate(const SegParams& p, const GroupCt
           const bool on = sj[u] >= 0 && c4 < g.cv;
           // with a second factor (pair-init backward): the [R, C] rows are a stream, the per-node table is what L2 should keep
           if (MODE & 1) {
-            x[u][v] = on ? seg_ldg(X4 + (int64_t)sj[u] * g.cv + c4, pol.stream) : f4_zero();
+            x[u][v] = on ? seg_ldg(X4 + (int64_t)((MODE & 2) ? sj[u] : (sj[u] >> p.x_shift)) * g.cv + c4, pol.stream) : f4_zero();
             if (MODE & 2) xm[u][v] = on ? seg_ldg(Xm4 + (int64_t)(sj[u] ^ 1) * g.cv + c4, pol.stream) : f4_zero();
             y[u][v] = on ? seg_ldg(X24 + (int64_t)m2j[u] * g.cv + c4, pol.keep) : f4_zero();
           } else {
@@ -529,6 +530,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   TW_CHECK_ARG(!(a->row_flip && (a->M & 1)), "seg_reduce: row_flip needs an even row count");
   TW_CHECK_ARG((a->X2 == nullptr) == (a->mul_idx == nullptr), "seg_reduce: X2 and mul_idx go together");
   TW_CHECK_ARG(!a->pair_sum || a->X2 != nullptr, "seg_reduce: pair_sum is only built together with X2");
+  TW_CHECK_ARG(a->pair_sum >= 0 && a->pair_sum <= 2, "seg_reduce: pair_sum = %d (0, 1 or 2)", a->pair_sum);
   TW_CHECK_ARG(!a->out2 || (!a->X2 && !a->flip && !a->row_flip && !a->accumulate && aligned16(a->out2) && aligned16(a->partial2)),
                "seg_reduce: dual output goes with a plain, unflipped, non-accumulating gather");
   const bool planned = a->plan_counts != nullptr;
@@ -545,7 +547,7 @@ extern "C" int twowl_seg_reduce(const twowl_seg_args* a, void* stream) {
   p.ptr = a->ptr, p.col = a->col, p.M = a->M, p.X = a->X, p.C = a->C, p.flip = a->flip, p.row_flip = a->row_flip;
   p.src_scale = a->src_scale, p.skip_mask = a->skip_mask, p.row_skip_mask = a->row_skip_mask;
   p.skip_self = a->skip_self, p.self_mode = a->self_mode, p.dst_scale = a->dst_scale, p.bias = a->bias;
-  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum, p.entry_mask = a->entry_mask;
+  p.X2 = a->X2, p.mul_idx = a->mul_idx, p.out = a->out, p.accumulate = a->accumulate, p.pair_sum = a->pair_sum == 1, p.x_shift = a->pair_sum == 2 ? 1 : 0, p.entry_mask = a->entry_mask;
   p.plan_counts = a->plan_counts, p.long_row = a->long_row, p.long_base = a->long_base, p.chunk_owner = a->chunk_owner;
   p.partial = a->partial;
   p.src_scale2 = a->src_scale2, p.out2 = a->out2, p.partial2 = a->partial2, p.Xm = a->X_mate;

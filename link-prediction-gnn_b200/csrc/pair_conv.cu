@@ -167,7 +167,9 @@ struct PcRing {
 
 // CTA b works on column window b % nsplit of the tiles (b / nsplit) + j * (gridDim.x / nsplit): the CTAs that share a
 // tile run side by side, so the re-reads of its A slabs are L2 hits.
-template <int NG, bool DUAL>
+// PSUM (compile time, its own instantiation - a runtime flag changed the register allocation of every other one and cost the
+// forward launches 1 ms each): out has M/2 rows, out[k] = result[2k] + result[2k+1]
+template <int NG, bool DUAL, bool PSUM = false>
 __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1) {
   extern __shared__ uint8_t pc_smem_raw[];
@@ -500,11 +502,25 @@ __global__ void __launch_bounds__(kPcThreads, 1) k_pair_conv(const ConvParams p,
           const int rl = i * 4 + lrow;
           const int64_t row = wrow0 + rl;
           float4 o = *reinterpret_cast<const float4*>(Et + rl * 128 + ((lchunk ^ (rl & 7)) << 4));
-          if (row < p.M && cok) {
+          const bool live = row < p.M && cok;
+          if (live) {
 #pragma unroll
             for (int g = 0; g < NGA; ++g)
               if (NG > g && (!DUAL || g == dd)) f4_fma(o, cf[g][i], gv[g][i]);
             f4_add(o, bias4);
+          }
+          if constexpr (PSUM) {
+            // rows 2k / 2k+1 (the two directions of one pair) sit in lanes l and l ^ 8 (lrow = lane >> 3): the consumer - the
+            // pair-init backward - only ever wants their SUM, so one row per pair is written (half the bytes here, half the
+            // bytes of both of its passes). Whole-warp shuffles outside the `live` branch; M is even, so mates live together.
+            float4 m;
+            m.x = __shfl_xor_sync(0xffffffffu, o.x, 8), m.y = __shfl_xor_sync(0xffffffffu, o.y, 8);
+            m.z = __shfl_xor_sync(0xffffffffu, o.z, 8), m.w = __shfl_xor_sync(0xffffffffu, o.w, 8);
+            if (live && !(lrow & 1)) {
+              f4_add(o, m);
+              __stcs(reinterpret_cast<float4*>(p.out + (row >> 1) * Tld + col), o);
+            }
+          } else if (live) {
             // written once, read by a later kernel: evict first
             __stcs(reinterpret_cast<float4*>((dd ? p.out2 : p.out) + row * Tld + (col - dd * pdual)), o);
             f4_add(bsum, o);
@@ -651,10 +667,10 @@ static int pc_make_tmap(CUtensorMap* tm, const float* A, int64_t M, int Kd) {
   return make_tmap_2d_f32(tm, A, M, Kd, 32, kPcTileM, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int NG, bool DUAL = false>
+template <int NG, bool DUAL = false, bool PSUM = false>
 static int pc_launch(const ConvParams& p, size_t smem, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t s) {
-  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<NG, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_conv<NG, DUAL><<<pc_grid(p.M, p.nsplit), kPcThreads, smem, s>>>(p, t0, t1);
+  TW_CUDA(cudaFuncSetAttribute(k_pair_conv<NG, DUAL, PSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pair_conv<NG, DUAL, PSUM><<<pc_grid(p.M, p.nsplit), kPcThreads, smem, s>>>(p, t0, t1);
   TW_LAUNCH_CHECK();
   return 0;
 }
@@ -711,6 +727,10 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     p.rs[1] = a->row_scale[1];
     p.out2 = a->out2, p.dual = a->Nd / 2;
   }
+  if (a->pair_sum_out) {
+    TW_CHECK_ARG(!a->dual && !want_stats && a->M % 2 == 0 && a->ngather == 2,
+                 "pair_conv: pair_sum_out is built for the pair layer's input gradient: two gathers, an even M, no statistics, no dual launch");
+  }
   p.nsrc = a->nsrc, p.ngather = a->ngather, p.M = a->M, p.Kd = a->Kd, p.Nd = a->Nd, p.bias = a->bias, p.out = a->out;
   p.Nsub = cfg.Nsub, p.nsplit = cfg.nsplit, p.stages = cfg.stages, p.lo_stages = cfg.lo_stages, p.tmem_cols = cfg.tmem_cols, p.group = cfg.group;
   cudaStream_t s = (cudaStream_t)stream;
@@ -727,6 +747,7 @@ extern "C" int twowl_pair_conv(const twowl_conv_args* a, void* ws, size_t ws_byt
     if (rc_t) return rc_t;
   }
   const int rc = a->dual           ? pc_launch<2, true>(p, cfg.smem, tm[0], tm[1], s)
+                 : a->pair_sum_out ? pc_launch<2, false, true>(p, cfg.smem, tm[0], tm[1], s)
                  : a->ngather == 0 ? pc_launch<0>(p, cfg.smem, tm[0], tm[1], s)
                  : a->ngather == 1 ? pc_launch<1>(p, cfg.smem, tm[0], tm[1], s)
                                    : pc_launch<2>(p, cfg.smem, tm[0], tm[1], s);

@@ -379,7 +379,8 @@ def _pl_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)   # no zero-filled [R,C] gradients for the saved-state outputs
 
 
-def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars, dWs=None, dh_out=None):
+def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, dOs, dpars, dWs=None, dh_out=None,
+                 pair_sum_out=False):
     """Backward of the structured pair-level GCNConv pair from the gradients dO_f, dO_r of its two outputs:
     -> dh and, per direction, (dW, dbias, d gn.weight, d gn.bias, d gn.mean_scale).
     dWs: the (selfw_d * dO_d)^T H parts when the caller already has them (pair_dw_gn)."""
@@ -403,8 +404,9 @@ def _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf,
         dSWs.append(ops.linear_bwd_input(dSs[d], w))
         dpar = dpars[d]
         res.append((dW, dpar[3 * C:], dpar[:C], dpar[C:2 * C], dpar[2 * C:3 * C]))
+    # pair_sum_out: dh is [R/2, C] and holds dH[2k] + dH[2k+1] - all the pair-init backward wants of it (pair_init_layer_readout)
     dh = ops.pair_conv(dOs, [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
-                       gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])], out=dh_out)
+                       gathers=[(dSWs[0], bnode[0], dinv[0]), (dSWs[1], bnode[1], dinv[1])], out=dh_out, pair_sum_out=pair_sum_out)
     return dh, res
 
 
@@ -434,7 +436,12 @@ def pair_layer_readout(h: Tensor, wf: Tensor, bf: Tensor, gwf: Tensor, gbf: Tens
                        selfw: Tensor, bnode: Tensor, blocked: Optional[Tensor], n_node: int, eps: float, p_drop: float,
                        seed_f: int, seed_r: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> (pred [L,1], O_f, O_r, stats_f, stats_r, SH_f, SH_r); only pred is differentiable, the rest is saved state."""
-    h = h.contiguous()
+    return _plr_forward(h.contiguous(), wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, centre, dinv,
+                        selfw, blocked, n_node, eps, p_drop, seed_f, seed_r)
+
+
+def _plr_forward(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, centre, dinv, selfw, blocked,
+                 n_node, eps, p_drop, seed_f, seed_r):
     # both directions' in-list sums from one pass over the mated 2-row blocks of h: SH_r gathers h[a], SH_f h[a^1]
     SHr, SHf = ops.seg_reduce(in_ptr, in_ids, n_node, h, plan=in_plan, src_scale=dinv[1], skip_mask=blocked, dual=True,
                               src_scale2=dinv[0])
@@ -465,9 +472,16 @@ def _plr_setup(ctx, inputs, output):
 
 
 def _plr_bwd(ctx, g, *_unused):
-    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr,
-     SHf, SHr) = ctx.saved_tensors
     n_node, p_drop, seed_f, seed_r = ctx.meta
+    dh, res, dpw, dpb = _plr_backward(g, ctx.saved_tensors, n_node, p_drop, seed_f, seed_r)
+    return (dh,) + res[0] + res[1] + (None, dpw, dpb) + (None,) * 16
+
+
+def _plr_backward(g, saved, n_node, p_drop, seed_f, seed_r, pair_sum_out=False):
+    """Backward of the fused last pair layer + readout from d pred: -> (dh, per-direction parameter gradients, d pred.weight,
+    d pred.bias). pair_sum_out: dh is [R/2, C], the sum of the two directions' rows of every pair."""
+    (h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids, out_plan, dinv, selfw, bnode, Of, Or, sf, sr,
+     SHf, SHr) = saved
     C = wf.shape[0]
     if ops.pair_dw_supported(C) and h.shape[1] == C:
         # the dense GraphNorm-backward pass rides on the weight-gradient kernel's shared-memory pass (twowl_pair_dw_gn)
@@ -483,12 +497,68 @@ def _plr_bwd(ctx, g, *_unused):
         dOf, dOr, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r,
                                                            True, idx, pw.contiguous(), g.reshape(-1))
         dWs = None
+    dh_out = None
+    if inplace:      # h is not read by that launch: dH (or its pair sums, in the first half of the buffer) may take its place
+        dh_out = h.view(-1)[:(h.shape[0] // 2) * h.shape[1]].view(h.shape[0] // 2, h.shape[1]) if pair_sum_out else h
     dh, res = _pl_bwd_core(h, wf, wr, out_ptr, out_ids, out_plan, dinv, selfw, bnode, SHf, SHr, n_node, [dOf, dOr], [dpf, dpr],
-                           dWs=dWs, dh_out=h if inplace else None)      # h is not read by that launch: dH may take its place
-    return (dh,) + res[0] + res[1] + (None, dpw.reshape(pw.shape), dpb) + (None,) * 16
+                           dWs=dWs, dh_out=dh_out, pair_sum_out=pair_sum_out)
+    return dh, res, dpw.reshape(pw.shape), dpb
 
 
 pair_layer_readout.register_autograd(_plr_bwd, setup_context=_plr_setup)
+
+
+# The same with the pair init (model.py:75) inside the op, for a model whose ONLY pair layer is that last one (depth2 = 1): then
+# the gradient of H = x[src] * x[dst] is consumed by nothing but the pair-init backward, which adds the two directions' rows of
+# every pair before anything else - so the input-gradient GEMM writes ONE row per pair (twowl_conv_args.pair_sum_out: half its
+# output bytes) and the pair-init backward reads that (twowl_seg_args.pair_sum = 2: half of both of its passes). Same terms, same
+# order: bit-identical to pair_init -> pair_layer_readout.
+
+
+@torch.library.custom_op("twowl::pair_init_layer_readout", mutates_args=())
+def pair_init_layer_readout(x: Tensor, src: Tensor, dst: Tensor, ptr_s: Tensor, ids_s: Tensor, plan_s: Optional[Tensor], wf: Tensor,
+                            bf: Tensor, gwf: Tensor, gbf: Tensor, gmf: Tensor, wr: Tensor, br: Tensor, gwr: Tensor, gbr: Tensor,
+                            gmr: Tensor, idx: Tensor, pw: Tensor, pb: Tensor, in_ptr: Tensor, in_ids: Tensor, in_plan: Tensor,
+                            out_ptr: Tensor, out_ids: Tensor, out_plan: Tensor, centre: Tensor, dinv: Tensor, selfw: Tensor,
+                            bnode: Tensor, blocked: Optional[Tensor], n_node: int, eps: float, p_drop: float, seed_f: int,
+                            seed_r: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (pred [L,1], H, O_f, O_r, stats_f, stats_r, SH_f, SH_r); only pred is differentiable, the rest is saved state."""
+    h = ops.pair_init_fwd(x.contiguous(), src, dst)
+    return (h,) + _plr_forward(h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, centre, dinv,
+                               selfw, blocked, n_node, eps, p_drop, seed_f, seed_r)
+
+
+@pair_init_layer_readout.register_fake
+def _(x, src, dst, ptr_s, ids_s, plan_s, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, out_ptr,
+      out_ids, out_plan, centre, dinv, selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r):
+    C = wf.shape[0]
+    h = x.new_empty((src.numel(), x.shape[1]))
+    o = x.new_empty((src.numel(), C))
+    return (h, x.new_empty((idx.numel() // 2, 1)), o, torch.empty_like(o), x.new_empty((2 * C,)), x.new_empty((2 * C,)),
+            x.new_empty((n_node, x.shape[1])), x.new_empty((n_node, x.shape[1])))
+
+
+def _pilr_setup(ctx, inputs, output):
+    (x, src, dst, ptr_s, ids_s, plan_s, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, pb, in_ptr, in_ids, in_plan, out_ptr,
+     out_ids, out_plan, centre, dinv, selfw, bnode, blocked, n_node, eps, p_drop, seed_f, seed_r) = inputs
+    h, pred, Of, Or, sf, sr, SHf, SHr = output
+    ctx.save_for_backward(x, dst, ptr_s, ids_s, plan_s, h, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, idx, pw, out_ptr, out_ids,
+                          out_plan, dinv, selfw, bnode, Of, Or, sf, sr, SHf, SHr)
+    ctx.meta = (n_node, p_drop, seed_f, seed_r)
+    ctx.mark_non_differentiable(h, Of, Or, sf, sr, SHf, SHr)
+    ctx.set_materialize_grads(False)
+
+
+def _pilr_bwd(ctx, _g_h, g, *_unused):
+    x, dst, ptr_s, ids_s, plan_s, *saved = ctx.saved_tensors
+    n_node, p_drop, seed_f, seed_r = ctx.meta
+    dh2, res, dpw, dpb = _plr_backward(g, saved, n_node, p_drop, seed_f, seed_r, pair_sum_out=True)
+    # dx[n] = sum over the pair rows p with src[p] = n of (dH[p] + dH[p^1]) * x[dst[p]], the sum read from dh2[p >> 1]
+    dx = ops.seg_reduce(ptr_s, ids_s, x.shape[0], dh2, plan=plan_s, X2=x, mul_idx=dst, x_pairs=True)
+    return (dx,) + (None,) * 5 + res[0] + res[1] + (None, dpw, dpb) + (None,) * 16
+
+
+pair_init_layer_readout.register_autograd(_pilr_bwd, setup_context=_pilr_setup)
 
 
 def pair_layer_supported(wedges, C: int, seq_f, seq_r) -> bool:
@@ -528,6 +598,21 @@ def pair_layer_readout_apply(x, wedges, seq_f, seq_r, training: bool, idx, pred)
                              wedges.out_ptr, wedges.out_ids, wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked,
                              wedges.n_node, gf.eps, p, seeds[0], seeds[1])
     return out[0]
+
+
+def pair_init_layer_readout_apply(x, pt, wedges, seq_f, seq_r, training: bool, idx, pred):
+    """model.py:75-83 for depth2 = 1 in one op: pair init + the only pair layer + readout (pt: graph.PairTable, doubled layout)."""
+    cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
+    cr, gr = seq_r.modlist[0], seq_r.modlist[1]
+    p = dpf.p if (training and dpf.p > 0.0) else 0.0
+    seeds = [ops.next_seed() for _ in range(2)] if p > 0.0 else [0, 0]
+    _, centre, dinv, selfw, bnode = wedges.prepared()
+    out = pair_init_layer_readout(x, pt.src, pt.dst, pt.ptr_s, pt.ids_s, pt.plan_s, cf.lin.weight, cf.bias, gf.weight, gf.bias,
+                                  gf.mean_scale, cr.lin.weight, cr.bias, gr.weight, gr.bias, gr.mean_scale, idx, pred.weight,
+                                  pred.bias, wedges.in_ptr, wedges.in_ids, wedges.in_plan, wedges.out_ptr, wedges.out_ids,
+                                  wedges.out_plan, centre, dinv, selfw, bnode, wedges.blocked, wedges.n_node, gf.eps, p, seeds[0],
+                                  seeds[1])
+    return out[1]
 
 
 # ------------------------------------------------------------------------------ loss (train.py:37)

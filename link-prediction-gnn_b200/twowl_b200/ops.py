@@ -391,7 +391,8 @@ def seg_plan(ptr: torch.Tensor, M: int, nnz: int) -> torch.Tensor:
 
 def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=None, skip_mask=None,
                row_skip_mask=None, skip_self=False, self_mode=0, dst_scale=None, bias=None, X2=None, mul_idx=None,
-               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None, rows=None, X_mate=None, out2=None):
+               out=None, accumulate=False, pair_sum=False, entry_mask=None, dual=False, src_scale2=None, rows=None, X_mate=None, out2=None,
+               x_pairs=False):
     """dual=True -> (out, out2): out2[m] = sum src_scale2[s^1] * X[s^1] over the same entries (see twowl_seg_args).
     rows=(lo, hi): only output rows [lo, hi) are computed (and written into `out`, which keeps its full [M, C] shape)."""
     _need_cuda(ptr, col, X)
@@ -404,7 +405,8 @@ def seg_reduce(ptr, col, M: int, X, *, plan=None, flip=0, row_flip=0, src_scale=
     a = SegArgs(ptr=ptr.data_ptr(), col=col.data_ptr(), M=M, X=X.data_ptr(), C=C, flip=int(flip), row_flip=int(row_flip),
                 src_scale=_p(src_scale), skip_mask=_p(skip_mask), row_skip_mask=_p(row_skip_mask),
                 skip_self=int(skip_self), self_mode=int(self_mode), dst_scale=_p(dst_scale), bias=_p(bias), X2=_p(X2),
-                mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate), pair_sum=int(pair_sum), entry_mask=_p(entry_mask))
+                mul_idx=_p(mul_idx), out=out.data_ptr(), accumulate=int(accumulate), pair_sum=2 if x_pairs else int(pair_sum),
+                entry_mask=_p(entry_mask))
     if rows is not None:
         a.row_begin, a.row_end = int(rows[0]), int(rows[1])
         if a.row_end <= a.row_begin:
@@ -826,21 +828,26 @@ def pair_conv_supported(Kd: int, Nd: int, nsrc: int) -> bool:
 
 
 def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_scale=None, eps: float = 1e-5,
-              want_moments: bool = False, out=None):
+              want_moments: bool = False, out=None, pair_sum_out: bool = False):
     """out = sum_s (row_scale_s * A_s) B_s^T + sum_g coef_g * T_g[idx_g] + bias on tcgen05 (3xTF32).
     A, W, w_kn, row_scale: sequences of length nsrc; gathers: sequence of (T, idx int32, coef).
     Returns out, or (out, stats[2*Nd]) when stats_mean_scale is given (GraphNorm mean / inv_std of out), or
-    (out, moments float64[2*Nd]) with want_moments (raw column sum / sum of squares, for a row-sharded caller)."""
+    (out, moments float64[2*Nd]) with want_moments (raw column sum / sum of squares, for a row-sharded caller).
+    pair_sum_out: out is [M/2, Nd] and holds out[2k] + out[2k+1] (what the pair-init backward consumes: seg_reduce(x_pairs=True))."""
     nsrc = len(A)
     M, Kd = A[0].shape
     Nd = W[0].shape[1] if w_kn[0] else W[0].shape[0]
     dev = A[0].device
     _need_cuda(*A, *W)
+    Mo = M // 2 if pair_sum_out else M
+    if pair_sum_out:
+        assert M % 2 == 0 and stats_mean_scale is None, "pair_conv: pair_sum_out needs an even M and no statistics"
     if out is None:
-        out = torch.empty((M, Nd), dtype=torch.float32, device=dev)
+        out = torch.empty((Mo, Nd), dtype=torch.float32, device=dev)
     else:   # a caller-owned [M, Nd] buffer that is none of this launch's inputs (the in-place backward, see INPLACE_BACKWARD)
-        assert out.shape == (M, Nd) and out.is_contiguous() and all(out.data_ptr() != x.data_ptr() for x in A)
-    a = ConvArgs(nsrc=nsrc, ngather=len(gathers), Kd=Kd, Nd=Nd, M=M, bias=_p(bias), out=out.data_ptr(), eps=float(eps))
+        assert out.shape == (Mo, Nd) and out.is_contiguous() and all(out.data_ptr() != x.data_ptr() for x in A)
+    a = ConvArgs(nsrc=nsrc, ngather=len(gathers), Kd=Kd, Nd=Nd, M=M, bias=_p(bias), out=out.data_ptr(), eps=float(eps),
+                 pair_sum_out=int(pair_sum_out))
     keep = []
     for s in range(nsrc):
         x = A[s].contiguous()
@@ -860,7 +867,7 @@ def pair_conv(A, W, w_kn, *, row_scale=None, gathers=(), bias=None, stats_mean_s
         assert stats is not None, "pair_conv: moments need stats_mean_scale"
         moments = torch.zeros(2 * Nd, dtype=torch.float64, device=dev)   # zeros: an empty row block contributes nothing
         a.moments = moments.data_ptr()
-    nbytes = M * (4 * Kd * nsrc + 4 * Nd + 8 * len(gathers) + (4 * Nd + 8) * len(gathers))
+    nbytes = M * (4 * Kd * nsrc + 8 * len(gathers) + (4 * Nd + 8) * len(gathers)) + Mo * 4 * Nd
     with _P("pair_conv", nbytes):
         check(lib.twowl_pair_conv(ctypes.byref(a), _p(ws), nb, _stream()), "pair_conv")
     _count(1 if stats is None else 2)

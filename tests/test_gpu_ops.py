@@ -559,6 +559,35 @@ def test_pair_conv_tcgen05_vs_fp64(U, M, Kd, Nd, nsrc, ngather, stats):
             assert_close(res[1][Nd:], inv, absum=inv * dvar / (2 * (var + 1e-5)), nterms=nterms, mma=True, what="pair_conv inv_std")
 
 
+@pytest.mark.parametrize("M,C", [(2, 64), (126, 32), (130, 64), (40002, 64), (20002, 128), (3002, 24), (9002, 256)])
+def test_pair_conv_pair_sum_out_and_its_consumer_are_bit_identical(U, M, C):
+    """twowl_conv_args.pair_sum_out: out[k] = result[2k] + result[2k+1], exactly the full-height result's rows added;
+    twowl_seg_args.pair_sum = 2 (seg_reduce(x_pairs=True)) on that tensor = pair_sum = 1 on the full-height one, bit for bit."""
+    from twowl_b200 import ops
+    if not ops.pair_conv_supported(C, C, 2):
+        pytest.skip("shape not covered by the tcgen05 kernel")
+    torch.manual_seed(M + C)
+    NT = 333
+    A = [torch.randn(M, C, device="cuda") for _ in range(2)]
+    rs = [torch.rand(M, device="cuda") * (torch.rand(M, device="cuda") > 0.3) for _ in range(2)]
+    W = [torch.randn(C, C, device="cuda") / C ** 0.5 for _ in range(2)]
+    gathers = [(torch.randn(NT, C, device="cuda"), torch.randint(-1, NT, (M,), device="cuda").int(), torch.rand(M, device="cuda"))
+               for _ in range(2)]
+    full = ops.pair_conv(A, W, [1, 1], row_scale=rs, gathers=gathers)
+    half = ops.pair_conv(A, W, [1, 1], row_scale=rs, gathers=gathers, pair_sum_out=True)
+    assert half.shape == (M // 2, C) and torch.equal(half, full[0::2] + full[1::2])
+    # the consumer: dx[n] = sum over the rows p with src[p] = n of (g[p] + g[p^1]) * x[dst[p]]
+    n = 97
+    src = torch.randint(0, n, (M,), device="cuda")
+    dst = torch.randint(0, n, (M,), device="cuda").int()
+    x = torch.randn(n, C, device="cuda")
+    ptr, ids = ops.csr_build(src, n)
+    plan = ops.seg_plan(ptr, n, M)
+    a = ops.seg_reduce(ptr, ids, n, full, plan=plan, X2=x, mul_idx=dst, pair_sum=True)
+    b = ops.seg_reduce(ptr, ids, n, half, plan=plan, X2=x, mul_idx=dst, x_pairs=True)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("ratio,M", [(3.0, 40001), (10.0, 40001), (30.0, 300000)])
 def test_pair_conv_statistics_with_a_large_mean(U, ratio, M):
     """GraphNorm statistics out of pair_conv's epilogue are raw moments: fp32 (sum, sum of squares) per 32-row block, added in
