@@ -436,7 +436,7 @@ def _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, pf, pr)
     return Os[0], Os[1], sf, sr, SH
 
 
-def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr):
+def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr, pair_sum_out=False):
     """From the gradients of the two pre-GraphNorm outputs (and the (selfw*dO)^T H parts of the weight gradients) to
     (dH, dW_f, dW_r) on this block: the dS exchange and the input-gradient pass."""
     _, dinv, selfw, bnode = rows
@@ -455,8 +455,9 @@ def _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
         dWf = dWf + ops.linear_bwd_weight(dS[0, lo:hi], SH[0, lo:hi])
         dWr = dWr + ops.linear_bwd_weight(dS[1, lo:hi], SH[1, lo:hi])
     dSW = [ops.linear_bwd_input(dS[0], wf), ops.linear_bwd_input(dS[1], wr)]
+    # pair_sum_out: dh is [Rl / 2, C], dH[2k] + dH[2k+1] per pair - all the pair-init backward reads (functional.pair_init_layer_readout)
     dh = ops.pair_conv([dOf, dOr], [wf, wr], [1, 1], row_scale=[selfw[0], selfw[1]],
-                       gathers=[(dSW[0], bnode[0], dinv[0]), (dSW[1], bnode[1], dinv[1])])
+                       gathers=[(dSW[0], bnode[0], dinv[0]), (dSW[1], bnode[1], dinv[1])], pair_sum_out=pair_sum_out)
     return dh, dWf, dWr
 
 
@@ -523,26 +524,32 @@ class _ShardedPairLayer(torch.autograd.Function):
 
 class _ShardedLastLayer(torch.autograd.Function):
     """The last conv2s / conv2s_r layer (model.py:77) + readout (model.py:78-83) on one row block: H [Rl, C] -> [L, 1] with the
-    logits of the target links inside the block and 0 for the others (idx_l = -1 there)."""
+    logits of the target links inside the block and 0 for the others (idx_l = -1 there).
+    init_inside (depth2 = 1): the first argument is the node features x [N, C]; the pair init (model.py:75) runs inside, and the
+    backward returns dx: the input-gradient GEMM writes one row per pair and the pair-init backward - pipelined with the dx
+    exchange as in _ShardedPairInit - reads that (functional.pair_init_layer_readout on one row block)."""
 
     @staticmethod
     def forward(ctx, H, wf, bf, gwf, gbf, gmf, wr, br, gwr, gbr, gmr, pw, pb, shard, loc, rows, idx_l, blocked_l, R_total, n_node,
-                eps, p_drop, seed_f, seed_r):
+                eps, p_drop, seed_f, seed_r, init_inside=False):
         H = H.contiguous()
+        x = H if init_inside else H.new_empty(0)
+        if init_inside:
+            H = ops.pair_init_fwd(x, loc.src, loc.dst)
         Of, Or, sf, sr, SH = _layer_forward(shard, loc, rows, blocked_l, R_total, n_node, eps, H, (wf, bf, gmf), (wr, br, gmr))
         if idx_l.numel():
             pred = ops.gn2_readout_fwd(Of, Or, sf, sr, (gwf, gbf, gmf), (gwr, gbr, gmr), p_drop, seed_f, seed_r, True, idx_l,
                                        pw.contiguous(), pb)
         else:
             pred = H.new_empty((0, 1))
-        ctx.save_for_backward(H, wf, gwf, gbf, gmf, wr, gwr, gbr, gmr, pw, idx_l, Of, Or, sf, sr, SH, *rows)
-        ctx.meta = (shard, loc, R_total, n_node, p_drop, seed_f, seed_r)
+        ctx.save_for_backward(x, H, wf, gwf, gbf, gmf, wr, gwr, gbr, gmr, pw, idx_l, Of, Or, sf, sr, SH, *rows)
+        ctx.meta = (shard, loc, R_total, n_node, p_drop, seed_f, seed_r, bool(init_inside))
         return pred
 
     @staticmethod
     def backward(ctx, g):
-        H, wf, gwf, gbf, gmf, wr, gwr, gbr, gmr, pw, idx_l, Of, Or, sf, sr, SH, *rows = ctx.saved_tensors
-        shard, loc, R_total, n_node, p_drop, seed_f, seed_r = ctx.meta
+        x, H, wf, gwf, gbf, gmf, wr, gwr, gbr, gmr, pw, idx_l, Of, Or, sf, sr, SH, *rows = ctx.saved_tensors
+        shard, loc, R_total, n_node, p_drop, seed_f, seed_r, init_inside = ctx.meta
         C = wf.shape[0]
         pf, pr = (gwf, gbf, gmf), (gwr, gbr, gmr)
         Gp, head, nxt, colsums = ops.gn2_readout_bwd_rows(Of, Or, sf, sr, pf, pr, p_drop, seed_f, seed_r, True, idx_l, pw.contiguous(),
@@ -550,9 +557,16 @@ class _ShardedLastLayer(torch.autograd.Function):
         shard.all_reduce(colsums, "readout / GraphNorm-backward column sums [6,C] f64")
         consts, dpf, dpr, dpw, dpb = ops.gn2_readout_bwd_finish(colsums, R_total, sf, sr, pf, pr)
         dOf, dOr, dWf, dWr = ops.pair_dw_gn(Of, Or, consts, Gp, head, nxt, p_drop, seed_f, seed_r, True, rows[2][0], rows[2][1], H)
-        dh, dWf, dWr = _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr)
+        dh, dWf, dWr = _layer_backward(shard, loc, rows, n_node, H, wf, wr, SH, dOf, dOr, dWf, dWr, pair_sum_out=init_inside)
+        if init_inside:      # dh holds one row per pair: this block's part of dx from it, summed over the ranks range by range
+            N, dh2 = x.shape[0], dh
+            dh = torch.empty_like(x)
+            shard.reduce_in_chunks(loc.xout_cuts,
+                                   lambda lo, hi, lg: ops.seg_reduce(loc.xout_ptr, loc.xout_ids, N, dh2, plan=loc.xout_plan if lg else None,
+                                                                     X2=x, mul_idx=loc.dst, x_pairs=True, out=dh, rows=(lo, hi)),
+                                   (dh,), "d(x) [N,C]")
         gf, gr = _param_grads(shard, C, dpf, dpr, extra=(dpw, dpb))
-        return (dh, dWf) + gf + (dWr,) + gr + (dpw.reshape(pw.shape), dpb) + (None,) * 11
+        return (dh, dWf) + gf + (dWr,) + gr + (dpw.reshape(pw.shape), dpb) + (None,) * 12
 
 
 class _SumLogits(torch.autograd.Function):
@@ -646,8 +660,9 @@ def forward_pairs(model, x, pos, idx, ei2):
     rows = (centre, dinv, selfw, bnode)
     blocked_l = wedges.blocked[ranges[0][0]:ranges[0][1]] if wedges.blocked is not None else None
     idx_l, link_dest = own_links_first(mask_links(idx, ranges))
-    H = _ShardedPairInit.apply(x, loc, shard)
     last = len(model.conv2s) - 1
+    init_inside = last == 0 and getattr(model, "fused_pair_init", True)      # depth2 = 1: the pair init joins the last layer's node
+    H = x if init_inside else _ShardedPairInit.apply(x, loc, shard)
     for i, (seq_f, seq_r) in enumerate(zip(model.conv2s, model.conv2s_r)):
         cf, gf, dpf = seq_f.modlist[0], seq_f.modlist[1], seq_f.modlist[2]
         cr, gr = seq_r.modlist[0], seq_r.modlist[1]
@@ -658,5 +673,5 @@ def forward_pairs(model, x, pos, idx, ei2):
             H = _ShardedPairLayer.apply(H, *par, shard, loc, rows, blocked_l, pt.R, wedges.n_node, gf.eps, p, seeds[0], seeds[1])
         else:
             pred_l = _ShardedLastLayer.apply(H, *par, model.pred.weight, model.pred.bias, shard, loc, rows, idx_l, blocked_l, pt.R,
-                                             wedges.n_node, gf.eps, p, seeds[0], seeds[1])
+                                             wedges.n_node, gf.eps, p, seeds[0], seeds[1], init_inside)
     return _SumLogits.apply(pred_l.index_select(0, link_dest), shard)       # back to the caller's link order
